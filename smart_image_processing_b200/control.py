@@ -1,0 +1,90 @@
+"""Host-side control path around the accelerated pixel path: file decode, page-quad localisation, skew-angle
+estimate, optional stage dumps.  These parts of the reference (DocScanner.py:15-24, 76-109, 218-231,
+282-346) produce a handful of scalars per page from irregular, sequential algorithms (contours, Hough
+peaks) and are out of scope for the CUDA path (SURVEY.md §8f lists them as the next rows).  They run on
+the host with OpenCV when it is installed; every function raises if it is not, so callers can instead
+supply `quad=` / `angle=` themselves.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def _cv2():
+    try:
+        import cv2
+    except ImportError as e:  # pragma: no cover
+        raise RuntimeError("the control path (image decode, quad localisation, skew estimate) needs OpenCV on the "
+                           "host; install opencv-python or pass quad= / angle= explicitly") from e
+    return cv2
+
+
+def load_image(path: str) -> np.ndarray:
+    img = _cv2().imread(path, _cv2().IMREAD_COLOR)
+    if img is None:
+        raise FileNotFoundError(f"Cannot load image: {path}")
+    return img
+
+
+def quad_area(quad) -> float:
+    q = np.asarray(quad, np.float64).reshape(4, 2)
+    x, y = q[:, 0], q[:, 1]
+    return float(abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1))) * 0.5)
+
+
+def _ordered(pts: np.ndarray) -> np.ndarray:
+    total, delta = pts.sum(axis=1), np.diff(pts, axis=1).ravel()
+    return np.stack([pts[np.argmin(total)], pts[np.argmin(delta)], pts[np.argmax(total)], pts[np.argmax(delta)]]).astype(np.float32)
+
+
+def localize_document(img, canny_low=50, canny_high=150, min_area_ratio=0.2, max_area_ratio=0.98):
+    """Largest 4-gon among the external contours of (Canny edges OR their probabilistic-Hough segments);
+    same recipe as DocScanner.py:76-109.  Returns TL, TR, BR, BL as float32 (4, 2), or None."""
+    cv2 = _cv2()
+    edges = cv2.Canny(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), canny_low, canny_high)
+    segments = cv2.HoughLinesP(edges, 1, np.pi / 180, threshold=80, minLineLength=80, maxLineGap=10)
+    strokes = np.zeros_like(edges)
+    for seg in ([] if segments is None else segments):
+        x1, y1, x2, y2 = seg[0]
+        cv2.line(strokes, (x1, y1), (x2, y2), 255, 2)
+    contours, _ = cv2.findContours(cv2.bitwise_or(edges, strokes), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+    if not contours:
+        return None
+    frame = max(img.shape[0] * img.shape[1], 1)
+    sized = [c for c in contours if min_area_ratio <= abs(cv2.contourArea(c)) / frame <= max_area_ratio]
+    best, best_area = None, 0.0
+    for c in (sized or contours):
+        poly = cv2.approxPolyDP(c, 0.02 * cv2.arcLength(c, True), True)
+        if len(poly) == 4 and abs(cv2.contourArea(poly)) > best_area:
+            best, best_area = poly.reshape(-1, 2).astype(np.float32), abs(cv2.contourArea(poly))
+    if best is None:
+        best = cv2.boxPoints(cv2.minAreaRect(max(contours, key=cv2.contourArea))).astype(np.float32)
+    return _ordered(best)
+
+
+def estimate_skew_angle(gray, canny_low=50, canny_high=150, max_rotate=10.0) -> float:
+    """Median Hough-line angle folded into (-90, 90], zero when it exceeds max_rotate (DocScanner.py:218-231).
+    The arithmetic is kept in the dtype numpy gives it (float32 thetas), because the reference hands exactly
+    that Python float to getRotationMatrix2D."""
+    cv2 = _cv2()
+    lines = cv2.HoughLines(cv2.Canny(gray, canny_low, canny_high), 1, np.pi / 180, 150)
+    if lines is None or len(lines) == 0:
+        return 0.0
+    folded = [((theta * 180.0 / np.pi) + 90.0) % 180.0 - 90.0 for _, theta in lines[:, 0, :]]
+    angle = float(np.median(folded))
+    return 0.0 if abs(angle) > max_rotate else angle
+
+
+_DUMP_NAMES = {"warped": "scan_03_warped.png", "illum": "scan_04_illum.png", "stretch": "scan_05_stretch.png",
+               "inkmask": "scan_05a_inkmask.png", "adapt": "scan_06_adapt.png", "weighted": "scan_06b_weighted.png",
+               "deskew": "scan_07_deskew.png", "clean": "scan_08_clean.png"}
+
+
+def save_stage_dumps(out_dir: str, stages: dict) -> None:
+    cv2 = _cv2()
+    os.makedirs(out_dir, exist_ok=True)
+    for key, name in _DUMP_NAMES.items():
+        if key in stages:
+            cv2.imwrite(os.path.join(out_dir, name), stages[key])

@@ -1,0 +1,304 @@
+// cv2.adaptiveThreshold(..., ADAPTIVE_THRESH_GAUSSIAN_C, THRESH_BINARY, k, C) (DocScanner.py:167) and the
+// ink-mask combine + masked blend that follows it (DocScanner.py:207-212, 338-339).
+//
+// GAUSSIAN_C is the one floating-point stage of the path: OpenCV converts the page to fp32, runs a
+// separable fp32 Gaussian (BORDER_REPLICATE) and rounds the mean to uint8.  The result depends on the
+// order of the fp32 operations, so the kernel reproduces it: row taps left to right with one fma per
+// tap, column taps as symmetric pairs (a rounded add, then an fma), outermost pair last.
+// Same marching layout as blur.cu: 128-column strips, 16 rows per step, fp32 ring of row-filtered
+// rows in shared memory; row pass register-blocked 16 outputs/thread, column pass one column and 16
+// rows per thread with the whole column window held in registers.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 128, BR = 16, NT = 128;
+constexpr int RPF = 132;      // ring row pitch in floats
+
+struct AdaptLaunch {
+    int k, r, delta, c_param, seg_rows, spf, ring_rows, nblk;
+    const float* g_row;       // 16 zeros + k taps + zeros up to 16*nblk + 32
+    const float* g_col;       // g_col[j] = g[r + j] for j <= r, zero up to 64
+};
+
+__device__ __forceinline__ int stage_index(int c) { return c + (c >> 4); }   // one pad float per 16: no bank conflicts
+
+template <int RMAX>
+__global__ void __launch_bounds__(NT) adaptive_gauss_kernel(const AdaptJob* __restrict__ jobs, const AdaptLaunch L) {
+    const AdaptJob J = jobs[blockIdx.z];
+    const int x0 = blockIdx.x * TW;
+    const int y_begin = blockIdx.y * L.seg_rows;
+    if (x0 >= J.w || y_begin >= J.h) return;
+    const int y_end = min(J.h, y_begin + L.seg_rows);
+    const int rows_out = y_end - y_begin;
+    const int tid = threadIdx.x;
+    const int r = L.r, r4 = L.r + L.delta;
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* s_grow = reinterpret_cast<float*>(smem_raw);            // 16*nblk + 32
+    float* s_gcol = s_grow + 16 * L.nblk + 32;                     // 64
+    float* s_stage = s_gcol + 64;                                  // BR * spf
+    float* s_ring = s_stage + BR * L.spf;                          // ring_rows * RPF
+    for (int i = tid; i < 16 * L.nblk + 32; i += NT) s_grow[i] = L.g_row[i];
+    if (tid < 64) s_gcol[tid] = L.g_col[tid];
+
+    const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
+    const int stage_words = (TW + 16 * L.nblk) >> 2;   // every column the row pass can touch holds a finite value
+    const int D = (2 * r + BR - 1) / BR;
+    const int n_vb = (rows_out + BR - 1) / BR;
+    const bool row_identity = J.w == 1, col_identity = J.h == 1;   // cv::GaussianBlur shrinks the kernel on 1-px axes
+
+    for (int hb = 0; hb < n_vb + D; hb++) {
+        for (int idx = tid; idx < BR * stage_words; idx += NT) {
+            const int row = idx / stage_words, wi = idx - row * stage_words;
+            const int ysrc = ds_clamp(y_begin - r + hb * BR + row, 0, J.h - 1);
+            const int gx = x0 - r4 + 4 * wi;
+            const uint8_t* rowp = J.src + (size_t)ysrc * J.src_pitch;
+            uint32_t word;
+            if (src_al && gx >= 0 && gx + 3 < J.w) word = ds_ldg32(rowp + gx);
+            else {
+                word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[ds_clamp(gx + b, 0, J.w - 1)] << (8 * b);
+            }
+            float* sp = s_stage + row * L.spf;
+#pragma unroll
+            for (int b = 0; b < 4; b++) sp[stage_index(4 * wi + b)] = (float)((word >> (8 * b)) & 255u);
+        }
+        __syncthreads();
+        {   // ---- row pass: out[xo + o] = sum_i g[i] * f[xo + o + i - r], taps in increasing i, one fma each
+            const int hr = tid >> 3, cg = tid & 7;
+            const float* srow = s_stage + hr * L.spf;
+            const int base = cg * 16 + L.delta;
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = 0.0f;
+            float G[32];
+            {
+                const float4* g4 = reinterpret_cast<const float4*>(s_grow);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { float4 t = g4[i]; G[16 + 4 * i] = t.x; G[17 + 4 * i] = t.y; G[18 + 4 * i] = t.z; G[19 + 4 * i] = t.w; }
+            }
+            for (int b = 0; b < L.nblk; b++) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) G[i] = G[i + 16];
+                const float4* g4 = reinterpret_cast<const float4*>(s_grow + 16 * b + 16);
+#pragma unroll
+                for (int i = 0; i < 4; i++) { float4 t = g4[i]; G[16 + 4 * i] = t.x; G[17 + 4 * i] = t.y; G[18 + 4 * i] = t.z; G[19 + 4 * i] = t.w; }
+#pragma unroll
+                for (int u = 0; u < 16; u++) {
+                    const float f = srow[stage_index(base + 16 * b + u)];
+#pragma unroll
+                    for (int o = 0; o < 16; o++) acc[o] = __fmaf_rn(f, G[u - o + 16], acc[o]);
+                }
+            }
+            if (row_identity) {
+#pragma unroll
+                for (int o = 0; o < 16; o++) acc[o] = srow[stage_index(base + r + o)];
+            }
+            const int slot = (hb * BR + hr) % L.ring_rows;
+            float4* dst = reinterpret_cast<float4*>(s_ring + slot * RPF + cg * 16);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            dst[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+            dst[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
+        }
+        __syncthreads();
+        if (hb < D) continue;
+        // ---- column pass: thread = one column, 16 rows; centre of output o sits at window index o + RMAX
+        const int vb = hb - D;
+        const int col = tid;
+        const int x = x0 + col;
+        float Wn[BR + 2 * RMAX];
+        const int shift = RMAX - r;                 // window index i <-> virtual row vb*BR + i - shift
+#pragma unroll
+        for (int i = 0; i < BR + 2 * RMAX; i++) {
+            const int rel = i - shift;
+            float v = 0.0f;
+            if (rel >= 0 && rel <= BR - 1 + 2 * r) v = s_ring[((vb * BR + rel) % L.ring_rows) * RPF + col];
+            Wn[i] = v;
+        }
+        float acc[BR];
+        const float gc0 = s_gcol[0];
+#pragma unroll
+        for (int o = 0; o < BR; o++) acc[o] = __fmul_rn(gc0, Wn[o + RMAX]);
+#pragma unroll
+        for (int j = 1; j <= RMAX; j++) {
+            const float gj = s_gcol[j];
+#pragma unroll
+            for (int o = 0; o < BR; o++) acc[o] = __fmaf_rn(__fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j]), gj, acc[o]);
+        }
+        if (x < J.w) {
+#pragma unroll
+            for (int o = 0; o < BR; o++) {
+                const int y = y_begin + vb * BR + o;
+                if (y >= y_end) break;
+                const float m = col_identity ? Wn[o + RMAX] : acc[o];
+                const int mean = min(max(__float2int_rn(m), 0), 255);
+                const int s = J.src[(size_t)y * J.src_pitch + x];
+                J.dst[(size_t)y * J.dst_pitch + x] = (s - mean > -L.c_param) ? 255 : 0;
+            }
+        }
+    }
+}
+
+// Last w % 8 columns the way cv2's AVX2 build evaluates them (see oracle/docscan_oracle.c, A.9):
+// row filter: one 4-wide fma chunk, then scalar mul+add whose last (k-1) % 4 taps are fma;
+// column filter: mul+add.  One thread per tail pixel; O(k^2) each, but there are at most 7 columns.
+__global__ void adaptive_gauss_tail_kernel(const AdaptJob* __restrict__ jobs, int k, int c_param,
+                                           const float* __restrict__ g /* k taps */) {
+    const AdaptJob J = jobs[blockIdx.z];
+    const int tail = J.w & 7;
+    if (tail == 0) return;
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    const int tx = blockIdx.y;
+    if (y >= J.h || tx >= tail) return;
+    const int r = k >> 1;
+    const int xt_col = J.w - tail;
+    const int xt_row = xt_col + (tail >= 4 ? 4 : 0);
+    const int x = xt_col + tx;
+    const bool row_fused = x < xt_row;
+    const int first_fused_tap = row_fused ? 1 : k - ((k - 1) & 3);
+    auto row_value = [&](int yy) -> float {
+        const uint8_t* rowp = J.src + (size_t)ds_clamp(yy, 0, J.h - 1) * J.src_pitch;
+        if (J.w == 1) return (float)rowp[0];
+        float acc = __fmul_rn(g[0], (float)rowp[ds_clamp(x - r, 0, J.w - 1)]);
+        for (int i = 1; i < k; i++) {
+            const float f = (float)rowp[ds_clamp(x - r + i, 0, J.w - 1)];
+            if (i >= first_fused_tap) acc = __fmaf_rn(f, g[i], acc);
+            else acc = __fadd_rn(acc, __fmul_rn(g[i], f));
+        }
+        return acc;
+    };
+    float acc;
+    if (J.h == 1) acc = row_value(y);
+    else {
+        acc = __fmul_rn(g[r], row_value(y));
+        for (int j = 1; j <= r; j++) {
+            const float pr = __fadd_rn(row_value(y + j), row_value(y - j));
+            acc = __fadd_rn(acc, __fmul_rn(g[r + j], pr));
+        }
+    }
+    const int mean = min(max(__float2int_rn(acc), 0), 255);
+    const int s = J.src[(size_t)y * J.src_pitch + x];
+    J.dst[(size_t)y * J.dst_pitch + x] = (s - mean > -c_param) ? 255 : 0;
+}
+
+// combined = max(ink_sub_n > t_sub, bh_n > t_bh) -> dilate rect 2x2 x iters (window {x-n..x} x {y-n..y},
+// out-of-image ignored) -> bin = base where combined else 255.  The normalise + threshold of both
+// branches is folded into the raw cut-offs computed by scalars.cu.
+__global__ void __launch_bounds__(128) mask_blend_kernel(const BlendJob* __restrict__ jobs, int n_dil, int mask_only) {
+    const BlendJob J = jobs[blockIdx.z];
+    const int y = blockIdx.y;
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+    if (y >= J.h || x >= J.w) return;
+    const int cut_a = J.sc->cut_a, cut_b = J.sc->cut_b;
+    uint32_t hit = 0;   // bit i: pixel x+i has ink in its window
+    for (int dy = 0; dy <= n_dil; dy++) {
+        const int yy = y - dy;
+        if (yy < 0) break;
+        const uint8_t* ra = J.ink_sub + (size_t)yy * J.pitch_sub;
+        const uint8_t* rb = J.bh + (size_t)yy * J.pitch_bh;
+        uint32_t rowbits = 0;   // bit j <-> column x - n_dil + j
+        for (int j = 0; j < 4 + n_dil; j++) {
+            const int xx = x - n_dil + j;
+            if (xx < 0 || xx >= J.w) continue;
+            if ((int)ra[xx] >= cut_a || (int)rb[xx] >= cut_b) rowbits |= 1u << j;
+        }
+        for (int i = 0; i < 4; i++) {
+            const uint32_t win = (rowbits >> i) & ((2u << n_dil) - 1u);
+            if (win) hit |= 1u << i;
+        }
+    }
+    uint8_t* rd = J.dst + (size_t)y * J.pitch_dst;
+    const uint8_t* rbase = mask_only ? nullptr : J.base + (size_t)y * J.pitch_base;
+    for (int i = 0; i < 4 && x + i < J.w; i++) {
+        const bool ink = (hit >> i) & 1u;
+        rd[x + i] = mask_only ? (ink ? 255 : 0) : (ink ? rbase[x + i] : 255);
+    }
+}
+
+template <int RMAX>
+int launch_adaptive(docscan_ctx* ctx, const AdaptJob* jd, const AdaptLaunch& L, dim3 grid, size_t smem) {
+    if (smem > 48 * 1024)
+        DS_CUDA(ctx, cudaFuncSetAttribute(adaptive_gauss_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    adaptive_gauss_kernel<RMAX><<<grid, NT, smem, ctx->stream>>>(jd, L);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}
+
+}  // namespace
+
+int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, const AdaptJob* jobs_host, int n,
+                          int max_w, int max_h) {
+    if (k < 3 || (k & 1) == 0 || k > 65)
+        return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "adaptive GAUSSIAN_C block size must be odd and in 3..65 (got %d)", k);
+    AdaptLaunch L{};
+    L.k = k; L.r = k / 2; L.delta = (4 - (L.r & 3)) & 3; L.c_param = c;
+    L.nblk = (k + 15 + 15) / 16;
+    L.spf = TW + 16 * L.nblk;
+    L.spf += L.spf / 16 + 2;
+    L.ring_rows = ((2 * L.r + BR - 1) / BR + 1) * BR;
+    // coefficient tables (device, cached per k)
+    const uint64_t key = ((uint64_t)7 << 32) | (uint32_t)k;
+    const int n_row = 16 * L.nblk + 32;
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        std::vector<float> g(k), host(n_row + 64 + k, 0.0f);
+        docscan_gaussian_kernel_f32(k, g.data());
+        for (int i = 0; i < k; i++) host[16 + i] = g[i];
+        for (int j = 0; j <= L.r; j++) host[n_row + j] = g[L.r + j];
+        for (int i = 0; i < k; i++) host[n_row + 64 + i] = g[i];
+        void* dev = nullptr;
+        DS_CUDA(ctx, cudaMalloc(&dev, host.size() * sizeof(float)));
+        DS_CUDA(ctx, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->tables.emplace(key, dev).first;
+    }
+    const float* tab = (const float*)it->second;
+    L.g_row = tab; L.g_col = tab + n_row;
+    const float* g_plain = tab + n_row + 64;
+
+    const int strips = n * ((max_w + TW - 1) / TW);
+    int segs = (4 * ctx->sm_count + strips - 1) / strips;
+    if (segs < 1) segs = 1;
+    int seg = (max_h + segs - 1) / segs;
+    const int seg_min = max(64, 4 * L.r);
+    if (seg < seg_min) seg = seg_min;
+    seg = (seg + BR - 1) / BR * BR;
+    L.seg_rows = seg;
+    const size_t smem = sizeof(float) * ((size_t)n_row + 64 + (size_t)BR * L.spf + (size_t)L.ring_rows * RPF);
+    void* dev = nullptr;
+    DS_TRY(ds_upload(ctx, jobs_host, sizeof(AdaptJob) * n, &dev));
+    const AdaptJob* jd = (const AdaptJob*)dev;
+    dim3 grid((max_w + TW - 1) / TW, (max_h + seg - 1) / seg, n);
+    int rc;
+    if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, grid, smem);
+    else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, grid, smem);
+    else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, grid, smem);
+    else if (L.r <= 17) rc = launch_adaptive<17>(ctx, jd, L, grid, smem);
+    else if (L.r <= 25) rc = launch_adaptive<25>(ctx, jd, L, grid, smem);
+    else rc = launch_adaptive<32>(ctx, jd, L, grid, smem);
+    DS_TRY(rc);
+    if (cv_tail_compat && k >= 11) {
+        bool any = false;
+        for (int i = 0; i < n; i++) any = any || (jobs_host[i].w & 7) != 0;
+        if (any) {
+            dim3 tgrid((max_h + 127) / 128, 7, n);
+            adaptive_gauss_tail_kernel<<<tgrid, 128, 0, ctx->stream>>>(jd, k, c, g_plain);
+            DS_CHECK_LAUNCH(ctx);
+        }
+    }
+    return DOCSCAN_OK;
+}
+
+int k_mask_blend_jobs(docscan_ctx* ctx, int dilate_iters, int write_mask_only, const BlendJob* jobs_host, int n,
+                      int max_w, int max_h) {
+    if (dilate_iters < 0 || dilate_iters > 24) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "ink dilate iterations must be in 0..24");
+    void* dev = nullptr;
+    DS_TRY(ds_upload(ctx, jobs_host, sizeof(BlendJob) * n, &dev));
+    dim3 grid((max_w + 511) / 512, max_h, n);
+    mask_blend_kernel<<<grid, 128, 0, ctx->stream>>>((const BlendJob*)dev, dilate_iters, write_mask_only);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}

@@ -1,0 +1,306 @@
+// Separable integer blur of uint8 pages with a fused per-pixel epilogue.
+//
+//   kind 0  cv2.GaussianBlur(u8, (k,k), 0), BORDER_REFLECT_101 (DocScanner.py:153,184): OpenCV's 8.8
+//           fixed-point kernel; H pass exact in u16, V pass exact in u32, dst = (V + 32768) >> 16.
+//   kind 1  k x k box sum with BORDER_REPLICATE, mean = round(V / k^2): the local mean of
+//           cv2.adaptiveThreshold(ADAPTIVE_THRESH_MEAN_C) (DocScanner.py:167).
+//
+// One CTA owns a 128-column strip of one page segment and marches down it.  Per step it stages 16
+// source rows (halo columns resolved through the border rule) in shared memory, H-filters them with
+// dp4a (4 taps per instruction, coefficient words pre-shifted on the host so that all loads are
+// 32-bit aligned) into a ring of u16 rows, then V-filters 16 output rows out of the ring with a
+// register-blocked 8-row x 2-column accumulator tile per thread.  Every source byte is read from
+// HBM/L2 once per strip (plus the halo), the H pass is never recomputed inside a segment, and the
+// epilogue (subtract / divide / threshold, min-max, histogram) is applied before the only store.
+// All sums are exact integers, so the regrouping is bit-exact with OpenCV.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TW = 128;       // output columns per strip
+constexpr int BR = 16;        // rows per march step
+constexpr int NT = 128;       // threads per CTA
+constexpr int RP = 68;        // ring row pitch in 32-bit words (64 + 4 pad)
+
+struct BlurTable {
+    int k_eff, r_eff, delta, M, nb;
+    uint32_t kk;              // k*k (box) or 0
+    const uint4* qH;          // M + 6 entries (3 zero entries each side)
+    const uint32_t* qV;       // 8*nb + 16 entries, tap j at index j + 8
+};
+
+struct BlurLaunch {
+    BlurTable t;
+    int seg_rows, border, c_param;
+    int spw;                  // staging row pitch in words (odd)
+    int ring_rows;
+};
+
+__device__ __forceinline__ int border_map(int p, int len, int border) {
+    return border == 0 ? ds_reflect101(p, len) : ds_clamp(p, 0, len - 1);
+}
+
+template <int EPI, bool STATS>
+__global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restrict__ jobs, const BlurLaunch L) {
+    const BlurJob J = jobs[blockIdx.z];
+    const int x0 = blockIdx.x * TW;
+    const int y_begin = blockIdx.y * L.seg_rows;
+    if (x0 >= J.w || y_begin >= J.h) return;
+    const int y_end = min(J.h, y_begin + L.seg_rows);
+    const int rows_out = y_end - y_begin;
+    const int tid = threadIdx.x;
+    const BlurTable& T = L.t;
+    const int r = T.r_eff;
+    const int r4 = r + T.delta;
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint4* s_qH = reinterpret_cast<uint4*>(smem_raw);
+    uint32_t* s_qV = reinterpret_cast<uint32_t*>(s_qH + (T.M + 6));
+    uint32_t* s_stage = s_qV + (8 * T.nb + 16);
+    uint32_t* s_ring = s_stage + BR * L.spw;
+    s_ring = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_ring) + 15) & ~(uintptr_t)15);
+    uint32_t* s_hist = s_ring + L.ring_rows * RP;    // 4 x 256, only when STATS && J.hist
+
+    for (int i = tid; i < T.M + 6; i += NT) s_qH[i] = T.qH[i];
+    for (int i = tid; i < 8 * T.nb + 16; i += NT) s_qV[i] = T.qV[i];
+    if (STATS && J.hist)
+        for (int i = tid; i < 4 * 256; i += NT) s_hist[i] = 0;
+
+    const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
+    const int D = (2 * r + BR - 1) / BR;                       // V batch lags the H batch by D steps
+    const int n_vb = (rows_out + BR - 1) / BR;
+    uint32_t st_lo = 255, st_hi = 0, zero_count = 0;
+
+    for (int hb = 0; hb < n_vb + D; hb++) {
+        // ---- stage BR source rows: virtual row v <-> source row border(y_begin - r + v)
+        for (int idx = tid; idx < BR * L.spw; idx += NT) {
+            const int row = idx / L.spw, wi = idx - row * L.spw;
+            const int ysrc = border_map(y_begin - r + hb * BR + row, J.h, L.border);
+            const int gx = x0 - r4 + 4 * wi;
+            const uint8_t* rowp = J.src + (size_t)ysrc * J.src_pitch;
+            uint32_t word;
+            if (src_al && gx >= 0 && gx + 3 < J.w) {
+                word = ds_ldg32(rowp + gx);
+            } else {
+                word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[border_map(gx + b, J.w, L.border)] << (8 * b);
+            }
+            s_stage[idx] = word;
+        }
+        __syncthreads();
+        // ---- H pass: thread = (row, 16 consecutive columns)
+        {
+            const int hr = tid >> 3, cg = tid & 7;
+            const uint32_t* srow = s_stage + hr * L.spw + cg * 4;
+            uint32_t acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = 0;
+            uint4 q0 = s_qH[0], q1 = s_qH[1], q2 = s_qH[2], q3;    // zero entries: q[wi + 3 - g], g = 3,2,1
+            for (int wi = 0; wi < T.M + 3; wi++) {
+                q3 = s_qH[wi + 3];
+                const uint32_t W = srow[wi];
+                // group g uses coefficient word m = wi - g  -> table entry m + 3
+                acc[0] = __dp4a(W, q3.x, acc[0]);  acc[1] = __dp4a(W, q3.y, acc[1]);
+                acc[2] = __dp4a(W, q3.z, acc[2]);  acc[3] = __dp4a(W, q3.w, acc[3]);
+                acc[4] = __dp4a(W, q2.x, acc[4]);  acc[5] = __dp4a(W, q2.y, acc[5]);
+                acc[6] = __dp4a(W, q2.z, acc[6]);  acc[7] = __dp4a(W, q2.w, acc[7]);
+                acc[8] = __dp4a(W, q1.x, acc[8]);  acc[9] = __dp4a(W, q1.y, acc[9]);
+                acc[10] = __dp4a(W, q1.z, acc[10]); acc[11] = __dp4a(W, q1.w, acc[11]);
+                acc[12] = __dp4a(W, q0.x, acc[12]); acc[13] = __dp4a(W, q0.y, acc[13]);
+                acc[14] = __dp4a(W, q0.z, acc[14]); acc[15] = __dp4a(W, q0.w, acc[15]);
+                q0 = q1; q1 = q2; q2 = q3;
+            }
+            const int slot = (hb * BR + hr) % L.ring_rows;
+            uint4* dst = reinterpret_cast<uint4*>(s_ring + slot * RP + cg * 8);
+            dst[0] = make_uint4(acc[0] | (acc[1] << 16), acc[2] | (acc[3] << 16), acc[4] | (acc[5] << 16), acc[6] | (acc[7] << 16));
+            dst[1] = make_uint4(acc[8] | (acc[9] << 16), acc[10] | (acc[11] << 16), acc[12] | (acc[13] << 16), acc[14] | (acc[15] << 16));
+        }
+        __syncthreads();
+        if (hb < D) continue;
+        // ---- V pass: thread = (column pair, 8 rows)
+        const int vb = hb - D;
+        const int cp = tid & 63, rg = tid >> 6;
+        const int vbase = vb * BR + rg * 8;
+        uint32_t a0[8], a1[8];
+#pragma unroll
+        for (int o = 0; o < 8; o++) { a0[o] = 0; a1[o] = 0; }
+        uint32_t C[16];
+        {
+            const uint4* qv4 = reinterpret_cast<const uint4*>(s_qV);
+            uint4 t0 = qv4[0], t1 = qv4[1];
+            C[8] = t0.x; C[9] = t0.y; C[10] = t0.z; C[11] = t0.w; C[12] = t1.x; C[13] = t1.y; C[14] = t1.z; C[15] = t1.w;
+        }
+        int slot = vbase % L.ring_rows;
+        for (int b = 0; b < T.nb; b++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) C[i] = C[i + 8];
+            {
+                const uint4* qv4 = reinterpret_cast<const uint4*>(s_qV + 8 * b + 8);
+                uint4 t0 = qv4[0], t1 = qv4[1];
+                C[8] = t0.x; C[9] = t0.y; C[10] = t0.z; C[11] = t0.w; C[12] = t1.x; C[13] = t1.y; C[14] = t1.z; C[15] = t1.w;
+            }
+            const uint32_t* rp = s_ring + slot * RP + cp;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const uint32_t word = rp[u * RP];
+                const uint32_t lo = word & 0xffffu, hi = word >> 16;
+#pragma unroll
+                for (int o = 0; o < 8; o++) {
+                    a0[o] += lo * C[u - o + 8];
+                    a1[o] += hi * C[u - o + 8];
+                }
+            }
+            slot += 8;
+            if (slot >= L.ring_rows) slot -= L.ring_rows;
+        }
+        // ---- epilogue
+        const int x = x0 + 2 * cp;
+        if (x < J.w) {
+            const bool two = x + 1 < J.w;
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                const int y = y_begin + vbase + o;
+                if (y >= y_end) break;
+                uint32_t b0, b1;
+                if (T.kk) { b0 = (2 * a0[o] + T.kk) / (2 * T.kk); b1 = (2 * a1[o] + T.kk) / (2 * T.kk); }
+                else { b0 = (a0[o] + 32768u) >> 16; b1 = (a1[o] + 32768u) >> 16; }
+                uint32_t v0 = b0, v1 = b1;
+                if (EPI != DS_EPI_BLUR) {
+                    const uint8_t* sp = J.src + (size_t)y * J.src_pitch + x;
+                    const int s0 = sp[0], s1 = two ? sp[1] : 0;
+                    if (EPI == DS_EPI_SUB) { v0 = max(s0 - (int)b0, 0); v1 = max(s1 - (int)b1, 0); }
+                    else if (EPI == DS_EPI_RSUB) { v0 = max((int)b0 - s0, 0); v1 = max((int)b1 - s1, 0); }
+                    else if (EPI == DS_EPI_DIV) { v0 = ds_div255((uint8_t)s0, (uint8_t)b0); v1 = ds_div255((uint8_t)s1, (uint8_t)b1); }
+                    else if (EPI == DS_EPI_ATHRESH) { v0 = (s0 - (int)b0 > -L.c_param) ? 255 : 0; v1 = (s1 - (int)b1 > -L.c_param) ? 255 : 0; }
+                }
+                uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x;
+                dp[0] = (uint8_t)v0;
+                if (two) dp[1] = (uint8_t)v1;
+                if (STATS) {
+                    st_lo = min(st_lo, v0); st_hi = max(st_hi, v0);
+                    if (two) { st_lo = min(st_lo, v1); st_hi = max(st_hi, v1); }
+                    if (J.hist) {
+                        uint32_t* hw = s_hist + (tid >> 5) * 256;
+                        if (v0) atomicAdd(&hw[v0], 1u); else zero_count++;
+                        if (two) { if (v1) atomicAdd(&hw[v1], 1u); else zero_count++; }
+                    }
+                }
+            }
+        }
+    }
+    if (STATS) {
+        if (J.minmax) {
+            for (int o = 16; o; o >>= 1) {
+                st_lo = min(st_lo, __shfl_xor_sync(0xffffffffu, st_lo, o));
+                st_hi = max(st_hi, __shfl_xor_sync(0xffffffffu, st_hi, o));
+            }
+            if ((tid & 31) == 0) { atomicMin(&J.minmax[0], st_lo); atomicMax(&J.minmax[1], st_hi); }
+        }
+        if (J.hist) {
+            for (int o = 16; o; o >>= 1) zero_count += __shfl_xor_sync(0xffffffffu, zero_count, o);
+            if ((tid & 31) == 0 && zero_count) atomicAdd(&s_hist[(tid >> 5) * 256], zero_count);
+            __syncthreads();
+            for (int i = tid; i < 256; i += NT) {
+                const uint32_t s = s_hist[i] + s_hist[256 + i] + s_hist[512 + i] + s_hist[768 + i];
+                if (s) atomicAdd(&J.hist[i], s);
+            }
+        }
+    }
+}
+
+// ---- host: coefficient tables ----------------------------------------------------------------------
+int get_table(docscan_ctx* ctx, int kind, int k, BlurTable* out) {
+    std::vector<int32_t> q(k);
+    if (kind == 0) {
+        if (docscan_gaussian_kernel_q8(k, q.data()) != DOCSCAN_OK) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "bad blur ksize %d", k);
+    } else {
+        for (int i = 0; i < k; i++) q[i] = 1;
+    }
+    int z = 0;
+    while (z < k / 2 && q[z] == 0) z++;            // the quantised Gaussian has zero tails: trim them
+    const int k_eff = k - 2 * z, r_eff = k_eff / 2;
+    const int delta = (4 - (r_eff & 3)) & 3;
+    const int M = (delta + k_eff + 2) / 4 + 1;
+    const int nb = (k_eff + 7 + 7) / 8;
+    out->k_eff = k_eff; out->r_eff = r_eff; out->delta = delta; out->M = M; out->nb = nb;
+    out->kk = kind == 1 ? (uint32_t)k * (uint32_t)k : 0;
+    const uint64_t key = ((uint64_t)(kind + 1) << 32) | (uint32_t)k;
+    const size_t qh_bytes = sizeof(uint4) * (M + 6), qv_bytes = sizeof(uint32_t) * (8 * nb + 16);
+    auto it = ctx->tables.find(key);
+    if (it == ctx->tables.end()) {
+        std::vector<uint8_t> host(qh_bytes + qv_bytes, 0);
+        uint8_t* qh = host.data();
+        uint32_t* qv = reinterpret_cast<uint32_t*>(host.data() + qh_bytes);
+        auto tap = [&](int jp) -> int {            // q'[j'] : taps shifted right by delta
+            const int j = jp - delta;
+            return (j >= 0 && j < k_eff) ? q[z + j] : 0;
+        };
+        for (int m = 0; m < M; m++)
+            for (int s = 0; s < 4; s++)
+                for (int b = 0; b < 4; b++)
+                    qh[(size_t)(m + 3) * 16 + s * 4 + b] = (uint8_t)tap(4 * m + b - s);
+        for (int j = 0; j < k_eff; j++) qv[j + 8] = (uint32_t)q[z + j];
+        void* dev = nullptr;
+        DS_CUDA(ctx, cudaMalloc(&dev, host.size()));
+        DS_CUDA(ctx, cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
+        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->tables.emplace(key, dev).first;
+    }
+    out->qH = reinterpret_cast<const uint4*>(it->second);
+    out->qV = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(it->second) + qh_bytes);
+    return DOCSCAN_OK;
+}
+
+template <int EPI, bool STATS>
+int launch(docscan_ctx* ctx, const BlurJob* jobs_dev, const BlurLaunch& L, dim3 grid, size_t smem) {
+    if (smem > 48 * 1024)
+        DS_CUDA(ctx, cudaFuncSetAttribute(blur_march_kernel<EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    blur_march_kernel<EPI, STATS><<<grid, NT, smem, ctx->stream>>>(jobs_dev, L);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}
+
+}  // namespace
+
+int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const BlurJob* jobs_host, int n,
+                int max_w, int max_h) {
+    if (k < 1 || (k & 1) == 0 || k > 255) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "blur ksize must be odd and in 1..255 (got %d)", k);
+    if (kind == 0 && k == 1) kind = 1;             // 1x1 Gaussian is the identity; so is the 1x1 box mean
+    BlurLaunch L{};
+    DS_TRY(get_table(ctx, kind, k, &L.t));
+    L.border = kind == 0 ? 0 : 1;
+    L.c_param = c_param;
+    L.spw = (TW / 4 + L.t.M + 3) | 1;
+    L.ring_rows = ((2 * L.t.r_eff + BR - 1) / BR + 1) * BR;
+    bool stats = false;
+    for (int i = 0; i < n; i++) stats = stats || jobs_host[i].minmax || jobs_host[i].hist;
+    // segment height: enough CTAs to fill the machine, but tall enough to amortise the 2r warm-up rows
+    const int strips = n * ((max_w + TW - 1) / TW);
+    int segs = (4 * ctx->sm_count + strips - 1) / strips;
+    if (segs < 1) segs = 1;
+    int seg = (max_h + segs - 1) / segs;
+    const int seg_min = max(64, 4 * L.t.r_eff);
+    if (seg < seg_min) seg = seg_min;
+    seg = (seg + BR - 1) / BR * BR;
+    L.seg_rows = seg;
+    const size_t smem = sizeof(uint4) * (L.t.M + 6) + sizeof(uint32_t) * (8 * L.t.nb + 16) +
+                        sizeof(uint32_t) * BR * L.spw + 16 + sizeof(uint32_t) * L.ring_rows * RP +
+                        (stats ? 4 * 256 * sizeof(uint32_t) : 0);
+    void* dev = nullptr;
+    DS_TRY(ds_upload(ctx, jobs_host, sizeof(BlurJob) * n, &dev));
+    dim3 grid((max_w + TW - 1) / TW, (max_h + seg - 1) / seg, n);
+    const BlurJob* jd = (const BlurJob*)dev;
+#define DS_BLUR_CASE(E)                                                            \
+    case E:                                                                        \
+        return stats ? launch<E, true>(ctx, jd, L, grid, smem) : launch<E, false>(ctx, jd, L, grid, smem);
+    switch (epi) {
+        DS_BLUR_CASE(DS_EPI_BLUR)
+        DS_BLUR_CASE(DS_EPI_SUB)
+        DS_BLUR_CASE(DS_EPI_RSUB)
+        DS_BLUR_CASE(DS_EPI_DIV)
+        DS_BLUR_CASE(DS_EPI_ATHRESH)
+        default: return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "bad blur epilogue %d", epi);
+    }
+#undef DS_BLUR_CASE
+}

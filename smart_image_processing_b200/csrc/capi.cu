@@ -1,0 +1,583 @@
+// extern "C" entry points of libdocscan.so (see include/docscan.h) and the batched page pipeline.
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace {
+
+size_t host_bytes(const docscan_image* im) {
+    return (im && im->space == DOCSCAN_HOST) ? ds_image_bytes(im->width, im->height, im->channels) : 0;
+}
+size_t plane_bytes(int w, int h) { return ds_image_bytes(w, h, 1); }
+
+int begin_call(docscan_ctx* ctx, size_t scratch) {
+    if (!ctx) return DOCSCAN_ERR_BAD_ARG;
+    ctx->err.clear();
+    DS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ds_arena_reserve(ctx, scratch + (1 << 20));
+}
+
+int same_size(docscan_ctx* ctx, const docscan_image* a, const docscan_image* b, const char* what) {
+    if (a->width != b->width || a->height != b->height)
+        return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "%s: size mismatch (%dx%d vs %dx%d)", what, a->width, a->height, b->width, b->height);
+    return DOCSCAN_OK;
+}
+
+bool is_host(const docscan_image* im) { return im && im->space == DOCSCAN_HOST; }
+
+int read_back(docscan_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+    void* pin = nullptr;
+    DS_TRY(ds_pinned_alloc(ctx, bytes, &pin));
+    DS_CUDA(ctx, cudaMemcpyAsync(pin, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(host_dst, pin, bytes);
+    return DOCSCAN_OK;
+}
+
+int new_scalars(docscan_ctx* ctx, int n, PageScalars** out) {
+    void* p = nullptr;
+    DS_TRY(ds_arena_alloc(ctx, sizeof(PageScalars) * n, &p));
+    *out = (PageScalars*)p;
+    return k_scalars_reset(ctx, *out, n);
+}
+
+int upload_npix(docscan_ctx* ctx, const std::vector<DImg>& imgs, int32_t** out) {
+    std::vector<int32_t> npix(imgs.size());
+    for (size_t i = 0; i < imgs.size(); i++) npix[i] = imgs[i].w * imgs[i].h;
+    void* p = nullptr;
+    DS_TRY(ds_upload(ctx, npix.data(), sizeof(int32_t) * npix.size(), &p));
+    *out = (int32_t*)p;
+    return DOCSCAN_OK;
+}
+
+void max_dims(const std::vector<DImg>& v, int* mw, int* mh) {
+    *mw = 0; *mh = 0;
+    for (const DImg& d : v) { *mw = std::max(*mw, d.w); *mh = std::max(*mh, d.h); }
+}
+
+// ---- batched building blocks (device views) ------------------------------------------------------------
+int blur_batch(docscan_ctx* ctx, int kind, int k, int epi, int c, const std::vector<DImg>& src, const std::vector<DImg>& dst,
+               PageScalars* sc, bool want_minmax, int hist_sel /*0 none, 1 hist_a, 2 hist_b*/) {
+    const int n = (int)src.size();
+    std::vector<BlurJob> jobs(n);
+    for (int i = 0; i < n; i++) {
+        BlurJob& j = jobs[i];
+        j.src = src[i].p; j.src_pitch = src[i].pitch; j.dst = dst[i].p; j.dst_pitch = dst[i].pitch; j.w = src[i].w; j.h = src[i].h;
+        j.minmax = (sc && want_minmax) ? sc[i].minmax : nullptr;
+        j.hist = (sc && hist_sel) ? (hist_sel == 1 ? sc[i].hist_a : sc[i].hist_b) : nullptr;
+    }
+    int mw, mh; max_dims(src, &mw, &mh);
+    return k_blur_jobs(ctx, kind, k, epi, c, jobs.data(), n, mw, mh);
+}
+
+int morph_batch(docscan_ctx* ctx, int is_dilate, int kw, int kh, int iterations, const std::vector<DImg>& src,
+                const std::vector<DImg>& dst, const std::vector<DImg>* ref, PageScalars* sc, int hist_sel) {
+    const int n = (int)src.size();
+    // n iterations with a rectangle == one pass with the rectangle grown by (n-1)(k-1) and the anchor scaled
+    const int KW = kw + (iterations - 1) * (kw - 1), KH = kh + (iterations - 1) * (kh - 1);
+    const int ax = (kw / 2) * iterations, ay = (kh / 2) * iterations;
+    std::vector<MorphJob> jobs(n);
+    for (int i = 0; i < n; i++) {
+        MorphJob& j = jobs[i];
+        j.src = src[i].p; j.src_pitch = src[i].pitch; j.dst = dst[i].p; j.dst_pitch = dst[i].pitch; j.w = src[i].w; j.h = src[i].h;
+        j.ref = ref ? (*ref)[i].p : nullptr; j.ref_pitch = ref ? (*ref)[i].pitch : 0;
+        j.hist = (sc && hist_sel) ? (hist_sel == 1 ? sc[i].hist_a : sc[i].hist_b) : nullptr;
+    }
+    int mw, mh; max_dims(src, &mw, &mh);
+    return k_morph_jobs(ctx, is_dilate, KW, KH, ax, ay, jobs.data(), n, mw, mh);
+}
+
+int copy_batch(docscan_ctx* ctx, const std::vector<DImg>& src, const std::vector<DImg>& dst) {
+    for (size_t i = 0; i < src.size(); i++)
+        DS_CUDA(ctx, cudaMemcpy2DAsync(dst[i].p, dst[i].pitch, src[i].p, src[i].pitch, (size_t)src[i].w * src[i].ch, src[i].h,
+                                       cudaMemcpyDeviceToDevice, ctx->stream));
+    return DOCSCAN_OK;
+}
+
+int alloc_planes(docscan_ctx* ctx, const std::vector<DImg>& like, std::vector<DImg>* out) {
+    out->resize(like.size());
+    for (size_t i = 0; i < like.size(); i++) DS_TRY(ds_arena_image(ctx, like[i].w, like[i].h, 1, &(*out)[i]));
+    return DOCSCAN_OK;
+}
+
+// morphologyEx(CLOSE / OPEN / BLACKHAT) and erode / dilate on a batch
+int morph_op_batch(docscan_ctx* ctx, int op, int kw, int kh, int iterations, const std::vector<DImg>& src,
+                   const std::vector<DImg>& dst, PageScalars* sc, int hist_sel) {
+    if (iterations <= 0 || (kw == 1 && kh == 1)) {
+        if (op == DOCSCAN_MORPH_BLACKHAT) {     // close(src) == src -> all zeros
+            for (size_t i = 0; i < dst.size(); i++)
+                DS_CUDA(ctx, cudaMemset2DAsync(dst[i].p, dst[i].pitch, 0, dst[i].w, dst[i].h, ctx->stream));
+            if (sc && hist_sel) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "black-hat histogram with an empty element");
+            return DOCSCAN_OK;
+        }
+        return copy_batch(ctx, src, dst);
+    }
+    switch (op) {
+        case DOCSCAN_MORPH_ERODE: return morph_batch(ctx, 0, kw, kh, iterations, src, dst, nullptr, sc, hist_sel);
+        case DOCSCAN_MORPH_DILATE: return morph_batch(ctx, 1, kw, kh, iterations, src, dst, nullptr, sc, hist_sel);
+        case DOCSCAN_MORPH_CLOSE:
+        case DOCSCAN_MORPH_BLACKHAT:
+        case DOCSCAN_MORPH_OPEN: {
+            std::vector<DImg> mid;
+            DS_TRY(alloc_planes(ctx, src, &mid));
+            const int first = op == DOCSCAN_MORPH_OPEN ? 0 : 1;
+            DS_TRY(morph_batch(ctx, first, kw, kh, iterations, src, mid, nullptr, nullptr, 0));
+            return morph_batch(ctx, 1 - first, kw, kh, iterations, mid, dst, op == DOCSCAN_MORPH_BLACKHAT ? &src : nullptr, sc, hist_sel);
+        }
+        default: return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "bad morphology op %d", op);
+    }
+}
+
+int adaptive_batch(docscan_ctx* ctx, int method, int k, int c, int tail_compat, const std::vector<DImg>& src,
+                   const std::vector<DImg>& dst) {
+    if (k % 2 == 0 || k < 3) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "adaptive block size must be odd and >= 3 (got %d)", k);
+    const int n = (int)src.size();
+    int mw, mh; max_dims(src, &mw, &mh);
+    if (method == DOCSCAN_ADAPTIVE_MEAN) return blur_batch(ctx, 1, k, DS_EPI_ATHRESH, c, src, dst, nullptr, false, 0);
+    std::vector<AdaptJob> jobs(n);
+    for (int i = 0; i < n; i++) {
+        AdaptJob& j = jobs[i];
+        j.src = src[i].p; j.src_pitch = src[i].pitch; j.dst = dst[i].p; j.dst_pitch = dst[i].pitch; j.w = src[i].w; j.h = src[i].h;
+    }
+    return k_adaptive_gauss_jobs(ctx, k, c, tail_compat, jobs.data(), n, mw, mh);
+}
+
+// _compute_ink_mask up to the raw cut-offs (DocScanner.py:182-204): ink_sub, bh planes + scalars
+int ink_branches(docscan_ctx* ctx, const std::vector<DImg>& gray, int blur_k, int kw, int kh, int offset, PageScalars* sc,
+                 std::vector<DImg>* ink_sub, std::vector<DImg>* bh) {
+    DS_TRY(alloc_planes(ctx, gray, ink_sub));
+    DS_TRY(alloc_planes(ctx, gray, bh));
+    DS_TRY(blur_batch(ctx, 0, blur_k, DS_EPI_RSUB, 0, gray, *ink_sub, sc, false, 1));
+    DS_TRY(morph_op_batch(ctx, DOCSCAN_MORPH_BLACKHAT, kw, kh, 1, gray, *bh, sc, 2));
+    int32_t* npix = nullptr;
+    DS_TRY(upload_npix(ctx, gray, &npix));
+    return k_otsu_cuts(ctx, sc, (int)gray.size(), offset, npix);
+}
+
+int blend_batch(docscan_ctx* ctx, int dilate_iters, int mask_only, const std::vector<DImg>& ink_sub, const std::vector<DImg>& bh,
+                const std::vector<DImg>* base, const std::vector<DImg>& dst, PageScalars* sc) {
+    const int n = (int)dst.size();
+    std::vector<BlendJob> jobs(n);
+    for (int i = 0; i < n; i++) {
+        BlendJob& j = jobs[i];
+        j.ink_sub = ink_sub[i].p; j.pitch_sub = ink_sub[i].pitch; j.bh = bh[i].p; j.pitch_bh = bh[i].pitch;
+        j.base = base ? (*base)[i].p : nullptr; j.pitch_base = base ? (*base)[i].pitch : 0;
+        j.dst = dst[i].p; j.pitch_dst = dst[i].pitch; j.w = dst[i].w; j.h = dst[i].h; j.sc = sc + i;
+    }
+    int mw, mh; max_dims(dst, &mw, &mh);
+    return k_mask_blend_jobs(ctx, dilate_iters, mask_only, jobs.data(), n, mw, mh);
+}
+
+int illum_ksize(int w, int h, double frac) {   // DocScanner.py:150-152 (Python round = half to even)
+    int base = std::max(15, (int)std::nearbyint((double)std::min(h, w) * frac));
+    if (base % 2 == 0) base += 1;
+    return base;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// single-op entry points
+// =====================================================================================================
+#define DS_ARGS2(src, dst, chs, chd, name)                      \
+    if (!ctx) return DOCSCAN_ERR_BAD_ARG;                       \
+    DS_TRY(ds_check_image(ctx, src, chs, name ": src"));        \
+    DS_TRY(ds_check_image(ctx, dst, chd, name ": dst"));
+
+extern "C" int docscan_bgr2gray(docscan_ctx* ctx, const docscan_image* src, docscan_image* dst, int swap_rb) {
+    DS_ARGS2(src, dst, 3, 1, "bgr2gray");
+    DS_TRY(same_size(ctx, src, dst, "bgr2gray"));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    DImg s, d;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    DS_TRY(k_bgr2gray(ctx, s, d, swap_rb));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+extern "C" int docscan_gaussian_blur(docscan_ctx* ctx, const docscan_image* src, int k, docscan_image* dst) {
+    DS_ARGS2(src, dst, 1, 1, "gaussian_blur");
+    DS_TRY(same_size(ctx, src, dst, "gaussian_blur"));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    std::vector<DImg> s(1), d(1);
+    DS_TRY(ds_stage_in(ctx, src, &s[0]));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d[0]));
+    DS_TRY(blur_batch(ctx, 0, k, DS_EPI_BLUR, 0, s, d, nullptr, false, 0));
+    DS_TRY(ds_stage_out_end(ctx, dst, d[0]));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+extern "C" int docscan_binary_op(docscan_ctx* ctx, int op, const docscan_image* a, const docscan_image* b, docscan_image* dst) {
+    if (!ctx) return DOCSCAN_ERR_BAD_ARG;
+    if (op < DOCSCAN_OP_SUB || op > DOCSCAN_OP_MASK_SELECT) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "bad binary op %d", op);
+    DS_TRY(ds_check_image(ctx, a, 1, "binary_op: a"));
+    DS_TRY(ds_check_image(ctx, b, 1, "binary_op: b"));
+    DS_TRY(ds_check_image(ctx, dst, 1, "binary_op: dst"));
+    DS_TRY(same_size(ctx, a, b, "binary_op"));
+    DS_TRY(same_size(ctx, a, dst, "binary_op"));
+    DS_TRY(begin_call(ctx, host_bytes(a) + host_bytes(b) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    DImg da, db, dd;
+    DS_TRY(ds_stage_in(ctx, a, &da));
+    DS_TRY(ds_stage_in(ctx, b, &db));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &dd));
+    DS_TRY(k_binary_op(ctx, op, da, db, dd));
+    DS_TRY(ds_stage_out_end(ctx, dst, dd));
+    return ds_finish(ctx, is_host(a) || is_host(b) || is_host(dst));
+}
+
+extern "C" int docscan_minmax(docscan_ctx* ctx, const docscan_image* src, int32_t* mn, int32_t* mx) {
+    if (!ctx || !mn || !mx) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, src, 1, "minmax: src"));
+    DS_TRY(begin_call(ctx, host_bytes(src)));
+    ArenaScope scope(ctx);
+    DImg s;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    PageScalars* sc = nullptr;
+    DS_TRY(new_scalars(ctx, 1, &sc));
+    DS_TRY(k_stats(ctx, s, sc->minmax, nullptr));
+    uint32_t res[2];
+    DS_TRY(read_back(ctx, res, sc->minmax, sizeof(res)));
+    *mn = (int32_t)res[0]; *mx = (int32_t)res[1];
+    return DOCSCAN_OK;
+}
+
+extern "C" int docscan_hist256(docscan_ctx* ctx, const docscan_image* src, int32_t hist[256]) {
+    if (!ctx || !hist) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, src, 1, "hist256: src"));
+    DS_TRY(begin_call(ctx, host_bytes(src)));
+    ArenaScope scope(ctx);
+    DImg s;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    PageScalars* sc = nullptr;
+    DS_TRY(new_scalars(ctx, 1, &sc));
+    DS_TRY(k_stats(ctx, s, nullptr, sc->hist_a));
+    return read_back(ctx, hist, sc->hist_a, 256 * sizeof(int32_t));
+}
+
+extern "C" int docscan_normalize_minmax(docscan_ctx* ctx, const docscan_image* src, docscan_image* dst) {
+    DS_ARGS2(src, dst, 1, 1, "normalize_minmax");
+    DS_TRY(same_size(ctx, src, dst, "normalize_minmax"));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    DImg s, d;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    PageScalars* sc = nullptr;
+    DS_TRY(new_scalars(ctx, 1, &sc));
+    DS_TRY(k_stats(ctx, s, sc->minmax, nullptr));
+    DS_TRY(k_build_norm_lut(ctx, sc, 1, 0));
+    DS_TRY(k_apply_lut(ctx, s, sc->lut, d));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+extern "C" int docscan_otsu_threshold(docscan_ctx* ctx, const docscan_image* src, double* t, docscan_image* dst) {
+    if (!ctx || !t) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, src, 1, "otsu_threshold: src"));
+    if (dst) {
+        DS_TRY(ds_check_image(ctx, dst, 1, "otsu_threshold: dst"));
+        DS_TRY(same_size(ctx, src, dst, "otsu_threshold"));
+    }
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    std::vector<DImg> s(1);
+    DImg d{};
+    DS_TRY(ds_stage_in(ctx, src, &s[0]));
+    if (dst) DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    PageScalars* sc = nullptr;
+    DS_TRY(new_scalars(ctx, 1, &sc));
+    DS_TRY(k_stats(ctx, s[0], nullptr, sc->hist_a));
+    int32_t* npix = nullptr;
+    DS_TRY(upload_npix(ctx, s, &npix));
+    DS_TRY(k_otsu_plain(ctx, sc, 1, npix));
+    if (dst) {
+        DS_TRY(k_threshold(ctx, s[0], &sc->otsu_a, 0, d));
+        DS_TRY(ds_stage_out_end(ctx, dst, d));
+    }
+    int32_t ti = 0;
+    DS_TRY(read_back(ctx, &ti, &sc->otsu_a, sizeof(ti)));
+    *t = (double)ti;
+    return DOCSCAN_OK;
+}
+
+extern "C" int docscan_threshold_binary(docscan_ctx* ctx, const docscan_image* src, int t, docscan_image* dst) {
+    DS_ARGS2(src, dst, 1, 1, "threshold_binary");
+    DS_TRY(same_size(ctx, src, dst, "threshold_binary"));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    DImg s, d;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    DS_TRY(k_threshold(ctx, s, nullptr, t, d));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+extern "C" int docscan_morph_rect(docscan_ctx* ctx, int op, const docscan_image* src, int kw, int kh, int iterations,
+                                  docscan_image* dst) {
+    DS_ARGS2(src, dst, 1, 1, "morph_rect");
+    DS_TRY(same_size(ctx, src, dst, "morph_rect"));
+    if (kw < 1 || kh < 1) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "morph_rect: bad element %dx%d", kw, kh);
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst) + 4 * plane_bytes(src->width, src->height)));
+    ArenaScope scope(ctx);
+    std::vector<DImg> s(1), d(1);
+    DS_TRY(ds_stage_in(ctx, src, &s[0]));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d[0]));
+    DS_TRY(morph_op_batch(ctx, op, kw, kh, iterations, s, d, nullptr, 0));
+    DS_TRY(ds_stage_out_end(ctx, dst, d[0]));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+extern "C" int docscan_adaptive_threshold(docscan_ctx* ctx, const docscan_image* src, int method, int k, int c,
+                                          int cv_tail_compat, docscan_image* dst) {
+    DS_ARGS2(src, dst, 1, 1, "adaptive_threshold");
+    DS_TRY(same_size(ctx, src, dst, "adaptive_threshold"));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    std::vector<DImg> s(1), d(1);
+    DS_TRY(ds_stage_in(ctx, src, &s[0]));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d[0]));
+    DS_TRY(adaptive_batch(ctx, method, k, c, cv_tail_compat, s, d));
+    DS_TRY(ds_stage_out_end(ctx, dst, d[0]));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+extern "C" int docscan_warp_perspective(docscan_ctx* ctx, const docscan_image* src, const double m_fwd[9],
+                                        docscan_image* dst, docscan_image* gray_out) {
+    if (!ctx || !m_fwd) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, src, 0, "warp_perspective: src"));
+    DS_TRY(ds_check_image(ctx, dst, src->channels, "warp_perspective: dst"));
+    if (gray_out) {
+        if (src->channels != 3) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "warp_perspective: gray_out needs a 3-channel source");
+        DS_TRY(ds_check_image(ctx, gray_out, 1, "warp_perspective: gray_out"));
+        DS_TRY(same_size(ctx, dst, gray_out, "warp_perspective"));
+    }
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst) + host_bytes(gray_out)));
+    ArenaScope scope(ctx);
+    DImg s, d, g{};
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    if (gray_out) DS_TRY(ds_stage_out_begin(ctx, gray_out, &g));
+    WarpPJob j{};
+    j.src = s.p; j.src_pitch = s.pitch; j.sw = s.w; j.sh = s.h; j.ch = s.ch;
+    j.dst = d.p; j.dst_pitch = d.pitch; j.dw = d.w; j.dh = d.h;
+    j.gray = gray_out ? g.p : nullptr; j.gray_pitch = g.pitch;
+    j.block_w = 1024 / std::min(16, d.h);
+    hm_invert3x3(m_fwd, j.m);
+    DS_TRY(k_warp_perspective_jobs(ctx, &j, 1, d.w, d.h));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    if (gray_out) DS_TRY(ds_stage_out_end(ctx, gray_out, g));
+    return ds_finish(ctx, is_host(src) || is_host(dst) || is_host(gray_out));
+}
+
+extern "C" int docscan_warp_affine(docscan_ctx* ctx, const docscan_image* src, const double m_fwd[6], docscan_image* dst) {
+    if (!m_fwd) return DOCSCAN_ERR_BAD_ARG;
+    DS_ARGS2(src, dst, 1, 1, "warp_affine");
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    ArenaScope scope(ctx);
+    DImg s, d;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    WarpAJob j{};
+    j.src = s.p; j.src_pitch = s.pitch; j.sw = s.w; j.sh = s.h;
+    j.dst = d.p; j.dst_pitch = d.pitch; j.dw = d.w; j.dh = d.h;
+    hm_invert_affine(m_fwd, j.m);
+    DS_TRY(k_warp_affine_jobs(ctx, &j, 1, d.w, d.h));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+// =====================================================================================================
+// fused reference stage functions
+// =====================================================================================================
+extern "C" int docscan_illumination_correction(docscan_ctx* ctx, const docscan_image* gray, int method, int k, docscan_image* dst) {
+    DS_ARGS2(gray, dst, 1, 1, "illumination_correction");
+    DS_TRY(same_size(ctx, gray, dst, "illumination_correction"));
+    DS_TRY(begin_call(ctx, host_bytes(gray) + host_bytes(dst) + plane_bytes(gray->width, gray->height)));
+    ArenaScope scope(ctx);
+    std::vector<DImg> s(1), tmp, d(1);
+    DS_TRY(ds_stage_in(ctx, gray, &s[0]));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d[0]));
+    DS_TRY(alloc_planes(ctx, s, &tmp));
+    PageScalars* sc = nullptr;
+    DS_TRY(new_scalars(ctx, 1, &sc));
+    DS_TRY(blur_batch(ctx, 0, k, method == 1 ? DS_EPI_DIV : DS_EPI_SUB, 0, s, tmp, sc, true, 0));
+    DS_TRY(k_build_norm_lut(ctx, sc, 1, 0));
+    DS_TRY(k_apply_lut(ctx, tmp[0], sc->lut, d[0]));
+    DS_TRY(ds_stage_out_end(ctx, dst, d[0]));
+    return ds_finish(ctx, is_host(gray) || is_host(dst));
+}
+
+extern "C" int docscan_ink_mask(docscan_ctx* ctx, const docscan_image* gray, int mask_blur_ksize, int kw_bh, int kh_bh,
+                                int dilate_iters, int threshold_offset, docscan_image* dst) {
+    DS_ARGS2(gray, dst, 1, 1, "ink_mask");
+    DS_TRY(same_size(ctx, gray, dst, "ink_mask"));
+    DS_TRY(begin_call(ctx, host_bytes(gray) + host_bytes(dst) + 6 * plane_bytes(gray->width, gray->height)));
+    ArenaScope scope(ctx);
+    std::vector<DImg> s(1), d(1), ink_sub, bh;
+    DS_TRY(ds_stage_in(ctx, gray, &s[0]));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d[0]));
+    PageScalars* sc = nullptr;
+    DS_TRY(new_scalars(ctx, 1, &sc));
+    DS_TRY(ink_branches(ctx, s, mask_blur_ksize, kw_bh, kh_bh, threshold_offset, sc, &ink_sub, &bh));
+    DS_TRY(blend_batch(ctx, std::max(dilate_iters, 0), 1, ink_sub, bh, nullptr, d, sc));
+    DS_TRY(ds_stage_out_end(ctx, dst, d[0]));
+    return ds_finish(ctx, is_host(gray) || is_host(dst));
+}
+
+// =====================================================================================================
+// the whole per-pixel path for a batch of pages
+// =====================================================================================================
+namespace {
+
+size_t page_scratch(const docscan_page& pg) {
+    const int w = pg.binary.width, h = pg.binary.height;
+    return host_bytes(&pg.src) + host_bytes(&pg.warped) + host_bytes(&pg.binary) + 16 * plane_bytes(w, h) +
+           (pg.warped.data ? 0 : ds_image_bytes(w, h, 3)) + 4096;
+}
+
+int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params& P) {
+    ArenaScope scope(ctx);
+    std::vector<DImg> src(n), warped(n), gray, binary(n);
+    std::vector<WarpPJob> wj(n);
+    for (int i = 0; i < n; i++) {
+        docscan_page& pg = pages[i];
+        DS_TRY(ds_stage_in(ctx, &pg.src, &src[i]));
+        DS_TRY(ds_stage_out_begin(ctx, &pg.warped, &warped[i]));
+        DS_TRY(ds_stage_out_begin(ctx, &pg.binary, &binary[i]));
+    }
+    DS_TRY(alloc_planes(ctx, binary, &gray));
+    int mw, mh; max_dims(binary, &mw, &mh);
+    // a1 + a2: perspective warp with fused BGR2GRAY
+    for (int i = 0; i < n; i++) {
+        WarpPJob& j = wj[i];
+        j = WarpPJob{};
+        j.src = src[i].p; j.src_pitch = src[i].pitch; j.sw = src[i].w; j.sh = src[i].h; j.ch = 3;
+        j.dst = warped[i].p; j.dst_pitch = warped[i].pitch; j.dw = warped[i].w; j.dh = warped[i].h;
+        j.gray = gray[i].p; j.gray_pitch = gray[i].pitch;
+        j.block_w = 1024 / std::min(16, warped[i].h);
+        const float dstq[8] = {0, 0, (float)(warped[i].w - 1), 0, (float)(warped[i].w - 1), (float)(warped[i].h - 1), 0, (float)(warped[i].h - 1)};
+        double m[9];
+        DS_TRY(docscan_get_perspective_transform(pages[i].quad, dstq, m));
+        hm_invert3x3(m, j.m);
+    }
+    DS_TRY(k_warp_perspective_jobs(ctx, wj.data(), n, mw, mh));
+    for (int i = 0; i < n; i++) DS_TRY(ds_stage_out_end(ctx, &pages[i].warped, warped[i]));
+
+    // a3 + a4: illumination correction; its MINMAX LUT and contrast_stretch's fold into one LUT
+    PageScalars* sc = nullptr;
+    DS_TRY(new_scalars(ctx, n, &sc));
+    std::vector<DImg> stretched;
+    DS_TRY(alloc_planes(ctx, binary, &stretched));
+    // blur kernel size depends on the page size (DocScanner.py:150): group pages by k
+    {
+        std::vector<int> ks(n);
+        for (int i = 0; i < n; i++) ks[i] = illum_ksize(gray[i].w, gray[i].h, P.illum_blur_frac);
+        std::vector<char> done(n, 0);
+        for (int i = 0; i < n; i++) {
+            if (done[i]) continue;
+            std::vector<DImg> gs, gd;
+            std::vector<PageScalars*> idx;
+            // pages with the same k must be contiguous in the scalar array: launch per run of equal k
+            int e = i;
+            while (e < n && ks[e] == ks[i]) { gs.push_back(gray[e]); gd.push_back(stretched[e]); done[e] = 1; e++; }
+            DS_TRY(blur_batch(ctx, 0, ks[i], P.illum_method == 1 ? DS_EPI_DIV : DS_EPI_SUB, 0, gs, gd, sc + i, true, 0));
+        }
+    }
+    DS_TRY(k_build_norm_lut(ctx, sc, n, 1));
+    {
+        std::vector<const uint8_t*> luts(n);
+        for (int i = 0; i < n; i++) luts[i] = sc[i].lut;
+        DS_TRY(k_apply_lut_jobs(ctx, stretched.data(), stretched.data(), luts.data(), n));
+    }
+    // a5: ink mask branches -> raw cut-offs
+    int blur_k = P.mask_blur_ksize;
+    if (blur_k % 2 == 0) blur_k += 1;
+    int bk = P.blackhat_ksize;
+    if (bk < 3) bk = 3;
+    if (bk % 2 == 0) bk += 1;
+    int bh_h = std::max(3, (int)std::nearbyint((double)bk * P.blackhat_vertical_ratio));
+    if (bh_h % 2 == 0) bh_h += 1;
+    std::vector<DImg> ink_sub, bh;
+    DS_TRY(ink_branches(ctx, stretched, blur_k, bk, bh_h, P.mask_thresh_offset, sc, &ink_sub, &bh));
+    // a6: adaptive threshold
+    int block = P.block_size;
+    if (block % 2 == 0) block += 1;
+    std::vector<DImg> base;
+    DS_TRY(alloc_planes(ctx, binary, &base));
+    DS_TRY(adaptive_batch(ctx, P.thresh_method, block, P.C, P.cv_tail_compat, stretched, base));
+    // what follows: rotate (a8) unless every angle is 0, close (a9) unless ksize <= 1
+    const bool do_close = P.morph_ksize > 1;
+    std::vector<DImg> blend_dst, rot_dst;
+    if (do_close) {
+        DS_TRY(alloc_planes(ctx, binary, &blend_dst));
+        DS_TRY(alloc_planes(ctx, binary, &rot_dst));
+    } else {
+        DS_TRY(alloc_planes(ctx, binary, &blend_dst));
+        rot_dst = binary;
+    }
+    // a7: mask combine + 2x2 dilate + masked blend
+    DS_TRY(blend_batch(ctx, std::max(P.ink_dilate_iters, 0), 0, ink_sub, bh, &base, blend_dst, sc));
+    // a8: deskew rotation
+    {
+        std::vector<WarpAJob> aj(n);
+        for (int i = 0; i < n; i++) {
+            WarpAJob& j = aj[i];
+            j = WarpAJob{};
+            j.src = blend_dst[i].p; j.src_pitch = blend_dst[i].pitch; j.sw = blend_dst[i].w; j.sh = blend_dst[i].h;
+            j.dst = rot_dst[i].p; j.dst_pitch = rot_dst[i].pitch; j.dw = rot_dst[i].w; j.dh = rot_dst[i].h;
+            double m[6];
+            DS_TRY(docscan_get_rotation_matrix(blend_dst[i].w / 2.0, blend_dst[i].h / 2.0, pages[i].angle_deg, m));
+            hm_invert_affine(m, j.m);
+        }
+        DS_TRY(k_warp_affine_jobs(ctx, aj.data(), n, mw, mh));
+    }
+    // a9: morph_cleanup (close)
+    if (do_close) DS_TRY(morph_op_batch(ctx, DOCSCAN_MORPH_CLOSE, P.morph_ksize, P.morph_ksize, P.morph_iters, rot_dst, binary, nullptr, 0));
+    for (int i = 0; i < n; i++) DS_TRY(ds_stage_out_end(ctx, &pages[i].binary, binary[i]));
+    return DOCSCAN_OK;
+}
+
+}  // namespace
+
+extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params* params) {
+    if (!ctx || n < 0 || (n && !pages) || !params) return DOCSCAN_ERR_BAD_ARG;
+    if (n == 0) return DOCSCAN_OK;
+    bool any_host = false;
+    size_t max_page = 0;
+    for (int i = 0; i < n; i++) {
+        docscan_page& pg = pages[i];
+        DS_TRY(ds_check_image(ctx, &pg.src, 3, "process_pages: src"));
+        DS_TRY(ds_check_image(ctx, &pg.warped, 3, "process_pages: warped"));
+        DS_TRY(ds_check_image(ctx, &pg.binary, 1, "process_pages: binary"));
+        DS_TRY(same_size(ctx, &pg.warped, &pg.binary, "process_pages"));
+        any_host = any_host || is_host(&pg.src) || is_host(&pg.warped) || is_host(&pg.binary);
+        max_page = std::max(max_page, page_scratch(pg));
+    }
+    // pages per launch group: big enough to fill the GPU, small enough that the group's intermediates
+    // (about 16 planes per page) stay resident in L2 between the kernels of the chain
+    const size_t l2 = ctx->l2_bytes ? ctx->l2_bytes : (size_t)96 << 20;
+    const size_t inter = 12 * plane_bytes(pages[0].binary.width, pages[0].binary.height);
+    int group = (int)std::max<size_t>(1, std::min<size_t>(8, (l2 * 3 / 4) / std::max<size_t>(inter, 1)));
+    group = std::min(group, n);
+    DS_TRY(begin_call(ctx, max_page * group));
+    for (int i = 0; i < n; i += group) DS_TRY(run_group(ctx, std::min(group, n - i), pages + i, *params));
+    return ds_finish(ctx, any_host);
+}
+
+extern "C" int docscan_synth_page(docscan_ctx* ctx, uint64_t seed, docscan_image* dst, float quad_out[8]) {
+    if (!ctx) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, dst, 3, "synth_page: dst"));
+    DS_TRY(begin_call(ctx, host_bytes(dst)));
+    ArenaScope scope(ctx);
+    DImg d;
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    DS_TRY(k_synth_page(ctx, seed, d, quad_out));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    return ds_finish(ctx, is_host(dst));
+}

@@ -1,0 +1,209 @@
+// Internal declarations shared by the libdocscan.so translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "docscan.h"
+
+#ifndef __CUDA_ARCH__
+#define DS_HOST_ONLY 1
+#endif
+
+#define DS_SM_COUNT_FALLBACK 148
+
+// ---------------------------------------------------------------------------------------------
+// device image view (uint8, interleaved channels)
+struct DImg {
+    uint8_t* p;
+    int w, h, pitch, ch;
+};
+
+struct GaussTable;   // blur.cu
+
+struct docscan_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = DS_SM_COUNT_FALLBACK;
+    size_t l2_bytes = 0;
+    // bump arena for per-call device scratch
+    uint8_t* arena = nullptr;
+    size_t arena_size = 0, arena_off = 0;
+    std::vector<uint8_t*> retired;       // old arena blocks, freed at the next sync point
+    // pinned host staging (job arrays, small read-backs)
+    uint8_t* pinned = nullptr;
+    size_t pinned_size = 0, pinned_off = 0;
+    // cached device coefficient tables, keyed by (kind, k, delta)
+    std::map<uint64_t, void*> tables;
+    std::vector<void*> user_allocs;
+};
+
+int ds_fail(docscan_ctx* ctx, int code, const char* fmt, ...);
+
+#define DS_CUDA(ctx, expr)                                                                         \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ds_fail((ctx), DOCSCAN_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                            \
+    } while (0)
+
+#define DS_TRY(expr)                                                                               \
+    do {                                                                                           \
+        int _rc = (expr);                                                                          \
+        if (_rc != DOCSCAN_OK) return _rc;                                                         \
+    } while (0)
+
+#define DS_CHECK_LAUNCH(ctx)                                                                       \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess)                                                                     \
+            return ds_fail((ctx), DOCSCAN_ERR_CUDA, "kernel launch failed: %s (%s:%d)",           \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                            \
+    } while (0)
+
+// ---- arena ------------------------------------------------------------------------------------
+struct ArenaScope {     // everything allocated inside the scope is released when it ends
+    docscan_ctx* ctx;
+    size_t off0, pin0;
+    explicit ArenaScope(docscan_ctx* c) : ctx(c), off0(c->arena_off), pin0(c->pinned_off) {}
+    ~ArenaScope() { ctx->arena_off = off0; ctx->pinned_off = pin0; }
+};
+int ds_arena_reserve(docscan_ctx* ctx, size_t total_bytes);   // call before the first alloc of a big call
+int ds_arena_alloc(docscan_ctx* ctx, size_t bytes, void** out);
+int ds_arena_image(docscan_ctx* ctx, int w, int h, int ch, DImg* out);
+int ds_pinned_alloc(docscan_ctx* ctx, size_t bytes, void** out);
+static inline size_t ds_image_bytes(int w, int h, int ch) {
+    size_t pitch = ((size_t)w * ch + 127) & ~(size_t)127;
+    return pitch * (size_t)h + 256;
+}
+
+// ---- staging of API images ----------------------------------------------------------------------
+int ds_check_image(docscan_ctx* ctx, const docscan_image* im, int channels, const char* what);
+// input: returns a device view (copying host images into the arena)
+int ds_stage_in(docscan_ctx* ctx, const docscan_image* im, DImg* out);
+// output: returns a device view to write into; ds_stage_out copies it back for host images
+int ds_stage_out_begin(docscan_ctx* ctx, const docscan_image* im, DImg* out);
+int ds_stage_out_end(docscan_ctx* ctx, const docscan_image* im, const DImg& dev);
+int ds_finish(docscan_ctx* ctx, bool any_host);   // stream sync when host images were involved
+
+// ---- kernel front-ends (device views, enqueue only) -----------------------------------------------
+// pointwise.cu
+int k_bgr2gray(docscan_ctx*, const DImg& src, const DImg& dst, int swap_rb);
+int k_binary_op(docscan_ctx*, int op, const DImg& a, const DImg& b, const DImg& dst);
+int k_apply_lut(docscan_ctx*, const DImg& src, const uint8_t* lut_dev, const DImg& dst);
+int k_apply_lut_jobs(docscan_ctx*, const DImg* src, const DImg* dst, const uint8_t* const* luts, int n);
+int k_threshold(docscan_ctx*, const DImg& src, const int32_t* t_dev, int t_imm, const DImg& dst);
+int k_stats(docscan_ctx*, const DImg& src, uint32_t* minmax_dev, uint32_t* hist_dev);   // either may be null
+int k_zero_u32(docscan_ctx*, uint32_t* p, int n, uint32_t value_even, uint32_t value_odd);
+// scalars.cu : per-page scalar block (device)
+struct PageScalars {
+    uint32_t minmax[2];        // running min / max (atomics)
+    uint32_t hist_a[256];
+    uint32_t hist_b[256];
+    uint8_t lut[256];          // normalize LUT (or composed LUT)
+    int32_t cut_a, cut_b;      // raw cut-offs: mask = value >= cut
+    int32_t otsu_a, otsu_b;    // Otsu thresholds (in normalised units)
+    uint32_t pad[2];
+};
+int k_scalars_reset(docscan_ctx*, PageScalars* s, int n);
+// lut[v] = normalize(min,max)(v); when `compose` the contrast-stretch LUT of the result is folded in
+int k_build_norm_lut(docscan_ctx*, PageScalars* s, int n, int compose_stretch);
+// hist_a / hist_b -> normalise -> Otsu -> (t - offset) -> raw cut-offs
+int k_otsu_cuts(docscan_ctx*, PageScalars* s, int n, int threshold_offset, const int32_t* npix_dev);
+// plain Otsu of hist_a (no normalisation): result in otsu_a
+int k_otsu_plain(docscan_ctx*, PageScalars* s, int n, const int32_t* npix_dev);
+// blur.cu
+#define DS_EPI_BLUR 0      // dst = blur(src)
+#define DS_EPI_SUB 1       // dst = sat(src - blur)
+#define DS_EPI_RSUB 2      // dst = sat(blur - src)
+#define DS_EPI_DIV 3       // dst = divide(src, blur, 255)
+#define DS_EPI_ATHRESH 4   // box mean: dst = src - mean > -C ? 255 : 0
+struct BlurJob {
+    const uint8_t* src; uint8_t* dst;
+    int src_pitch, dst_pitch, w, h;
+    uint32_t* minmax;     // may be null
+    uint32_t* hist;       // may be null
+};
+// gaussian (REFLECT_101, 8.8 fixed point) for kind 0, box (REPLICATE, ones) for kind 1
+int k_blur_jobs(docscan_ctx*, int kind, int k, int epi, int c_param, const BlurJob* jobs_host, int n,
+                int max_w, int max_h);
+// morph.cu
+struct MorphJob {
+    const uint8_t* src; uint8_t* dst;
+    const uint8_t* ref;   // blackhat: dst = sat(result - ref); null otherwise
+    int src_pitch, dst_pitch, ref_pitch, w, h;
+    uint32_t* hist;       // may be null
+};
+int k_morph_jobs(docscan_ctx*, int is_dilate, int kw, int kh, int ax, int ay, const MorphJob* jobs_host, int n,
+                 int max_w, int max_h);
+// adaptive.cu (gaussian, fp32 ordered fma)
+struct AdaptJob {
+    const uint8_t* src; uint8_t* dst;
+    int src_pitch, dst_pitch, w, h;
+};
+int k_adaptive_gauss_jobs(docscan_ctx*, int k, int c, int cv_tail_compat, const AdaptJob* jobs_host, int n,
+                          int max_w, int max_h);
+// mask + blend (DocScanner.py:207-212, 338-339)
+struct BlendJob {
+    const uint8_t* ink_sub; const uint8_t* bh; const uint8_t* base; uint8_t* dst;
+    int pitch_sub, pitch_bh, pitch_base, pitch_dst, w, h;
+    const PageScalars* sc;
+};
+int k_mask_blend_jobs(docscan_ctx*, int dilate_iters, int write_mask_only, const BlendJob* jobs_host, int n,
+                      int max_w, int max_h);
+// warp.cu
+struct WarpPJob {
+    const uint8_t* src; uint8_t* dst; uint8_t* gray;
+    int src_pitch, dst_pitch, gray_pitch, sw, sh, dw, dh, ch;
+    int block_w;          // 1024 / min(16, dh): OpenCV's coordinate block width
+    double m[9];          // inverse matrix (dst -> src)
+};
+int k_warp_perspective_jobs(docscan_ctx*, const WarpPJob* jobs_host, int n, int max_w, int max_h);
+struct WarpAJob {
+    const uint8_t* src; uint8_t* dst;
+    int src_pitch, dst_pitch, sw, sh, dw, dh;
+    double m[6];          // inverse matrix
+    int identity;
+};
+int k_warp_affine_jobs(docscan_ctx*, const WarpAJob* jobs_host, int n, int max_w, int max_h);
+// synth.cu
+int k_synth_page(docscan_ctx*, uint64_t seed, const DImg& dst, float quad_out[8]);
+
+// upload a host job array into arena memory (stream ordered); returns the device pointer
+int ds_upload(docscan_ctx* ctx, const void* host, size_t bytes, void** dev_out);
+
+// host math (hostmath.cpp)
+void hm_invert3x3(const double S[9], double T[9]);
+void hm_invert_affine(const double Min[6], double M[6]);
+void hm_gaussian_kernel_f64(int k, double* c);
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// device helpers
+__device__ __forceinline__ int ds_reflect101(int p, int len) {
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p;
+        else p = 2 * len - 2 - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+__device__ __forceinline__ int ds_clamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
+__device__ __forceinline__ uint32_t ds_ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+__device__ __forceinline__ uint8_t ds_div255(uint8_t a, uint8_t b) {
+    if (b == 0) return 0;
+    float q = __fdiv_rn(__fmul_rn((float)a, 255.0f), (float)b);
+    int v = __float2int_rn(q);
+    return (uint8_t)min(max(v, 0), 255);
+}
+#endif

@@ -1,0 +1,161 @@
+// Geometric resampling stages.
+//   cv2.warpPerspective(u8, M, INTER_LINEAR, BORDER_CONSTANT 0)   DocScanner.py:143  (+ fused BGR2GRAY, :316)
+//   cv2.warpAffine(u8c1, M, INTER_LINEAR, BORDER_REPLICATE)        DocScanner.py:235
+// Both reproduce OpenCV's fixed-point pipeline: source coordinates are rounded (half-to-even) to 1/32 px
+// (INTER_BITS = 5), the four bilinear weights are the integers (32-ax)(32-ay)*32 ... that sum to 2^15, and
+// the result is (sum + 2^14) >> 15.  Texture units are not used: their 9-bit filtering cannot give these
+// roundings.  The perspective coordinates are evaluated in fp64 in the same operation order as OpenCV
+// (per 64-pixel block origin, no fma contraction), the affine ones in OpenCV's 10-bit fixed point.
+#include <climits>
+
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint8_t gray15(int b, int g, int r) {
+    return (uint8_t)((3735 * b + 19235 * g + 9798 * r + 16384) >> 15);
+}
+
+__device__ __forceinline__ int round_clamped(double v) {
+    v = fmax((double)INT_MIN, fmin((double)INT_MAX, v));
+    return __double2int_rn(v);
+}
+
+template <int CH>
+__global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* __restrict__ jobs) {
+    const WarpPJob& J = jobs[blockIdx.z];
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (y >= J.dh || x4 >= J.dw) return;
+    const double m0 = J.m[0], m1 = J.m[1], m2 = J.m[2], m3 = J.m[3], m4 = J.m[4], m5 = J.m[5], m6 = J.m[6], m7 = J.m[7], m8 = J.m[8];
+    // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows))
+    int xb = x4 - x4 % J.block_w;
+    const double dy = (double)y;
+    double dxb = (double)xb;
+    double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
+    double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m3, dxb), __dmul_rn(m4, dy)), m5);
+    double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m6, dxb), __dmul_rn(m7, dy)), m8);
+    const uint8_t* __restrict__ src = J.src;
+    const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
+    uint8_t out[4 * CH];
+    uint8_t gr[4];
+    const int nvalid = min(4, J.dw - x4);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (x4 + i - xb >= J.block_w) {              // only when the block width is not a multiple of 4 (dst < 16 rows)
+            xb += J.block_w;
+            dxb = (double)xb;
+            X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
+            Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m3, dxb), __dmul_rn(m4, dy)), m5);
+            W0 = __dadd_rn(__dadd_rn(__dmul_rn(m6, dxb), __dmul_rn(m7, dy)), m8);
+        }
+        const double x1 = (double)(x4 + i - xb);
+        double W = __dadd_rn(W0, __dmul_rn(m6, x1));
+        W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+        const double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W);
+        const double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W);
+        const int X = round_clamped(fX), Y = round_clamped(fY);
+        const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+        const int ax = X & 31, ay = Y & 31;
+        const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+        int acc[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) acc[c] = 16384;
+        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+            const uint8_t* p0 = src + (size_t)sy * sp + sx * CH;
+            const uint8_t* p1 = p0 + sp;
+#pragma unroll
+            for (int c = 0; c < CH; c++)
+                acc[c] += w00 * __ldg(p0 + c) + w01 * __ldg(p0 + CH + c) + w10 * __ldg(p1 + c) + w11 * __ldg(p1 + CH + c);
+        } else {
+            const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+            const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                if (y0in && x0in) acc[c] += w00 * src[(size_t)sy * sp + sx * CH + c];
+                if (y0in && x1in) acc[c] += w01 * src[(size_t)sy * sp + (sx + 1) * CH + c];
+                if (y1in && x0in) acc[c] += w10 * src[(size_t)(sy + 1) * sp + sx * CH + c];
+                if (y1in && x1in) acc[c] += w11 * src[(size_t)(sy + 1) * sp + (sx + 1) * CH + c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) out[i * CH + c] = (uint8_t)(acc[c] >> 15);   // <= 255 by construction
+        if (CH == 3) gr[i] = gray15(out[i * 3], out[i * 3 + 1], out[i * 3 + 2]);
+    }
+    uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + (size_t)x4 * CH;
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(dp) & 3) == 0) {
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);
+#pragma unroll
+        for (int w = 0; w < CH; w++)
+            d32[w] = out[4 * w] | (out[4 * w + 1] << 8) | (out[4 * w + 2] << 16) | ((uint32_t)out[4 * w + 3] << 24);
+    } else {
+        for (int i = 0; i < nvalid * CH; i++) dp[i] = out[i];
+    }
+    if (CH == 3 && J.gray) {
+        uint8_t* gp = J.gray + (size_t)y * J.gray_pitch + x4;
+        if (nvalid == 4 && (reinterpret_cast<uintptr_t>(gp) & 3) == 0)
+            *reinterpret_cast<uint32_t*>(gp) = gr[0] | (gr[1] << 8) | (gr[2] << 16) | ((uint32_t)gr[3] << 24);
+        else
+            for (int i = 0; i < nvalid; i++) gp[i] = gr[i];
+    }
+}
+
+__global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __restrict__ jobs) {
+    const WarpAJob& J = jobs[blockIdx.z];
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (y >= J.dh || x4 >= J.dw) return;
+    const double dy = (double)y;
+    // cv::warpAffine: X0 = saturate_cast<int>((M[1]*y + M[2])*1024) + 16, adelta[x] = saturate_cast<int>(M[0]*x*1024)
+    const int X0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[1], dy), J.m[2]), 1024.0)) + 16;
+    const int Y0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[4], dy), J.m[5]), 1024.0)) + 16;
+    const uint8_t* __restrict__ src = J.src;
+    const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
+    uint8_t out[4];
+    const int nvalid = min(4, J.dw - x4);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double dx = (double)(x4 + i);
+        const int ad = round_clamped(__dmul_rn(__dmul_rn(J.m[0], dx), 1024.0));
+        const int bd = round_clamped(__dmul_rn(__dmul_rn(J.m[3], dx), 1024.0));
+        const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+        const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+        const int ax = X & 31, ay = Y & 31;
+        const int xa = ds_clamp(sx, 0, sw - 1), xb = ds_clamp(sx + 1, 0, sw - 1);
+        const int ya = ds_clamp(sy, 0, sh - 1), yb = ds_clamp(sy + 1, 0, sh - 1);
+        const uint8_t* r0 = src + (size_t)ya * sp;
+        const uint8_t* r1 = src + (size_t)yb * sp;
+        const int acc = (32 - ax) * (32 - ay) * 32 * __ldg(r0 + xa) + ax * (32 - ay) * 32 * __ldg(r0 + xb) +
+                        (32 - ax) * ay * 32 * __ldg(r1 + xa) + ax * ay * 32 * __ldg(r1 + xb) + 16384;
+        out[i] = (uint8_t)(acc >> 15);
+    }
+    uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x4;
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(dp) & 3) == 0)
+        *reinterpret_cast<uint32_t*>(dp) = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+    else
+        for (int i = 0; i < nvalid; i++) dp[i] = out[i];
+}
+
+}  // namespace
+
+int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, int max_w, int max_h) {
+    void* dev = nullptr;
+    DS_TRY(ds_upload(ctx, jobs_host, sizeof(WarpPJob) * n, &dev));
+    const int ch = jobs_host[0].ch;
+    for (int i = 1; i < n; i++)
+        if (jobs_host[i].ch != ch) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "mixed channel counts in one warp batch");
+    dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
+    if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    else warp_perspective_kernel<1><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}
+
+int k_warp_affine_jobs(docscan_ctx* ctx, const WarpAJob* jobs_host, int n, int max_w, int max_h) {
+    void* dev = nullptr;
+    DS_TRY(ds_upload(ctx, jobs_host, sizeof(WarpAJob) * n, &dev));
+    dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
+    warp_affine_kernel<<<grid, block, 0, ctx->stream>>>((const WarpAJob*)dev);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}

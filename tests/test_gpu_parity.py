@@ -1,0 +1,274 @@
+"""GPU (-m gpu): the CUDA path (through the C ABI) against the oracle on the same seeded inputs, against the
+committed goldens, and on the edge cases.  Integer / byte work must be bit-exact; the one floating-point stage
+(GAUSSIAN_C local mean) is compared after its uint8 rounding + threshold, which is what the path consumes, and is
+also required to be bit-exact (tolerance 0)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_npz
+from oracle import oracle as O
+from smart_image_processing_b200 import DocScanner as DS
+from smart_image_processing_b200 import morph_seq as MS
+from smart_image_processing_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def eq(a, b, what=""):
+    assert a.shape == b.shape and a.dtype == b.dtype, what
+    bad = int(np.count_nonzero(a != b))
+    assert bad == 0, f"{what}: {bad} differing values of {a.size}"
+
+
+def page_like(rng, h, w):
+    im = np.full((h, w), 205.0, np.float32)
+    for i in range(max(1, h // 14)):
+        y, x = 4 + 14 * i, 4
+        while x < w - 12:
+            ww = int(rng.integers(4, 40))
+            im[y:y + 7, x:x + ww] = rng.integers(15, 95)
+            x += ww + int(rng.integers(3, 14))
+    im = im * (0.55 + 0.45 * np.linspace(0, 1, w)[None, :]) + rng.normal(0, 3, (h, w))
+    return np.clip(im, 0, 255).astype(np.uint8)
+
+
+SHAPES = [(97, 131), (64, 128), (33, 260), (200, 333), (1, 50), (50, 1), (7, 5), (130, 1031), (257, 129)]
+
+
+def test_bgr2gray():
+    rng = np.random.default_rng(0)
+    for h, w in [(37, 41), (64, 128), (5, 3), (1, 1), (100, 1001)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        eq(ops.bgr2gray(img), O.bgr2gray(img), f"bgr2gray {h}x{w}")
+        eq(ops.bgr2gray(img, swap_rb=True), O.bgr2gray(img, True), f"rgb2gray {h}x{w}")
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 9, 11, 15, 23, 43, 51, 57, 101, 141, 217, 255])
+def test_gaussian_blur(k):
+    rng = np.random.default_rng(k)
+    for h, w in SHAPES:
+        g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"blur k={k} {h}x{w}")
+
+
+def test_gaussian_blur_tall_segments():
+    rng = np.random.default_rng(99)
+    g = rng.integers(0, 256, (1500, 300), dtype=np.uint8)     # several vertical segments per strip
+    for k in (23, 51):
+        eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"blur tall k={k}")
+
+
+def test_pointwise_ops_exhaustive():
+    a = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 256, 1)
+    b = a.T.copy()
+    eq(ops.subtract(a, b), O.subtract(a, b), "subtract")
+    eq(ops.divide255(a, b), O.divide255(a, b), "divide255")
+    eq(ops.divide255(a, b), load_npz("ops.npz")["div_table"], "divide255 vs cv2 golden")
+    eq(ops.maximum(a, b), O.maximum(a, b), "max")
+    eq(ops.mask_select(a, b), O.mask_select(a, b), "mask_select")
+    rng = np.random.default_rng(1)
+    for h, w in [(3, 5), (19, 1023)]:
+        x, y = rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h, w), dtype=np.uint8)
+        eq(ops.subtract(x, y), O.subtract(x, y), "subtract ragged")
+        eq(ops.divide255(x, y), O.divide255(x, y), "divide ragged")
+        eq(ops.threshold_binary(x, 100), O.threshold_binary(x, 100), "threshold")
+
+
+def test_stats_normalize_otsu():
+    rng = np.random.default_rng(2)
+    for h, w in [(75, 101), (300, 517), (1, 9), (64, 64)]:
+        g = page_like(rng, h, w)
+        assert ops.minmax(g) == O.minmax(g)
+        assert np.array_equal(ops.hist256(g), O.hist256(g))
+        eq(ops.normalize_minmax(g), O.normalize_minmax(g), "normalize")
+        assert ops.otsu_threshold(g) == O.otsu_threshold(g)
+        t, b = ops.otsu_threshold(g, return_image=True)
+        eq(b, O.threshold_binary(g, int(t)), "otsu image")
+    # every (min, max) pair through the LUT
+    for mn in range(0, 256, 5):
+        for mx in range(mn, 256, 7):
+            v = np.arange(mn, mx + 1, dtype=np.uint8)[None, :]
+            eq(ops.normalize_minmax(v), O.normalize_minmax(v), f"normalize {mn}..{mx}")
+    const = np.full((9, 13), 77, np.uint8)
+    assert (ops.normalize_minmax(const) == 0).all() and ops.otsu_threshold(const) == 0.0
+
+
+@pytest.mark.parametrize("kw,kh", [(2, 2), (3, 3), (4, 4), (9, 19), (5, 2), (1, 7), (31, 31), (15, 31), (99, 3), (2, 99), (217, 217)])
+def test_morphology(kw, kh):
+    rng = np.random.default_rng(kw * 100 + kh)
+    for h, w in [(61, 47), (130, 600), (1, 40), (40, 1), (300, 70)]:
+        g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        for it in (1, 2):
+            if max(kw, kh) > 100 and it > 1:
+                continue
+            eq(ops.erode(g, kw, kh, it), O.erode(g, kw, kh, it), f"erode {kw}x{kh} it{it} {h}x{w}")
+            eq(ops.dilate(g, kw, kh, it), O.dilate(g, kw, kh, it), f"dilate {kw}x{kh} it{it} {h}x{w}")
+            eq(ops.morph_close(g, kw, kh, it), O.morph_close(g, kw, kh, it), f"close {kw}x{kh} it{it} {h}x{w}")
+    g = page_like(rng, 120, 170)
+    eq(ops.blackhat(g, kw, kh), O.blackhat(g, kw, kh), f"blackhat {kw}x{kh}")
+    eq(ops.morph_close(g, kw, kh, 0), g, "close with 0 iterations is a copy")
+
+
+@pytest.mark.parametrize("k", [3, 5, 9, 11, 15, 21, 31, 35, 51])
+def test_adaptive_threshold(k):
+    rng = np.random.default_rng(k)
+    for h, w in [(120, 163), (90, 200), (77, 81), (60, 64), (33, 7), (64, 260), (40, 71), (1, 99), (99, 1), (300, 1131)]:
+        g = page_like(rng, h, w)
+        for c in (3, 10, -2):
+            eq(ops.adaptive_threshold(g, "gaussian", k, c), O.adaptive_threshold(g, "gaussian", k, c), f"gauss k={k} c={c} {h}x{w}")
+            eq(ops.adaptive_threshold(g, "gaussian", k, c, cv_tail_compat=False),
+               O.adaptive_threshold(g, "gaussian", k, c, unfused_tail=0), f"gauss all-fma k={k} c={c} {h}x{w}")
+            if k <= 35:
+                eq(ops.adaptive_threshold(g, "mean", k, c), O.adaptive_threshold(g, "mean", k, c), f"mean k={k} c={c} {h}x{w}")
+
+
+def test_adaptive_threshold_random_noise_is_exact():
+    # pure noise puts many local means next to rounding ties: the ordered fp32 evaluation must still match
+    rng = np.random.default_rng(5)
+    g = rng.integers(0, 256, (500, 700), dtype=np.uint8)
+    for k, c in ((31, 3), (35, 10), (11, 0)):
+        eq(ops.adaptive_threshold(g, "gaussian", k, c), O.adaptive_threshold(g, "gaussian", k, c), f"noise k={k}")
+
+
+def test_warp_perspective():
+    rng = np.random.default_rng(6)
+    for t in range(14):
+        H, W = int(rng.integers(20, 300)), int(rng.integers(20, 400))
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        spread = 0.15 * min(W, H) if t % 3 else 0.5 * min(W, H)          # some quads poke outside the image
+        quad = (np.array([[0.1 * W, 0.07 * H], [0.9 * W, 0.09 * H], [0.93 * W, 0.93 * H], [0.07 * W, 0.91 * H]])
+                + rng.uniform(-spread, spread, (4, 2))).astype(np.float32)
+        tw, th = int(rng.integers(2, 333)), int(rng.integers(1, 300))
+        dst = np.array([[0, 0], [tw - 1, 0], [tw - 1, th - 1], [0, th - 1]], np.float32)
+        m = O.get_perspective_transform(quad, dst)
+        ref = O.warp_perspective(img, m, (tw, th))
+        out, gray = ops.warp_perspective(img, m, (tw, th), return_gray=True)
+        eq(out, ref, f"warp {H}x{W}->{th}x{tw}")
+        eq(gray, O.bgr2gray(ref), "fused gray")
+        eq(ops.warp_perspective(img[:, :, 1].copy(), m, (tw, th)), O.warp_perspective(img[:, :, 1].copy(), m, (tw, th)), "warp c1")
+
+
+def test_warp_affine():
+    rng = np.random.default_rng(7)
+    for t in range(30):
+        H, W = int(rng.integers(1, 300)), int(rng.integers(1, 400))
+        g = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        ang = float(rng.integers(-20, 21)) * 0.5 if t % 2 else float(rng.uniform(-180, 180))
+        m = O.rotation_matrix((W / 2.0, H / 2.0), ang)
+        eq(ops.warp_affine(g, m, (W, H)), O.warp_affine(g, m, (W, H)), f"affine {H}x{W} {ang}")
+        eq(DS.rotate(g, ang), O.rotate(g, ang), "rotate")
+    g = rng.integers(0, 256, (123, 77), dtype=np.uint8)
+    eq(DS.rotate(g, 0.0), g, "angle 0 is an exact copy")
+
+
+def test_reference_stage_functions():
+    rng = np.random.default_rng(8)
+    for h, w in [(240, 170), (333, 500), (64, 64), (700, 495)]:
+        g = page_like(rng, h, w)
+        for method, frac in (("subtract", 0.02), ("divide", 0.05), ("divide", 0.3)):
+            eq(DS.illumination_correction(g, method, frac), O.illumination_correction(g, method, frac), f"illum {method} {frac}")
+        eq(DS.contrast_stretch(g), O.contrast_stretch(g), "stretch")
+        eq(DS._compute_ink_mask(g), O._compute_ink_mask(g), "ink mask (default 61)")
+        eq(DS._compute_ink_mask(g, mask_blur_ksize=51), O._compute_ink_mask(g, mask_blur_ksize=51), "ink mask 51")
+        eq(DS._compute_ink_mask(g, 30, 4, 1.5, 2, 3), O._compute_ink_mask(g, 30, 4, 1.5, 2, 3), "ink mask odd params")
+        eq(DS._compute_ink_mask(g, dilate_iters=0), O._compute_ink_mask(g, dilate_iters=0), "ink mask no dilate")
+        eq(DS.adaptive_binarize(g), O.adaptive_binarize(g), "adaptive default")
+        eq(DS.adaptive_binarize(g, 30, 3, "mean"), O.adaptive_binarize(g, 30, 3, "mean"), "adaptive mean even block")
+        eq(DS.morph_cleanup(g), O.morph_cleanup(g), "cleanup")
+        assert DS.morph_cleanup(g, 1, 0) is g
+
+
+def test_kat1_morphseq_and_kat2_constant_chain():
+    kat = load_npz("kat.npz")
+    eq(MS.grayscale_erosion(kat["morphseq_01_gray"]), kat["morphseq_02_eroded"], "KAT-1 erode 2x2")
+    shape = tuple(int(v) for v in kat["scan_03_warped_shape"])
+    warped = np.empty(shape, np.uint8)
+    warped[:] = kat["scan_03_warped_value"]
+    gray = ops.bgr2gray(warped)
+    illum = DS.illumination_correction(gray, "divide", 0.05)
+    stretch = DS.contrast_stretch(illum)
+    ink = DS._compute_ink_mask(stretch, mask_blur_ksize=51)
+    adapt = DS.adaptive_binarize(stretch, block_size=31, C=3)
+    weighted = ops.mask_select(adapt, ink)
+    desk = DS.rotate(weighted, 0.0)
+    clean = DS.morph_cleanup(desk, 1, 0)
+    for name, img in (("04_illum", illum), ("05_stretch", stretch), ("05a_inkmask", ink), ("06_adapt", adapt),
+                      ("06b_weighted", weighted), ("07_deskew", desk), ("08_clean", clean)):
+        assert (img == kat[f"scan_{name}_value"][0]).all(), name
+    # morph_seq chain
+    g = kat["morphseq_01_gray"]
+    eq(MS.otsu_binarize(MS.grayscale_erosion(g)), O.otsu_binarize(O.grayscale_erosion(g)), "morph_seq otsu")
+    eq(MS.binary_closing(MS.otsu_binarize(g)), O.binary_closing(O.otsu_binarize(g)), "morph_seq closing")
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_crops_golden_every_stage_and_fused_batch(tag):
+    z = load_npz("crops.npz")
+    p = json.loads(str(z[f"{tag}_params"]))
+    for drop in ("canny_low", "canny_high", "max_rotate"):
+        p.pop(drop)
+    page, scale_long = p.pop("page"), p.pop("scale_long")
+    angle = float(z[f"{tag}_angle"])
+    out = DS.hot_path(z[f"{tag}_input"], z[f"{tag}_quad"], angle, page=page, scale_long=scale_long, **p)
+    for k, v in out.items():
+        eq(v, z[f"{tag}_{k}"], f"crop {tag} stage {k}")
+    w, b = DS.process_pages([z[f"{tag}_input"]], [z[f"{tag}_quad"]], [angle], page=page, scale_long=scale_long, **p)
+    eq(w[0], z[f"{tag}_warped"], "fused warped")
+    eq(b[0], z[f"{tag}_clean"], "fused binary")
+
+
+@pytest.mark.parametrize("preset", ["cli", "gui"])
+def test_sample_jpg_golden(preset):
+    """BASELINE.json config 1."""
+    meta = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+    color = load_npz("sample_bgr.npz")["bgr"]
+    g = meta["presets"][preset]
+    p = dict(g["params"])
+    for drop in ("canny_low", "canny_high", "max_rotate"):
+        p.pop(drop)
+    page, scale_long = p.pop("page"), p.pop("scale_long")
+    quad = np.frombuffer(bytes.fromhex(g["quad_f32_hex"]), np.float32).reshape(4, 2)
+    angle = float.fromhex(g["angle_hex"])
+    out = DS.hot_path(color, quad, angle, page=page, scale_long=scale_long, **p)
+    for k, v in out.items():
+        assert sha(v) == g["sha256"][k], (preset, k)
+    w, b = DS.process_pages([color, color], [quad, quad], [angle, 0.0], page=page, scale_long=scale_long, **p)
+    assert sha(w[0]) == g["sha256"]["warped"] and sha(b[0]) == g["sha256"]["clean"]
+    eq(w[1], w[0], "batch page 1 warped")
+
+
+def test_batch_of_mixed_pages_matches_oracle():
+    rng = np.random.default_rng(11)
+    imgs, quads, angles = [], [], []
+    for i in range(5):
+        H, W = int(rng.integers(300, 520)), int(rng.integers(260, 420))
+        base = page_like(rng, H, W)
+        img = np.stack([np.clip(base * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1)
+        quad = (np.array([[0.08 * W, 0.06 * H], [0.93 * W, 0.08 * H], [0.95 * W, 0.94 * H], [0.05 * W, 0.92 * H]])
+                + rng.uniform(-8, 8, (4, 2))).astype(np.float32)
+        imgs.append(img); quads.append(quad); angles.append(float(rng.integers(-6, 7)) * 0.5)
+    for kw in (dict(scale_long=500), dict(scale_long=430, illum_method="divide", illum_blur_frac=0.05, block_size=31, C=3,
+                                          morph_ksize=1, morph_iters=0), dict(scale_long=400, thresh_method="mean", page="custom")):
+        w, b = DS.process_pages(imgs, quads, angles, **kw)
+        for i in range(len(imgs)):
+            ref = O.hot_path(imgs[i], quads[i], angles[i], **kw)
+            eq(w[i], ref["warped"], f"batch warped {i}")
+            eq(b[i], ref["clean"], f"batch binary {i}")
+
+
+def test_errors_are_loud():
+    from smart_image_processing_b200._capi import DocscanError
+    with pytest.raises(DocscanError):
+        ops.gaussian_blur(np.zeros((8, 8), np.uint8), 4)          # even kernel
+    with pytest.raises(TypeError):
+        ops.gaussian_blur(np.zeros((8, 8), np.float32), 3)
+    with pytest.raises(ValueError):
+        ops.subtract(np.zeros((8, 8), np.uint8), np.zeros((8, 9), np.uint8))
