@@ -113,7 +113,7 @@ def image_of(a: np.ndarray) -> Image:
         raise ValueError(f"unsupported image shape {a.shape}")
     if a.size and (a.strides[-1] != 1 or (a.ndim == 3 and a.strides[1] != ch)):
         raise ValueError("image rows must be densely packed")
-    return Image(a.ctypes.data, w, h, a.strides[0] if h > 0 else w * ch, ch, HOST)
+    return Image(a.ctypes.data, w, h, a.strides[0] if h > 1 else w * ch, ch, HOST)
 
 
 def device_image(ptr: int, width: int, height: int, pitch: int, channels: int) -> Image:
