@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""bench.py — DocScanner per-pixel pipeline throughput (input megapixels/s) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the whole hot path (warp -> gray -> illumination -> stretch -> ink mask || adaptive
+threshold -> blend -> rotate -> close; DocScanner.py:310-346, CLI defaults, scale_long=1600) over one batch
+of 256 synthetic 12 MP uint8 BGR pages per GPU (BASELINE.json configs[1]); pages are independent, so N GPUs
+each process their own batch (weak scaling, no collective on the data path).
+
+`value`   : device-resident inputs/outputs, CUDA-event time on the launching stream, max over ranks.
+`e2e`     : the same metric through the C-ABI call with HOST (pinned) buffers, H2D of every input page and
+            D2H of both result images (warped, binary) inside the timed region.
+`roofline`: the kernel with the largest share of the step, timed live with CUDA events in a second,
+            instrumented pass (docscan_profile_enable) — algorithmic bytes / average launch time vs the
+            measured HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` / `--impl reference`: the reference's own CPU path (the cv2 call chain of DocScanner.py,
+            oracle/ref_cv2.py) on this box's host cores, page-parallel over all cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "docscanner_pipeline_input_megapixels_per_s"
+PAGE_H, PAGE_W = 4000, 3000
+PAGE_MP = PAGE_H * PAGE_W / 1e6
+SCALE_LONG = 1600
+WORKLOAD = ("synthetic 12 MP uint8 BGR page batch through all DocScanner stages "
+            "(perspective warp, gray, illumination, stretch, ink mask, adaptive threshold, blend, rotate, close; "
+            "CLI defaults, scale_long=1600)")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--pages", type=int, default=256, help="pages per GPU per step")
+    ap.add_argument("--e2e-distinct", type=int, default=16, help="distinct pinned host pages the e2e leg cycles through")
+    ap.add_argument("--ref-pages", type=int, default=96, help="page-jobs per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+_W = {}
+
+
+def _cpu_worker_init(path, quads, angles):
+    """Worker process: one cv2 thread, pages memory-mapped from a scratch file."""
+    from oracle import ref_cv2
+    if ref_cv2.HAVE_CV2:
+        import cv2
+        cv2.setNumThreads(1)
+    _W["pages"] = np.load(path, mmap_mode="r")
+    _W["quads"], _W["angles"] = quads, angles
+    _W["fn"] = ref_cv2.hot_path if ref_cv2.HAVE_CV2 else None
+
+
+def _cpu_worker_job(j):
+    i = j % len(_W["quads"])
+    page = np.asarray(_W["pages"][i])
+    if _W["fn"] is not None:
+        _W["fn"](page, _W["quads"][i], _W["angles"][i], scale_long=SCALE_LONG)
+    else:
+        from oracle import oracle as O
+        O.hot_path(page, _W["quads"][i], _W["angles"][i], scale_long=SCALE_LONG)
+    return 0
+
+
+class CpuReference:
+    """The reference's own CPU path — the cv2 call chain of DocScanner.py (oracle/ref_cv2.py) — page-parallel over
+    every host core: os.cpu_count() spawned worker processes with one cv2 thread each (SURVEY.md 8d mode B, the
+    faster of the two modes the survey measured).  Never forks after cv2/CUDA have been initialised."""
+
+    def __init__(self, pages, quads, angles):
+        import multiprocessing as mp
+        import tempfile
+        from oracle import ref_cv2
+        self.cores = os.cpu_count() or 1
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        fd, self.path = tempfile.mkstemp(suffix=".npy", dir=base)
+        os.close(fd)
+        np.save(self.path, np.stack(pages))
+        self.n_distinct = len(pages)
+        self.how = (f"cv2 call chain of DocScanner.py (oracle/ref_cv2.py), {self.cores} worker processes x 1 cv2 thread"
+                    if ref_cv2.HAVE_CV2 else f"C oracle (cv2 not installed), {self.cores} worker processes")
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init,
+                                                 initargs=(self.path, [np.asarray(q) for q in quads], list(angles)))
+        self.run(2 * self.cores)                                   # imports + first-touch, not timed
+
+    def run(self, jobs: int):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_worker_job, range(jobs), chunksize=1)
+        dt = time.perf_counter() - t0
+        return jobs * PAGE_MP / dt, dt
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from smart_image_processing_b200.synth import synth_angle, synth_page_numpy
+    distinct = 2
+    pages, quads, angles = [], [], []
+    for s in range(distinct):
+        img, quad = synth_page_numpy(s, PAGE_W, PAGE_H)
+        pages.append(img); quads.append(quad); angles.append(synth_angle(s))
+    ref = CpuReference(pages, quads, angles)
+    for _ in range(args.warmup):
+        ref.run(max(ref.cores, 8))
+    total = 0.0
+    for _ in range(args.steps):
+        total += ref.run(args.ref_pages)[1]
+    ref.close()
+    value = args.steps * args.ref_pages * PAGE_MP / total
+    sample = f"{args.ref_pages} page-jobs per step over {distinct} distinct synthetic 12 MP pages; {ref.how}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "page": f"{PAGE_H}x{PAGE_W}x3", "scale_long": SCALE_LONG, "pages_per_step": args.ref_pages},
+        "cpu_baseline": {"value": value, "unit": "MP/s", "cores": ref.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from smart_image_processing_b200 import DocScanner as DS
+    from smart_image_processing_b200 import _capi
+    from smart_image_processing_b200.synth import synth_angle
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    ctx = _capi.Context(local, stream=stream.cuda_stream)
+    P = args.pages
+    params = DS.make_params()
+
+    # ---- device-resident synthetic batch (generated on the device; not timed)
+    src = torch.empty((P, PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
+    quads, angles = [], []
+    q8 = (C.c_float * 8)()
+    for i in range(P):
+        seed = rank * P + i
+        im = _capi.device_image(src[i].data_ptr(), PAGE_W, PAGE_H, PAGE_W * 3, 3)
+        ctx.call("docscan_synth_page", C.c_uint64(seed), C.byref(im), q8)
+        quads.append(np.array(list(q8), np.float32).reshape(4, 2))
+        angles.append(synth_angle(seed))
+    sizes = [DS.target_size(q, "A4", SCALE_LONG) for q in quads]
+    tw, th = sizes[0]
+    assert all(s == (tw, th) for s in sizes)
+    pw3, pw1 = (tw * 3 + 127) // 128 * 128, (tw + 127) // 128 * 128
+    warped = torch.empty((P, th, pw3), dtype=torch.uint8, device=dev)
+    binary = torch.empty((P, th, pw1), dtype=torch.uint8, device=dev)
+    pages = (_capi.Page * P)()
+    for i in range(P):
+        pages[i].src = _capi.device_image(src[i].data_ptr(), PAGE_W, PAGE_H, PAGE_W * 3, 3)
+        pages[i].quad = (C.c_float * 8)(*quads[i].reshape(8).tolist())
+        pages[i].angle_deg = angles[i]
+        pages[i].warped = _capi.device_image(warped[i].data_ptr(), tw, th, pw3, 3)
+        pages[i].binary = _capi.device_image(binary[i].data_ptr(), tw, th, pw1, 1)
+    ctx.sync()
+
+    def step():
+        ctx.call("docscan_process_pages", P, pages, C.byref(params))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ctx.launches
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+    launches = ctx.launches - l0
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * P * PAGE_MP * args.steps / (ms_total / 1e3)
+
+    # ---- per-kernel pass (instrumented; not the number reported as `value`)
+    ctx.profile(True)
+    step()
+    prof = ctx.profile_dump()
+    ctx.profile(False)
+    kernel_ms = sum(v[1] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    n_l, t_ms, nbytes = top[1]
+    achieved = nbytes / n_l / (t_ms / n_l * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top[0].split("_k")[0])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "share_of_step": t_ms / kernel_ms,
+                "algorithmic_bytes_per_launch": nbytes / n_l, "avg_launch_ms": t_ms / n_l,
+                "note": "kernel is instruction-issue bound, not HBM bound (see DESIGN.md); fraction reported as required",
+                "kernels": {k: {"launches": v[0], "ms": round(v[1], 4), "GB/s": (round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None)}
+                            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+
+    # ---- e2e: host (pinned) buffers through the same C-ABI call, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        D = min(args.e2e_distinct, P)
+        h_src = [ctx.pinned_empty((PAGE_H, PAGE_W, 3)) for _ in range(D)]
+        h_w = [ctx.pinned_empty((th, tw, 3)) for _ in range(D)]
+        h_b = [ctx.pinned_empty((th, tw)) for _ in range(D)]
+        for i in range(D):
+            _capi.lib().docscan_memcpy_d2h(ctx._h, h_src[i].ctypes.data, C.c_void_p(src[i].data_ptr()), h_src[i].nbytes)
+        hpages = (_capi.Page * P)()
+        for i in range(P):
+            d = i % D
+            hpages[i].src = _capi.image_of(h_src[d])
+            hpages[i].quad = (C.c_float * 8)(*quads[d].reshape(8).tolist())
+            hpages[i].angle_deg = angles[d]
+            hpages[i].warped = _capi.image_of(h_w[d])
+            hpages[i].binary = _capi.image_of(h_b[d])
+
+        def hstep():
+            ctx.call("docscan_process_pages", P, hpages, C.byref(params))
+
+        hstep()
+        barrier()
+        esteps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(esteps):
+            hstep()
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * P * PAGE_MP * esteps / (float(ems.item()) / 1e3), "unit": "MP/s",
+               "h2d_bytes_per_step": P * PAGE_H * PAGE_W * 3, "d2h_bytes_per_step": P * th * tw * 4,
+               "steps": esteps, "host_buffers": f"pinned; {D} distinct pages cycled, every page copied every step"}
+
+    # ---- CPU baseline beside it (rank 0, single-GPU run only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        D = 4
+        hp = [np.empty((PAGE_H, PAGE_W, 3), np.uint8) for _ in range(D)]
+        for i in range(D):
+            _capi.lib().docscan_memcpy_d2h(ctx._h, hp[i].ctypes.data, C.c_void_p(src[i].data_ptr()), hp[i].nbytes)
+        ref = CpuReference(hp, quads[:D], angles[:D])
+        _, dt1 = ref.run(2 * ref.cores)
+        jobs = int(max(2 * ref.cores, min(4096, 12.0 / max(dt1 / (2 * ref.cores), 1e-6))))
+        v, dt = ref.run(jobs)
+        ref.close()
+        cpu = {"value": v, "unit": "MP/s", "cores": ref.cores, "kind": "port",
+               "sample": f"{jobs} page-jobs over {D} distinct pages of this run's batch, {dt:.1f} s; {ref.how}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pages_per_gpu": P, "page": f"{PAGE_H}x{PAGE_W}x3", "warped": f"{th}x{tw}",
+                       "scale_long": SCALE_LONG, "parallelism": f"pages sharded over {world} GPU(s), no collective",
+                       "l2": f"inputs larger than L2 ({P * PAGE_H * PAGE_W * 3 / 1e9:.1f} GB read per step per GPU)"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,11 @@ DOCSCAN_API int docscan_sync(docscan_ctx* ctx);
 DOCSCAN_API const char* docscan_last_error(docscan_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 DOCSCAN_API int64_t docscan_launch_count(docscan_ctx* ctx);
+/* per-kernel timing for bench.py: when enabled every kernel launch is bracketed by CUDA events on the
+ * context's stream.  docscan_profile_dump syncs, writes one line per kernel name
+ * ("name launches total_ms algorithmic_bytes\n") into buf, clears the records and returns the length. */
+DOCSCAN_API int docscan_profile_enable(docscan_ctx* ctx, int on);
+DOCSCAN_API int docscan_profile_dump(docscan_ctx* ctx, char* buf, size_t cap);
 /* pinned host memory for the fast HOST path */
 DOCSCAN_API int docscan_host_alloc(docscan_ctx* ctx, size_t bytes, void** out);
 DOCSCAN_API int docscan_host_free(docscan_ctx* ctx, void* p);

@@ -49,6 +49,8 @@ _SIGS = {
     "docscan_sync": (C.c_int, [C.c_void_p]),
     "docscan_last_error": (C.c_char_p, [C.c_void_p]),
     "docscan_launch_count": (C.c_int64, [C.c_void_p]),
+    "docscan_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "docscan_profile_dump": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "docscan_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "docscan_host_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "docscan_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -156,6 +158,21 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self._lib.docscan_launch_count(self._h))
+
+    def profile(self, on: bool):
+        self.call("docscan_profile_enable", int(on))
+
+    def profile_dump(self) -> dict:
+        """{kernel name: (launches, total_ms, algorithmic_bytes)} since the last dump."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self._lib.docscan_profile_dump(self._h, buf, len(buf))
+        if n < 0:
+            self.check(n, "docscan_profile_dump")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms, nbytes = line.split()
+            out[name] = (int(cnt), float(ms), float(nbytes))
+        return out
 
     # pinned numpy arrays for the fast host path
     def pinned_empty(self, shape, dtype=np.uint8) -> np.ndarray:

@@ -16,7 +16,7 @@ constexpr int TW = 128, BR = 16, NT = 128;
 constexpr int RPF = 132;      // ring row pitch in floats
 
 struct AdaptLaunch {
-    int k, r, delta, c_param, seg_rows, spf, ring_rows, nblk;
+    int k, r, delta, c_param, seg_rows, spf, ring_rows, nblk, tail_compat;
     const float* g_row;       // 16 zeros + k taps + zeros up to 16*nblk + 32
     const float* g_col;       // g_col[j] = g[r + j] for j <= r, zero up to 64
 };
@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(NT) adaptive_gauss_kernel(const AdaptJob* __re
     const int D = (2 * r + BR - 1) / BR;
     const int n_vb = (rows_out + BR - 1) / BR;
     const bool row_identity = J.w == 1, col_identity = J.h == 1;   // cv::GaussianBlur shrinks the kernel on 1-px axes
+    // columns cv2's AVX2 build evaluates without fma (k <= 9: the taps are dyadic, every order is exact)
+    const int tail = (L.tail_compat && L.k >= 11) ? (J.w & 7) : 0;
+    const int xt_col = J.w - tail;                                  // column filter: mul+add from here on
+    const int xt_row = xt_col + (tail >= 4 ? 4 : 0);                // row filter: scalar code from here on
 
     for (int hb = 0; hb < n_vb + D; hb++) {
         for (int idx = tid; idx < BR * stage_words; idx += NT) {
@@ -95,6 +99,21 @@ __global__ void __launch_bounds__(NT) adaptive_gauss_kernel(const AdaptJob* __re
             if (row_identity) {
 #pragma unroll
                 for (int o = 0; o < 16; o++) acc[o] = srow[stage_index(base + r + o)];
+            } else if (xt_row < J.w && x0 + cg * 16 + 15 >= xt_row) {
+                // cv2's row filter leaves the last w % 4 columns to scalar code: mul+add per tap, except that the
+                // (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  At most 3 columns per row.
+                const int first_fused = L.k - ((L.k - 1) & 3);
+#pragma unroll
+                for (int o = 0; o < 16; o++) {
+                    const int x = x0 + cg * 16 + o;
+                    if (x < xt_row || x >= J.w) continue;
+                    float a = __fmul_rn(s_grow[16], srow[stage_index(base + o)]);
+                    for (int i = 1; i < L.k; i++) {
+                        const float f = srow[stage_index(base + o + i)];
+                        a = i >= first_fused ? __fmaf_rn(f, s_grow[16 + i], a) : __fadd_rn(a, __fmul_rn(s_grow[16 + i], f));
+                    }
+                    acc[o] = a;
+                }
             }
             const int slot = (hb * BR + hr) % L.ring_rows;
             float4* dst = reinterpret_cast<float4*>(s_ring + slot * RPF + cg * 16);
@@ -122,11 +141,20 @@ __global__ void __launch_bounds__(NT) adaptive_gauss_kernel(const AdaptJob* __re
         const float gc0 = s_gcol[0];
 #pragma unroll
         for (int o = 0; o < BR; o++) acc[o] = __fmul_rn(gc0, Wn[o + RMAX]);
+        if (x < xt_col) {
 #pragma unroll
-        for (int j = 1; j <= RMAX; j++) {
-            const float gj = s_gcol[j];
+            for (int j = 1; j <= RMAX; j++) {
+                const float gj = s_gcol[j];
 #pragma unroll
-            for (int o = 0; o < BR; o++) acc[o] = __fmaf_rn(__fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j]), gj, acc[o]);
+                for (int o = 0; o < BR; o++) acc[o] = __fmaf_rn(__fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j]), gj, acc[o]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 1; j <= RMAX; j++) {
+                const float gj = s_gcol[j];
+#pragma unroll
+                for (int o = 0; o < BR; o++) acc[o] = __fadd_rn(acc[o], __fmul_rn(gj, __fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j])));
+            }
         }
         if (x < J.w) {
 #pragma unroll
@@ -140,48 +168,6 @@ __global__ void __launch_bounds__(NT) adaptive_gauss_kernel(const AdaptJob* __re
             }
         }
     }
-}
-
-// Last w % 8 columns the way cv2's AVX2 build evaluates them (see oracle/docscan_oracle.c, A.9):
-// row filter: one 4-wide fma chunk, then scalar mul+add whose last (k-1) % 4 taps are fma;
-// column filter: mul+add.  One thread per tail pixel; O(k^2) each, but there are at most 7 columns.
-__global__ void adaptive_gauss_tail_kernel(const AdaptJob* __restrict__ jobs, int k, int c_param,
-                                           const float* __restrict__ g /* k taps */) {
-    const AdaptJob J = jobs[blockIdx.z];
-    const int tail = J.w & 7;
-    if (tail == 0) return;
-    const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    const int tx = blockIdx.y;
-    if (y >= J.h || tx >= tail) return;
-    const int r = k >> 1;
-    const int xt_col = J.w - tail;
-    const int xt_row = xt_col + (tail >= 4 ? 4 : 0);
-    const int x = xt_col + tx;
-    const bool row_fused = x < xt_row;
-    const int first_fused_tap = row_fused ? 1 : k - ((k - 1) & 3);
-    auto row_value = [&](int yy) -> float {
-        const uint8_t* rowp = J.src + (size_t)ds_clamp(yy, 0, J.h - 1) * J.src_pitch;
-        if (J.w == 1) return (float)rowp[0];
-        float acc = __fmul_rn(g[0], (float)rowp[ds_clamp(x - r, 0, J.w - 1)]);
-        for (int i = 1; i < k; i++) {
-            const float f = (float)rowp[ds_clamp(x - r + i, 0, J.w - 1)];
-            if (i >= first_fused_tap) acc = __fmaf_rn(f, g[i], acc);
-            else acc = __fadd_rn(acc, __fmul_rn(g[i], f));
-        }
-        return acc;
-    };
-    float acc;
-    if (J.h == 1) acc = row_value(y);
-    else {
-        acc = __fmul_rn(g[r], row_value(y));
-        for (int j = 1; j <= r; j++) {
-            const float pr = __fadd_rn(row_value(y + j), row_value(y - j));
-            acc = __fadd_rn(acc, __fmul_rn(g[r + j], pr));
-        }
-    }
-    const int mean = min(max(__float2int_rn(acc), 0), 255);
-    const int s = J.src[(size_t)y * J.src_pitch + x];
-    J.dst[(size_t)y * J.dst_pitch + x] = (s - mean > -c_param) ? 255 : 0;
 }
 
 // combined = max(ink_sub_n > t_sub, bh_n > t_bh) -> dilate rect 2x2 x iters (window {x-n..x} x {y-n..y},
@@ -234,7 +220,7 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     if (k < 3 || (k & 1) == 0 || k > 65)
         return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "adaptive GAUSSIAN_C block size must be odd and in 3..65 (got %d)", k);
     AdaptLaunch L{};
-    L.k = k; L.r = k / 2; L.delta = (4 - (L.r & 3)) & 3; L.c_param = c;
+    L.k = k; L.r = k / 2; L.delta = (4 - (L.r & 3)) & 3; L.c_param = c; L.tail_compat = cv_tail_compat;
     L.nblk = (k + 15 + 15) / 16;
     L.spf = TW + 16 * L.nblk;
     L.spf += L.spf / 16 + 2;
@@ -257,7 +243,6 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     }
     const float* tab = (const float*)it->second;
     L.g_row = tab; L.g_col = tab + n_row;
-    const float* g_plain = tab + n_row + 64;
 
     const int strips = n * ((max_w + TW - 1) / TW);
     int segs = (4 * ctx->sm_count + strips - 1) / strips;
@@ -272,23 +257,19 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(AdaptJob) * n, &dev));
     const AdaptJob* jd = (const AdaptJob*)dev;
     dim3 grid((max_w + TW - 1) / TW, (max_h + seg - 1) / seg, n);
+    double px = 0;
+    for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
     int rc;
+    {
+    ProfScope prof(ctx, "adaptive_gauss_k" + std::to_string(k), 2.0 * px);
     if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, grid, smem);
     else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, grid, smem);
     else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, grid, smem);
     else if (L.r <= 17) rc = launch_adaptive<17>(ctx, jd, L, grid, smem);
     else if (L.r <= 25) rc = launch_adaptive<25>(ctx, jd, L, grid, smem);
     else rc = launch_adaptive<32>(ctx, jd, L, grid, smem);
-    DS_TRY(rc);
-    if (cv_tail_compat && k >= 11) {
-        bool any = false;
-        for (int i = 0; i < n; i++) any = any || (jobs_host[i].w & 7) != 0;
-        if (any) {
-            dim3 tgrid((max_h + 127) / 128, 7, n);
-            adaptive_gauss_tail_kernel<<<tgrid, 128, 0, ctx->stream>>>(jd, k, c, g_plain);
-            DS_CHECK_LAUNCH(ctx);
-        }
     }
+    DS_TRY(rc);
     return DOCSCAN_OK;
 }
 
@@ -298,6 +279,9 @@ int k_mask_blend_jobs(docscan_ctx* ctx, int dilate_iters, int write_mask_only, c
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(BlendJob) * n, &dev));
     dim3 grid((max_w + 511) / 512, max_h, n);
+    double px = 0;
+    for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
+    ProfScope prof(ctx, "mask_blend", (write_mask_only ? 3.0 : 4.0) * px);
     mask_blend_kernel<<<grid, 128, 0, ctx->stream>>>((const BlendJob*)dev, dilate_iters, write_mask_only);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;

@@ -291,6 +291,9 @@ int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const B
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(BlurJob) * n, &dev));
     dim3 grid((max_w + TW - 1) / TW, (max_h + seg - 1) / seg, n);
     const BlurJob* jd = (const BlurJob*)dev;
+    double px = 0;
+    for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
+    ProfScope prof(ctx, std::string(kind == 0 ? "blur_gauss_k" : "blur_box_k") + std::to_string(k), 2.0 * px);
 #define DS_BLUR_CASE(E)                                                            \
     case E:                                                                        \
         return stats ? launch<E, true>(ctx, jd, L, grid, smem) : launch<E, false>(ctx, jd, L, grid, smem);

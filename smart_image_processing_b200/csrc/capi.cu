@@ -559,11 +559,11 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         any_host = any_host || is_host(&pg.src) || is_host(&pg.warped) || is_host(&pg.binary);
         max_page = std::max(max_page, page_scratch(pg));
     }
-    // pages per launch group: big enough to fill the GPU, small enough that the group's intermediates
-    // (about 16 planes per page) stay resident in L2 between the kernels of the chain
-    const size_t l2 = ctx->l2_bytes ? ctx->l2_bytes : (size_t)96 << 20;
-    const size_t inter = 12 * plane_bytes(pages[0].binary.width, pages[0].binary.height);
-    int group = (int)std::max<size_t>(1, std::min<size_t>(8, (l2 * 3 / 4) / std::max<size_t>(inter, 1)));
+    // pages per launch group: enough 128-column strips to give every SM a few CTAs without cutting pages
+    // into short vertical segments (each segment repeats a 2r-row warm-up in the stencil kernels)
+    const int strips_per_page = (pages[0].binary.width + 127) / 128;
+    int group = (2 * ctx->sm_count + strips_per_page - 1) / strips_per_page;
+    group = std::max(4, std::min(group, 32));
     group = std::min(group, n);
     DS_TRY(begin_call(ctx, max_page * group));
     for (int i = 0; i < n; i += group) DS_TRY(run_group(ctx, std::min(group, n - i), pages + i, *params));

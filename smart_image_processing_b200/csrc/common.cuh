@@ -43,6 +43,27 @@ struct docscan_ctx {
     // cached device coefficient tables, keyed by (kind, k, delta)
     std::map<uint64_t, void*> tables;
     std::vector<void*> user_allocs;
+    // optional per-kernel timing (docscan_profile_enable): one event pair per launch
+    bool prof_on = false;
+    struct ProfRec { std::string name; double bytes; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+};
+
+// Brackets one kernel launch with CUDA events when profiling is on (bench.py's roofline pass).
+struct ProfScope {
+    docscan_ctx* ctx;
+    bool on;
+    ProfScope(docscan_ctx* c, const std::string& name, double alg_bytes) : ctx(c), on(c->prof_on) {
+        if (!on) return;
+        docscan_ctx::ProfRec r{name, alg_bytes, nullptr, nullptr};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, c->stream);
+        c->prof.push_back(r);
+    }
+    ~ProfScope() {
+        if (on) cudaEventRecord(ctx->prof.back().b, ctx->stream);
+    }
 };
 
 int ds_fail(docscan_ctx* ctx, int code, const char* fmt, ...);

@@ -90,6 +90,36 @@ extern "C" int docscan_sync(docscan_ctx* ctx) {
 extern "C" const char* docscan_last_error(docscan_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 extern "C" int64_t docscan_launch_count(docscan_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+extern "C" int docscan_profile_enable(docscan_ctx* ctx, int on) {
+    if (!ctx) return DOCSCAN_ERR_BAD_ARG;
+    ctx->prof_on = on != 0;
+    return DOCSCAN_OK;
+}
+
+extern "C" int docscan_profile_dump(docscan_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return DOCSCAN_ERR_BAD_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    struct Agg { long n = 0; double ms = 0, bytes = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        Agg& a = agg[r.name];
+        a.n++; a.ms += ms; a.bytes += r.bytes;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    ctx->prof.clear();
+    size_t off = 0;
+    for (auto& kv : agg) {
+        int w = snprintf(buf + off, cap - off, "%s %ld %.6f %.0f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes);
+        if (w < 0 || (size_t)w >= cap - off) break;
+        off += (size_t)w;
+    }
+    buf[off < cap ? off : cap - 1] = 0;
+    return (int)off;
+}
+
 extern "C" int docscan_host_alloc(docscan_ctx* ctx, size_t bytes, void** out) {
     if (!ctx || !out) return DOCSCAN_ERR_BAD_ARG;
     DS_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -75,8 +75,10 @@ __global__ void __launch_bounds__(NT) morph_1d_kernel(const MorphJob* __restrict
     int P = 1;
     while (P * 2 <= k) P *= 2;
 
+    // thread layout: 16 lines x 16 lanes; a lane strides along its line, so no index division anywhere
+    const int ty = tid >> 4, tx = tid & 15;
     if (AXIS == 0) {
-        const int tx0 = blockIdx.x * L.len, ty0 = blockIdx.y * L.cnt;
+        const int tx0 = blockIdx.x * L.len, ty0 = blockIdx.y * L.cnt;       // L.cnt == 16 rows
         if (tx0 >= J.w || ty0 >= J.h) return;
         const int nw = L.nw, total = nw * L.cnt;
         uint32_t* bufA = smem_u32;
@@ -85,30 +87,34 @@ __global__ void __launch_bounds__(NT) morph_1d_kernel(const MorphJob* __restrict
         if (s_hist) for (int i = tid; i < 8 * 256; i += NT) s_hist[i] = 0;
         const int gx0 = (tx0 - L.a) & ~3;            // floor to a multiple of 4 (also for negatives)
         const int delta = (tx0 - L.a) - gx0;
-        for (int idx = tid; idx < total; idx += NT) {
-            const int row = idx / nw, wi = idx - row * nw;
-            bufA[idx] = load_word(J, ty0 + row, gx0 + 4 * wi, neutral, src_al);
+        {
+            const int gy = ty0 + ty;
+            uint32_t* r = bufA + ty * nw;
+            for (int wi = tx; wi < nw; wi += 16) r[wi] = load_word(J, gy, gx0 + 4 * wi, neutral, src_al);
         }
         __syncthreads();
         uint32_t* cur = bufA;
         uint32_t* nxt = bufB;
         for (int p = 1; p < P; p *= 2) {
-            for (int idx = tid; idx < total; idx += NT) {
-                const int row = idx / nw, wi = idx - row * nw;
-                const uint32_t* r = cur + row * nw;
-                const uint32_t other = p < 4 ? __funnelshift_r(r[wi], r[min(wi + 1, nw - 1)], 8 * p) : r[min(wi + (p >> 2), nw - 1)];
-                nxt[idx] = op4(r[wi], other, L.is_dilate);
+            const uint32_t* r = cur + ty * nw;
+            uint32_t* w = nxt + ty * nw;
+            if (p < 4) {
+                for (int wi = tx; wi < nw; wi += 16) w[wi] = op4(r[wi], __funnelshift_r(r[wi], r[min(wi + 1, nw - 1)], 8 * p), L.is_dilate);
+            } else {
+                const int off = p >> 2;
+                for (int wi = tx; wi < nw; wi += 16) w[wi] = op4(r[wi], r[min(wi + off, nw - 1)], L.is_dilate);
             }
             __syncthreads();
             uint32_t* t = cur; cur = nxt; nxt = t;
         }
-        const int out_words = L.len >> 2;
-        for (int idx = tid; idx < out_words * L.cnt; idx += NT) {
-            const int row = idx / out_words, wo = idx - row * out_words;
-            const uint32_t* r = cur + row * nw;
-            uint32_t res = read_bytes(r, delta + 4 * wo, nw - 1);
-            if (k > P) res = op4(res, read_bytes(r, delta + 4 * wo + (k - P), nw - 1), L.is_dilate);
-            store_word(J, ty0 + row, tx0 + 4 * wo, res, s_hist, dst_al);
+        {
+            const int out_words = L.len >> 2;
+            const uint32_t* r = cur + ty * nw;
+            for (int wo = tx; wo < out_words; wo += 16) {
+                uint32_t res = read_bytes(r, delta + 4 * wo, nw - 1);
+                if (k > P) res = op4(res, read_bytes(r, delta + 4 * wo + (k - P), nw - 1), L.is_dilate);
+                store_word(J, ty0 + ty, tx0 + 4 * wo, res, s_hist, dst_al);
+            }
         }
         if (s_hist) {
             __syncthreads();
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(NT) morph_1d_kernel(const MorphJob* __restrict
             if (s) atomicAdd(&J.hist[tid], s);
         }
     } else {
-        const int cw = L.cnt;                         // word columns per tile
+        const int cw = L.cnt;                         // 16 word columns per tile
         const int tx0 = blockIdx.x * cw * 4, ty0 = blockIdx.y * L.len;
         if (tx0 >= J.w || ty0 >= J.h) return;
         const int nr = L.nw, total = nr * cw;
@@ -125,27 +131,20 @@ __global__ void __launch_bounds__(NT) morph_1d_kernel(const MorphJob* __restrict
         uint32_t* bufB = smem_u32 + total;
         uint32_t* s_hist = J.hist ? smem_u32 + 2 * total : nullptr;
         if (s_hist) for (int i = tid; i < 8 * 256; i += NT) s_hist[i] = 0;
-        for (int idx = tid; idx < total; idx += NT) {
-            const int row = idx / cw, wi = idx - row * cw;
-            bufA[idx] = load_word(J, ty0 - L.a + row, tx0 + 4 * wi, neutral, src_al);
-        }
+        for (int row = ty; row < nr; row += 16) bufA[row * cw + tx] = load_word(J, ty0 - L.a + row, tx0 + 4 * tx, neutral, src_al);
         __syncthreads();
         uint32_t* cur = bufA;
         uint32_t* nxt = bufB;
         for (int p = 1; p < P; p *= 2) {
-            for (int idx = tid; idx < total; idx += NT) {
-                const int row = idx / cw;
-                const int orow = min(row + p, nr - 1);
-                nxt[idx] = op4(cur[idx], cur[idx + (orow - row) * cw], L.is_dilate);
-            }
+            for (int row = ty; row < nr; row += 16)
+                nxt[row * cw + tx] = op4(cur[row * cw + tx], cur[min(row + p, nr - 1) * cw + tx], L.is_dilate);
             __syncthreads();
             uint32_t* t = cur; cur = nxt; nxt = t;
         }
-        for (int idx = tid; idx < L.len * cw; idx += NT) {
-            const int row = idx / cw, wi = idx - row * cw;
-            uint32_t res = cur[idx];
-            if (k > P) res = op4(res, cur[min(row + (k - P), nr - 1) * cw + wi], L.is_dilate);
-            store_word(J, ty0 + row, tx0 + 4 * wi, res, s_hist, dst_al);
+        for (int row = ty; row < L.len; row += 16) {
+            uint32_t res = cur[row * cw + tx];
+            if (k > P) res = op4(res, cur[min(row + (k - P), nr - 1) * cw + tx], L.is_dilate);
+            store_word(J, ty0 + row, tx0 + 4 * tx, res, s_hist, dst_al);
         }
         if (s_hist) {
             __syncthreads();
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(NT) morph_1d_kernel(const MorphJob* __restrict
 }
 
 int launch_axis(docscan_ctx* ctx, int axis, int is_dilate, int k, int a, const MorphJob* jobs_dev, int n, int max_w,
-                int max_h, bool hist) {
+                int max_h, bool hist, double alg_bytes) {
     MorphLaunch L{};
     L.k = k; L.a = a; L.is_dilate = is_dilate;
     dim3 grid;
@@ -177,6 +176,7 @@ int launch_axis(docscan_ctx* ctx, int axis, int is_dilate, int k, int a, const M
         grid = dim3((max_w + 4 * L.cnt - 1) / (4 * L.cnt), (max_h + L.len - 1) / L.len, n);
     }
     const size_t smem = (words + (hist ? 8 * 256 : 0)) * sizeof(uint32_t);
+    ProfScope prof(ctx, std::string(axis == 0 ? "morph_h_k" : "morph_v_k") + std::to_string(k), alg_bytes);
     if (smem > 200 * 1024) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "structuring element %d too large", k);
     if (axis == 0) {
         if (smem > 48 * 1024) DS_CUDA(ctx, cudaFuncSetAttribute(morph_1d_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -208,7 +208,12 @@ int k_morph_jobs(docscan_ctx* ctx, int is_dilate, int kw, int kh, int ax, int ay
     void *dh = nullptr, *dv = nullptr;
     DS_TRY(ds_upload(ctx, hjobs.data(), sizeof(MorphJob) * n, &dh));
     DS_TRY(ds_upload(ctx, vjobs.data(), sizeof(MorphJob) * n, &dv));
-    DS_TRY(launch_axis(ctx, 0, is_dilate, kw, ax, (const MorphJob*)dh, n, max_w, max_h, false));
-    DS_TRY(launch_axis(ctx, 1, is_dilate, kh, ay, (const MorphJob*)dv, n, max_w, max_h, hist));
+    double px = 0, refpx = 0;
+    for (int i = 0; i < n; i++) {
+        px += (double)jobs_host[i].w * jobs_host[i].h;
+        if (jobs_host[i].ref) refpx += (double)jobs_host[i].w * jobs_host[i].h;
+    }
+    DS_TRY(launch_axis(ctx, 0, is_dilate, kw, ax, (const MorphJob*)dh, n, max_w, max_h, false, 2.0 * px));
+    DS_TRY(launch_axis(ctx, 1, is_dilate, kh, ay, (const MorphJob*)dv, n, max_w, max_h, hist, 2.0 * px + refpx));
     return DOCSCAN_OK;
 }

@@ -87,6 +87,10 @@ static int pw_launch(docscan_ctx* ctx, int op, const PwJob* jobs_host, int n, in
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(PwJob) * n, &dev));
     dim3 grid((max_w + 511) / 512, max_h, n), block(128);
     const PwJob* j = (const PwJob*)dev;
+    static const char* names[] = {"pw_subtract", "pw_divide255", "pw_max", "pw_mask_select", "pw_lut", "pw_threshold", "pw_bgr2gray", "pw_rgb2gray"};
+    double px = 0;
+    for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
+    ProfScope prof(ctx, names[op], px * (op <= PW_SELECT ? 3 : (op >= PW_GRAY_BGR ? 4 : 2)));
     switch (op) {
         case PW_SUB: pw_kernel<PW_SUB><<<grid, block, 0, ctx->stream>>>(j); break;
         case PW_DIV: pw_kernel<PW_DIV><<<grid, block, 0, ctx->stream>>>(j); break;
@@ -189,6 +193,7 @@ int k_zero_u32(docscan_ctx* ctx, uint32_t* p, int n, uint32_t value_even, uint32
 
 int k_stats(docscan_ctx* ctx, const DImg& src, uint32_t* minmax_dev, uint32_t* hist_dev) {
     int blocks = min(src.h, ctx->sm_count * 4);
+    ProfScope prof(ctx, "stats_minmax_hist", (double)src.w * src.h);
     stats_kernel<<<blocks, 256, 0, ctx->stream>>>(src.p, src.pitch, src.w, src.h, minmax_dev, hist_dev);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;

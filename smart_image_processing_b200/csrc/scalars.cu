@@ -20,6 +20,7 @@ __global__ void scalars_reset_kernel(PageScalars* s, int n) {
 }
 
 int k_scalars_reset(docscan_ctx* ctx, PageScalars* s, int n) {
+    ProfScope prof(ctx, "scalars_reset", 0);
     scalars_reset_kernel<<<n, 256, 0, ctx->stream>>>(s, n);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
@@ -55,6 +56,7 @@ __global__ void build_norm_lut_kernel(PageScalars* s, int n, int compose_stretch
 }
 
 int k_build_norm_lut(docscan_ctx* ctx, PageScalars* s, int n, int compose_stretch) {
+    ProfScope prof(ctx, "scalars_norm_lut", 0);
     build_norm_lut_kernel<<<n, 256, 0, ctx->stream>>>(s, n, compose_stretch);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
@@ -149,12 +151,14 @@ __global__ void __launch_bounds__(64) otsu_cuts_kernel(PageScalars* s, int n, in
 }
 
 int k_otsu_cuts(docscan_ctx* ctx, PageScalars* s, int n, int threshold_offset, const int32_t* npix_dev) {
+    ProfScope prof(ctx, "scalars_otsu", 0);
     otsu_cuts_kernel<<<n, 64, 0, ctx->stream>>>(s, n, threshold_offset, npix_dev, 1);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
 }
 
 int k_otsu_plain(docscan_ctx* ctx, PageScalars* s, int n, const int32_t* npix_dev) {
+    ProfScope prof(ctx, "scalars_otsu", 0);
     otsu_cuts_kernel<<<n, 64, 0, ctx->stream>>>(s, n, 0, npix_dev, 0);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;

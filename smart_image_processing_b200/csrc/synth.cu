@@ -89,6 +89,7 @@ int k_synth_page(docscan_ctx* ctx, uint64_t seed, const DImg& dst, float quad_ou
     for (int i = 0; i < 9; i++) P.hinv[i] = (float)m[i];
     P.page_w = pw; P.page_h = ph; P.seed = s32;
     dim3 grid((dst.w + 63) / 64, (dst.h + 3) / 4);
+    ProfScope prof(ctx, "synth_page", 3.0 * dst.w * dst.h);
     synth_page_kernel<<<grid, 256, 0, ctx->stream>>>(dst.p, dst.pitch, dst.w, dst.h, P);
     DS_CHECK_LAUNCH(ctx);
     if (quad_out)

@@ -7,6 +7,7 @@
 // roundings.  The perspective coordinates are evaluated in fp64 in the same operation order as OpenCV
 // (per 64-pixel block origin, no fma contraction), the affine ones in OpenCV's 10-bit fixed point.
 #include <climits>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -145,6 +146,26 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     for (int i = 1; i < n; i++)
         if (jobs_host[i].ch != ch) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "mixed channel counts in one warp batch");
     dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
+    // algorithmic bytes: source pixels under the quad, at most 4 taps per output pixel, read once;
+    // destination (and the fused gray plane) written once
+    double bytes = 0;
+    for (int i = 0; i < n; i++) {
+        const WarpPJob& j = jobs_host[i];
+        const double cx[4] = {0, (double)j.dw, (double)j.dw, 0}, cy[4] = {0, 0, (double)j.dh, (double)j.dh};
+        double sx[4], sy[4];
+        for (int c = 0; c < 4; c++) {
+            const double w = j.m[6] * cx[c] + j.m[7] * cy[c] + j.m[8];
+            sx[c] = (j.m[0] * cx[c] + j.m[1] * cy[c] + j.m[2]) / w;
+            sy[c] = (j.m[3] * cx[c] + j.m[4] * cy[c] + j.m[5]) / w;
+        }
+        double area = 0;
+        for (int c = 0; c < 4; c++) area += sx[c] * sy[(c + 1) & 3] - sx[(c + 1) & 3] * sy[c];
+        area = fabs(area) * 0.5;
+        const double np = (double)j.dw * j.dh;
+        const double src_px = fmin(fmin(area, 4.0 * np), (double)j.sw * j.sh);
+        bytes += j.ch * (src_px + np) + (j.gray ? np : 0.0);
+    }
+    ProfScope prof(ctx, ch == 3 ? "warp_perspective_c3" : "warp_perspective_c1", bytes);
     if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else warp_perspective_kernel<1><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     DS_CHECK_LAUNCH(ctx);
@@ -155,6 +176,9 @@ int k_warp_affine_jobs(docscan_ctx* ctx, const WarpAJob* jobs_host, int n, int m
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(WarpAJob) * n, &dev));
     dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
+    double px = 0;
+    for (int i = 0; i < n; i++) px += (double)jobs_host[i].dw * jobs_host[i].dh;
+    ProfScope prof(ctx, "warp_affine", 2.0 * px);
     warp_affine_kernel<<<grid, block, 0, ctx->stream>>>((const WarpAJob*)dev);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
