@@ -199,6 +199,7 @@ def run_ours(args):
     import torch.distributed as dist
     from smart_image_processing_b200 import DocScanner as DS
     from smart_image_processing_b200 import _capi
+    from smart_image_processing_b200 import sharding
     from smart_image_processing_b200.synth import synth_angle
 
     rank = int(os.environ.get("RANK", "0"))
@@ -220,8 +221,9 @@ def run_ours(args):
     src = torch.empty((P, PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
     quads, angles = [], []
     q8 = (C.c_float * 8)()
+    seeds = sharding.weak_batch_seeds(P, rank)
     for i in range(P):
-        seed = rank * P + i
+        seed = seeds[i]
         im = _capi.device_image(src[i].data_ptr(), PAGE_W, PAGE_H, PAGE_W * 3, 3)
         ctx.call("docscan_synth_page", C.c_uint64(seed), C.byref(im), q8)
         quads.append(np.array(list(q8), np.float32).reshape(4, 2))
@@ -262,10 +264,7 @@ def run_ours(args):
         e1.record(stream)
         barrier()
     launches = ctx.launches - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
     value = world * P * PAGE_MP * args.steps / (ms_total / 1e3)
 
     # ---- per-kernel pass (instrumented; not the number reported as `value`)
@@ -327,10 +326,8 @@ def run_ours(args):
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
-        ems = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * P * PAGE_MP * esteps / (float(ems.item()) / 1e3), "unit": "MP/s",
+        ems = sharding.max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3), dev)
+        e2e = {"value": world * P * PAGE_MP * esteps / (ems / 1e3), "unit": "MP/s",
                "h2d_bytes_per_step": P * PAGE_H * PAGE_W * 3, "d2h_bytes_per_step": P * th * tw * 4,
                "steps": esteps, "host_buffers": f"pinned; {D} distinct pages cycled, every page copied every step"}
 

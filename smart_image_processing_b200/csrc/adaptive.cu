@@ -53,11 +53,11 @@ __global__ void __launch_bounds__(NT) adaptive_gauss_kernel(const AdaptJob* __re
     const int xt_row = xt_col + (tail >= 4 ? 4 : 0);                // row filter: scalar code from here on
 
     for (int hb = 0; hb < n_vb + D; hb++) {
-        for (int idx = tid; idx < BR * stage_words; idx += NT) {
-            const int row = idx / stage_words, wi = idx - row * stage_words;
-            const int ysrc = ds_clamp(y_begin - r + hb * BR + row, 0, J.h - 1);
+        const int srow_id = tid >> 3;                  // 16 rows x 8 lanes; a lane strides along its row
+        const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - r + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
+        for (int wi = tid & 7; wi < stage_words; wi += 8) {
+            const int row = srow_id;
             const int gx = x0 - r4 + 4 * wi;
-            const uint8_t* rowp = J.src + (size_t)ysrc * J.src_pitch;
             uint32_t word;
             if (src_al && gx >= 0 && gx + 3 < J.w) word = ds_ldg32(rowp + gx);
             else {
@@ -130,11 +130,16 @@ __global__ void __launch_bounds__(NT) adaptive_gauss_kernel(const AdaptJob* __re
         const int x = x0 + col;
         float Wn[BR + 2 * RMAX];
         const int shift = RMAX - r;                 // window index i <-> virtual row vb*BR + i - shift
+        const int slot0 = (vb * BR) % L.ring_rows;
 #pragma unroll
         for (int i = 0; i < BR + 2 * RMAX; i++) {
             const int rel = i - shift;
             float v = 0.0f;
-            if (rel >= 0 && rel <= BR - 1 + 2 * r) v = s_ring[((vb * BR + rel) % L.ring_rows) * RPF + col];
+            if (rel >= 0 && rel <= BR - 1 + 2 * r) {
+                int slot = slot0 + rel;
+                if (slot >= L.ring_rows) slot -= L.ring_rows;
+                v = s_ring[slot * RPF + col];
+            }
             Wn[i] = v;
         }
         float acc[BR];

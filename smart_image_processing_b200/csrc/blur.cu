@@ -73,11 +73,11 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
 
     for (int hb = 0; hb < n_vb + D; hb++) {
         // ---- stage BR source rows: virtual row v <-> source row border(y_begin - r + v)
-        for (int idx = tid; idx < BR * L.spw; idx += NT) {
-            const int row = idx / L.spw, wi = idx - row * L.spw;
-            const int ysrc = border_map(y_begin - r + hb * BR + row, J.h, L.border);
+        const int srow_id = tid >> 3;                  // 16 rows x 8 lanes; a lane strides along its row
+        const uint8_t* rowp = J.src + (size_t)border_map(y_begin - r + hb * BR + srow_id, J.h, L.border) * J.src_pitch;
+        for (int wi = tid & 7; wi < L.spw; wi += 8) {
+            const int idx = srow_id * L.spw + wi;
             const int gx = x0 - r4 + 4 * wi;
-            const uint8_t* rowp = J.src + (size_t)ysrc * J.src_pitch;
             uint32_t word;
             if (src_al && gx >= 0 && gx + 3 < J.w) {
                 word = ds_ldg32(rowp + gx);

@@ -437,20 +437,19 @@ namespace {
 
 size_t page_scratch(const docscan_page& pg) {
     const int w = pg.binary.width, h = pg.binary.height;
-    return host_bytes(&pg.src) + host_bytes(&pg.warped) + host_bytes(&pg.binary) + 16 * plane_bytes(w, h) +
-           (pg.warped.data ? 0 : ds_image_bytes(w, h, 3)) + 4096;
+    return 16 * plane_bytes(w, h) + 4096;
 }
 
-int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params& P) {
+size_t page_staging(const docscan_page& pg) {
+    return host_bytes(&pg.src) + host_bytes(&pg.warped) + host_bytes(&pg.binary);
+}
+
+// The chain for n pages whose images are already device views (src read-only; warped, binary written).
+int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params& P, const std::vector<DImg>& src,
+              const std::vector<DImg>& warped, const std::vector<DImg>& binary) {
     ArenaScope scope(ctx);
-    std::vector<DImg> src(n), warped(n), gray, binary(n);
+    std::vector<DImg> gray;
     std::vector<WarpPJob> wj(n);
-    for (int i = 0; i < n; i++) {
-        docscan_page& pg = pages[i];
-        DS_TRY(ds_stage_in(ctx, &pg.src, &src[i]));
-        DS_TRY(ds_stage_out_begin(ctx, &pg.warped, &warped[i]));
-        DS_TRY(ds_stage_out_begin(ctx, &pg.binary, &binary[i]));
-    }
     DS_TRY(alloc_planes(ctx, binary, &gray));
     int mw, mh; max_dims(binary, &mw, &mh);
     // a1 + a2: perspective warp with fused BGR2GRAY
@@ -467,7 +466,6 @@ int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params
         hm_invert3x3(m, j.m);
     }
     DS_TRY(k_warp_perspective_jobs(ctx, wj.data(), n, mw, mh));
-    for (int i = 0; i < n; i++) DS_TRY(ds_stage_out_end(ctx, &pages[i].warped, warped[i]));
 
     // a3 + a4: illumination correction; its MINMAX LUT and contrast_stretch's fold into one LUT
     PageScalars* sc = nullptr;
@@ -539,7 +537,21 @@ int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params
     }
     // a9: morph_cleanup (close)
     if (do_close) DS_TRY(morph_op_batch(ctx, DOCSCAN_MORPH_CLOSE, P.morph_ksize, P.morph_ksize, P.morph_iters, rot_dst, binary, nullptr, 0));
-    for (int i = 0; i < n; i++) DS_TRY(ds_stage_out_end(ctx, &pages[i].binary, binary[i]));
+    return DOCSCAN_OK;
+}
+
+DImg view_of(const docscan_image& im) {
+    DImg d;
+    d.p = (uint8_t*)im.data; d.w = im.width; d.h = im.height; d.pitch = im.pitch; d.ch = im.channels;
+    return d;
+}
+
+int copy_2d(docscan_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, int rows,
+            cudaMemcpyKind kind, cudaStream_t st) {
+    if (dpitch == row_bytes && spitch == row_bytes)
+        DS_CUDA(ctx, cudaMemcpyAsync(dst, src, row_bytes * (size_t)rows, kind, st));
+    else
+        DS_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, kind, st));
     return DOCSCAN_OK;
 }
 
@@ -564,10 +576,89 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
     const int strips_per_page = (pages[0].binary.width + 127) / 128;
     int group = (2 * ctx->sm_count + strips_per_page - 1) / strips_per_page;
     group = std::max(4, std::min(group, 32));
+    if (any_host) group = std::min(group, 8);          // finer pipeline granularity: copies overlap compute
     group = std::min(group, n);
-    DS_TRY(begin_call(ctx, max_page * group));
-    for (int i = 0; i < n; i += group) DS_TRY(run_group(ctx, std::min(group, n - i), pages + i, *params));
-    return ds_finish(ctx, any_host);
+    if (!any_host) {
+        DS_TRY(begin_call(ctx, max_page * group));
+        for (int i = 0; i < n; i += group) {
+            const int m = std::min(group, n - i);
+            std::vector<DImg> src(m), warped(m), binary(m);
+            for (int j = 0; j < m; j++) {
+                src[j] = view_of(pages[i + j].src); warped[j] = view_of(pages[i + j].warped); binary[j] = view_of(pages[i + j].binary);
+            }
+            DS_TRY(run_group(ctx, m, pages + i, *params, src, warped, binary));
+        }
+        return DOCSCAN_OK;
+    }
+
+    // ---- host buffers: three-stage pipeline over groups (H2D | kernels | D2H) on three streams with two
+    // staging sets, so the PCIe copies of neighbouring groups overlap the compute of the current one.
+    size_t max_stage = 0;
+    for (int i = 0; i < n; i++) max_stage = std::max(max_stage, page_staging(pages[i]) + 1024);
+    DS_TRY(begin_call(ctx, (max_page + 2 * max_stage) * group));
+    ArenaScope scope(ctx);
+    if (!ctx->copy_in) {
+        DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        for (int e = 0; e < 7; e++) DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->pipe_ev[e], cudaEventDisableTiming));
+    }
+    uint8_t* stage_base[2];
+    for (int sset = 0; sset < 2; sset++) {
+        void* p = nullptr;
+        DS_TRY(ds_arena_alloc(ctx, max_stage * group, &p));
+        stage_base[sset] = (uint8_t*)p;
+    }
+    cudaEvent_t* in_done = &ctx->pipe_ev[0];     // [2]
+    cudaEvent_t* comp_done = &ctx->pipe_ev[2];   // [2]
+    cudaEvent_t* out_done = &ctx->pipe_ev[4];    // [2]
+    cudaEvent_t start = ctx->pipe_ev[6];
+    DS_CUDA(ctx, cudaEventRecord(start, ctx->stream));
+    DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, start, 0));
+    DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, start, 0));
+    int g = 0;
+    for (int i = 0; i < n; i += group, g++) {
+        const int m = std::min(group, n - i);
+        const int sset = g & 1;
+        std::vector<DImg> src(m), warped(m), binary(m);
+        if (g >= 2) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, comp_done[sset], 0));     // set's inputs consumed
+        uint8_t* cur = stage_base[sset];
+        auto carve = [&](const docscan_image& im) {
+            DImg d;
+            const size_t pitch = ((size_t)im.width * im.channels + 127) & ~(size_t)127;
+            d.p = cur; d.w = im.width; d.h = im.height; d.pitch = (int)pitch; d.ch = im.channels;
+            cur += ds_image_bytes(im.width, im.height, im.channels);
+            cur = (uint8_t*)(((uintptr_t)cur + 255) & ~(uintptr_t)255);
+            return d;
+        };
+        for (int j = 0; j < m; j++) {
+            docscan_page& pg = pages[i + j];
+            if (is_host(&pg.src)) {
+                src[j] = carve(pg.src);
+                DS_TRY(copy_2d(ctx, src[j].p, src[j].pitch, pg.src.data, pg.src.pitch, (size_t)pg.src.width * 3, pg.src.height,
+                               cudaMemcpyHostToDevice, ctx->copy_in));
+            } else src[j] = view_of(pg.src);
+            warped[j] = is_host(&pg.warped) ? carve(pg.warped) : view_of(pg.warped);
+            binary[j] = is_host(&pg.binary) ? carve(pg.binary) : view_of(pg.binary);
+        }
+        DS_CUDA(ctx, cudaEventRecord(in_done[sset], ctx->copy_in));
+        DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, in_done[sset], 0));
+        if (g >= 2) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, out_done[sset], 0));       // set's outputs drained
+        DS_TRY(run_group(ctx, m, pages + i, *params, src, warped, binary));
+        DS_CUDA(ctx, cudaEventRecord(comp_done[sset], ctx->stream));
+        DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, comp_done[sset], 0));
+        for (int j = 0; j < m; j++) {
+            docscan_page& pg = pages[i + j];
+            if (is_host(&pg.warped))
+                DS_TRY(copy_2d(ctx, pg.warped.data, pg.warped.pitch, warped[j].p, warped[j].pitch, (size_t)pg.warped.width * 3,
+                               pg.warped.height, cudaMemcpyDeviceToHost, ctx->copy_out));
+            if (is_host(&pg.binary))
+                DS_TRY(copy_2d(ctx, pg.binary.data, pg.binary.pitch, binary[j].p, binary[j].pitch, (size_t)pg.binary.width,
+                               pg.binary.height, cudaMemcpyDeviceToHost, ctx->copy_out));
+        }
+        DS_CUDA(ctx, cudaEventRecord(out_done[sset], ctx->copy_out));
+    }
+    for (int sset = 0; sset < std::min(g, 2); sset++) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, out_done[sset], 0));
+    return ds_finish(ctx, true);
 }
 
 extern "C" int docscan_synth_page(docscan_ctx* ctx, uint64_t seed, docscan_image* dst, float quad_out[8]) {

@@ -43,6 +43,9 @@ struct docscan_ctx {
     // cached device coefficient tables, keyed by (kind, k, delta)
     std::map<uint64_t, void*> tables;
     std::vector<void*> user_allocs;
+    // host-buffer pipeline of docscan_process_pages: copy streams + events (created on first use)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t pipe_ev[7] = {};
     // optional per-kernel timing (docscan_profile_enable): one event pair per launch
     bool prof_on = false;
     struct ProfRec { std::string name; double bytes; cudaEvent_t a, b; };

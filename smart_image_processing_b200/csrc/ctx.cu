@@ -75,6 +75,11 @@ extern "C" int docscan_destroy(docscan_ctx* ctx) {
     for (void* p : ctx->user_allocs) cudaFree(p);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->copy_in) {
+        cudaStreamDestroy(ctx->copy_in);
+        cudaStreamDestroy(ctx->copy_out);
+        for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DOCSCAN_OK;
