@@ -277,7 +277,7 @@ int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const B
     for (int i = 0; i < n; i++) stats = stats || jobs_host[i].minmax || jobs_host[i].hist;
     // segment height: enough CTAs to fill the machine, but tall enough to amortise the 2r warm-up rows
     const int strips = n * ((max_w + TW - 1) / TW);
-    int segs = (4 * ctx->sm_count + strips - 1) / strips;
+    int segs = (8 * ctx->sm_count + strips - 1) / strips;
     if (segs < 1) segs = 1;
     int seg = (max_h + segs - 1) / segs;
     const int seg_min = max(64, 4 * L.t.r_eff);

@@ -197,6 +197,7 @@ struct WarpAJob {
     int src_pitch, dst_pitch, sw, sh, dw, dh;
     double m[6];          // inverse matrix
     int identity;
+    int2* delta;          // per-column fixed-point increments (filled by k_warp_affine_jobs)
 };
 int k_warp_affine_jobs(docscan_ctx*, const WarpAJob* jobs_host, int n, int max_w, int max_h);
 // synth.cu

@@ -101,34 +101,50 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
     }
 }
 
+// cv::warpAffine precomputes adelta[x] = saturate_cast<int>(M[0]*x*1024), bdelta[x] = saturate_cast<int>(M[3]*x*1024)
+// once per call; so do we (one tiny kernel), which keeps fp64 out of the per-pixel loop.
+__global__ void affine_delta_kernel(const WarpAJob* __restrict__ jobs) {
+    const WarpAJob& J = jobs[blockIdx.y];
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= J.dw) return;
+    const double dx = (double)x;
+    J.delta[x] = make_int2(round_clamped(__dmul_rn(__dmul_rn(J.m[0], dx), 1024.0)),
+                           round_clamped(__dmul_rn(__dmul_rn(J.m[3], dx), 1024.0)));
+}
+
 __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __restrict__ jobs) {
     const WarpAJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
     if (y >= J.dh || x4 >= J.dw) return;
     const double dy = (double)y;
-    // cv::warpAffine: X0 = saturate_cast<int>((M[1]*y + M[2])*1024) + 16, adelta[x] = saturate_cast<int>(M[0]*x*1024)
+    // cv::warpAffine: X0 = saturate_cast<int>((M[1]*y + M[2])*1024) + 16
     const int X0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[1], dy), J.m[2]), 1024.0)) + 16;
     const int Y0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[4], dy), J.m[5]), 1024.0)) + 16;
     const uint8_t* __restrict__ src = J.src;
     const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
     uint8_t out[4];
     const int nvalid = min(4, J.dw - x4);
+    int2 dl[4];
+    if (nvalid == 4) {
+        const int4 t0 = __ldg(reinterpret_cast<const int4*>(J.delta + x4)), t1 = __ldg(reinterpret_cast<const int4*>(J.delta + x4 + 2));
+        dl[0] = make_int2(t0.x, t0.y); dl[1] = make_int2(t0.z, t0.w); dl[2] = make_int2(t1.x, t1.y); dl[3] = make_int2(t1.z, t1.w);
+    } else {
+        for (int i = 0; i < 4; i++) dl[i] = i < nvalid ? J.delta[x4 + i] : make_int2(0, 0);
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const double dx = (double)(x4 + i);
-        const int ad = round_clamped(__dmul_rn(__dmul_rn(J.m[0], dx), 1024.0));
-        const int bd = round_clamped(__dmul_rn(__dmul_rn(J.m[3], dx), 1024.0));
-        const int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5;
+        const int X = (X0 + dl[i].x) >> 5, Y = (Y0 + dl[i].y) >> 5;
         const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
         const int ax = X & 31, ay = Y & 31;
         const int xa = ds_clamp(sx, 0, sw - 1), xb = ds_clamp(sx + 1, 0, sw - 1);
         const int ya = ds_clamp(sy, 0, sh - 1), yb = ds_clamp(sy + 1, 0, sh - 1);
         const uint8_t* r0 = src + (size_t)ya * sp;
         const uint8_t* r1 = src + (size_t)yb * sp;
-        const int acc = (32 - ax) * (32 - ay) * 32 * __ldg(r0 + xa) + ax * (32 - ay) * 32 * __ldg(r0 + xb) +
-                        (32 - ax) * ay * 32 * __ldg(r1 + xa) + ax * ay * 32 * __ldg(r1 + xb) + 16384;
-        out[i] = (uint8_t)(acc >> 15);
+        // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) * ((32-ax) p00 + ax p01) + ay * ((32-ax) p10 + ax p11)] exactly
+        const int h0 = (32 - ax) * __ldg(r0 + xa) + ax * __ldg(r0 + xb);
+        const int h1 = (32 - ax) * __ldg(r1 + xa) + ax * __ldg(r1 + xb);
+        out[i] = (uint8_t)(((32 - ay) * h0 + ay * h1 + 512) >> 10);
     }
     uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x4;
     if (nvalid == 4 && (reinterpret_cast<uintptr_t>(dp) & 3) == 0)
@@ -172,9 +188,21 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     return DOCSCAN_OK;
 }
 
-int k_warp_affine_jobs(docscan_ctx* ctx, const WarpAJob* jobs_host, int n, int max_w, int max_h) {
+int k_warp_affine_jobs(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, int max_w, int max_h) {
+    std::vector<WarpAJob> jobs(jobs_in, jobs_in + n);
+    for (int i = 0; i < n; i++) {
+        void* t = nullptr;
+        DS_TRY(ds_arena_alloc(ctx, sizeof(int2) * ((size_t)jobs[i].dw + 4), &t));
+        jobs[i].delta = (int2*)t;
+    }
+    const WarpAJob* jobs_host = jobs.data();
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(WarpAJob) * n, &dev));
+    {
+        ProfScope prof(ctx, "warp_affine_deltas", 0);
+        affine_delta_kernel<<<dim3((max_w + 127) / 128, n), 128, 0, ctx->stream>>>((const WarpAJob*)dev);
+        DS_CHECK_LAUNCH(ctx);
+    }
     dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
     double px = 0;
     for (int i = 0; i < n; i++) px += (double)jobs_host[i].dw * jobs_host[i].dh;
