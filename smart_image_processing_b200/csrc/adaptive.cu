@@ -17,11 +17,16 @@ constexpr int RPF = 132;      // ring row pitch in floats
 
 struct AdaptLaunch {
     int k, r, delta, c_param, seg_rows, spf, ring_rows, nblk, tail_compat;
-    const float* g_row;       // 16 zeros + k taps + zeros up to 16*nblk + 32
+    const float* g_row;       // 8 zeros + k taps + zeros up to 8*nblk + 16
     const float* g_col;       // g_col[j] = g[r + j] for j <= r, zero up to 64
 };
 
-__device__ __forceinline__ int stage_index(int c) { return c + (c >> 4); }   // one pad float per 16: no bank conflicts
+// rare path of the staging load (strip edges, unaligned caller buffers): kept out of line
+__device__ __noinline__ uint32_t fetch_word_clamped(const uint8_t* rowp, int gx, int w) {
+    uint32_t word = 0;
+    for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[ds_clamp(gx + b, 0, w - 1)] << (8 * b);
+    return word;
+}
 
 template <int RMAX>
 __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* __restrict__ jobs, const AdaptLaunch L) {
@@ -35,15 +40,15 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
     const int r = L.r, r4 = L.r + L.delta;
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float* s_grow = reinterpret_cast<float*>(smem_raw);            // 16*nblk + 32
-    float* s_gcol = s_grow + 16 * L.nblk + 32;                     // 64
-    float* s_stage = s_gcol + 64;                                  // BR * spf
+    float* s_grow = reinterpret_cast<float*>(smem_raw);            // 8*nblk + 16: 8 zeros, k taps, zeros
+    float* s_gcol = s_grow + 8 * L.nblk + 16;                      // 64
+    float* s_stage = s_gcol + 64;                                  // BR * spf, spf == 1 (mod 32)
     float* s_ring = s_stage + BR * L.spf;                          // ring_rows * RPF
-    for (int i = tid; i < 16 * L.nblk + 32; i += NT) s_grow[i] = L.g_row[i];
+    for (int i = tid; i < 8 * L.nblk + 16; i += NT) s_grow[i] = L.g_row[i];
     if (tid < 64) s_gcol[tid] = L.g_col[tid];
 
     const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
-    const int stage_words = (TW + 16 * L.nblk) >> 2;   // every column the row pass can touch holds a finite value
+    const int stage_words = (TW + 8 * L.nblk + 4) >> 2;   // every column the row pass can touch holds a finite value
     const int D = (2 * r + BR - 1) / BR;
     const int n_vb = (rows_out + BR - 1) / BR;
     const bool row_identity = J.w == 1, col_identity = J.h == 1;   // cv::GaussianBlur shrinks the kernel on 1-px axes
@@ -53,74 +58,74 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
     const int xt_row = xt_col + (tail >= 4 ? 4 : 0);                // row filter: scalar code from here on
 
     for (int hb = 0; hb < n_vb + D; hb++) {
-        const int srow_id = tid >> 3;                  // 16 rows x 8 lanes; a lane strides along its row
-        const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - r + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
-        for (int wi = tid & 7; wi < stage_words; wi += 8) {
-            const int row = srow_id;
-            const int gx = x0 - r4 + 4 * wi;
-            uint32_t word;
-            if (src_al && gx >= 0 && gx + 3 < J.w) word = ds_ldg32(rowp + gx);
-            else {
-                word = 0;
+        {
+            const int srow_id = tid >> 3;              // 16 rows x 8 lanes; a lane strides along its row
+            const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - r + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
+            float* sp = s_stage + srow_id * L.spf;
+            for (int wi = tid & 7; wi < stage_words; wi += 8) {
+                const int gx = x0 - r4 + 4 * wi;
+                const uint32_t word = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
+                // u8 -> fp32 without the slow I2F unit: 2^23 + v is exact in fp32, subtract 2^23 again
 #pragma unroll
-                for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[ds_clamp(gx + b, 0, J.w - 1)] << (8 * b);
+                for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(0x4B000000u | ((word >> (8 * b)) & 255u)), 8388608.0f);
             }
-            float* sp = s_stage + row * L.spf;
-#pragma unroll
-            for (int b = 0; b < 4; b++) sp[stage_index(4 * wi + b)] = (float)((word >> (8 * b)) & 255u);
         }
         __syncthreads();
-        {   // ---- row pass: out[xo + o] = sum_i g[i] * f[xo + o + i - r], taps in increasing i, one fma each
-            const int hr = tid >> 3, cg = tid & 7;
-            const float* srow = s_stage + hr * L.spf;
-            const int base = cg * 16 + L.delta;
-            float acc[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) acc[i] = 0.0f;
-            float G[32];
-            {
-                const float4* g4 = reinterpret_cast<const float4*>(s_grow);
-#pragma unroll
-                for (int i = 0; i < 4; i++) { float4 t = g4[i]; G[16 + 4 * i] = t.x; G[17 + 4 * i] = t.y; G[18 + 4 * i] = t.z; G[19 + 4 * i] = t.w; }
-            }
-            for (int b = 0; b < L.nblk; b++) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) G[i] = G[i + 16];
-                const float4* g4 = reinterpret_cast<const float4*>(s_grow + 16 * b + 16);
-#pragma unroll
-                for (int i = 0; i < 4; i++) { float4 t = g4[i]; G[16 + 4 * i] = t.x; G[17 + 4 * i] = t.y; G[18 + 4 * i] = t.z; G[19 + 4 * i] = t.w; }
-#pragma unroll
-                for (int u = 0; u < 16; u++) {
-                    const float f = srow[stage_index(base + 16 * b + u)];
-#pragma unroll
-                    for (int o = 0; o < 16; o++) acc[o] = __fmaf_rn(f, G[u - o + 16], acc[o]);
-                }
-            }
-            if (row_identity) {
-#pragma unroll
-                for (int o = 0; o < 16; o++) acc[o] = srow[stage_index(base + r + o)];
-            } else if (xt_row < J.w && x0 + cg * 16 + 15 >= xt_row) {
-                // cv2's row filter leaves the last w % 4 columns to scalar code: mul+add per tap, except that the
-                // (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  At most 3 columns per row.
-                const int first_fused = L.k - ((L.k - 1) & 3);
-#pragma unroll
-                for (int o = 0; o < 16; o++) {
-                    const int x = x0 + cg * 16 + o;
-                    if (x < xt_row || x >= J.w) continue;
-                    float a = __fmul_rn(s_grow[16], srow[stage_index(base + o)]);
-                    for (int i = 1; i < L.k; i++) {
-                        const float f = srow[stage_index(base + o + i)];
-                        a = i >= first_fused ? __fmaf_rn(f, s_grow[16 + i], a) : __fadd_rn(a, __fmul_rn(s_grow[16 + i], f));
-                    }
-                    acc[o] = a;
-                }
-            }
+        {   // ---- row pass: out[c] = sum_i g[i] * f[c + i - r], taps in increasing i, one fma each.
+            // lane <-> staged row (16 rows x 2 column groups per warp): with the row pitch == 1 (mod 32) a warp's loads
+            // hit 32 different banks.  8 outputs per group, sliding window of 16 coefficients in registers.
+            const int lane = tid & 31, wrp = tid >> 5;
+            const int hr = lane & 15, hh = lane >> 4;
+            const float* srow = s_stage + hr * L.spf + L.delta;
             const int slot = (hb * BR + hr) % L.ring_rows;
-            float4* dst = reinterpret_cast<float4*>(s_ring + slot * RPF + cg * 16);
-            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            dst[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
-            dst[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
+#pragma unroll 1
+            for (int it = 0; it < 2; it++) {
+                const int pr = wrp * 2 + it;
+                const int c0 = 8 * ((pr >> 1) * 4 + (pr & 1) + 2 * hh);
+                const float* sp = srow + c0;
+                float acc[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+                float G[16];
+                {
+                    const float4 t0 = *reinterpret_cast<const float4*>(s_grow), t1 = *reinterpret_cast<const float4*>(s_grow + 4);
+                    G[8] = t0.x; G[9] = t0.y; G[10] = t0.z; G[11] = t0.w; G[12] = t1.x; G[13] = t1.y; G[14] = t1.z; G[15] = t1.w;
+                }
+                for (int b = 0; b < L.nblk; b++) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) G[i] = G[i + 8];
+                    const float4 t0 = *reinterpret_cast<const float4*>(s_grow + 8 * b + 8), t1 = *reinterpret_cast<const float4*>(s_grow + 8 * b + 12);
+                    G[8] = t0.x; G[9] = t0.y; G[10] = t0.z; G[11] = t0.w; G[12] = t1.x; G[13] = t1.y; G[14] = t1.z; G[15] = t1.w;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const float f = sp[8 * b + u];
+#pragma unroll
+                        for (int o = 0; o < 8; o++) acc[o] = __fmaf_rn(f, G[u - o + 8], acc[o]);
+                    }
+                }
+                if (row_identity) {
+#pragma unroll
+                    for (int o = 0; o < 8; o++) acc[o] = sp[r + o];
+                } else if (xt_row < J.w && x0 + c0 + 7 >= xt_row) {
+                    // cv2's row filter leaves the last w % 4 columns to scalar code: mul+add per tap, except that the
+                    // (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  At most 3 columns per row.
+                    const int first_fused = L.k - ((L.k - 1) & 3);
+#pragma unroll
+                    for (int o = 0; o < 8; o++) {
+                        const int x = x0 + c0 + o;
+                        if (x < xt_row || x >= J.w) continue;
+                        float a = __fmul_rn(s_grow[8], sp[o]);
+                        for (int i = 1; i < L.k; i++) {
+                            const float f = sp[o + i];
+                            a = i >= first_fused ? __fmaf_rn(f, s_grow[8 + i], a) : __fadd_rn(a, __fmul_rn(s_grow[8 + i], f));
+                        }
+                        acc[o] = a;
+                    }
+                }
+                float4* dst = reinterpret_cast<float4*>(s_ring + slot * RPF + c0);
+                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
         }
         __syncthreads();
         if (hb < D) continue;
@@ -131,16 +136,28 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
         float Wn[BR + 2 * RMAX];
         const int shift = RMAX - r;                 // window index i <-> virtual row vb*BR + i - shift
         const int slot0 = (vb * BR) % L.ring_rows;
+        if (shift == 0) {                              // exact instantiation (k = 2*RMAX+1): no range predicates
+            const float* base = s_ring + slot0 * RPF + col;
+            if (slot0 + BR - 1 + 2 * RMAX < L.ring_rows) {
 #pragma unroll
-        for (int i = 0; i < BR + 2 * RMAX; i++) {
-            const int rel = i - shift;
-            float v = 0.0f;
-            if (rel >= 0 && rel <= BR - 1 + 2 * r) {
-                int slot = slot0 + rel;
-                if (slot >= L.ring_rows) slot -= L.ring_rows;
-                v = s_ring[slot * RPF + col];
+                for (int i = 0; i < BR + 2 * RMAX; i++) Wn[i] = base[i * RPF];
+            } else {
+                const int wrap = L.ring_rows - slot0;   // first window index that wraps
+#pragma unroll
+                for (int i = 0; i < BR + 2 * RMAX; i++) Wn[i] = base[(i >= wrap ? i - L.ring_rows : i) * RPF];
             }
-            Wn[i] = v;
+        } else {
+#pragma unroll
+            for (int i = 0; i < BR + 2 * RMAX; i++) {
+                const int rel = i - shift;
+                float v = 0.0f;
+                if (rel >= 0 && rel <= BR - 1 + 2 * r) {
+                    int slot = slot0 + rel;
+                    if (slot >= L.ring_rows) slot -= L.ring_rows;
+                    v = s_ring[slot * RPF + col];
+                }
+                Wn[i] = v;
+            }
         }
         float acc[BR];
         const float gc0 = s_gcol[0];
@@ -162,14 +179,17 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
             }
         }
         if (x < J.w) {
+            const int y0 = y_begin + vb * BR;
+            const uint8_t* sp = J.src + (size_t)y0 * J.src_pitch + x;
+            uint8_t* dp = J.dst + (size_t)y0 * J.dst_pitch + x;
+            const int rows = min(BR, y_end - y0);
 #pragma unroll
             for (int o = 0; o < BR; o++) {
-                const int y = y_begin + vb * BR + o;
-                if (y >= y_end) break;
+                if (o >= rows) break;
                 const float m = col_identity ? Wn[o + RMAX] : acc[o];
                 const int mean = min(max(__float2int_rn(m), 0), 255);
-                const int s = J.src[(size_t)y * J.src_pitch + x];
-                J.dst[(size_t)y * J.dst_pitch + x] = (s - mean > -L.c_param) ? 255 : 0;
+                *dp = ((int)*sp - mean > -L.c_param) ? 255 : 0;
+                sp += J.src_pitch; dp += J.dst_pitch;
             }
         }
     }
@@ -254,18 +274,18 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
         return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "adaptive GAUSSIAN_C block size must be odd and in 3..65 (got %d)", k);
     AdaptLaunch L{};
     L.k = k; L.r = k / 2; L.delta = (4 - (L.r & 3)) & 3; L.c_param = c; L.tail_compat = cv_tail_compat;
-    L.nblk = (k + 15 + 15) / 16;
-    L.spf = TW + 16 * L.nblk;
-    L.spf += L.spf / 16 + 2;
+    L.nblk = (k + 7 + 7) / 8;
+    L.spf = TW + 8 * L.nblk + 8;
+    L.spf += (33 - (L.spf & 31)) & 31;                 // pitch == 1 (mod 32): lanes of a warp read different banks
     L.ring_rows = ((2 * L.r + BR - 1) / BR + 1) * BR;
     // coefficient tables (device, cached per k)
     const uint64_t key = ((uint64_t)7 << 32) | (uint32_t)k;
-    const int n_row = 16 * L.nblk + 32;
+    const int n_row = 8 * L.nblk + 16;
     auto it = ctx->tables.find(key);
     if (it == ctx->tables.end()) {
         std::vector<float> g(k), host(n_row + 64 + k, 0.0f);
         docscan_gaussian_kernel_f32(k, g.data());
-        for (int i = 0; i < k; i++) host[16 + i] = g[i];
+        for (int i = 0; i < k; i++) host[8 + i] = g[i];
         for (int j = 0; j <= L.r; j++) host[n_row + j] = g[L.r + j];
         for (int i = 0; i < k; i++) host[n_row + 64 + i] = g[i];
         void* dev = nullptr;
@@ -298,7 +318,8 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, grid, smem);
     else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, grid, smem);
     else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, grid, smem);
-    else if (L.r <= 17) rc = launch_adaptive<17>(ctx, jd, L, grid, smem);
+    else if (L.r == 15) rc = launch_adaptive<15>(ctx, jd, L, grid, smem);      // k = 31 (GUI preset), exact
+    else if (L.r <= 17) rc = launch_adaptive<17>(ctx, jd, L, grid, smem);      // k = 35 (CLI default), exact
     else if (L.r <= 25) rc = launch_adaptive<25>(ctx, jd, L, grid, smem);
     else rc = launch_adaptive<32>(ctx, jd, L, grid, smem);
     }

@@ -622,9 +622,12 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         std::vector<DImg> src(m), warped(m), binary(m);
         if (g >= 2) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, comp_done[sset], 0));     // set's inputs consumed
         uint8_t* cur = stage_base[sset];
-        auto carve = [&](const docscan_image& im) {
+        auto carve = [&](const docscan_image& im, bool dense) {
             DImg d;
-            const size_t pitch = ((size_t)im.width * im.channels + 127) & ~(size_t)127;
+            // inputs are staged densely when the caller's rows are dense: one contiguous DMA per page instead of a
+            // row-by-row 2-D copy (the gathering warp kernel does not need aligned rows)
+            const size_t row = (size_t)im.width * im.channels;
+            const size_t pitch = (dense && (size_t)im.pitch == row && (row & 3) == 0) ? row : ((row + 127) & ~(size_t)127);
             d.p = cur; d.w = im.width; d.h = im.height; d.pitch = (int)pitch; d.ch = im.channels;
             cur += ds_image_bytes(im.width, im.height, im.channels);
             cur = (uint8_t*)(((uintptr_t)cur + 255) & ~(uintptr_t)255);
@@ -633,12 +636,12 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         for (int j = 0; j < m; j++) {
             docscan_page& pg = pages[i + j];
             if (is_host(&pg.src)) {
-                src[j] = carve(pg.src);
+                src[j] = carve(pg.src, true);
                 DS_TRY(copy_2d(ctx, src[j].p, src[j].pitch, pg.src.data, pg.src.pitch, (size_t)pg.src.width * 3, pg.src.height,
                                cudaMemcpyHostToDevice, ctx->copy_in));
             } else src[j] = view_of(pg.src);
-            warped[j] = is_host(&pg.warped) ? carve(pg.warped) : view_of(pg.warped);
-            binary[j] = is_host(&pg.binary) ? carve(pg.binary) : view_of(pg.binary);
+            warped[j] = is_host(&pg.warped) ? carve(pg.warped, false) : view_of(pg.warped);
+            binary[j] = is_host(&pg.binary) ? carve(pg.binary, false) : view_of(pg.binary);
         }
         DS_CUDA(ctx, cudaEventRecord(in_done[sset], ctx->copy_in));
         DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, in_done[sset], 0));

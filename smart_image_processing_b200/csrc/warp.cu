@@ -59,26 +59,21 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
         const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
         const int ax = X & 31, ay = Y & 31;
         const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+        // branch-free taps: out-of-image taps get weight 0 (BORDER_CONSTANT 0) and a clamped, always-valid address,
+        // so the loads of all four pixels can be issued back to back
+        const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+        const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+        const int cx0 = ds_clamp(sx, 0, sw - 1), cx1 = ds_clamp(sx + 1, 0, sw - 1);
+        const int cy0 = ds_clamp(sy, 0, sh - 1), cy1 = ds_clamp(sy + 1, 0, sh - 1);
+        const int v00 = (x0in && y0in) ? w00 : 0, v01 = (x1in && y0in) ? w01 : 0;
+        const int v10 = (x0in && y1in) ? w10 : 0, v11 = (x1in && y1in) ? w11 : 0;
+        const uint8_t* r0 = src + (size_t)cy0 * sp;
+        const uint8_t* r1 = src + (size_t)cy1 * sp;
         int acc[CH];
 #pragma unroll
-        for (int c = 0; c < CH; c++) acc[c] = 16384;
-        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-            const uint8_t* p0 = src + (size_t)sy * sp + sx * CH;
-            const uint8_t* p1 = p0 + sp;
-#pragma unroll
-            for (int c = 0; c < CH; c++)
-                acc[c] += w00 * __ldg(p0 + c) + w01 * __ldg(p0 + CH + c) + w10 * __ldg(p1 + c) + w11 * __ldg(p1 + CH + c);
-        } else {
-            const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-            const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
-#pragma unroll
-            for (int c = 0; c < CH; c++) {
-                if (y0in && x0in) acc[c] += w00 * src[(size_t)sy * sp + sx * CH + c];
-                if (y0in && x1in) acc[c] += w01 * src[(size_t)sy * sp + (sx + 1) * CH + c];
-                if (y1in && x0in) acc[c] += w10 * src[(size_t)(sy + 1) * sp + sx * CH + c];
-                if (y1in && x1in) acc[c] += w11 * src[(size_t)(sy + 1) * sp + (sx + 1) * CH + c];
-            }
-        }
+        for (int c = 0; c < CH; c++)
+            acc[c] = 16384 + v00 * __ldg(r0 + cx0 * CH + c) + v01 * __ldg(r0 + cx1 * CH + c) +
+                     v10 * __ldg(r1 + cx0 * CH + c) + v11 * __ldg(r1 + cx1 * CH + c);
 #pragma unroll
         for (int c = 0; c < CH; c++) out[i * CH + c] = (uint8_t)(acc[c] >> 15);   // <= 255 by construction
         if (CH == 3) gr[i] = gray15(out[i * 3], out[i * 3 + 1], out[i * 3 + 2]);
