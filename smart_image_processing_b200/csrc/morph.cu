@@ -7,6 +7,7 @@
 // default morphology border: they are loaded as the neutral element (255 for erode, 0 for dilate).
 // The last pass can fuse the black-hat subtraction (close(src) - src) and a 256-bin histogram.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -158,225 +159,176 @@ __global__ void __launch_bounds__(NT) morph_1d_kernel(const MorphJob* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Register-resident streaming variant for small rectangles (default anchor, one iteration): one warp owns a strip and
-// marches down it, reading only the source row and writing only the result row (2 B/px), no block barrier.  KW, KH
-// and the operation are template parameters, so every shift, ring index and window offset is a compile-time constant.
-// Pixels are widened to 16-bit lanes (2 px per register) so that min/max is the native VIMNMX.U16x2.
-// A lane owns 8 output pixels of a row (four u16x2 registers); its H halo comes from the raw words of the next
-// lanes (shuffles of packed words), the H window doubling runs on a register array, the V doubling rings are
-// registers (the top ring moves to shared memory only when kh - P > 4).  ~10 instructions per pixel.
+// helpers for the register-array kernels: pixels widened to 16-bit lanes (2 px per register) so that min/max is the
+// native VIMNMX.U16x2
 template <bool DIL> __device__ __forceinline__ uint32_t opx(uint32_t a, uint32_t b) { return DIL ? __vmaxu2(a, b) : __vminu2(a, b); }
 __device__ __forceinline__ uint32_t odd_shift(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5432); }   // px (2i+1, 2i+2)
 
 __host__ __device__ constexpr int ilog2_floor(int v) { int l = 0; while ((2 << l) <= v) l++; return l; }
-__host__ __device__ constexpr int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
-struct FixedLaunch { int seg_rows; };
-
-// slow path of a 4-pixel load: any alignment, neutral outside the row (kept out of line: it is rare and would
-// otherwise be replicated in every unrolled row)
+// slow path of a 4-pixel load: any alignment, neutral outside the row (kept out of line: it is rare)
 __device__ __noinline__ uint32_t load_word_slow(const uint8_t* rowp, int x, int w, uint32_t neutral_byte) {
     uint32_t wv = 0;
     for (int b = 0; b < 4; b++) wv |= ((x + b >= 0 && x + b < w) ? (uint32_t)rowp[x + b] : neutral_byte) << (8 * b);
     return wv;
 }
 
-// Histogram without atomics: every lane owns a private set of 256 16-bit counters, laid out [bin][lane] so that
-// the 32 lanes of a warp always touch 32 different half-words (at most 2-way bank conflicts).  A plain
-// load / add / store per pixel replaces one shared-memory atomic (2 LSU cycles per lane, the bottleneck of every
-// per-pixel-atomic histogram); counters are folded into the page histogram once per CTA.
-__device__ __forceinline__ void lane_hist_add(uint16_t* h, int lane, uint32_t val) {
-    volatile uint16_t* p = h + val * 32 + lane;
-    *p = (uint16_t)(*p + 1);
+// ---------------------------------------------------------------------------------------------------------
+// Block-marching variant for the rectangles the reference uses (9x19 black-hat, 3x3 close, 2x2 erode) and the odd
+// squares of BASELINE.json config 4, default anchor, one iteration: same layout as blur.cu — a CTA
+// owns a 128-column strip and marches down it 32 rows at a time; rows are staged in shared memory (neutral outside
+// the image), H-filtered into a ring of packed rows, then V-filtered out of the ring.  Both passes run the window
+// doubling on register arrays of 16-bit lanes (native VIMNMX.U16x2) with every index a compile-time constant:
+// H: 32 outputs per thread, V: one 4-pixel column x 8 rows per thread.  No vertical recompute inside a segment.
+namespace march {
+constexpr int TWm = 128, BRm = 32, NTm = 128, RPW = 36;   // strip width, rows per step, threads, ring pitch (words)
+
+template <int N, int K, bool DIL>
+__device__ __forceinline__ void windows_h(uint32_t (&r)[N]) {           // r[i] = px (2i, 2i+1)  ->  forward windows of K
+    constexpr int PW = 1 << ilog2_floor(K);
+    if (PW > 1) {
+#pragma unroll
+        for (int i = 0; i < N; i++) r[i] = opx<DIL>(r[i], odd_shift(r[i], r[i + 1 < N ? i + 1 : N - 1]));   // last: low lane only
+    }
+#pragma unroll
+    for (int p = 2; p < PW; p *= 2) {
+#pragma unroll
+        for (int i = 0; i + p / 2 < N; i++) r[i] = opx<DIL>(r[i], r[i + p / 2]);
+    }
+    if (K > PW) {
+        constexpr int O = K - PW;
+#pragma unroll
+        for (int i = 0; i + (O + 1) / 2 < N; i++) r[i] = opx<DIL>(r[i], (O & 1) ? odd_shift(r[i + O / 2], r[i + O / 2 + 1]) : r[i + O / 2]);
+    }
 }
 
+struct MarchLaunch { int seg_rows, spw, ring_rows; };
+
 template <int KW, int KH, bool DIL>
-__global__ void __launch_bounds__(128) morph_fixed_kernel(const MorphJob* __restrict__ jobs, const FixedLaunch L) {
+__global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __restrict__ jobs, const MarchLaunch L) {
     constexpr int AX = KW / 2, AY = KH / 2;
-    constexpr int AXW = ((AX + 3) / 4) * 4;            // the warp's load window starts AXW px left of its first output
-    constexpr int OFF = AXW - AX;                      // array index of the window start of the lane's first output
-    constexpr int NPX = OFF + 8 + KW - 1;              // pixels a lane needs
-    constexpr int NWORDS = (NPX + 3) / 4, NR = NWORDS * 2;
-    constexpr int LANE_HALO = (NWORDS - 1) / 2;        // following lanes a lane borrows raw words from
-    constexpr int STRIDE = 8 * (32 - LANE_HALO);       // valid output columns per warp
-    constexpr int PH = 1 << ilog2_floor(KW);
-    constexpr int NLEV = ilog2_floor(KH), P = 1 << NLEV, BACK = KH - P;
-    constexpr int NREG = NLEV < 3 ? NLEV : 3;          // levels 0..2 (rings of 1, 2, 4 rows) live in registers
-    constexpr int TR = BACK > 0 ? pow2_ceil(BACK) : 1;
-    constexpr bool TOP_SMEM = BACK > 4;
-    constexpr int U = 4;                               // row-loop unroll: multiple of every register ring size
-    // shared-memory rings (uint4 per thread per slot): levels >= 3, then the top ring
-    constexpr int SLOTS_L3 = NLEV > 3 ? 8 : 0, SLOTS_L4 = NLEV > 4 ? 16 : 0, SLOTS_TOP = TOP_SMEM ? TR : 0;
-    constexpr int RING_SLOTS = SLOTS_L3 + SLOTS_L4 + SLOTS_TOP;
-    constexpr uint32_t NEUTRAL = DIL ? 0u : 0x00ff00ffu, NEUTRAL_W = DIL ? 0u : 0xffffffffu;
-    static_assert(NLEV <= 5, "kh up to 63");
-
+    constexpr int AXW = ((AX + 3) / 4) * 4, OFF = AXW - AX;
+    constexpr int NWH = (OFF + 31 + KW + 3) / 4, NH = 2 * NWH;         // words / registers a thread needs per row (H)
+    constexpr int NRW = 8 + KH - 1;                                     // ring rows a thread needs (V)
+    constexpr int PV = 1 << ilog2_floor(KH);
+    constexpr int D = (KH - 1 + BRm - 1) / BRm;                         // V step lags the H step by D steps
+    constexpr uint32_t NEUTRAL_W = DIL ? 0u : 0xffffffffu;
     const MorphJob J = jobs[blockIdx.z];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int xo = (blockIdx.x * 4 + warp) * STRIDE + 8 * lane;     // lane's first output column
+    const int x0 = blockIdx.x * TWm;
     const int y_begin = blockIdx.y * L.seg_rows;
+    if (x0 >= J.w || y_begin >= J.h) return;
+    const int y_end = min(J.h, y_begin + L.seg_rows);
+    const int tid = threadIdx.x;
     extern __shared__ __align__(16) uint32_t smem_u32[];
-    uint4* s_ring = reinterpret_cast<uint4*>(smem_u32);               // [RING_SLOTS][128]
-    uint16_t* s_hist = reinterpret_cast<uint16_t*>(smem_u32 + 4 * RING_SLOTS * 128) + warp * 256 * 32;   // [4][256][32]
-    if (J.hist) {
-        uint32_t* hz = smem_u32 + 4 * RING_SLOTS * 128;
-        for (int i = threadIdx.x; i < 4 * 256 * 32 / 2; i += 128) hz[i] = 0;
-        __syncthreads();
-    }
-    if ((blockIdx.x * 4 + warp) * STRIDE < J.w && y_begin < J.h) {
-        const int y_end = min(J.h, y_begin + L.seg_rows);
-        const int gx = xo - AXW;                                      // lane's first loaded column (multiple of 4)
-        const bool al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
-        const bool dst_al = ((reinterpret_cast<uintptr_t>(J.dst) | (uintptr_t)J.dst_pitch) & 3) == 0;
-        const bool in0 = al && gx >= 0 && gx + 3 < J.w, in1 = al && gx + 4 >= 0 && gx + 7 < J.w;
-        const bool store_lane = lane < 32 - LANE_HALO && xo < J.w;
-        const int nvalid = min(8, J.w - xo);
-        const int t_first = y_begin - AY;
-        const int n_rows = (y_end - y_begin) + KH - 1;
-        auto load_row = [&](int ti, uint32_t& w0, uint32_t& w1) {
-            const int t = t_first + ti;
-            w0 = NEUTRAL_W; w1 = NEUTRAL_W;
-            if (t >= 0 && t < J.h && ti < n_rows) {
-                const uint8_t* rowp = J.src + (size_t)t * J.src_pitch;
-                w0 = in0 ? ds_ldg32(rowp + gx) : load_word_slow(rowp, gx, J.w, NEUTRAL_W & 255u);
-                w1 = in1 ? ds_ldg32(rowp + gx + 4) : load_word_slow(rowp, gx + 4, J.w, NEUTRAL_W & 255u);
+    uint32_t* s_stage = smem_u32;                                        // BRm * spw
+    uint32_t* s_ring = s_stage + BRm * L.spw;                            // ring_rows * RPW
+    s_ring = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_ring) + 15) & ~(uintptr_t)15);
+    uint32_t* s_hist = s_ring + L.ring_rows * RPW;                       // 4 x 256 when J.hist
+    if (J.hist) for (int i = tid; i < 4 * 256; i += NTm) s_hist[i] = 0;
+    const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
+    const bool dst_al = ((reinterpret_cast<uintptr_t>(J.dst) | (uintptr_t)J.dst_pitch) & 3) == 0;
+    const int n_vb = (y_end - y_begin + BRm - 1) / BRm;
+    for (int hb = 0; hb < n_vb + D; hb++) {
+        {   // ---- stage 32 source rows: virtual row v <-> source row y_begin - AY + v (neutral outside the image)
+            const int srow = tid >> 2;
+            const int gy = y_begin - AY + hb * BRm + srow;
+            const bool row_in = gy >= 0 && gy < J.h;
+            const uint8_t* rowp = J.src + (size_t)(row_in ? gy : 0) * J.src_pitch;
+            for (int wi = tid & 3; wi < L.spw; wi += 4) {
+                const int gx = x0 - AXW + 4 * wi;
+                uint32_t word = NEUTRAL_W;
+                if (row_in) word = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : load_word_slow(rowp, gx, J.w, NEUTRAL_W & 255u);
+                s_stage[srow * L.spw + wi] = word;
             }
-        };
-        uint32_t ring[NREG > 0 ? NREG : 1][4][4];                     // [level][slot][register]
+        }
+        __syncthreads();
+        {   // ---- H pass: thread = (row, 32 consecutive outputs)
+            const int hr = tid >> 2, cg = tid & 3;
+            const uint32_t* sp = s_stage + hr * L.spw + cg * 8;
+            uint32_t r[NH];
 #pragma unroll
-        for (int l = 0; l < NREG; l++)
+            for (int j = 0; j < NWH; j++) { const uint32_t w = sp[j]; r[2 * j] = __byte_perm(w, 0, 0x4140); r[2 * j + 1] = __byte_perm(w, 0, 0x4342); }
+            windows_h<NH, KW, DIL>(r);
+            uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 8; j++) {
+                const uint32_t a = (OFF & 1) ? odd_shift(r[OFF / 2 + 2 * j], r[OFF / 2 + 2 * j + 1]) : r[OFF / 2 + 2 * j];
+                const uint32_t b = (OFF & 1) ? odd_shift(r[OFF / 2 + 2 * j + 1], r[OFF / 2 + 2 * j + 2]) : r[OFF / 2 + 2 * j + 1];
+                o[j] = __byte_perm(a, b, 0x6420);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(s_ring + ((hb * BRm + hr) % L.ring_rows) * RPW + cg * 8);
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        __syncthreads();
+        if (hb < D) continue;
+        // ---- V pass: thread = (4-pixel column, 8 rows)
+        const int vb = hb - D;
+        const int cw = tid & 31, rg = tid >> 5;
+        int slot = (vb * BRm + rg * 8) % L.ring_rows;
+        uint32_t va[NRW], vbq[NRW];
 #pragma unroll
-                for (int c = 0; c < 4; c++) ring[l][i][c] = NEUTRAL;
-        uint32_t top[TOP_SMEM ? 1 : TR][4];
+        for (int i = 0; i < NRW; i++) {
+            const uint32_t w = s_ring[slot * RPW + cw];
+            va[i] = __byte_perm(w, 0, 0x4140); vbq[i] = __byte_perm(w, 0, 0x4342);
+            if (++slot == L.ring_rows) slot = 0;
+        }
 #pragma unroll
-        for (int i = 0; i < (TOP_SMEM ? 1 : TR); i++)
+        for (int p = 1; p < PV; p *= 2) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) top[i][c] = NEUTRAL;
-        for (int i = 0; i < RING_SLOTS; i++) s_ring[i * 128 + threadIdx.x] = make_uint4(NEUTRAL, NEUTRAL, NEUTRAL, NEUTRAL);
-        uint32_t pw0[U], pw1[U];                                      // rows in flight (loaded U rows ahead)
+            for (int i = 0; i + p < NRW; i++) { va[i] = opx<DIL>(va[i], va[i + p]); vbq[i] = opx<DIL>(vbq[i], vbq[i + p]); }
+        }
+        if (KH > PV) {
 #pragma unroll
-        for (int u = 0; u < U; u++) load_row(u, pw0[u], pw1[u]);
-        for (int t0 = 0; t0 < n_rows; t0 += U) {
+            for (int i = 0; i < 8; i++) { va[i] = opx<DIL>(va[i], va[i + KH - PV]); vbq[i] = opx<DIL>(vbq[i], vbq[i + KH - PV]); }
+        }
+        const int x = x0 + 4 * cw;
+        if (x < J.w) {
+            const int nvalid = min(4, J.w - x);
+            const int yb = y_begin + vb * BRm + rg * 8;
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int ti = t0 + u;
-                // ---- raw words: own two + halo from the following lanes
-                uint32_t raw[NWORDS];
-                raw[0] = pw0[u]; raw[1] = pw1[u];
-#pragma unroll
-                for (int j = 2; j < NWORDS; j++) raw[j] = __shfl_down_sync(0xffffffffu, (j & 1) ? pw1[u] : pw0[u], j >> 1);
-                load_row(ti + U, pw0[u], pw1[u]);                     // refill the slot just consumed
-                uint32_t r[NR];
-#pragma unroll
-                for (int j = 0; j < NWORDS; j++) { r[2 * j] = __byte_perm(raw[j], 0, 0x4140); r[2 * j + 1] = __byte_perm(raw[j], 0, 0x4342); }
-                // ---- H pass: forward windows A_p[j] = op(px j..j+p-1), p = 1, 2, 4, .. PH, then KW
-#pragma unroll
-                for (int p = 1; p < PH; p *= 2) {
-#pragma unroll
-                    for (int i = 0; i < NR; i++) {
-                        const int i2 = i + (p >> 1) < NR - 1 ? i + (p >> 1) : NR - 1;
-                        const uint32_t other = p == 1 ? odd_shift(r[i], r[i + 1 < NR ? i + 1 : NR - 1]) : r[i2];
-                        r[i] = opx<DIL>(r[i], other);
-                    }
+            for (int i = 0; i < 8; i++) {
+                const int y = yb + i;
+                if (y >= y_end) break;
+                uint32_t res = __byte_perm(va[i], vbq[i], 0x6420);
+                if (J.ref) {                                          // black-hat: sat(close(src) - src)
+                    const uint8_t* rp = J.ref + (size_t)y * J.ref_pitch + x;
+                    const uint32_t rw = (nvalid == 4 && (reinterpret_cast<uintptr_t>(rp) & 3) == 0) ? ds_ldg32(rp) : load_word_slow(rp - x, x, J.w, 0);
+                    res = __vsubus4(res, rw);
                 }
-                if (KW > PH) {
-                    constexpr int O = KW - PH;
+                if (J.hist) {
 #pragma unroll
-                    for (int i = 0; i < NR; i++) {
-                        const int lo = i + O / 2 < NR - 1 ? i + O / 2 : NR - 1, hi = lo + 1 < NR ? lo + 1 : NR - 1;
-                        const uint32_t other = (O & 1) ? odd_shift(r[lo], r[hi]) : r[lo];
-                        r[i] = opx<DIL>(r[i], other);
-                    }
+                    for (int b = 0; b < 4; b++)
+                        if (b < nvalid) atomicAdd(&s_hist[(tid >> 5) * 256 + ((res >> (8 * b)) & 255u)], 1u);
                 }
-                uint32_t v[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) v[c] = (OFF & 1) ? odd_shift(r[OFF / 2 + c], r[OFF / 2 + c + 1]) : r[OFF / 2 + c];
-                // ---- V pass: backward windows by doubling down the rows
-#pragma unroll
-                for (int l = 0; l < NREG; l++) {
-                    const int slot = u & ((1 << l) - 1);                // static: u is an unrolled constant
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const uint32_t old = ring[l][slot][c];
-                        ring[l][slot][c] = v[c];
-                        v[c] = opx<DIL>(v[c], old);
-                    }
-                }
-                if (NLEV > 3) {
-                    uint4* q = s_ring + (ti & 7) * 128 + threadIdx.x;
-                    const uint4 old = *q;
-                    *q = make_uint4(v[0], v[1], v[2], v[3]);
-                    v[0] = opx<DIL>(v[0], old.x); v[1] = opx<DIL>(v[1], old.y); v[2] = opx<DIL>(v[2], old.z); v[3] = opx<DIL>(v[3], old.w);
-                }
-                if (NLEV > 4) {
-                    uint4* q = s_ring + (SLOTS_L3 + (ti & 15)) * 128 + threadIdx.x;
-                    const uint4 old = *q;
-                    *q = make_uint4(v[0], v[1], v[2], v[3]);
-                    v[0] = opx<DIL>(v[0], old.x); v[1] = opx<DIL>(v[1], old.y); v[2] = opx<DIL>(v[2], old.z); v[3] = opx<DIL>(v[3], old.w);
-                }
-                if (BACK > 0) {
-                    if (TOP_SMEM) {
-                        uint4* base = s_ring + (SLOTS_L3 + SLOTS_L4) * 128 + threadIdx.x;
-                        const uint4 old = base[((ti - BACK) & (TR - 1)) * 128];
-                        base[(ti & (TR - 1)) * 128] = make_uint4(v[0], v[1], v[2], v[3]);
-                        v[0] = opx<DIL>(v[0], old.x); v[1] = opx<DIL>(v[1], old.y); v[2] = opx<DIL>(v[2], old.z); v[3] = opx<DIL>(v[3], old.w);
-                    } else {
-                        const int rd = (u - BACK) & (TR - 1), wr = u & (TR - 1);   // TR <= 4 divides U
-#pragma unroll
-                        for (int c = 0; c < 4; c++) {
-                            const uint32_t old = top[TOP_SMEM ? 0 : rd][c];
-                            top[TOP_SMEM ? 0 : wr][c] = v[c];
-                            v[c] = opx<DIL>(v[c], old);
-                        }
-                    }
-                }
-                // ---- output row
-                const int y = y_begin + ti - (KH - 1);
-                if (ti >= KH - 1 && y < y_end && store_lane) {
-                    uint32_t o0 = __byte_perm(v[0], v[1], 0x6420), o1 = __byte_perm(v[2], v[3], 0x6420);
-                    if (J.ref) {                                      // black-hat: sat(close(src) - src)
-                        const uint8_t* rp = J.ref + (size_t)y * J.ref_pitch + xo;
-                        uint32_t r0, r1;
-                        if (nvalid == 8 && (reinterpret_cast<uintptr_t>(rp) & 3) == 0) { r0 = ds_ldg32(rp); r1 = ds_ldg32(rp + 4); }
-                        else { r0 = load_word_slow(rp - xo, xo, J.w, 0); r1 = load_word_slow(rp - xo, xo + 4, J.w, 0); }
-                        o0 = __vsubus4(o0, r0); o1 = __vsubus4(o1, r1);
-                    }
-                    if (J.hist) {
-#pragma unroll
-                        for (int bb = 0; bb < 8; bb++)
-                            if (bb < nvalid) lane_hist_add(s_hist, lane, ((bb < 4 ? o0 : o1) >> (8 * (bb & 3))) & 255u);
-                    }
-                    uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + xo;
-                    if (dst_al && nvalid == 8) { reinterpret_cast<uint32_t*>(dp)[0] = o0; reinterpret_cast<uint32_t*>(dp)[1] = o1; }
-                    else for (int bb = 0; bb < nvalid; bb++) dp[bb] = (uint8_t)((bb < 4 ? o0 : o1) >> (8 * (bb & 3)));
-                }
+                uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x;
+                if (dst_al && nvalid == 4) *reinterpret_cast<uint32_t*>(dp) = res;
+                else for (int b = 0; b < nvalid; b++) dp[b] = (uint8_t)(res >> (8 * b));
             }
         }
     }
     if (J.hist) {
-        __syncwarp();
-        // fold the 32 lane-private counters of each bin; lane j owns bins j, j+32, ...
-        for (int bin = lane; bin < 256; bin += 32) {
-            uint32_t sum = 0;
-            for (int k = 0; k < 32; k++) sum += s_hist[bin * 32 + ((k + lane) & 31)];
-            if (sum) atomicAdd(&J.hist[bin], sum);
+        __syncthreads();
+        for (int i = tid; i < 256; i += NTm) {
+            const uint32_t sum = s_hist[i] + s_hist[256 + i] + s_hist[512 + i] + s_hist[768 + i];
+            if (sum) atomicAdd(&J.hist[i], sum);
         }
     }
 }
 
 template <int KW, int KH, bool DIL>
-int launch_fixed_t(docscan_ctx* ctx, const MorphJob* jobs_host, int n, int max_w, int max_h) {
-    constexpr int AX = KW / 2, AXW = ((AX + 3) / 4) * 4, OFF = AXW - AX, NPX = OFF + 8 + KW - 1, NWORDS = (NPX + 3) / 4;
-    constexpr int STRIDE = 8 * (32 - (NWORDS - 1) / 2);
-    constexpr int NLEV = ilog2_floor(KH), BACK = KH - (1 << NLEV), TR = BACK > 0 ? pow2_ceil(BACK) : 1;
-    constexpr int RING_SLOTS = (NLEV > 3 ? 8 : 0) + (NLEV > 4 ? 16 : 0) + (BACK > 4 ? TR : 0);
-    const int strips = (max_w + STRIDE - 1) / STRIDE, ctas_x = (strips + 3) / 4;
-    int segs = (6 * ctx->sm_count + ctas_x * n - 1) / (ctas_x * n);
+int launch_t(docscan_ctx* ctx, const MorphJob* jobs_host, int n, int max_w, int max_h) {
+    constexpr int AX = KW / 2, AXW = ((AX + 3) / 4) * 4, OFF = AXW - AX, NWH = (OFF + 31 + KW + 3) / 4;
+    constexpr int D = (KH - 1 + BRm - 1) / BRm;
+    MarchLaunch L{};
+    L.spw = (24 + NWH + 1) | 1;
+    L.ring_rows = (D + 1) * BRm;
+    const int strips = n * ((max_w + TWm - 1) / TWm);
+    int segs = (8 * ctx->sm_count + strips - 1) / strips;
     if (segs < 1) segs = 1;
-    int seg = std::max((max_h + segs - 1) / segs, std::max(32, 4 * KH));
-    FixedLaunch L{seg};
+    int seg = std::max((max_h + segs - 1) / segs, std::max(64, 4 * KH));
+    seg = (seg + BRm - 1) / BRm * BRm;
+    L.seg_rows = seg;
     bool hist = false;
     double px = 0, refpx = 0;
     for (int i = 0; i < n; i++) {
@@ -384,34 +336,33 @@ int launch_fixed_t(docscan_ctx* ctx, const MorphJob* jobs_host, int n, int max_w
         px += (double)jobs_host[i].w * jobs_host[i].h;
         if (jobs_host[i].ref) refpx += (double)jobs_host[i].w * jobs_host[i].h;
     }
-    const size_t smem = (size_t)RING_SLOTS * 128 * 16 + (hist ? (size_t)4 * 256 * 32 * 2 : 0);
+    const size_t smem = sizeof(uint32_t) * ((size_t)BRm * L.spw + 4 + (size_t)L.ring_rows * RPW + (hist ? 4 * 256 : 0));
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(MorphJob) * n, &dev));
-    dim3 grid(ctas_x, (max_h + seg - 1) / seg, n);
-    ProfScope prof(ctx, "morph_fixed_" + std::to_string(KW) + "x" + std::to_string(KH), 2.0 * px + refpx);
+    dim3 grid((max_w + TWm - 1) / TWm, (max_h + seg - 1) / seg, n);
+    ProfScope prof(ctx, "morph_march_" + std::to_string(KW) + "x" + std::to_string(KH), 2.0 * px + refpx);
     if (smem > 48 * 1024)
-        DS_CUDA(ctx, cudaFuncSetAttribute(morph_fixed_kernel<KW, KH, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    morph_fixed_kernel<KW, KH, DIL><<<grid, 128, smem, ctx->stream>>>((const MorphJob*)dev, L);
+        DS_CUDA(ctx, cudaFuncSetAttribute(morph_march_kernel<KW, KH, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    morph_march_kernel<KW, KH, DIL><<<grid, NTm, smem, ctx->stream>>>((const MorphJob*)dev, L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
 }
+}  // namespace march
 
-// Rectangles with a static instantiation.  Measured on B200 (profiles/README.md): the register-resident kernel wins
-// for small rectangles (3x3 close: 1.64 ms vs 2.73 ms per 256 pages); for 9x19 its one-warp-per-strip march has too
-// few warps in flight and the shared-memory doubling kernels are faster, so larger shapes stay on those.
-#define DS_FIXED_SHAPES(X) X(2, 2) X(3, 3) X(5, 5) X(7, 7)
+#define DS_MARCH_SHAPES(X) X(2, 2) X(3, 3) X(5, 5) X(7, 7) X(9, 19) X(9, 9) X(11, 11) X(13, 13) X(15, 15) X(17, 17) X(19, 19) \
+    X(21, 21) X(23, 23) X(25, 25) X(27, 27) X(29, 29) X(31, 31)
 
-bool launch_fixed(docscan_ctx* ctx, int is_dilate, int kw, int kh, int ax, int ay, const MorphJob* jobs_host, int n, int max_w,
+bool launch_march(docscan_ctx* ctx, int is_dilate, int kw, int kh, int ax, int ay, const MorphJob* jobs_host, int n, int max_w,
                   int max_h, int* rc) {
     if (ax != kw / 2 || ay != kh / 2) return false;
-#define DS_FIXED_CASE(W, H)                                                                                       \
+#define DS_MARCH_CASE(W, H)                                                                                       \
     if (kw == W && kh == H) {                                                                                     \
-        *rc = is_dilate ? launch_fixed_t<W, H, true>(ctx, jobs_host, n, max_w, max_h)                             \
-                        : launch_fixed_t<W, H, false>(ctx, jobs_host, n, max_w, max_h);                           \
+        *rc = is_dilate ? march::launch_t<W, H, true>(ctx, jobs_host, n, max_w, max_h)                            \
+                        : march::launch_t<W, H, false>(ctx, jobs_host, n, max_w, max_h);                          \
         return true;                                                                                              \
     }
-    DS_FIXED_SHAPES(DS_FIXED_CASE)
-#undef DS_FIXED_CASE
+    DS_MARCH_SHAPES(DS_MARCH_CASE)
+#undef DS_MARCH_CASE
     return false;
 }
 
@@ -458,7 +409,7 @@ int k_morph_jobs(docscan_ctx* ctx, int is_dilate, int kw, int kh, int ax, int ay
     if (kw < 1 || kh < 1) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "bad structuring element %dx%d", kw, kh);
     {
         int rc = DOCSCAN_OK;
-        if (launch_fixed(ctx, is_dilate, kw, kh, ax, ay, jobs_host, n, max_w, max_h, &rc)) return rc;
+        if (launch_march(ctx, is_dilate, kw, kh, ax, ay, jobs_host, n, max_w, max_h, &rc)) return rc;
     }
     std::vector<MorphJob> hjobs(jobs_host, jobs_host + n), vjobs(jobs_host, jobs_host + n);
     bool hist = false;

@@ -101,7 +101,7 @@ def test_stats_normalize_otsu():
     assert (ops.normalize_minmax(const) == 0).all() and ops.otsu_threshold(const) == 0.0
 
 
-@pytest.mark.parametrize("kw,kh", [(2, 2), (3, 3), (4, 4), (9, 19), (5, 2), (1, 7), (31, 31), (15, 31), (99, 3), (2, 99), (217, 217)])
+@pytest.mark.parametrize("kw,kh", [(2, 2), (3, 3), (5, 5), (7, 7), (9, 9), (11, 11), (13, 13), (15, 15), (4, 4), (9, 19), (5, 2), (1, 7), (31, 31), (15, 31), (99, 3), (2, 99), (217, 217)])
 def test_morphology(kw, kh):
     rng = np.random.default_rng(kw * 100 + kh)
     for h, w in [(61, 47), (130, 600), (1, 40), (40, 1), (300, 70)]:
