@@ -37,10 +37,6 @@ __global__ void __launch_bounds__(128) pw_kernel(const PwJob* __restrict__ jobs)
     if (y >= J.h) return;
     const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
     if (x >= J.w) return;
-    __shared__ uint8_t s_lut[256];
-    if (OP == PW_LUT) {
-        // every thread of the block that survived the early exits shares the LUT; load cooperatively
-    }
     int t = J.t;
     if (OP == PW_THRESH && J.t_dev) t = *J.t_dev;
     const uint8_t* ra = J.a + (size_t)y * J.pa;
@@ -79,7 +75,6 @@ __global__ void __launch_bounds__(128) pw_kernel(const PwJob* __restrict__ jobs)
     } else {
         for (int i = 0; i < 4 && x + i < J.w; i++) rd[x + i] = pw_px<OP>(ra[x + i], TWO ? rb[x + i] : 0, J.lut, t);
     }
-    (void)s_lut;
 }
 
 static int pw_launch(docscan_ctx* ctx, int op, const PwJob* jobs_host, int n, int max_w, int max_h) {

@@ -272,3 +272,29 @@ def test_errors_are_loud():
         ops.gaussian_blur(np.zeros((8, 8), np.float32), 3)
     with pytest.raises(ValueError):
         ops.subtract(np.zeros((8, 8), np.uint8), np.zeros((8, 9), np.uint8))
+
+
+def test_process_document_drop_in(tmp_path):
+    """The whole drop-in: file in, control path on the host (control.py), pixel path on the GPU, dict out —
+    against the oracle chain fed with the same quad / angle."""
+    cv2 = pytest.importorskip("cv2")
+    from smart_image_processing_b200 import control
+    from smart_image_processing_b200.synth import synth_page_numpy
+    img, _ = synth_page_numpy(5, 900, 1200)
+    path = str(tmp_path / "page.png")
+    cv2.imwrite(path, img)
+    res = DS.process_document(path, out_dir=str(tmp_path / "out"), scale_long=800, save_stages=True)
+    assert set(res) == {"quad", "warped", "binary"}
+    quad = control.localize_document(img)
+    assert quad is not None and np.array_equal(res["quad"], quad)
+    st = O.hot_path(img, quad, 0.0, scale_long=800)
+    angle = control.estimate_skew_angle(st["weighted"])
+    ref = O.hot_path(img, quad, angle, scale_long=800)
+    eq(res["warped"], ref["warped"], "process_document warped")
+    eq(res["binary"], ref["clean"], "process_document binary")
+    assert os.path.exists(tmp_path / "out" / "scan_08_clean.png")
+    # supplying the control-path outputs takes the single fused C-ABI call
+    res2 = DS.process_document(path, scale_long=800, quad=quad, angle=angle)
+    eq(res2["binary"], ref["clean"], "process_document (fused) binary")
+    with pytest.raises(FileNotFoundError):
+        DS.process_document(str(tmp_path / "missing.png"))
