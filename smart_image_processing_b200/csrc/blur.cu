@@ -20,13 +20,13 @@ namespace {
 constexpr int TW = 128;       // output columns per strip
 constexpr int BR = 16;        // rows per march step
 constexpr int NT = 128;       // threads per CTA
-constexpr int RP = 68;        // ring row pitch in 32-bit words (64 + 4 pad)
+constexpr int RP2 = 132;      // ring pitch in 32-bit words per ROW PAIR (one word = rows 2P, 2P+1 of a column; 128 + 4 pad)
 
 struct BlurTable {
     int k_eff, r_eff, delta, M, nb;
     uint32_t kk;              // k*k (box) or 0
     const uint4* qH;          // M + 6 entries (3 zero entries each side)
-    const uint32_t* qV;       // 8*nb + 16 entries, tap j at index j + 8
+    const uint32_t* qV;       // 2 * (4*nb + 8) entries: even-aligned tap pairs, then odd-aligned tap pairs (dp2a operands)
 };
 
 struct BlurLaunch {
@@ -56,13 +56,13 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint4* s_qH = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* s_qV = reinterpret_cast<uint32_t*>(s_qH + (T.M + 6));
-    uint32_t* s_stage = s_qV + (8 * T.nb + 16);
+    uint32_t* s_stage = s_qV + 2 * (4 * T.nb + 8);
     uint32_t* s_ring = s_stage + BR * L.spw;
     s_ring = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_ring) + 15) & ~(uintptr_t)15);
-    uint32_t* s_hist = s_ring + L.ring_rows * RP;    // 4 x 256, only when STATS && J.hist
+    uint32_t* s_hist = s_ring + (L.ring_rows / 2) * RP2;   // 4 x 256, only when STATS && J.hist
 
     for (int i = tid; i < T.M + 6; i += NT) s_qH[i] = T.qH[i];
-    for (int i = tid; i < 8 * T.nb + 16; i += NT) s_qV[i] = T.qV[i];
+    for (int i = tid; i < 2 * (4 * T.nb + 8); i += NT) s_qV[i] = T.qV[i];
     if (STATS && J.hist)
         for (int i = tid; i < 4 * 256; i += NT) s_hist[i] = 0;
 
@@ -111,10 +111,22 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
                 acc[14] = __dp4a(W, q0.z, acc[14]); acc[15] = __dp4a(W, q0.w, acc[15]);
                 q0 = q1; q1 = q2; q2 = q3;
             }
-            const int slot = (hb * BR + hr) % L.ring_rows;
-            uint4* dst = reinterpret_cast<uint4*>(s_ring + slot * RP + cg * 8);
-            dst[0] = make_uint4(acc[0] | (acc[1] << 16), acc[2] | (acc[3] << 16), acc[4] | (acc[5] << 16), acc[6] | (acc[7] << 16));
-            dst[1] = make_uint4(acc[8] | (acc[9] << 16), acc[10] | (acc[11] << 16), acc[12] | (acc[13] << 16), acc[14] | (acc[15] << 16));
+            // The V pass consumes dp2a operands: one word = (row 2P, row 2P+1) of one column.  Rows hr and hr^1 live in
+            // lanes tid and tid^8 of the same warp: swap halves, so the even row's thread packs columns 0..7 and the odd
+            // row's thread packs columns 8..15 of the pair.
+            const bool odd = hr & 1;
+            uint32_t packed[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t send = odd ? acc[i] : acc[8 + i];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 8);
+                const uint32_t mine = odd ? acc[8 + i] : acc[i];
+                packed[i] = odd ? (recv | (mine << 16)) : (mine | (recv << 16));
+            }
+            const int pslot = ((hb * BR + hr) >> 1) % (L.ring_rows >> 1);
+            uint4* dst = reinterpret_cast<uint4*>(s_ring + pslot * RP2 + cg * 16 + (odd ? 8 : 0));
+            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
         }
         __syncthreads();
         if (hb < D) continue;
@@ -125,34 +137,35 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
         uint32_t a0[8], a1[8];
 #pragma unroll
         for (int o = 0; o < 8; o++) { a0[o] = 0; a1[o] = 0; }
-        uint32_t C[16];
+        // dp2a: acc += row(2P) * q[t] + row(2P+1) * q[t+1].  Output o at pair step P needs taps (2P - o, 2P + 1 - o):
+        // even o -> even-aligned pair E[P - o/2], odd o -> odd-aligned pair O[P - (o+1)/2]; 4 pair steps per block,
+        // sliding windows of 8 coefficient words each, all indices static.
+        const uint32_t* s_qE = s_qV;
+        const uint32_t* s_qO = s_qV + (4 * T.nb + 8);
+        uint32_t E[8], O[8];
         {
-            const uint4* qv4 = reinterpret_cast<const uint4*>(s_qV);
-            uint4 t0 = qv4[0], t1 = qv4[1];
-            C[8] = t0.x; C[9] = t0.y; C[10] = t0.z; C[11] = t0.w; C[12] = t1.x; C[13] = t1.y; C[14] = t1.z; C[15] = t1.w;
+            const uint4 e = *reinterpret_cast<const uint4*>(s_qE), o4 = *reinterpret_cast<const uint4*>(s_qO);
+            E[4] = e.x; E[5] = e.y; E[6] = e.z; E[7] = e.w; O[4] = o4.x; O[5] = o4.y; O[6] = o4.z; O[7] = o4.w;
         }
-        int slot = vbase % L.ring_rows;
+        int pslot = (vbase >> 1) % (L.ring_rows >> 1);
         for (int b = 0; b < T.nb; b++) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) C[i] = C[i + 8];
+            for (int i = 0; i < 4; i++) { E[i] = E[i + 4]; O[i] = O[i + 4]; }
             {
-                const uint4* qv4 = reinterpret_cast<const uint4*>(s_qV + 8 * b + 8);
-                uint4 t0 = qv4[0], t1 = qv4[1];
-                C[8] = t0.x; C[9] = t0.y; C[10] = t0.z; C[11] = t0.w; C[12] = t1.x; C[13] = t1.y; C[14] = t1.z; C[15] = t1.w;
+                const uint4 e = *reinterpret_cast<const uint4*>(s_qE + 4 * b + 4), o4 = *reinterpret_cast<const uint4*>(s_qO + 4 * b + 4);
+                E[4] = e.x; E[5] = e.y; E[6] = e.z; E[7] = e.w; O[4] = o4.x; O[5] = o4.y; O[6] = o4.z; O[7] = o4.w;
             }
-            const uint32_t* rp = s_ring + slot * RP + cp;
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const uint32_t word = rp[u * RP];
-                const uint32_t lo = word & 0xffffu, hi = word >> 16;
+            for (int u = 0; u < 4; u++) {
+                const uint2 w = *reinterpret_cast<const uint2*>(s_ring + pslot * RP2 + 2 * cp);   // two columns of one row pair
 #pragma unroll
                 for (int o = 0; o < 8; o++) {
-                    a0[o] += lo * C[u - o + 8];
-                    a1[o] += hi * C[u - o + 8];
+                    const uint32_t c = (o & 1) ? O[u - (o + 1) / 2 + 4] : E[u - o / 2 + 4];
+                    a0[o] = __dp2a_lo(w.x, c, a0[o]);
+                    a1[o] = __dp2a_lo(w.y, c, a1[o]);
                 }
+                if (++pslot == (L.ring_rows >> 1)) pslot = 0;
             }
-            slot += 8;
-            if (slot >= L.ring_rows) slot -= L.ring_rows;
         }
         // ---- epilogue
         const int x = x0 + 2 * cp;
@@ -222,11 +235,12 @@ int get_table(docscan_ctx* ctx, int kind, int k, BlurTable* out) {
     const int k_eff = k - 2 * z, r_eff = k_eff / 2;
     const int delta = (4 - (r_eff & 3)) & 3;
     const int M = (delta + k_eff + 2) / 4 + 1;
-    const int nb = (k_eff + 7 + 7) / 8;
+    const int nb = ((k_eff + 7 + 1) / 2 + 3) / 4;          // V pass: blocks of 4 row pairs covering 8 outputs + k_eff - 1 rows
     out->k_eff = k_eff; out->r_eff = r_eff; out->delta = delta; out->M = M; out->nb = nb;
     out->kk = kind == 1 ? (uint32_t)k * (uint32_t)k : 0;
     const uint64_t key = ((uint64_t)(kind + 1) << 32) | (uint32_t)k;
-    const size_t qh_bytes = sizeof(uint4) * (M + 6), qv_bytes = sizeof(uint32_t) * (8 * nb + 16);
+    const int nqv = 4 * nb + 8;
+    const size_t qh_bytes = sizeof(uint4) * (M + 6), qv_bytes = sizeof(uint32_t) * 2 * nqv;
     auto it = ctx->tables.find(key);
     if (it == ctx->tables.end()) {
         std::vector<uint8_t> host(qh_bytes + qv_bytes, 0);
@@ -240,7 +254,11 @@ int get_table(docscan_ctx* ctx, int kind, int k, BlurTable* out) {
             for (int s = 0; s < 4; s++)
                 for (int b = 0; b < 4; b++)
                     qh[(size_t)(m + 3) * 16 + s * 4 + b] = (uint8_t)tap(4 * m + b - s);
-        for (int j = 0; j < k_eff; j++) qv[j + 8] = (uint32_t)q[z + j];
+        auto qt = [&](int t) -> uint32_t { return (t >= 0 && t < k_eff) ? (uint32_t)q[z + t] : 0u; };
+        for (int m = -4; m < nqv - 4; m++) {
+            qv[m + 4] = qt(2 * m) | (qt(2 * m + 1) << 8);               // even-aligned pair (q[2m], q[2m+1])
+            qv[nqv + m + 4] = qt(2 * m + 1) | (qt(2 * m + 2) << 8);     // odd-aligned pair (q[2m+1], q[2m+2])
+        }
         void* dev = nullptr;
         DS_CUDA(ctx, cudaMalloc(&dev, host.size()));
         DS_CUDA(ctx, cudaMemcpyAsync(dev, host.data(), host.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -284,8 +302,8 @@ int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const B
     if (seg < seg_min) seg = seg_min;
     seg = (seg + BR - 1) / BR * BR;
     L.seg_rows = seg;
-    const size_t smem = sizeof(uint4) * (L.t.M + 6) + sizeof(uint32_t) * (8 * L.t.nb + 16) +
-                        sizeof(uint32_t) * BR * L.spw + 16 + sizeof(uint32_t) * L.ring_rows * RP +
+    const size_t smem = sizeof(uint4) * (L.t.M + 6) + sizeof(uint32_t) * 2 * (4 * L.t.nb + 8) +
+                        sizeof(uint32_t) * BR * L.spw + 16 + sizeof(uint32_t) * (L.ring_rows / 2) * RP2 +
                         (stats ? 4 * 256 * sizeof(uint32_t) : 0);
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(BlurJob) * n, &dev));
