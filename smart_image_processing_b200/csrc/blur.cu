@@ -40,6 +40,15 @@ __device__ __forceinline__ int border_map(int p, int len, int border) {
     return border == 0 ? ds_reflect101(p, len) : ds_clamp(p, 0, len - 1);
 }
 
+// rare path of the staging load (strip edges, unaligned caller buffers): kept out of line
+__device__ __noinline__ uint32_t fetch_word_slow(const uint8_t* rowp, int gx, int w, int border) {
+    uint32_t word = 0;
+    for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[border_map(gx + b, w, border)] << (8 * b);
+    return word;
+}
+
+constexpr int SB = 7;         // staging loads a thread keeps in flight (7 x 8 words covers k <= 63 in one go)
+
 template <int EPI, bool STATS>
 __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restrict__ jobs, const BlurLaunch L) {
     const BlurJob J = jobs[blockIdx.z];
@@ -73,20 +82,22 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
 
     for (int hb = 0; hb < n_vb + D; hb++) {
         // ---- stage BR source rows: virtual row v <-> source row border(y_begin - r + v)
-        const int srow_id = tid >> 3;                  // 16 rows x 8 lanes; a lane strides along its row
-        const uint8_t* rowp = J.src + (size_t)border_map(y_begin - r + hb * BR + srow_id, J.h, L.border) * J.src_pitch;
-        for (int wi = tid & 7; wi < L.spw; wi += 8) {
-            const int idx = srow_id * L.spw + wi;
-            const int gx = x0 - r4 + 4 * wi;
-            uint32_t word;
-            if (src_al && gx >= 0 && gx + 3 < J.w) {
-                word = ds_ldg32(rowp + gx);
-            } else {
-                word = 0;
+        {
+            const int srow_id = tid >> 3;              // 16 rows x 8 lanes; a lane strides along its row
+            const uint8_t* rowp = J.src + (size_t)border_map(y_begin - r + hb * BR + srow_id, J.h, L.border) * J.src_pitch;
+            uint32_t* srow_w = s_stage + srow_id * L.spw;
+            for (int w0 = tid & 7; w0 < L.spw; w0 += 8 * SB) {
+                uint32_t wv[SB];                       // issue SB independent loads, then store them
 #pragma unroll
-                for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[border_map(gx + b, J.w, L.border)] << (8 * b);
+                for (int j = 0; j < SB; j++) {
+                    const int wi = w0 + 8 * j;
+                    const int gx = x0 - r4 + 4 * wi;
+                    wv[j] = 0;
+                    if (wi < L.spw) wv[j] = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_slow(rowp, gx, J.w, L.border);
+                }
+#pragma unroll
+                for (int j = 0; j < SB; j++) if (w0 + 8 * j < L.spw) srow_w[w0 + 8 * j] = wv[j];
             }
-            s_stage[idx] = word;
         }
         __syncthreads();
         // ---- H pass: thread = (row, 16 consecutive columns)
@@ -171,17 +182,27 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
         const int x = x0 + 2 * cp;
         if (x < J.w) {
             const bool two = x + 1 < J.w;
+            const int rows_here = min(8, y_end - (y_begin + vbase));
+            int c0[8], c1[8];                          // centre pixels of the 8 rows, loaded up front
+            if (EPI != DS_EPI_BLUR) {
+                const uint8_t* cp0 = J.src + (size_t)(y_begin + vbase) * J.src_pitch + x;
+#pragma unroll
+                for (int o = 0; o < 8; o++) {
+                    c0[o] = 0; c1[o] = 0;
+                    if (o < rows_here) { c0[o] = cp0[0]; c1[o] = two ? cp0[1] : 0; }
+                    cp0 += J.src_pitch;
+                }
+            }
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 const int y = y_begin + vbase + o;
-                if (y >= y_end) break;
+                if (o >= rows_here) break;
                 uint32_t b0, b1;
                 if (T.kk) { b0 = (2 * a0[o] + T.kk) / (2 * T.kk); b1 = (2 * a1[o] + T.kk) / (2 * T.kk); }
                 else { b0 = (a0[o] + 32768u) >> 16; b1 = (a1[o] + 32768u) >> 16; }
                 uint32_t v0 = b0, v1 = b1;
                 if (EPI != DS_EPI_BLUR) {
-                    const uint8_t* sp = J.src + (size_t)y * J.src_pitch + x;
-                    const int s0 = sp[0], s1 = two ? sp[1] : 0;
+                    const int s0 = c0[o], s1 = c1[o];
                     if (EPI == DS_EPI_SUB) { v0 = max(s0 - (int)b0, 0); v1 = max(s1 - (int)b1, 0); }
                     else if (EPI == DS_EPI_RSUB) { v0 = max((int)b0 - s0, 0); v1 = max((int)b1 - s1, 0); }
                     else if (EPI == DS_EPI_DIV) { v0 = ds_div255((uint8_t)s0, (uint8_t)b0); v1 = ds_div255((uint8_t)s1, (uint8_t)b1); }
