@@ -62,12 +62,23 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
             const int srow_id = tid >> 3;              // 16 rows x 8 lanes; a lane strides along its row
             const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - r + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
             float* sp = s_stage + srow_id * L.spf;
-            for (int wi = tid & 7; wi < stage_words; wi += 8) {
-                const int gx = x0 - r4 + 4 * wi;
-                const uint32_t word = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
-                // u8 -> fp32 without the slow I2F unit: 2^23 + v is exact in fp32, subtract 2^23 again
+            for (int w0 = tid & 7; w0 < stage_words; w0 += 8 * 7) {
+                uint32_t wv[7];                            // issue the loads first, convert and store afterwards
 #pragma unroll
-                for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(0x4B000000u | ((word >> (8 * b)) & 255u)), 8388608.0f);
+                for (int j = 0; j < 7; j++) {
+                    const int wi = w0 + 8 * j;
+                    const int gx = x0 - r4 + 4 * wi;
+                    wv[j] = 0;
+                    if (wi < stage_words) wv[j] = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const int wi = w0 + 8 * j;
+                    if (wi >= stage_words) continue;
+                    // u8 -> fp32 without the slow I2F unit: 2^23 + v is exact in fp32, subtract 2^23 again
+#pragma unroll
+                    for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(0x4B000000u | ((wv[j] >> (8 * b)) & 255u)), 8388608.0f);
+                }
             }
         }
         __syncthreads();
@@ -183,13 +194,16 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
             const uint8_t* sp = J.src + (size_t)y0 * J.src_pitch + x;
             uint8_t* dp = J.dst + (size_t)y0 * J.dst_pitch + x;
             const int rows = min(BR, y_end - y0);
+            int cpx[BR];                                   // centre pixels, loaded up front
+#pragma unroll
+            for (int o = 0; o < BR; o++) { cpx[o] = o < rows ? (int)*sp : 0; sp += J.src_pitch; }
 #pragma unroll
             for (int o = 0; o < BR; o++) {
                 if (o >= rows) break;
                 const float m = col_identity ? Wn[o + RMAX] : acc[o];
                 const int mean = min(max(__float2int_rn(m), 0), 255);
-                *dp = ((int)*sp - mean > -L.c_param) ? 255 : 0;
-                sp += J.src_pitch; dp += J.dst_pitch;
+                *dp = (cpx[o] - mean > -L.c_param) ? 255 : 0;
+                dp += J.dst_pitch;
             }
         }
     }
