@@ -26,31 +26,33 @@ template <int CH>
 __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* __restrict__ jobs) {
     const WarpPJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    if (y >= J.dh || x4 >= J.dw) return;
+    const int xt = blockIdx.x * 128;                 // a warp covers 128 consecutive destination pixels of one row
+    if (y >= J.dh || xt >= J.dw) return;
     const double m0 = J.m[0], m1 = J.m[1], m2 = J.m[2], m3 = J.m[3], m4 = J.m[4], m5 = J.m[5], m6 = J.m[6], m7 = J.m[7], m8 = J.m[8];
-    // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows))
-    int xb = x4 - x4 % J.block_w;
     const double dy = (double)y;
-    double dxb = (double)xb;
-    double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
-    double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m3, dxb), __dmul_rn(m4, dy)), m5);
-    double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m6, dxb), __dmul_rn(m7, dy)), m8);
     const uint8_t* __restrict__ src = J.src;
     const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
-    uint8_t out[4 * CH];
-    uint8_t gr[4];
-    const int nvalid = min(4, J.dw - x4);
+    int xb = -1;
+    double X0 = 0, Y0 = 0, W0 = 0;
+    uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
+    uint8_t* grow = (CH == 3 && J.gray) ? J.gray + (size_t)y * J.gray_pitch : nullptr;
+    // lane l handles pixels xt + l, xt + 32 + l, xt + 64 + l, xt + 96 + l: every gather instruction of the warp then
+    // covers 32 ADJACENT destination pixels, i.e. a compact ~200-byte source span (2-3 cache lines) instead of the
+    // 7 lines a 4-pixels-per-lane layout touches.  The kernel is bound by L1 wavefronts, so this is the lever.
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        if (x4 + i - xb >= J.block_w) {              // only when the block width is not a multiple of 4 (dst < 16 rows)
-            xb += J.block_w;
-            dxb = (double)xb;
+        const int x = xt + 32 * i + threadIdx.x;
+        if (x >= J.dw) break;
+        // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows))
+        const int xbi = x - x % J.block_w;
+        if (xbi != xb) {
+            xb = xbi;
+            const double dxb = (double)xb;
             X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
             Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m3, dxb), __dmul_rn(m4, dy)), m5);
             W0 = __dadd_rn(__dadd_rn(__dmul_rn(m6, dxb), __dmul_rn(m7, dy)), m8);
         }
-        const double x1 = (double)(x4 + i - xb);
+        const double x1 = (double)(x - xb);
         double W = __dadd_rn(W0, __dmul_rn(m6, x1));
         W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
         const double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W);
@@ -59,8 +61,7 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
         const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
         const int ax = X & 31, ay = Y & 31;
         const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
-        // branch-free taps: out-of-image taps get weight 0 (BORDER_CONSTANT 0) and a clamped, always-valid address,
-        // so the loads of all four pixels can be issued back to back
+        // branch-free taps: out-of-image taps get weight 0 (BORDER_CONSTANT 0) and a clamped, always-valid address
         const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
         const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
         const int cx0 = ds_clamp(sx, 0, sw - 1), cx1 = ds_clamp(sx + 1, 0, sw - 1);
@@ -74,25 +75,10 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
         for (int c = 0; c < CH; c++)
             acc[c] = 16384 + v00 * __ldg(r0 + cx0 * CH + c) + v01 * __ldg(r0 + cx1 * CH + c) +
                      v10 * __ldg(r1 + cx0 * CH + c) + v11 * __ldg(r1 + cx1 * CH + c);
+        uint8_t* dp = drow + (size_t)x * CH;
 #pragma unroll
-        for (int c = 0; c < CH; c++) out[i * CH + c] = (uint8_t)(acc[c] >> 15);   // <= 255 by construction
-        if (CH == 3) gr[i] = gray15(out[i * 3], out[i * 3 + 1], out[i * 3 + 2]);
-    }
-    uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + (size_t)x4 * CH;
-    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(dp) & 3) == 0) {
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dp);
-#pragma unroll
-        for (int w = 0; w < CH; w++)
-            d32[w] = out[4 * w] | (out[4 * w + 1] << 8) | (out[4 * w + 2] << 16) | ((uint32_t)out[4 * w + 3] << 24);
-    } else {
-        for (int i = 0; i < nvalid * CH; i++) dp[i] = out[i];
-    }
-    if (CH == 3 && J.gray) {
-        uint8_t* gp = J.gray + (size_t)y * J.gray_pitch + x4;
-        if (nvalid == 4 && (reinterpret_cast<uintptr_t>(gp) & 3) == 0)
-            *reinterpret_cast<uint32_t*>(gp) = gr[0] | (gr[1] << 8) | (gr[2] << 16) | ((uint32_t)gr[3] << 24);
-        else
-            for (int i = 0; i < nvalid; i++) gp[i] = gr[i];
+        for (int c = 0; c < CH; c++) dp[c] = (uint8_t)(acc[c] >> 15);      // <= 255 by construction
+        if (CH == 3 && grow) grow[x] = gray15(acc[0] >> 15, acc[1] >> 15, acc[2] >> 15);
     }
 }
 
