@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
         const int x = xt + 32 * i + threadIdx.x;
         if (x >= J.dw) break;
         // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows))
-        const int xbi = x - x % J.block_w;
+        const int xbi = J.block_w == 64 ? (x & ~63) : x - x % J.block_w;
         if (xbi != xb) {
             xb = xbi;
             const double dxb = (double)xb;
@@ -96,26 +96,22 @@ __global__ void affine_delta_kernel(const WarpAJob* __restrict__ jobs) {
 __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __restrict__ jobs) {
     const WarpAJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
-    const int x4 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    if (y >= J.dh || x4 >= J.dw) return;
+    const int xt = blockIdx.x * 128;
+    if (y >= J.dh || xt >= J.dw) return;
     const double dy = (double)y;
     // cv::warpAffine: X0 = saturate_cast<int>((M[1]*y + M[2])*1024) + 16
     const int X0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[1], dy), J.m[2]), 1024.0)) + 16;
     const int Y0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[4], dy), J.m[5]), 1024.0)) + 16;
     const uint8_t* __restrict__ src = J.src;
     const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
-    uint8_t out[4];
-    const int nvalid = min(4, J.dw - x4);
-    int2 dl[4];
-    if (nvalid == 4) {
-        const int4 t0 = __ldg(reinterpret_cast<const int4*>(J.delta + x4)), t1 = __ldg(reinterpret_cast<const int4*>(J.delta + x4 + 2));
-        dl[0] = make_int2(t0.x, t0.y); dl[1] = make_int2(t0.z, t0.w); dl[2] = make_int2(t1.x, t1.y); dl[3] = make_int2(t1.z, t1.w);
-    } else {
-        for (int i = 0; i < 4; i++) dl[i] = i < nvalid ? J.delta[x4 + i] : make_int2(0, 0);
-    }
+    uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
+    // lane-interleaved pixels (see warp_perspective_kernel): compact gathers, coalesced byte stores
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int X = (X0 + dl[i].x) >> 5, Y = (Y0 + dl[i].y) >> 5;
+        const int x = xt + 32 * i + threadIdx.x;
+        if (x >= J.dw) break;
+        const int2 dl = __ldg(J.delta + x);
+        const int X = (X0 + dl.x) >> 5, Y = (Y0 + dl.y) >> 5;
         const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
         const int ax = X & 31, ay = Y & 31;
         const int xa = ds_clamp(sx, 0, sw - 1), xb = ds_clamp(sx + 1, 0, sw - 1);
@@ -125,13 +121,8 @@ __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __rest
         // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) * ((32-ax) p00 + ax p01) + ay * ((32-ax) p10 + ax p11)] exactly
         const int h0 = (32 - ax) * __ldg(r0 + xa) + ax * __ldg(r0 + xb);
         const int h1 = (32 - ax) * __ldg(r1 + xa) + ax * __ldg(r1 + xb);
-        out[i] = (uint8_t)(((32 - ay) * h0 + ay * h1 + 512) >> 10);
+        drow[x] = (uint8_t)(((32 - ay) * h0 + ay * h1 + 512) >> 10);
     }
-    uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x4;
-    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(dp) & 3) == 0)
-        *reinterpret_cast<uint32_t*>(dp) = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
-    else
-        for (int i = 0; i < nvalid; i++) dp[i] = out[i];
 }
 
 }  // namespace
