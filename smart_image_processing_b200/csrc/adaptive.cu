@@ -271,10 +271,16 @@ __global__ void __launch_bounds__(128) mask_blend_kernel(const BlendJob* __restr
     }
 }
 
+struct AdaptGridInfo { int strips, max_w, max_h, n, seg_min; };
+
 template <int RMAX>
-int launch_adaptive(docscan_ctx* ctx, const AdaptJob* jd, const AdaptLaunch& L, dim3 grid, size_t smem) {
+int launch_adaptive(docscan_ctx* ctx, const AdaptJob* jd, AdaptLaunch L, const AdaptGridInfo& G, size_t smem) {
     if (smem > 48 * 1024)
         DS_CUDA(ctx, cudaFuncSetAttribute(adaptive_gauss_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_gauss_kernel<RMAX>, NT, smem));
+    L.seg_rows = ds_pick_seg_rows(per_sm * ctx->sm_count, G.strips, G.max_h, G.seg_min, BR);
+    dim3 grid((G.max_w + TW - 1) / TW, (G.max_h + L.seg_rows - 1) / L.seg_rows, G.n);
     adaptive_gauss_kernel<RMAX><<<grid, NT, smem, ctx->stream>>>(jd, L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
@@ -311,31 +317,23 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     const float* tab = (const float*)it->second;
     L.g_row = tab; L.g_col = tab + n_row;
 
-    const int strips = n * ((max_w + TW - 1) / TW);
-    int segs = (4 * ctx->sm_count + strips - 1) / strips;
-    if (segs < 1) segs = 1;
-    int seg = (max_h + segs - 1) / segs;
-    const int seg_min = max(64, 4 * L.r);
-    if (seg < seg_min) seg = seg_min;
-    seg = (seg + BR - 1) / BR * BR;
-    L.seg_rows = seg;
+    const AdaptGridInfo G{n * ((max_w + TW - 1) / TW), max_w, max_h, n, max(64, 4 * L.r)};
     const size_t smem = sizeof(float) * ((size_t)n_row + 64 + (size_t)BR * L.spf + (size_t)L.ring_rows * RPF);
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(AdaptJob) * n, &dev));
     const AdaptJob* jd = (const AdaptJob*)dev;
-    dim3 grid((max_w + TW - 1) / TW, (max_h + seg - 1) / seg, n);
     double px = 0;
     for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
     int rc;
     {
     ProfScope prof(ctx, "adaptive_gauss_k" + std::to_string(k), 2.0 * px);
-    if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, grid, smem);
-    else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, grid, smem);
-    else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, grid, smem);
-    else if (L.r == 15) rc = launch_adaptive<15>(ctx, jd, L, grid, smem);      // k = 31 (GUI preset), exact
-    else if (L.r <= 17) rc = launch_adaptive<17>(ctx, jd, L, grid, smem);      // k = 35 (CLI default), exact
-    else if (L.r <= 25) rc = launch_adaptive<25>(ctx, jd, L, grid, smem);
-    else rc = launch_adaptive<32>(ctx, jd, L, grid, smem);
+    if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, G, smem);
+    else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, G, smem);
+    else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, G, smem);
+    else if (L.r == 15) rc = launch_adaptive<15>(ctx, jd, L, G, smem);      // k = 31 (GUI preset), exact
+    else if (L.r <= 17) rc = launch_adaptive<17>(ctx, jd, L, G, smem);      // k = 35 (CLI default), exact
+    else if (L.r <= 25) rc = launch_adaptive<25>(ctx, jd, L, G, smem);
+    else rc = launch_adaptive<32>(ctx, jd, L, G, smem);
     }
     DS_TRY(rc);
     return DOCSCAN_OK;

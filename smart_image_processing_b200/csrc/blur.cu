@@ -291,10 +291,16 @@ int get_table(docscan_ctx* ctx, int kind, int k, BlurTable* out) {
     return DOCSCAN_OK;
 }
 
+struct BlurGridInfo { int strips, max_w, max_h, n, seg_min; };
+
 template <int EPI, bool STATS>
-int launch(docscan_ctx* ctx, const BlurJob* jobs_dev, const BlurLaunch& L, dim3 grid, size_t smem) {
+int launch(docscan_ctx* ctx, const BlurJob* jobs_dev, BlurLaunch L, const BlurGridInfo& G, size_t smem) {
     if (smem > 48 * 1024)
         DS_CUDA(ctx, cudaFuncSetAttribute(blur_march_kernel<EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blur_march_kernel<EPI, STATS>, NT, smem));
+    L.seg_rows = ds_pick_seg_rows(per_sm * ctx->sm_count, G.strips, G.max_h, G.seg_min, BR);
+    dim3 grid((G.max_w + TW - 1) / TW, (G.max_h + L.seg_rows - 1) / L.seg_rows, G.n);
     blur_march_kernel<EPI, STATS><<<grid, NT, smem, ctx->stream>>>(jobs_dev, L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
@@ -314,28 +320,19 @@ int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const B
     L.ring_rows = ((2 * L.t.r_eff + BR - 1) / BR + 1) * BR;
     bool stats = false;
     for (int i = 0; i < n; i++) stats = stats || jobs_host[i].minmax || jobs_host[i].hist;
-    // segment height: enough CTAs to fill the machine, but tall enough to amortise the 2r warm-up rows
-    const int strips = n * ((max_w + TW - 1) / TW);
-    int segs = (8 * ctx->sm_count + strips - 1) / strips;
-    if (segs < 1) segs = 1;
-    int seg = (max_h + segs - 1) / segs;
-    const int seg_min = max(64, 4 * L.t.r_eff);
-    if (seg < seg_min) seg = seg_min;
-    seg = (seg + BR - 1) / BR * BR;
-    L.seg_rows = seg;
+    const BlurGridInfo G{n * ((max_w + TW - 1) / TW), max_w, max_h, n, max(64, 4 * L.t.r_eff)};
     const size_t smem = sizeof(uint4) * (L.t.M + 6) + sizeof(uint32_t) * 2 * (4 * L.t.nb + 8) +
                         sizeof(uint32_t) * BR * L.spw + 16 + sizeof(uint32_t) * (L.ring_rows / 2) * RP2 +
                         (stats ? 4 * 256 * sizeof(uint32_t) : 0);
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(BlurJob) * n, &dev));
-    dim3 grid((max_w + TW - 1) / TW, (max_h + seg - 1) / seg, n);
     const BlurJob* jd = (const BlurJob*)dev;
     double px = 0;
     for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
     ProfScope prof(ctx, std::string(kind == 0 ? "blur_gauss_k" : "blur_box_k") + std::to_string(k), 2.0 * px);
 #define DS_BLUR_CASE(E)                                                            \
     case E:                                                                        \
-        return stats ? launch<E, true>(ctx, jd, L, grid, smem) : launch<E, false>(ctx, jd, L, grid, smem);
+        return stats ? launch<E, true>(ctx, jd, L, G, smem) : launch<E, false>(ctx, jd, L, G, smem);
     switch (epi) {
         DS_BLUR_CASE(DS_EPI_BLUR)
         DS_BLUR_CASE(DS_EPI_SUB)

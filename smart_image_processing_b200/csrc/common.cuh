@@ -203,6 +203,17 @@ int k_warp_affine_jobs(docscan_ctx*, const WarpAJob* jobs_host, int n, int max_w
 // synth.cu
 int k_synth_page(docscan_ctx*, uint64_t seed, const DImg& dst, float quad_out[8]);
 
+// Segment height for the marching kernels: as many vertical segments as fit in ONE wave of resident CTAs
+// (strips * segs <= SMs * CTAs/SM).  More segments than that run as a partial second wave whose tail idles most of
+// the machine; fewer leave SMs empty.  Each segment repeats a warm-up of ~2r rows, hence the lower bound.
+static inline int ds_pick_seg_rows(int resident_ctas, int strips, int max_h, int min_rows, int quantum) {
+    int segs = strips > 0 ? resident_ctas / strips : 1;
+    if (segs < 1) segs = 1;
+    int seg = (max_h + segs - 1) / segs;
+    if (seg < min_rows) seg = min_rows;
+    return (seg + quantum - 1) / quantum * quantum;
+}
+
 // upload a host job array into arena memory (stream ordered); returns the device pointer
 int ds_upload(docscan_ctx* ctx, const void* host, size_t bytes, void** dev_out);
 

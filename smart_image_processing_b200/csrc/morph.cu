@@ -323,12 +323,6 @@ int launch_t(docscan_ctx* ctx, const MorphJob* jobs_host, int n, int max_w, int 
     MarchLaunch L{};
     L.spw = (24 + NWH + 1) | 1;
     L.ring_rows = (D + 1) * BRm;
-    const int strips = n * ((max_w + TWm - 1) / TWm);
-    int segs = (8 * ctx->sm_count + strips - 1) / strips;
-    if (segs < 1) segs = 1;
-    int seg = std::max((max_h + segs - 1) / segs, std::max(64, 4 * KH));
-    seg = (seg + BRm - 1) / BRm * BRm;
-    L.seg_rows = seg;
     bool hist = false;
     double px = 0, refpx = 0;
     for (int i = 0; i < n; i++) {
@@ -339,10 +333,13 @@ int launch_t(docscan_ctx* ctx, const MorphJob* jobs_host, int n, int max_w, int 
     const size_t smem = sizeof(uint32_t) * ((size_t)BRm * L.spw + 4 + (size_t)L.ring_rows * RPW + (hist ? 4 * 256 : 0));
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(MorphJob) * n, &dev));
-    dim3 grid((max_w + TWm - 1) / TWm, (max_h + seg - 1) / seg, n);
-    ProfScope prof(ctx, "morph_march_" + std::to_string(KW) + "x" + std::to_string(KH), 2.0 * px + refpx);
     if (smem > 48 * 1024)
         DS_CUDA(ctx, cudaFuncSetAttribute(morph_march_kernel<KW, KH, DIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, morph_march_kernel<KW, KH, DIL>, NTm, smem));
+    L.seg_rows = ds_pick_seg_rows(per_sm * ctx->sm_count, n * ((max_w + TWm - 1) / TWm), max_h, std::max(64, 4 * KH), BRm);
+    dim3 grid((max_w + TWm - 1) / TWm, (max_h + L.seg_rows - 1) / L.seg_rows, n);
+    ProfScope prof(ctx, "morph_march_" + std::to_string(KW) + "x" + std::to_string(KH), 2.0 * px + refpx);
     morph_march_kernel<KW, KH, DIL><<<grid, NTm, smem, ctx->stream>>>((const MorphJob*)dev, L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
