@@ -579,14 +579,40 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
     if (any_host) group = std::min(group, 8);          // finer pipeline granularity: copies overlap compute
     group = std::min(group, n);
     if (!any_host) {
-        DS_TRY(begin_call(ctx, max_page * group));
-        for (int i = 0; i < n; i += group) {
+        // Device-resident batch.  Consecutive groups alternate between the context's stream and a second compute
+        // stream (own scratch region each): the small serial kernels of one group (Otsu scan, LUTs) and its wave tails
+        // overlap the big kernels of the other.  With per-kernel profiling on, a single stream keeps timings clean.
+        const bool two_streams = n > group && !ctx->prof_on;
+        DS_TRY(begin_call(ctx, max_page * group * (two_streams ? 2 : 1)));
+        if (two_streams && !ctx->aux) {
+            DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+            DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[0], cudaEventDisableTiming));
+            DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[1], cudaEventDisableTiming));
+        }
+        cudaStream_t main_stream = ctx->stream;
+        if (two_streams) {
+            DS_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], main_stream));
+            DS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->aux_ev[0], 0));
+        }
+        const size_t base = ctx->arena_off, region = (max_page * group + 255) & ~(size_t)255;
+        int rc = DOCSCAN_OK, g = 0;
+        for (int i = 0; i < n && rc == DOCSCAN_OK; i += group, g++) {
             const int m = std::min(group, n - i);
             std::vector<DImg> src(m), warped(m), binary(m);
             for (int j = 0; j < m; j++) {
                 src[j] = view_of(pages[i + j].src); warped[j] = view_of(pages[i + j].warped); binary[j] = view_of(pages[i + j].binary);
             }
-            DS_TRY(run_group(ctx, m, pages + i, *params, src, warped, binary));
+            const bool on_aux = two_streams && (g & 1);
+            ctx->stream = on_aux ? ctx->aux : main_stream;
+            ctx->arena_off = base + (on_aux ? region : 0);
+            rc = run_group(ctx, m, pages + i, *params, src, warped, binary);
+        }
+        ctx->stream = main_stream;
+        ctx->arena_off = base;
+        DS_TRY(rc);
+        if (two_streams) {
+            DS_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], ctx->aux));
+            DS_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->aux_ev[1], 0));
         }
         return DOCSCAN_OK;
     }

@@ -46,6 +46,9 @@ struct docscan_ctx {
     // host-buffer pipeline of docscan_process_pages: copy streams + events (created on first use)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t pipe_ev[7] = {};
+    // second compute stream of the device-resident batch path
+    cudaStream_t aux = nullptr;
+    cudaEvent_t aux_ev[2] = {};
     // optional per-kernel timing (docscan_profile_enable): one event pair per launch
     bool prof_on = false;
     struct ProfRec { std::string name; double bytes; cudaEvent_t a, b; };

@@ -80,6 +80,11 @@ extern "C" int docscan_destroy(docscan_ctx* ctx) {
         cudaStreamDestroy(ctx->copy_out);
         for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
     }
+    if (ctx->aux) {
+        cudaStreamDestroy(ctx->aux);
+        cudaEventDestroy(ctx->aux_ev[0]);
+        cudaEventDestroy(ctx->aux_ev[1]);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DOCSCAN_OK;
