@@ -1,6 +1,7 @@
 // extern "C" entry points of libdocscan.so (see include/docscan.h) and the batched page pipeline.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -576,23 +577,26 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
     const int strips_per_page = (pages[0].binary.width + 127) / 128;
     int group = (2 * ctx->sm_count + strips_per_page - 1) / strips_per_page;
     group = std::max(4, std::min(group, 32));
+    if (const char* e = getenv("DOCSCAN_GROUP")) group = std::max(1, atoi(e));
     if (any_host) group = std::min(group, 8);          // finer pipeline granularity: copies overlap compute
     group = std::min(group, n);
     if (!any_host) {
-        // Device-resident batch.  Consecutive groups alternate between the context's stream and a second compute
-        // stream (own scratch region each): the small serial kernels of one group (Otsu scan, LUTs) and its wave tails
+        // Device-resident batch.  Consecutive groups rotate over the context's stream and up to DS_MAX_STREAMS-1 extra
+        // compute streams (own scratch region each): the small serial kernels of one group (Otsu scan, LUTs) and its wave tails
         // overlap the big kernels of the other.  With per-kernel profiling on, a single stream keeps timings clean.
-        const bool two_streams = n > group && !ctx->prof_on;
-        DS_TRY(begin_call(ctx, max_page * group * (two_streams ? 2 : 1)));
-        if (two_streams && !ctx->aux) {
-            DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
-            DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[0], cudaEventDisableTiming));
-            DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[1], cudaEventDisableTiming));
-        }
+        int ns = ctx->prof_on ? 1 : std::min(3, (n + group - 1) / group);      // 3 measured best on B200 (profiles/README.md)
+        if (const char* e = getenv("DOCSCAN_STREAMS")) ns = std::max(1, std::min(std::min(DS_MAX_STREAMS, (n + group - 1) / group), atoi(e)));
+        DS_TRY(begin_call(ctx, max_page * group * ns));
+        for (int k = 1; k < ns; k++)
+            if (!ctx->aux[k]) {
+                DS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
+                DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[k], cudaEventDisableTiming));
+            }
         cudaStream_t main_stream = ctx->stream;
-        if (two_streams) {
+        if (ns > 1) {
+            if (!ctx->aux_ev[0]) DS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_ev[0], cudaEventDisableTiming));
             DS_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], main_stream));
-            DS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->aux_ev[0], 0));
+            for (int k = 1; k < ns; k++) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[k], ctx->aux_ev[0], 0));
         }
         const size_t base = ctx->arena_off, region = (max_page * group + 255) & ~(size_t)255;
         int rc = DOCSCAN_OK, g = 0;
@@ -602,17 +606,17 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
             for (int j = 0; j < m; j++) {
                 src[j] = view_of(pages[i + j].src); warped[j] = view_of(pages[i + j].warped); binary[j] = view_of(pages[i + j].binary);
             }
-            const bool on_aux = two_streams && (g & 1);
-            ctx->stream = on_aux ? ctx->aux : main_stream;
-            ctx->arena_off = base + (on_aux ? region : 0);
+            const int k = g % ns;
+            ctx->stream = k ? ctx->aux[k] : main_stream;
+            ctx->arena_off = base + (size_t)k * region;
             rc = run_group(ctx, m, pages + i, *params, src, warped, binary);
         }
         ctx->stream = main_stream;
         ctx->arena_off = base;
         DS_TRY(rc);
-        if (two_streams) {
-            DS_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], ctx->aux));
-            DS_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->aux_ev[1], 0));
+        for (int k = 1; k < ns; k++) {
+            DS_CUDA(ctx, cudaEventRecord(ctx->aux_ev[k], ctx->aux[k]));
+            DS_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->aux_ev[k], 0));
         }
         return DOCSCAN_OK;
     }

@@ -15,6 +15,7 @@
 #endif
 
 #define DS_SM_COUNT_FALLBACK 148
+#define DS_MAX_STREAMS 4
 
 // ---------------------------------------------------------------------------------------------
 // device image view (uint8, interleaved channels)
@@ -47,8 +48,8 @@ struct docscan_ctx {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t pipe_ev[7] = {};
     // second compute stream of the device-resident batch path
-    cudaStream_t aux = nullptr;
-    cudaEvent_t aux_ev[2] = {};
+    cudaStream_t aux[DS_MAX_STREAMS] = {};      // [0] unused (the context's own stream)
+    cudaEvent_t aux_ev[DS_MAX_STREAMS] = {};
     // optional per-kernel timing (docscan_profile_enable): one event pair per launch
     bool prof_on = false;
     struct ProfRec { std::string name; double bytes; cudaEvent_t a, b; };

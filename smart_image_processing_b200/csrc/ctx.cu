@@ -80,10 +80,9 @@ extern "C" int docscan_destroy(docscan_ctx* ctx) {
         cudaStreamDestroy(ctx->copy_out);
         for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
     }
-    if (ctx->aux) {
-        cudaStreamDestroy(ctx->aux);
-        cudaEventDestroy(ctx->aux_ev[0]);
-        cudaEventDestroy(ctx->aux_ev[1]);
+    for (int k = 0; k < DS_MAX_STREAMS; k++) {
+        if (ctx->aux[k]) cudaStreamDestroy(ctx->aux[k]);
+        if (ctx->aux_ev[k]) cudaEventDestroy(ctx->aux_ev[k]);
     }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
