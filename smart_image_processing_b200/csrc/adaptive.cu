@@ -147,16 +147,24 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
         float Wn[BR + 2 * RMAX];
         const int shift = RMAX - r;                 // window index i <-> virtual row vb*BR + i - shift
         const int slot0 = (vb * BR) % L.ring_rows;
-        if (shift == 0) {                              // exact instantiation (k = 2*RMAX+1): no range predicates
-            const float* base = s_ring + slot0 * RPF + col;
-            if (slot0 + BR - 1 + 2 * RMAX < L.ring_rows) {
-#pragma unroll
-                for (int i = 0; i < BR + 2 * RMAX; i++) Wn[i] = base[i * RPF];
-            } else {
-                const int wrap = L.ring_rows - slot0;   // first window index that wraps
-#pragma unroll
-                for (int i = 0; i < BR + 2 * RMAX; i++) Wn[i] = base[(i >= wrap ? i - L.ring_rows : i) * RPF];
+        if (shift == 0) {
+            // exact instantiation (k = 2*RMAX+1): the ring size is a compile-time constant and a window starts at a
+            // multiple of 16 rows, so every ring offset (wrap included) is an immediate
+            constexpr int RR = ((2 * RMAX + BR - 1) / BR + 1) * BR;
+            const float* colp = s_ring + col;
+#define DS_LOAD_WINDOW(S0)                                                                      \
+    _Pragma("unroll") for (int i = 0; i < BR + 2 * RMAX; i++) Wn[i] = colp[(((S0) + i) % RR) * RPF];
+            switch (slot0 / BR) {
+                case 0: DS_LOAD_WINDOW(0) break;
+                case 1: DS_LOAD_WINDOW(16) break;
+                case 2: DS_LOAD_WINDOW(32) break;
+                case 3: DS_LOAD_WINDOW(48) break;
+                case 4: DS_LOAD_WINDOW(64) break;
+                case 5: DS_LOAD_WINDOW(80) break;
+                case 6: DS_LOAD_WINDOW(96) break;
+                default: DS_LOAD_WINDOW(112) break;
             }
+#undef DS_LOAD_WINDOW
         } else {
 #pragma unroll
             for (int i = 0; i < BR + 2 * RMAX; i++) {
