@@ -14,11 +14,14 @@ namespace {
 
 constexpr int TW = 128, BR = 16, NT = 128;
 constexpr int RPF = 132;      // ring row pitch in floats
+constexpr int GMAX = 33;      // half-kernel table size (k <= 65)
 
+// The half kernel travels in the launch parameters: every tap index below is a compile-time constant, so the
+// coefficient of each fma is a constant-bank operand (no register, no shared-memory load).
 struct AdaptLaunch {
-    int k, r, delta, c_param, seg_rows, spf, ring_rows, nblk, tail_compat;
-    const float* g_row;       // 8 zeros + k taps + zeros up to 8*nblk + 16
-    const float* g_col;       // g_col[j] = g[r + j] for j <= r, zero up to 64
+    int k, r, c_param, seg_rows, spf, tail_compat;
+    float gh[GMAX];           // gh[j] = g[r + j] for j <= r, 0 beyond (zero taps leave an fp32 accumulator unchanged)
+    const float* g_full;      // the k taps in order (device): only the rare cv2-tail columns read it
 };
 
 // rare path of the staging load (strip edges, unaligned caller buffers): kept out of line
@@ -28,8 +31,21 @@ __device__ __noinline__ uint32_t fetch_word_clamped(const uint8_t* rowp, int gx,
     return word;
 }
 
+// cv2's row filter leaves the last w % 4 columns (w % 8 >= 4: the last w % 8 - 4) to scalar code: mul+add per tap,
+// except that the (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  `in` points at tap 0.
+__device__ __noinline__ float row_tail_value(const float* in, const float* g, int k) {
+    const int first_fused = k - ((k - 1) & 3);
+    float a = __fmul_rn(g[0], in[0]);
+    for (int i = 1; i < k; i++) a = i >= first_fused ? __fmaf_rn(in[i], g[i], a) : __fadd_rn(a, __fmul_rn(g[i], in[i]));
+    return a;
+}
+
 template <int RMAX>
-__global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* __restrict__ jobs, const AdaptLaunch L) {
+__global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L) {
+    constexpr int DELTA = (4 - (RMAX & 3)) & 3;                    // staged column 0 <-> x0 - RMAX - DELTA (word aligned)
+    constexpr int STAGE_WORDS = (TW + 2 * RMAX + DELTA + 3) >> 2;
+    constexpr int RR = ((2 * RMAX + BR - 1) / BR + 1) * BR;         // ring rows
+    constexpr int D = (2 * RMAX + BR - 1) / BR;                     // the column pass lags the row pass by D steps
     const AdaptJob J = jobs[blockIdx.z];
     const int x0 = blockIdx.x * TW;
     const int y_begin = blockIdx.y * L.seg_rows;
@@ -37,19 +53,12 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
     const int y_end = min(J.h, y_begin + L.seg_rows);
     const int rows_out = y_end - y_begin;
     const int tid = threadIdx.x;
-    const int r = L.r, r4 = L.r + L.delta;
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float* s_grow = reinterpret_cast<float*>(smem_raw);            // 8*nblk + 16: 8 zeros, k taps, zeros
-    float* s_gcol = s_grow + 8 * L.nblk + 16;                      // 64
-    float* s_stage = s_gcol + 64;                                  // BR * spf, spf == 1 (mod 32)
-    float* s_ring = s_stage + BR * L.spf;                          // ring_rows * RPF
-    for (int i = tid; i < 8 * L.nblk + 16; i += NT) s_grow[i] = L.g_row[i];
-    if (tid < 64) s_gcol[tid] = L.g_col[tid];
+    float* s_stage = reinterpret_cast<float*>(smem_raw);           // BR * spf, spf == 1 (mod 32)
+    float* s_ring = s_stage + BR * L.spf;                          // RR * RPF
 
     const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
-    const int stage_words = (TW + 8 * L.nblk + 4) >> 2;   // every column the row pass can touch holds a finite value
-    const int D = (2 * r + BR - 1) / BR;
     const int n_vb = (rows_out + BR - 1) / BR;
     const bool row_identity = J.w == 1, col_identity = J.h == 1;   // cv::GaussianBlur shrinks the kernel on 1-px axes
     // columns cv2's AVX2 build evaluates without fma (k <= 9: the taps are dyadic, every order is exact)
@@ -59,98 +68,79 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
 
     for (int hb = 0; hb < n_vb + D; hb++) {
         {
+            // virtual row v of the segment <-> source row clamp(y_begin - RMAX + v): taps beyond r carry zero weight
             const int srow_id = tid >> 3;              // 16 rows x 8 lanes; a lane strides along its row
-            const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - r + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
+            const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - RMAX + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
             float* sp = s_stage + srow_id * L.spf;
-            for (int w0 = tid & 7; w0 < stage_words; w0 += 8 * 7) {
+            for (int w0 = tid & 7; w0 < STAGE_WORDS; w0 += 8 * 7) {
                 uint32_t wv[7];                            // issue the loads first, convert and store afterwards
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
                     const int wi = w0 + 8 * j;
-                    const int gx = x0 - r4 + 4 * wi;
+                    const int gx = x0 - RMAX - DELTA + 4 * wi;
                     wv[j] = 0;
-                    if (wi < stage_words) wv[j] = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
+                    if (wi < STAGE_WORDS) wv[j] = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
                 }
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
                     const int wi = w0 + 8 * j;
-                    if (wi >= stage_words) continue;
+                    if (wi >= STAGE_WORDS) continue;
                     // u8 -> fp32 without the slow I2F unit: 2^23 + v is exact in fp32, subtract 2^23 again
 #pragma unroll
-                    for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(0x4B000000u | ((wv[j] >> (8 * b)) & 255u)), 8388608.0f);
+                    for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(__byte_perm(wv[j], 0x4B000000u, 0x7440 + b)), 8388608.0f);
                 }
             }
         }
         __syncthreads();
         {   // ---- row pass: out[c] = sum_i g[i] * f[c + i - r], taps in increasing i, one fma each.
-            // lane <-> staged row (16 rows x 2 column groups per warp): with the row pitch == 1 (mod 32) a warp's loads
-            // hit 32 different banks.  8 outputs per group, sliding window of 16 coefficients in registers.
+            // thread = (staged row, 16 consecutive outputs); lane <-> row (16 rows x 2 column groups per warp): with the
+            // row pitch == 1 (mod 32) a warp's loads hit 32 different banks.  Each staged value is loaded once and fed to
+            // every output it belongs to; inputs ascend, so each accumulator sees its taps in increasing order.
             const int lane = tid & 31, wrp = tid >> 5;
-            const int hr = lane & 15, hh = lane >> 4;
-            const float* srow = s_stage + hr * L.spf + L.delta;
-            const int slot = (hb * BR + hr) % L.ring_rows;
-#pragma unroll 1
-            for (int it = 0; it < 2; it++) {
-                const int pr = wrp * 2 + it;
-                const int c0 = 8 * ((pr >> 1) * 4 + (pr & 1) + 2 * hh);
-                const float* sp = srow + c0;
-                float acc[8];
+            const int hr = lane & 15;
+            const int c0 = 16 * (2 * wrp + (lane >> 4));
+            const float* sp = s_stage + hr * L.spf + DELTA + c0;      // sp[u] <-> column x0 + c0 + u - RMAX
+            float acc[16];
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] = 0.0f;
-                float G[16];
-                {
-                    const float4 t0 = *reinterpret_cast<const float4*>(s_grow), t1 = *reinterpret_cast<const float4*>(s_grow + 4);
-                    G[8] = t0.x; G[9] = t0.y; G[10] = t0.z; G[11] = t0.w; G[12] = t1.x; G[13] = t1.y; G[14] = t1.z; G[15] = t1.w;
+            for (int o = 0; o < 16; o++) acc[o] = 0.0f;
+#pragma unroll
+            for (int u = 0; u < 16 + 2 * RMAX; u++) {
+                const float f = sp[u];
+#pragma unroll
+                for (int o = 0; o < 16; o++) {
+                    const int i = u - o;                              // tap index in the padded kernel
+                    if (i >= 0 && i <= 2 * RMAX) acc[o] = __fmaf_rn(f, L.gh[i < RMAX ? RMAX - i : i - RMAX], acc[o]);
                 }
-                for (int b = 0; b < L.nblk; b++) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) G[i] = G[i + 8];
-                    const float4 t0 = *reinterpret_cast<const float4*>(s_grow + 8 * b + 8), t1 = *reinterpret_cast<const float4*>(s_grow + 8 * b + 12);
-                    G[8] = t0.x; G[9] = t0.y; G[10] = t0.z; G[11] = t0.w; G[12] = t1.x; G[13] = t1.y; G[14] = t1.z; G[15] = t1.w;
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const float f = sp[8 * b + u];
-#pragma unroll
-                        for (int o = 0; o < 8; o++) acc[o] = __fmaf_rn(f, G[u - o + 8], acc[o]);
-                    }
-                }
-                if (row_identity) {
-#pragma unroll
-                    for (int o = 0; o < 8; o++) acc[o] = sp[r + o];
-                } else if (xt_row < J.w && x0 + c0 + 7 >= xt_row) {
-                    // cv2's row filter leaves the last w % 4 columns to scalar code: mul+add per tap, except that the
-                    // (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  At most 3 columns per row.
-                    const int first_fused = L.k - ((L.k - 1) & 3);
-#pragma unroll
-                    for (int o = 0; o < 8; o++) {
-                        const int x = x0 + c0 + o;
-                        if (x < xt_row || x >= J.w) continue;
-                        float a = __fmul_rn(s_grow[8], sp[o]);
-                        for (int i = 1; i < L.k; i++) {
-                            const float f = sp[o + i];
-                            a = i >= first_fused ? __fmaf_rn(f, s_grow[8 + i], a) : __fadd_rn(a, __fmul_rn(s_grow[8 + i], f));
-                        }
-                        acc[o] = a;
-                    }
-                }
-                float4* dst = reinterpret_cast<float4*>(s_ring + slot * RPF + c0);
-                dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
+            if (row_identity) {
+#pragma unroll
+                for (int o = 0; o < 16; o++) acc[o] = sp[RMAX + o];
+            } else if (xt_row < J.w && x0 + c0 + 15 >= xt_row) {
+                for (int o = 0; o < 16; o++) {                        // at most 3 columns per row
+                    const int x = x0 + c0 + o;
+                    if (x < xt_row || x >= J.w) continue;
+                    const float v = row_tail_value(sp + o + RMAX - L.r, L.g_full, L.k);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) if (q == o) acc[q] = v;
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(s_ring + ((hb * BR + hr) % RR) * RPF + c0);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            dst[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+            dst[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
         }
         __syncthreads();
         if (hb < D) continue;
-        // ---- column pass: thread = one column, 16 rows; centre of output o sits at window index o + RMAX
+        // ---- column pass: thread = one column, 16 rows; centre of output o sits at window index o + RMAX.
+        // The ring size is a compile-time constant and a window starts at a multiple of 16 rows, so every ring offset
+        // (wrap included) is an immediate.
         const int vb = hb - D;
         const int col = tid;
         const int x = x0 + col;
         float Wn[BR + 2 * RMAX];
-        const int shift = RMAX - r;                 // window index i <-> virtual row vb*BR + i - shift
-        const int slot0 = (vb * BR) % L.ring_rows;
-        if (shift == 0) {
-            // exact instantiation (k = 2*RMAX+1): the ring size is a compile-time constant and a window starts at a
-            // multiple of 16 rows, so every ring offset (wrap included) is an immediate
-            constexpr int RR = ((2 * RMAX + BR - 1) / BR + 1) * BR;
+        const int slot0 = (vb * BR) % RR;
+        {
             const float* colp = s_ring + col;
 #define DS_LOAD_WINDOW(S0)                                                                      \
     _Pragma("unroll") for (int i = 0; i < BR + 2 * RMAX; i++) Wn[i] = colp[(((S0) + i) % RR) * RPF];
@@ -165,36 +155,21 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
                 default: DS_LOAD_WINDOW(112) break;
             }
 #undef DS_LOAD_WINDOW
-        } else {
-#pragma unroll
-            for (int i = 0; i < BR + 2 * RMAX; i++) {
-                const int rel = i - shift;
-                float v = 0.0f;
-                if (rel >= 0 && rel <= BR - 1 + 2 * r) {
-                    int slot = slot0 + rel;
-                    if (slot >= L.ring_rows) slot -= L.ring_rows;
-                    v = s_ring[slot * RPF + col];
-                }
-                Wn[i] = v;
-            }
         }
         float acc[BR];
-        const float gc0 = s_gcol[0];
 #pragma unroll
-        for (int o = 0; o < BR; o++) acc[o] = __fmul_rn(gc0, Wn[o + RMAX]);
+        for (int o = 0; o < BR; o++) acc[o] = __fmul_rn(L.gh[0], Wn[o + RMAX]);
         if (x < xt_col) {
 #pragma unroll
             for (int j = 1; j <= RMAX; j++) {
-                const float gj = s_gcol[j];
 #pragma unroll
-                for (int o = 0; o < BR; o++) acc[o] = __fmaf_rn(__fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j]), gj, acc[o]);
+                for (int o = 0; o < BR; o++) acc[o] = __fmaf_rn(__fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j]), L.gh[j], acc[o]);
             }
         } else {
 #pragma unroll
             for (int j = 1; j <= RMAX; j++) {
-                const float gj = s_gcol[j];
 #pragma unroll
-                for (int o = 0; o < BR; o++) acc[o] = __fadd_rn(acc[o], __fmul_rn(gj, __fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j])));
+                for (int o = 0; o < BR; o++) acc[o] = __fadd_rn(acc[o], __fmul_rn(L.gh[j], __fadd_rn(Wn[o + RMAX + j], Wn[o + RMAX - j])));
             }
         }
         if (x < J.w) {
@@ -279,6 +254,81 @@ __global__ void __launch_bounds__(128) mask_blend_kernel(const BlendJob* __restr
     }
 }
 
+// Fast variant for the library's own planes (16-byte aligned rows): a thread owns a 16-pixel column chunk and marches
+// down BLEND_ROWS rows, so the ink decision of row y-1 is reused for row y and every access is 128 bits wide.
+constexpr int BLEND_ROWS = 8;
+template <int NDIL>
+__global__ void __launch_bounds__(128) mask_blend16_kernel(const BlendJob* __restrict__ jobs, int mask_only, int chunks, int row_groups) {
+    const BlendJob J = jobs[blockIdx.y];
+    const int id = blockIdx.x * 128 + threadIdx.x;
+    const int cpr = (J.w + 15) >> 4;                       // chunks per row of this page
+    const int rg = id / chunks, xc = id - rg * chunks;
+    if (rg >= row_groups || xc >= cpr) return;
+    const int x = xc * 16, y0 = rg * BLEND_ROWS;
+    if (y0 >= J.h) return;
+    const int cut_a = J.sc->cut_a, cut_b = J.sc->cut_b;
+    const uint32_t ca = cut_a > 255 ? 0u : (uint32_t)max(cut_a, 0) * 0x01010101u, cb = cut_b > 255 ? 0u : (uint32_t)max(cut_b, 0) * 0x01010101u;
+    const uint32_t all_a = cut_a <= 0 ? 0xffffffffu : 0u, none_a = cut_a > 255 ? 0u : 0xffffffffu;
+    const uint32_t all_b = cut_b <= 0 ? 0xffffffffu : 0u, none_b = cut_b > 255 ? 0u : 0xffffffffu;
+    auto ink4 = [&](uint32_t wa, uint32_t wb) -> uint32_t {     // 0xff where either branch is at / above its cut-off
+        return ((__vcmpgeu4(wa, ca) | all_a) & none_a) | ((__vcmpgeu4(wb, cb) | all_b) & none_b);
+    };
+    // horizontally dilated ink of one row: byte i <- OR of raw ink at columns x+i-NDIL .. x+i
+    auto row_ink = [&](int y, uint32_t (&m)[4]) {
+        if (y < 0) { m[0] = m[1] = m[2] = m[3] = 0u; return; }
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(J.ink_sub + (size_t)y * J.pitch_sub + x));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(J.bh + (size_t)y * J.pitch_bh + x));
+        uint32_t r[5];
+        r[0] = 0u;
+        if (NDIL > 0 && x > 0) r[0] = ink4(ds_ldg32(J.ink_sub + (size_t)y * J.pitch_sub + x - 4), ds_ldg32(J.bh + (size_t)y * J.pitch_bh + x - 4));
+        r[1] = ink4(a.x, b.x); r[2] = ink4(a.y, b.y); r[3] = ink4(a.z, b.z); r[4] = ink4(a.w, b.w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t v = r[j + 1];
+#pragma unroll
+            for (int sft = 1; sft <= NDIL; sft++) v |= __funnelshift_l(r[j], r[j + 1], 8 * sft);
+            m[j] = v;
+        }
+    };
+    uint32_t prev[NDIL > 0 ? NDIL : 1][4];
+#pragma unroll
+    for (int d = 0; d < NDIL; d++) row_ink(y0 - NDIL + d, prev[d]);
+    const int rows = min(BLEND_ROWS, J.h - y0);
+    const bool full = x + 16 <= J.w;
+#pragma unroll
+    for (int i = 0; i < BLEND_ROWS; i++) {
+        if (i >= rows) break;
+        const int y = y0 + i;
+        uint32_t cur[4], ink[4];
+        row_ink(y, cur);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            ink[j] = cur[j];
+#pragma unroll
+            for (int d = 0; d < NDIL; d++) ink[j] |= prev[d][j];
+        }
+#pragma unroll
+        for (int d = 0; d + 1 < NDIL; d++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) prev[d][j] = prev[d + 1][j];
+        if (NDIL > 0) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) prev[NDIL - 1][j] = cur[j];
+        }
+        uint4 out = make_uint4(ink[0], ink[1], ink[2], ink[3]);
+        if (!mask_only) {
+            const uint4 bs = __ldg(reinterpret_cast<const uint4*>(J.base + (size_t)y * J.pitch_base + x));
+            out = make_uint4((bs.x & ink[0]) | ~ink[0], (bs.y & ink[1]) | ~ink[1], (bs.z & ink[2]) | ~ink[2], (bs.w & ink[3]) | ~ink[3]);
+        }
+        uint8_t* dp = J.dst + (size_t)y * J.pitch_dst + x;
+        if (full) *reinterpret_cast<uint4*>(dp) = out;
+        else {
+            const uint32_t ow[4] = {out.x, out.y, out.z, out.w};
+            for (int b = 0; b < J.w - x; b++) dp[b] = (uint8_t)(ow[b >> 2] >> (8 * (b & 3)));
+        }
+    }
+}
+
 struct AdaptGridInfo { int strips, max_w, max_h, n, seg_min; };
 
 template <int RMAX>
@@ -301,32 +351,29 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     if (k < 3 || (k & 1) == 0 || k > 65)
         return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "adaptive GAUSSIAN_C block size must be odd and in 3..65 (got %d)", k);
     AdaptLaunch L{};
-    L.k = k; L.r = k / 2; L.delta = (4 - (L.r & 3)) & 3; L.c_param = c; L.tail_compat = cv_tail_compat;
-    L.nblk = (k + 7 + 7) / 8;
-    L.spf = TW + 8 * L.nblk + 8;
+    L.k = k; L.r = k / 2; L.c_param = c; L.tail_compat = cv_tail_compat;
+    const int rmax = L.r <= 5 ? 5 : L.r <= 9 ? 9 : L.r <= 13 ? 13 : L.r <= 15 ? 15 : L.r <= 17 ? 17 : L.r <= 25 ? 25 : 32;
+    const int delta = (4 - (rmax & 3)) & 3;
+    L.spf = TW + 2 * rmax + delta + 4;
     L.spf += (33 - (L.spf & 31)) & 31;                 // pitch == 1 (mod 32): lanes of a warp read different banks
-    L.ring_rows = ((2 * L.r + BR - 1) / BR + 1) * BR;
-    // coefficient tables (device, cached per k)
+    const int ring_rows = ((2 * rmax + BR - 1) / BR + 1) * BR;
+    // taps in order (device, cached per k) for the cv2-tail columns; the half kernel rides in the launch parameters
     const uint64_t key = ((uint64_t)7 << 32) | (uint32_t)k;
-    const int n_row = 8 * L.nblk + 16;
+    std::vector<float> g(k);
+    docscan_gaussian_kernel_f32(k, g.data());
+    for (int j = 0; j <= L.r; j++) L.gh[j] = g[L.r + j];
     auto it = ctx->tables.find(key);
     if (it == ctx->tables.end()) {
-        std::vector<float> g(k), host(n_row + 64 + k, 0.0f);
-        docscan_gaussian_kernel_f32(k, g.data());
-        for (int i = 0; i < k; i++) host[8 + i] = g[i];
-        for (int j = 0; j <= L.r; j++) host[n_row + j] = g[L.r + j];
-        for (int i = 0; i < k; i++) host[n_row + 64 + i] = g[i];
         void* dev = nullptr;
-        DS_CUDA(ctx, cudaMalloc(&dev, host.size() * sizeof(float)));
-        DS_CUDA(ctx, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        DS_CUDA(ctx, cudaMalloc(&dev, g.size() * sizeof(float)));
+        DS_CUDA(ctx, cudaMemcpyAsync(dev, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         it = ctx->tables.emplace(key, dev).first;
     }
-    const float* tab = (const float*)it->second;
-    L.g_row = tab; L.g_col = tab + n_row;
+    L.g_full = (const float*)it->second;
 
     const AdaptGridInfo G{n * ((max_w + TW - 1) / TW), max_w, max_h, n, max(64, 4 * L.r)};
-    const size_t smem = sizeof(float) * ((size_t)n_row + 64 + (size_t)BR * L.spf + (size_t)L.ring_rows * RPF);
+    const size_t smem = sizeof(float) * ((size_t)BR * L.spf + (size_t)ring_rows * RPF);
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(AdaptJob) * n, &dev));
     const AdaptJob* jd = (const AdaptJob*)dev;
@@ -356,6 +403,25 @@ int k_mask_blend_jobs(docscan_ctx* ctx, int dilate_iters, int write_mask_only, c
     double px = 0;
     for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
     ProfScope prof(ctx, "mask_blend", (write_mask_only ? 3.0 : 4.0) * px);
+    bool aligned16 = dilate_iters <= 2;
+    for (int i = 0; i < n && aligned16; i++) {
+        const BlendJob& j = jobs_host[i];
+        uintptr_t bits = reinterpret_cast<uintptr_t>(j.ink_sub) | reinterpret_cast<uintptr_t>(j.bh) | reinterpret_cast<uintptr_t>(j.dst) |
+                         (uintptr_t)j.pitch_sub | (uintptr_t)j.pitch_bh | (uintptr_t)j.pitch_dst;
+        if (!write_mask_only) bits |= reinterpret_cast<uintptr_t>(j.base) | (uintptr_t)j.pitch_base;
+        // whole 16-byte chunks are read up to the end of the last chunk: the row pitch must cover them
+        const int need = ((j.w + 15) >> 4) << 4;
+        aligned16 = (bits & 15) == 0 && j.pitch_sub >= need && j.pitch_bh >= need && (write_mask_only || j.pitch_base >= need);
+    }
+    if (aligned16) {
+        const int chunks = (max_w + 15) >> 4, row_groups = (max_h + BLEND_ROWS - 1) / BLEND_ROWS;
+        dim3 g16((chunks * row_groups + 127) / 128, n);
+        if (dilate_iters == 0) mask_blend16_kernel<0><<<g16, 128, 0, ctx->stream>>>((const BlendJob*)dev, write_mask_only, chunks, row_groups);
+        else if (dilate_iters == 1) mask_blend16_kernel<1><<<g16, 128, 0, ctx->stream>>>((const BlendJob*)dev, write_mask_only, chunks, row_groups);
+        else mask_blend16_kernel<2><<<g16, 128, 0, ctx->stream>>>((const BlendJob*)dev, write_mask_only, chunks, row_groups);
+        DS_CHECK_LAUNCH(ctx);
+        return DOCSCAN_OK;
+    }
     mask_blend_kernel<<<grid, 128, 0, ctx->stream>>>((const BlendJob*)dev, dilate_iters, write_mask_only);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __rest
     const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
     const bool dst_al = ((reinterpret_cast<uintptr_t>(J.dst) | (uintptr_t)J.dst_pitch) & 3) == 0;
     const int n_vb = (y_end - y_begin + BRm - 1) / BRm;
+    uint32_t zero_count = 0;
     for (int hb = 0; hb < n_vb + D; hb++) {
         {   // ---- stage 32 source rows: virtual row v <-> source row y_begin - AY + v (neutral outside the image)
             const int srow = tid >> 2;
@@ -297,9 +298,16 @@ __global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __rest
                     res = __vsubus4(res, rw);
                 }
                 if (J.hist) {
+                    // a black-hat page is mostly zeros: count those in a register instead of 32 lanes hammering bin 0
+                    if (res == 0) zero_count += nvalid;
+                    else {
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
-                        if (b < nvalid) atomicAdd(&s_hist[(tid >> 5) * 256 + ((res >> (8 * b)) & 255u)], 1u);
+                        for (int b = 0; b < 4; b++)
+                            if (b < nvalid) {
+                                const uint32_t v = (res >> (8 * b)) & 255u;
+                                if (v) atomicAdd(&s_hist[(tid >> 5) * 256 + v], 1u); else zero_count++;
+                            }
+                    }
                 }
                 uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x;
                 if (dst_al && nvalid == 4) *reinterpret_cast<uint32_t*>(dp) = res;
@@ -308,6 +316,8 @@ __global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __rest
         }
     }
     if (J.hist) {
+        for (int o = 16; o; o >>= 1) zero_count += __shfl_xor_sync(0xffffffffu, zero_count, o);
+        if ((tid & 31) == 0 && zero_count) atomicAdd(&s_hist[(tid >> 5) * 256], zero_count);
         __syncthreads();
         for (int i = tid; i < 256; i += NTm) {
             const uint32_t sum = s_hist[i] + s_hist[256 + i] + s_hist[512 + i] + s_hist[768 + i];
