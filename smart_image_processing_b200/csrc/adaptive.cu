@@ -21,7 +21,6 @@ constexpr int GMAX = 33;      // half-kernel table size (k <= 65)
 struct AdaptLaunch {
     int k, r, c_param, seg_rows, spf, tail_compat;
     float gh[GMAX];           // gh[j] = g[r + j] for j <= r, 0 beyond (zero taps leave an fp32 accumulator unchanged)
-    const float* g_full;      // the k taps in order (device): only the rare cv2-tail columns read it
 };
 
 // rare path of the staging load (strip edges, unaligned caller buffers): kept out of line
@@ -29,15 +28,6 @@ __device__ __noinline__ uint32_t fetch_word_clamped(const uint8_t* rowp, int gx,
     uint32_t word = 0;
     for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[ds_clamp(gx + b, 0, w - 1)] << (8 * b);
     return word;
-}
-
-// cv2's row filter leaves the last w % 4 columns (w % 8 >= 4: the last w % 8 - 4) to scalar code: mul+add per tap,
-// except that the (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  `in` points at tap 0.
-__device__ __noinline__ float row_tail_value(const float* in, const float* g, int k) {
-    const int first_fused = k - ((k - 1) & 3);
-    float a = __fmul_rn(g[0], in[0]);
-    for (int i = 1; i < k; i++) a = i >= first_fused ? __fmaf_rn(in[i], g[i], a) : __fadd_rn(a, __fmul_rn(g[i], in[i]));
-    return a;
 }
 
 template <int RMAX>
@@ -115,13 +105,31 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
             if (row_identity) {
 #pragma unroll
                 for (int o = 0; o < 16; o++) acc[o] = sp[RMAX + o];
-            } else if (xt_row < J.w && x0 + c0 + 15 >= xt_row) {
-                for (int o = 0; o < 16; o++) {                        // at most 3 columns per row
-                    const int x = x0 + c0 + o;
-                    if (x < xt_row || x >= J.w) continue;
-                    const float v = row_tail_value(sp + o + RMAX - L.r, L.g_full, L.k);
+            } else if (xt_row < J.w && x0 + c0 + 15 >= xt_row && x0 + c0 < J.w) {
+                // cv2's row filter leaves the last w % 4 columns (w % 8 >= 4: the last w % 8 - 4) to scalar code: mul+add per
+                // tap, except that the (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  At most 3 columns per
+                // row; their chains run side by side so the thread that owns them does not hold up its CTA.
+                const int o_first = max(0, xt_row - (x0 + c0));
+                const int nt = min(16, J.w - (x0 + c0)) - o_first;                  // 1..3 columns
+                const float* in = sp + o_first + RMAX - L.r;                        // tap 0 of the first tail column
+                const int first_fused = L.k - ((L.k - 1) & 3);
+                const float g0 = L.gh[L.r];
+                float a0 = __fmul_rn(g0, in[0]), a1 = __fmul_rn(g0, in[1]), a2 = __fmul_rn(g0, in[2]);
+                int i = 1;
+#pragma unroll 4
+                for (; i < first_fused; i++) {
+                    const float gi = L.gh[abs(i - L.r)];
+                    a0 = __fadd_rn(a0, __fmul_rn(gi, in[i])); a1 = __fadd_rn(a1, __fmul_rn(gi, in[i + 1])); a2 = __fadd_rn(a2, __fmul_rn(gi, in[i + 2]));
+                }
+                for (; i < L.k; i++) {
+                    const float gi = L.gh[abs(i - L.r)];
+                    a0 = __fmaf_rn(in[i], gi, a0); a1 = __fmaf_rn(in[i + 1], gi, a1); a2 = __fmaf_rn(in[i + 2], gi, a2);
+                }
 #pragma unroll
-                    for (int q = 0; q < 16; q++) if (q == o) acc[q] = v;
+                for (int q = 0; q < 16; q++) {
+                    if (q == o_first) acc[q] = a0;
+                    if (q == o_first + 1 && nt > 1) acc[q] = a1;
+                    if (q == o_first + 2 && nt > 2) acc[q] = a2;
                 }
             }
             float4* dst = reinterpret_cast<float4*>(s_ring + ((hb * BR + hr) % RR) * RPF + c0);
@@ -357,20 +365,9 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     L.spf = TW + 2 * rmax + delta + 4;
     L.spf += (33 - (L.spf & 31)) & 31;                 // pitch == 1 (mod 32): lanes of a warp read different banks
     const int ring_rows = ((2 * rmax + BR - 1) / BR + 1) * BR;
-    // taps in order (device, cached per k) for the cv2-tail columns; the half kernel rides in the launch parameters
-    const uint64_t key = ((uint64_t)7 << 32) | (uint32_t)k;
     std::vector<float> g(k);
     docscan_gaussian_kernel_f32(k, g.data());
-    for (int j = 0; j <= L.r; j++) L.gh[j] = g[L.r + j];
-    auto it = ctx->tables.find(key);
-    if (it == ctx->tables.end()) {
-        void* dev = nullptr;
-        DS_CUDA(ctx, cudaMalloc(&dev, g.size() * sizeof(float)));
-        DS_CUDA(ctx, cudaMemcpyAsync(dev, g.data(), g.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        it = ctx->tables.emplace(key, dev).first;
-    }
-    L.g_full = (const float*)it->second;
+    for (int j = 0; j <= L.r; j++) L.gh[j] = g[L.r + j];     // the half kernel rides in the launch parameters
 
     const AdaptGridInfo G{n * ((max_w + TW - 1) / TW), max_w, max_h, n, max(64, 4 * L.r)};
     const size_t smem = sizeof(float) * ((size_t)BR * L.spf + (size_t)ring_rows * RPF);

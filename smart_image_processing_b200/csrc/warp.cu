@@ -17,9 +17,10 @@ __device__ __forceinline__ uint8_t gray15(int b, int g, int r) {
     return (uint8_t)((3735 * b + 19235 * g + 9798 * r + 16384) >> 15);
 }
 
+// saturate_cast<int>(max(INT_MIN, min(INT_MAX, v))): the conversion instruction saturates on its own; std::min/max
+// as OpenCV writes them turn a NaN into INT_MAX
 __device__ __forceinline__ int round_clamped(double v) {
-    v = fmax((double)INT_MIN, fmin((double)INT_MAX, v));
-    return __double2int_rn(v);
+    return v != v ? INT_MAX : __double2int_rn(v);
 }
 
 template <int CH>
@@ -58,7 +59,9 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
         const double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W);
         const double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W);
         const int X = round_clamped(fX), Y = round_clamped(fY);
-        const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+        // OpenCV keeps sx, sy as saturated shorts; it also requires images below 32767 px, so a coordinate beyond that range is
+        // outside the image with or without the saturation
+        const int sx = X >> 5, sy = Y >> 5;
         const int ax = X & 31, ay = Y & 31;
         const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
         const int cy0 = ds_clamp(sy, 0, sh - 1), cy1 = ds_clamp(sy + 1, 0, sh - 1);
@@ -157,8 +160,11 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(WarpPJob) * n, &dev));
     const int ch = jobs_host[0].ch;
-    for (int i = 1; i < n; i++)
+    for (int i = 0; i < n; i++) {
         if (jobs_host[i].ch != ch) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "mixed channel counts in one warp batch");
+        if (jobs_host[i].sw >= 32767 || jobs_host[i].sh >= 32767)      // cv::remap's own limit (coordinates are shorts)
+            return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "warp source larger than 32766 px");
+    }
     dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
     // algorithmic bytes: source pixels under the quad, at most 4 taps per output pixel, read once;
     // destination (and the fused gray plane) written once
