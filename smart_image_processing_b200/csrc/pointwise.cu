@@ -77,6 +77,40 @@ __global__ void __launch_bounds__(128) pw_kernel(const PwJob* __restrict__ jobs)
     }
 }
 
+// LUT for the library's own planes (16-byte aligned rows): the 256-entry table sits in shared memory, a thread owns a
+// 16-pixel column chunk and walks LUT_ROWS rows, every global access is 128 bits wide.
+constexpr int LUT_ROWS = 8;
+__global__ void __launch_bounds__(256) lut16_kernel(const PwJob* __restrict__ jobs, int chunks, int row_groups) {
+    __shared__ uint32_t s_lut_w[64];
+    const PwJob J = jobs[blockIdx.y];
+    if (threadIdx.x < 64) s_lut_w[threadIdx.x] = ds_ldg32(J.lut + 4 * threadIdx.x);
+    __syncthreads();
+    const uint8_t* s_lut = reinterpret_cast<const uint8_t*>(s_lut_w);
+    const int id = blockIdx.x * 256 + threadIdx.x;
+    const int rg = id / chunks, xc = id - rg * chunks;
+    const int x = xc * 16, y0 = rg * LUT_ROWS;
+    if (rg >= row_groups || x >= J.w || y0 >= J.h) return;
+    const int rows = min(LUT_ROWS, J.h - y0);
+    const bool full = x + 16 <= J.w;
+    uint4 v[LUT_ROWS];
+#pragma unroll
+    for (int i = 0; i < LUT_ROWS; i++)
+        if (i < rows) v[i] = __ldg(reinterpret_cast<const uint4*>(J.a + (size_t)(y0 + i) * J.pa + x));
+#pragma unroll
+    for (int i = 0; i < LUT_ROWS; i++) {
+        if (i >= rows) break;
+        uint32_t in[4] = {v[i].x, v[i].y, v[i].z, v[i].w}, out[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t b0 = s_lut[in[j] & 255u], b1 = s_lut[(in[j] >> 8) & 255u], b2 = s_lut[(in[j] >> 16) & 255u], b3 = s_lut[in[j] >> 24];
+            out[j] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        }
+        uint8_t* dp = J.dst + (size_t)(y0 + i) * J.pd + x;
+        if (full) *reinterpret_cast<uint4*>(dp) = make_uint4(out[0], out[1], out[2], out[3]);
+        else for (int b = 0; b < J.w - x; b++) dp[b] = (uint8_t)(out[b >> 2] >> (8 * (b & 3)));
+    }
+}
+
 static int pw_launch(docscan_ctx* ctx, int op, const PwJob* jobs_host, int n, int max_w, int max_h) {
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(PwJob) * n, &dev));
@@ -129,7 +163,23 @@ int k_apply_lut_jobs(docscan_ctx* ctx, const DImg* src, const DImg* dst, const u
         j.lut = luts[i];
         mw = max(mw, j.w); mh = max(mh, j.h);
     }
-    return pw_launch(ctx, PW_LUT, jobs.data(), n, mw, mh);
+    bool aligned16 = true;
+    for (int i = 0; i < n && aligned16; i++) {
+        const PwJob& j = jobs[i];
+        const int need = ((j.w + 15) >> 4) << 4;      // whole chunks are read: the source pitch must cover them
+        aligned16 = ((reinterpret_cast<uintptr_t>(j.a) | reinterpret_cast<uintptr_t>(j.dst) | (uintptr_t)j.pa | (uintptr_t)j.pd) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(j.lut) & 3) == 0 && j.pa >= need;
+    }
+    if (!aligned16) return pw_launch(ctx, PW_LUT, jobs.data(), n, mw, mh);
+    void* dev = nullptr;
+    DS_TRY(ds_upload(ctx, jobs.data(), sizeof(PwJob) * n, &dev));
+    const int chunks = (mw + 15) >> 4, row_groups = (mh + LUT_ROWS - 1) / LUT_ROWS;
+    double px = 0;
+    for (int i = 0; i < n; i++) px += (double)jobs[i].w * jobs[i].h;
+    ProfScope prof(ctx, "pw_lut", 2.0 * px);
+    lut16_kernel<<<dim3((chunks * row_groups + 255) / 256, n), 256, 0, ctx->stream>>>((const PwJob*)dev, chunks, row_groups);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
 }
 
 // ---- min/max + 256-bin histogram ---------------------------------------------------------------------

@@ -111,6 +111,100 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
     }
 }
 
+// 3-channel variant used by the page pipeline.  Same arithmetic as warp_perspective_kernel<3>, organised in three phases
+// so that all 16 loads of a thread's 4 pixels are in flight together (the gathers are latency-bound otherwise):
+// coordinates -> loads -> filter + stores.  Interior pixels fetch the 6 bytes of a row's two taps through a 16-byte
+// window (two 64-bit loads at the enclosing 8-byte boundary); pixels whose taps touch the left/right image border take the
+// per-byte path of the generic kernel afterwards.  Requires sw >= 9.
+__global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* __restrict__ jobs) {
+    const WarpPJob& J = jobs[blockIdx.z];
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int xt = blockIdx.x * 128;                 // a warp covers 128 consecutive destination pixels of one row
+    if (y >= J.dh || xt >= J.dw) return;
+    const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
+    const uint8_t* __restrict__ src = J.src;
+    int Xs[4], Ys[4];
+    {
+        const double m0 = J.m[0], m1 = J.m[1], m2 = J.m[2], m3 = J.m[3], m4 = J.m[4], m5 = J.m[5], m6 = J.m[6], m7 = J.m[7], m8 = J.m[8];
+        const double dy = (double)y;
+        int xb = -1;
+        double X0 = 0, Y0 = 0, W0 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int x = xt + 32 * i + threadIdx.x;
+            // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows))
+            const int xbi = J.block_w == 64 ? (x & ~63) : x - x % J.block_w;
+            if (xbi != xb) {
+                xb = xbi;
+                const double dxb = (double)xb;
+                X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
+                Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m3, dxb), __dmul_rn(m4, dy)), m5);
+                W0 = __dadd_rn(__dadd_rn(__dmul_rn(m6, dxb), __dmul_rn(m7, dy)), m8);
+            }
+            const double x1 = (double)(x - xb);
+            double W = __dadd_rn(W0, __dmul_rn(m6, x1));
+            W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+            Xs[i] = round_clamped(__dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W));
+            Ys[i] = round_clamped(__dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W));
+        }
+    }
+    uint2 lo[4][2], hi[4][2];
+    uint32_t sft[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int sx = ds_clamp(Xs[i] >> 5, 3, sw - 6), sy = Ys[i] >> 5;
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const uintptr_t A = reinterpret_cast<uintptr_t>(src + (size_t)ds_clamp(sy + rr, 0, sh - 1) * sp + 3 * sx);
+            const uint2* base = reinterpret_cast<const uint2*>(A & ~(uintptr_t)7);
+            lo[i][rr] = __ldg(base); hi[i][rr] = __ldg(base + 1);
+            sft[i][rr] = (uint32_t)(A & 7);
+        }
+    }
+    uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
+    uint8_t* grow = J.gray ? J.gray + (size_t)y * J.gray_pitch : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int x = xt + 32 * i + threadIdx.x;
+        if (x >= J.dw) break;
+        const int sx = Xs[i] >> 5, sy = Ys[i] >> 5, ax = Xs[i] & 31, ay = Ys[i] & 31;
+        const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+        int acc[3];
+        if (sx >= 3 && sx <= sw - 6) {
+            // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) h0 + ay h1] exactly, so (.. + 2^14) >> 15 == (v + 512) >> 10
+            const uint32_t wx = (uint32_t)(32 - ax) | ((uint32_t)ax << 8);
+            const int wy0 = y0in ? 32 - ay : 0, wy1 = y1in ? ay : 0;         // rows outside the image: BORDER_CONSTANT 0
+            int h[2][3];
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const bool up = sft[i][rr] >= 4;
+                const uint32_t wa = up ? lo[i][rr].y : lo[i][rr].x, wb = up ? hi[i][rr].x : lo[i][rr].y, wc = up ? hi[i][rr].y : hi[i][rr].x;
+                const uint32_t b0 = __funnelshift_r(wa, wb, 8 * sft[i][rr]), b1 = __funnelshift_r(wb, wc, 8 * sft[i][rr]);   // shift mod 32
+                h[rr][0] = __dp4a(__byte_perm(b0, b1, 0x0030), wx, 0u);      // (B0, B1)
+                h[rr][1] = __dp4a(__byte_perm(b0, b1, 0x0041), wx, 0u);      // (G0, G1)
+                h[rr][2] = __dp4a(__byte_perm(b0, b1, 0x0052), wx, 0u);      // (R0, R1)
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] = (wy0 * h[0][c] + wy1 * h[1][c] + 512) >> 10;
+        } else {
+            const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+            const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+            const int cx0 = ds_clamp(sx, 0, sw - 1), cx1 = ds_clamp(sx + 1, 0, sw - 1);
+            const int v00 = (x0in && y0in) ? w00 : 0, v01 = (x1in && y0in) ? w01 : 0;
+            const int v10 = (x0in && y1in) ? w10 : 0, v11 = (x1in && y1in) ? w11 : 0;
+            const uint8_t* r0 = src + (size_t)ds_clamp(sy, 0, sh - 1) * sp;
+            const uint8_t* r1 = src + (size_t)ds_clamp(sy + 1, 0, sh - 1) * sp;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                acc[c] = (16384 + v00 * __ldg(r0 + cx0 * 3 + c) + v01 * __ldg(r0 + cx1 * 3 + c) +
+                          v10 * __ldg(r1 + cx0 * 3 + c) + v11 * __ldg(r1 + cx1 * 3 + c)) >> 15;
+        }
+        uint8_t* dp = drow + (size_t)x * 3;
+        dp[0] = (uint8_t)acc[0]; dp[1] = (uint8_t)acc[1]; dp[2] = (uint8_t)acc[2];      // <= 255 by construction
+        if (grow) grow[x] = gray15(acc[0], acc[1], acc[2]);
+    }
+}
+
 // cv::warpAffine precomputes adelta[x] = saturate_cast<int>(M[0]*x*1024), bdelta[x] = saturate_cast<int>(M[3]*x*1024)
 // once per call; so do we (one tiny kernel), which keeps fp64 out of the per-pixel loop.
 __global__ void affine_delta_kernel(const WarpAJob* __restrict__ jobs) {
@@ -186,7 +280,10 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
         bytes += j.ch * (src_px + np) + (j.gray ? np : 0.0);
     }
     ProfScope prof(ctx, ch == 3 ? "warp_perspective_c3" : "warp_perspective_c1", bytes);
-    if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    bool wide = ch == 3;
+    for (int i = 0; i < n; i++) wide = wide && jobs_host[i].sw >= 9;
+    if (wide) warp_perspective3_kernel<<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    else if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else warp_perspective_kernel<1><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
