@@ -158,7 +158,10 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
             const uint4 e = *reinterpret_cast<const uint4*>(s_qE), o4 = *reinterpret_cast<const uint4*>(s_qO);
             E[4] = e.x; E[5] = e.y; E[6] = e.z; E[7] = e.w; O[4] = o4.x; O[5] = o4.y; O[6] = o4.z; O[7] = o4.w;
         }
-        int pslot = (vbase >> 1) % (L.ring_rows >> 1);
+        // a block of 4 row pairs starts at a multiple of 4 pairs and the ring holds a multiple of 8: no wrap inside a block
+        const int ring_pairs = L.ring_rows >> 1;
+        const uint32_t* rp = s_ring + ((vbase >> 1) % ring_pairs) * RP2 + 2 * cp;
+        const uint32_t* const rend = s_ring + ring_pairs * RP2 + 2 * cp;
         for (int b = 0; b < T.nb; b++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) { E[i] = E[i + 4]; O[i] = O[i + 4]; }
@@ -168,15 +171,16 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const uint2 w = *reinterpret_cast<const uint2*>(s_ring + pslot * RP2 + 2 * cp);   // two columns of one row pair
+                const uint2 w = *reinterpret_cast<const uint2*>(rp + u * RP2);   // two columns of one row pair
 #pragma unroll
                 for (int o = 0; o < 8; o++) {
                     const uint32_t c = (o & 1) ? O[u - (o + 1) / 2 + 4] : E[u - o / 2 + 4];
                     a0[o] = __dp2a_lo(w.x, c, a0[o]);
                     a1[o] = __dp2a_lo(w.y, c, a1[o]);
                 }
-                if (++pslot == (L.ring_rows >> 1)) pslot = 0;
             }
+            rp += 4 * RP2;
+            if (rp >= rend) rp -= ring_pairs * RP2;
         }
         // ---- epilogue
         const int x = x0 + 2 * cp;
