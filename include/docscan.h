@@ -69,6 +69,9 @@ DOCSCAN_API int docscan_sync(docscan_ctx* ctx);
 DOCSCAN_API const char* docscan_last_error(docscan_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 DOCSCAN_API int64_t docscan_launch_count(docscan_ctx* ctx);
+/* bytes this context has copied between caller HOST images and the device so far (bench.py's h2d/d2h_bytes_per_step).
+ * docscan_process_pages uploads only the part of each HOST photo that lies under its quad. */
+DOCSCAN_API int docscan_transfer_bytes(docscan_ctx* ctx, int64_t* h2d, int64_t* d2h);
 /* per-kernel timing for bench.py: when enabled every kernel launch is bracketed by CUDA events on the
  * context's stream.  docscan_profile_dump syncs, writes one line per kernel name
  * ("name launches total_ms algorithmic_bytes\n") into buf, clears the records and returns the length. */

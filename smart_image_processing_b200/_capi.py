@@ -49,6 +49,7 @@ _SIGS = {
     "docscan_sync": (C.c_int, [C.c_void_p]),
     "docscan_last_error": (C.c_char_p, [C.c_void_p]),
     "docscan_launch_count": (C.c_int64, [C.c_void_p]),
+    "docscan_transfer_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "docscan_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "docscan_profile_dump": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "docscan_host_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -158,6 +159,13 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self._lib.docscan_launch_count(self._h))
+
+    @property
+    def transfer_bytes(self):
+        """(host->device, device->host) bytes copied for caller HOST images so far."""
+        a, b = C.c_int64(), C.c_int64()
+        self.call("docscan_transfer_bytes", C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     def profile(self, on: bool):
         self.call("docscan_profile_enable", int(on))

@@ -369,6 +369,7 @@ extern "C" int docscan_warp_perspective(docscan_ctx* ctx, const docscan_image* s
     j.dst = d.p; j.dst_pitch = d.pitch; j.dw = d.w; j.dh = d.h;
     j.gray = gray_out ? g.p : nullptr; j.gray_pitch = g.pitch;
     j.block_w = 1024 / std::min(16, d.h);
+    j.rx0 = 0; j.ry0 = 0; j.rx1 = s.w; j.ry1 = s.h;
     hm_invert3x3(m_fwd, j.m);
     DS_TRY(k_warp_perspective_jobs(ctx, &j, 1, d.w, d.h));
     DS_TRY(ds_stage_out_end(ctx, dst, d));
@@ -446,8 +447,42 @@ size_t page_staging(const docscan_page& pg) {
 }
 
 // The chain for n pages whose images are already device views (src read-only; warped, binary written).
+// Resident region of a page photo: the host pipeline uploads only the rows / columns the warp can touch.
+struct SrcRegion { int x0, y0, x1, y1; };
+
+// Source pixels the perspective warp of `pg` can read, as a box in the photo (with a margin for the rounding to
+// 1/32 px, the second bilinear tap and the 16-byte load window of the kernel).  The destination rectangle is convex and
+// a projective map whose denominator keeps one sign over it maps it onto the convex quadrilateral spanned by the images
+// of its corners; anything else (denominator changing sign, non-finite corners) keeps the whole photo.
+SrcRegion warp_footprint(const docscan_page& pg) {
+    const int sw = pg.src.width, sh = pg.src.height, dw = pg.warped.width, dh = pg.warped.height;
+    const SrcRegion whole{0, 0, sw, sh};
+    const float dstq[8] = {0, 0, (float)(dw - 1), 0, (float)(dw - 1), (float)(dh - 1), 0, (float)(dh - 1)};
+    double m[9], inv[9];
+    if (docscan_get_perspective_transform(pg.quad, dstq, m) != DOCSCAN_OK) return whole;
+    hm_invert3x3(m, inv);
+    double lo_x = 1e300, hi_x = -1e300, lo_y = 1e300, hi_y = -1e300, w_min = 1e300, w_max = -1e300;
+    for (int c = 0; c < 4; c++) {
+        const double x = dstq[2 * c], y = dstq[2 * c + 1];
+        const double w = inv[6] * x + inv[7] * y + inv[8];
+        const double X = (inv[0] * x + inv[1] * y + inv[2]) / w, Y = (inv[3] * x + inv[4] * y + inv[5]) / w;
+        if (!std::isfinite(w) || !std::isfinite(X) || !std::isfinite(Y)) return whole;
+        w_min = std::min(w_min, w); w_max = std::max(w_max, w);
+        lo_x = std::min(lo_x, X); hi_x = std::max(hi_x, X); lo_y = std::min(lo_y, Y); hi_y = std::max(hi_y, Y);
+    }
+    if (!(w_min > 0.0 || w_max < 0.0)) return whole;                                   // denominator changes sign
+    if (std::min(std::fabs(w_min), std::fabs(w_max)) < 1e-9 * std::max(std::fabs(w_min), std::fabs(w_max))) return whole;
+    if (hi_x - lo_x > 1e6 || hi_y - lo_y > 1e6) return whole;
+    SrcRegion r;
+    r.x0 = std::max(0, (int)std::floor(lo_x) - 8); r.x1 = std::min(sw, (int)std::ceil(hi_x) + 10);
+    r.y0 = std::max(0, (int)std::floor(lo_y) - 2); r.y1 = std::min(sh, (int)std::ceil(hi_y) + 4);
+    if (r.x1 - r.x0 < 16 || r.y1 - r.y0 < 2) return whole;
+    return r;
+}
+
+// `regions` (may be null = whole photos): src[i] then views only that part of page i's photo.
 int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params& P, const std::vector<DImg>& src,
-              const std::vector<DImg>& warped, const std::vector<DImg>& binary) {
+              const std::vector<DImg>& warped, const std::vector<DImg>& binary, const SrcRegion* regions = nullptr) {
     ArenaScope scope(ctx);
     std::vector<DImg> gray;
     std::vector<WarpPJob> wj(n);
@@ -457,7 +492,9 @@ int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params
     for (int i = 0; i < n; i++) {
         WarpPJob& j = wj[i];
         j = WarpPJob{};
-        j.src = src[i].p; j.src_pitch = src[i].pitch; j.sw = src[i].w; j.sh = src[i].h; j.ch = 3;
+        j.src = src[i].p; j.src_pitch = src[i].pitch; j.sw = pages[i].src.width; j.sh = pages[i].src.height; j.ch = 3;
+        if (regions) { j.rx0 = regions[i].x0; j.ry0 = regions[i].y0; j.rx1 = regions[i].x1; j.ry1 = regions[i].y1; }
+        else { j.rx0 = 0; j.ry0 = 0; j.rx1 = j.sw; j.ry1 = j.sh; }
         j.dst = warped[i].p; j.dst_pitch = warped[i].pitch; j.dw = warped[i].w; j.dh = warped[i].h;
         j.gray = gray[i].p; j.gray_pitch = gray[i].pitch;
         j.block_w = 1024 / std::min(16, warped[i].h);
@@ -549,6 +586,7 @@ DImg view_of(const docscan_image& im) {
 
 int copy_2d(docscan_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, int rows,
             cudaMemcpyKind kind, cudaStream_t st) {
+    (kind == cudaMemcpyHostToDevice ? ctx->h2d_bytes : ctx->d2h_bytes) += (int64_t)row_bytes * rows;
     if (dpitch == row_bytes && spitch == row_bytes)
         DS_CUDA(ctx, cudaMemcpyAsync(dst, src, row_bytes * (size_t)rows, kind, st));
     else
@@ -623,8 +661,14 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
 
     // ---- host buffers: three-stage pipeline over groups (H2D | kernels | D2H) on three streams with two
     // staging sets, so the PCIe copies of neighbouring groups overlap the compute of the current one.
+    // only the part of a photo under its quad is uploaded (the warp reads nothing else)
+    std::vector<SrcRegion> regions(n);
     size_t max_stage = 0;
-    for (int i = 0; i < n; i++) max_stage = std::max(max_stage, page_staging(pages[i]) + 1024);
+    for (int i = 0; i < n; i++) {
+        regions[i] = is_host(&pages[i].src) ? warp_footprint(pages[i]) : SrcRegion{0, 0, pages[i].src.width, pages[i].src.height};
+        const size_t src_stage = is_host(&pages[i].src) ? ds_image_bytes(regions[i].x1 - regions[i].x0, regions[i].y1 - regions[i].y0, 3) : 0;
+        max_stage = std::max(max_stage, src_stage + host_bytes(&pages[i].warped) + host_bytes(&pages[i].binary) + 1024);
+    }
     DS_TRY(begin_call(ctx, (max_page + 2 * max_stage) * group));
     ArenaScope scope(ctx);
     if (!ctx->copy_in) {
@@ -666,8 +710,12 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         for (int j = 0; j < m; j++) {
             docscan_page& pg = pages[i + j];
             if (is_host(&pg.src)) {
-                src[j] = carve(pg.src, true);
-                DS_TRY(copy_2d(ctx, src[j].p, src[j].pitch, pg.src.data, pg.src.pitch, (size_t)pg.src.width * 3, pg.src.height,
+                const SrcRegion& rg = regions[i + j];
+                docscan_image part = pg.src;
+                part.width = rg.x1 - rg.x0; part.height = rg.y1 - rg.y0;
+                part.data = (uint8_t*)pg.src.data + (size_t)rg.y0 * pg.src.pitch + (size_t)rg.x0 * 3;
+                src[j] = carve(part, part.width == pg.src.width);
+                DS_TRY(copy_2d(ctx, src[j].p, src[j].pitch, part.data, part.pitch, (size_t)part.width * 3, part.height,
                                cudaMemcpyHostToDevice, ctx->copy_in));
             } else src[j] = view_of(pg.src);
             warped[j] = is_host(&pg.warped) ? carve(pg.warped, false) : view_of(pg.warped);
@@ -676,7 +724,7 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         DS_CUDA(ctx, cudaEventRecord(in_done[sset], ctx->copy_in));
         DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, in_done[sset], 0));
         if (g >= 2) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, out_done[sset], 0));       // set's outputs drained
-        DS_TRY(run_group(ctx, m, pages + i, *params, src, warped, binary));
+        DS_TRY(run_group(ctx, m, pages + i, *params, src, warped, binary, regions.data() + i));
         DS_CUDA(ctx, cudaEventRecord(comp_done[sset], ctx->stream));
         DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, comp_done[sset], 0));
         for (int j = 0; j < m; j++) {

@@ -32,6 +32,7 @@ struct docscan_ctx {
     bool own_stream = false;
     std::string err;
     int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;     // bytes this context has moved between host and device buffers
     int sm_count = DS_SM_COUNT_FALLBACK;
     size_t l2_bytes = 0;
     // bump arena for per-call device scratch
@@ -193,6 +194,9 @@ struct WarpPJob {
     const uint8_t* src; uint8_t* dst; uint8_t* gray;
     int src_pitch, dst_pitch, gray_pitch, sw, sh, dw, dh, ch;
     int block_w;          // 1024 / min(16, dh): OpenCV's coordinate block width
+    // Resident part of the source image [rx0, rx1) x [ry0, ry1): `src` points at pixel (rx0, ry0).  The whole image
+    // (0, 0, sw, sh) unless the host pipeline uploaded only the rows / columns under the quad (capi.cu).
+    int rx0, ry0, rx1, ry1;
     double m[9];          // inverse matrix (dst -> src)
 };
 int k_warp_perspective_jobs(docscan_ctx*, const WarpPJob* jobs_host, int n, int max_w, int max_h);

@@ -98,6 +98,12 @@ extern "C" int docscan_sync(docscan_ctx* ctx) {
 
 extern "C" const char* docscan_last_error(docscan_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 extern "C" int64_t docscan_launch_count(docscan_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int docscan_transfer_bytes(docscan_ctx* ctx, int64_t* h2d, int64_t* d2h) {
+    if (!ctx) return DOCSCAN_ERR_BAD_ARG;
+    if (h2d) *h2d = ctx->h2d_bytes;
+    if (d2h) *d2h = ctx->d2h_bytes;
+    return DOCSCAN_OK;
+}
 
 extern "C" int docscan_profile_enable(docscan_ctx* ctx, int on) {
     if (!ctx) return DOCSCAN_ERR_BAD_ARG;
@@ -254,6 +260,7 @@ int ds_stage_in(docscan_ctx* ctx, const docscan_image* im, DImg* out) {
         return DOCSCAN_OK;
     }
     DS_TRY(ds_arena_image(ctx, im->width, im->height, im->channels, out));
+    ctx->h2d_bytes += (int64_t)im->width * im->channels * im->height;
     DS_CUDA(ctx, cudaMemcpy2DAsync(out->p, out->pitch, im->data, im->pitch, (size_t)im->width * im->channels,
                                    im->height, cudaMemcpyHostToDevice, ctx->stream));
     return DOCSCAN_OK;
@@ -269,6 +276,7 @@ int ds_stage_out_begin(docscan_ctx* ctx, const docscan_image* im, DImg* out) {
 
 int ds_stage_out_end(docscan_ctx* ctx, const docscan_image* im, const DImg& dev) {
     if (im->space == DOCSCAN_DEVICE) return DOCSCAN_OK;
+    ctx->d2h_bytes += (int64_t)im->width * im->channels * im->height;
     DS_CUDA(ctx, cudaMemcpy2DAsync(im->data, im->pitch, dev.p, dev.pitch, (size_t)im->width * im->channels,
                                    im->height, cudaMemcpyDeviceToHost, ctx->stream));
     return DOCSCAN_OK;

@@ -64,16 +64,16 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
         const int sx = X >> 5, sy = Y >> 5;
         const int ax = X & 31, ay = Y & 31;
         const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
-        const int cy0 = ds_clamp(sy, 0, sh - 1), cy1 = ds_clamp(sy + 1, 0, sh - 1);
-        const uint8_t* r0 = src + (size_t)cy0 * sp;
-        const uint8_t* r1 = src + (size_t)cy1 * sp;
+        const int cy0 = ds_clamp(sy, J.ry0, J.ry1 - 1) - J.ry0, cy1 = ds_clamp(sy + 1, J.ry0, J.ry1 - 1) - J.ry0;
+        const uint8_t* r0 = src + (size_t)cy0 * sp - (size_t)J.rx0 * CH;
+        const uint8_t* r1 = src + (size_t)cy1 * sp - (size_t)J.rx0 * CH;
         int acc[CH];
-        if (CH == 3 && sx >= 3 && sx <= sw - 6) {
+        if (CH == 3 && sx >= J.rx0 + 3 && sx <= J.rx1 - 6) {
             // Interior fast path.  The two taps of a source row are 6 consecutive bytes: fetch the 16-byte aligned-8 window
             // around them with two 64-bit loads (4 load instructions per pixel instead of 12 byte gathers: the kernel is
             // bound by L1 wavefronts), shift the 6 bytes down, and filter horizontally with dp4a on (p0, p1) x (32-ax, ax).
             // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) h0 + ay h1] exactly, so (.. + 2^14) >> 15 == (v + 512) >> 10.
-            // The window stays inside the row: 3*sx - 7 >= 2 and 3*sx + 15 <= 3*sw - 3.
+            // The window stays inside the resident row: 3*(sx-rx0) - 7 >= 2 and 3*(sx-rx0) + 15 <= 3*(rx1-rx0) - 3.
             const uint32_t wx = (uint32_t)(32 - ax) | ((uint32_t)ax << 8);
             const int wy0 = y0in ? 32 - ay : 0, wy1 = y1in ? ay : 0;         // rows outside the image: BORDER_CONSTANT 0
             int h[2][3];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
             // branch-free taps: out-of-image taps get weight 0 (BORDER_CONSTANT 0) and a clamped, always-valid address
             const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
             const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-            const int cx0 = ds_clamp(sx, 0, sw - 1), cx1 = ds_clamp(sx + 1, 0, sw - 1);
+            const int cx0 = ds_clamp(sx, J.rx0, J.rx1 - 1), cx1 = ds_clamp(sx + 1, J.rx0, J.rx1 - 1);
             const int v00 = (x0in && y0in) ? w00 : 0, v01 = (x1in && y0in) ? w01 : 0;
             const int v10 = (x0in && y1in) ? w10 : 0, v11 = (x1in && y1in) ? w11 : 0;
 #pragma unroll
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
 // so that all 16 loads of a thread's 4 pixels are in flight together (the gathers are latency-bound otherwise):
 // coordinates -> loads -> filter + stores.  Interior pixels fetch the 6 bytes of a row's two taps through a 16-byte
 // window (two 64-bit loads at the enclosing 8-byte boundary); pixels whose taps touch the left/right image border take the
-// per-byte path of the generic kernel afterwards.  Requires sw >= 9.
+// per-byte path of the generic kernel afterwards.  Requires a resident width of at least 9 px.
 __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* __restrict__ jobs) {
     const WarpPJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
@@ -152,10 +152,10 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
     uint32_t sft[4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int sx = ds_clamp(Xs[i] >> 5, 3, sw - 6), sy = Ys[i] >> 5;
+        const int sx = ds_clamp(Xs[i] >> 5, J.rx0 + 3, J.rx1 - 6) - J.rx0, sy = Ys[i] >> 5;
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
-            const uintptr_t A = reinterpret_cast<uintptr_t>(src + (size_t)ds_clamp(sy + rr, 0, sh - 1) * sp + 3 * sx);
+            const uintptr_t A = reinterpret_cast<uintptr_t>(src + (size_t)(ds_clamp(sy + rr, J.ry0, J.ry1 - 1) - J.ry0) * sp + 3 * sx);
             const uint2* base = reinterpret_cast<const uint2*>(A & ~(uintptr_t)7);
             lo[i][rr] = __ldg(base); hi[i][rr] = __ldg(base + 1);
             sft[i][rr] = (uint32_t)(A & 7);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
         const int sx = Xs[i] >> 5, sy = Ys[i] >> 5, ax = Xs[i] & 31, ay = Ys[i] & 31;
         const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
         int acc[3];
-        if (sx >= 3 && sx <= sw - 6) {
+        if (sx >= J.rx0 + 3 && sx <= J.rx1 - 6) {
             // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) h0 + ay h1] exactly, so (.. + 2^14) >> 15 == (v + 512) >> 10
             const uint32_t wx = (uint32_t)(32 - ax) | ((uint32_t)ax << 8);
             const int wy0 = y0in ? 32 - ay : 0, wy1 = y1in ? ay : 0;         // rows outside the image: BORDER_CONSTANT 0
@@ -189,11 +189,11 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
         } else {
             const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
             const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-            const int cx0 = ds_clamp(sx, 0, sw - 1), cx1 = ds_clamp(sx + 1, 0, sw - 1);
+            const int cx0 = ds_clamp(sx, J.rx0, J.rx1 - 1) - J.rx0, cx1 = ds_clamp(sx + 1, J.rx0, J.rx1 - 1) - J.rx0;
             const int v00 = (x0in && y0in) ? w00 : 0, v01 = (x1in && y0in) ? w01 : 0;
             const int v10 = (x0in && y1in) ? w10 : 0, v11 = (x1in && y1in) ? w11 : 0;
-            const uint8_t* r0 = src + (size_t)ds_clamp(sy, 0, sh - 1) * sp;
-            const uint8_t* r1 = src + (size_t)ds_clamp(sy + 1, 0, sh - 1) * sp;
+            const uint8_t* r0 = src + (size_t)(ds_clamp(sy, J.ry0, J.ry1 - 1) - J.ry0) * sp;
+            const uint8_t* r1 = src + (size_t)(ds_clamp(sy + 1, J.ry0, J.ry1 - 1) - J.ry0) * sp;
 #pragma unroll
             for (int c = 0; c < 3; c++)
                 acc[c] = (16384 + v00 * __ldg(r0 + cx0 * 3 + c) + v01 * __ldg(r0 + cx1 * 3 + c) +
@@ -256,8 +256,11 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     const int ch = jobs_host[0].ch;
     for (int i = 0; i < n; i++) {
         if (jobs_host[i].ch != ch) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "mixed channel counts in one warp batch");
-        if (jobs_host[i].sw >= 32767 || jobs_host[i].sh >= 32767)      // cv::remap's own limit (coordinates are shorts)
+        const WarpPJob& j = jobs_host[i];
+        if (j.sw >= 32767 || j.sh >= 32767)      // cv::remap's own limit (coordinates are shorts)
             return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "warp source larger than 32766 px");
+        if (j.rx0 < 0 || j.ry0 < 0 || j.rx1 > j.sw || j.ry1 > j.sh || j.rx1 <= j.rx0 || j.ry1 <= j.ry0)
+            return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "warp: bad resident region");
     }
     dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
     // algorithmic bytes: source pixels under the quad, at most 4 taps per output pixel, read once;
@@ -281,7 +284,7 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     }
     ProfScope prof(ctx, ch == 3 ? "warp_perspective_c3" : "warp_perspective_c1", bytes);
     bool wide = ch == 3;
-    for (int i = 0; i < n; i++) wide = wide && jobs_host[i].sw >= 9;
+    for (int i = 0; i < n; i++) wide = wide && jobs_host[i].rx1 - jobs_host[i].rx0 >= 9;
     if (wide) warp_perspective3_kernel<<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else warp_perspective_kernel<1><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);

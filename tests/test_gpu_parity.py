@@ -264,6 +264,36 @@ def test_batch_of_mixed_pages_matches_oracle():
             eq(b[i], ref["clean"], f"batch binary {i}")
 
 
+def test_footprint_upload_matches_whole_photo():
+    """docscan_process_pages uploads only the part of a HOST photo under its quad.  Quads inside, touching and partly
+    outside the photo, and one with a vanishing line through the page (whole photo is uploaded), against the oracle."""
+    from smart_image_processing_b200 import _capi
+    rng = np.random.default_rng(21)
+    H, W = 420, 520
+    base = page_like(rng, H, W)
+    img = np.stack([np.clip(base * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1)
+    quads = [
+        [[150, 100], [400, 110], [410, 330], [140, 320]],            # well inside: small footprint
+        [[0, 0], [W - 1, 0], [W - 1, H - 1], [0, H - 1]],             # the whole photo
+        [[-40, -30], [300, 10], [330, 300], [20, 380]],              # pokes out at the top-left
+        [[250, 200], [560, 180], [600, 470], [230, 440]],            # pokes out at the bottom-right
+        [[200, 150], [215, 150], [215, 170], [200, 170]],            # tiny quad (footprint narrower than a load window)
+        [[100, 100], [400, 120], [180, 300], [380, 330]],            # self-intersecting corner order
+    ]
+    ctx = _capi.default_context()
+    for qi, q in enumerate(quads):
+        quad = np.array(q, np.float32)
+        h0 = ctx.transfer_bytes[0]
+        w, b = DS.process_pages([img], [quad], [1.0], scale_long=300)
+        sent = ctx.transfer_bytes[0] - h0
+        ref = O.hot_path(img, quad, 1.0, scale_long=300)
+        eq(w[0], ref["warped"], f"footprint warped quad {qi}")
+        eq(b[0], ref["clean"], f"footprint binary quad {qi}")
+        assert sent <= img.nbytes
+        if qi == 0:
+            assert sent < 0.5 * img.nbytes, "only the rows/columns under the quad should travel"
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
