@@ -140,6 +140,15 @@ DOCSCAN_API int docscan_adaptive_threshold(docscan_ctx*, const docscan_image* sr
 /* cv2.warpAffine(gray, M, (w,h), INTER_LINEAR, BORDER_REPLICATE) u8c1    DocScanner.py:235 */
 DOCSCAN_API int docscan_warp_affine(docscan_ctx*, const docscan_image* src, const double m_fwd[6], docscan_image* dst);
 
+/* cv2.resize(img, (dst.width, dst.height), interpolation=INTER_AREA | INTER_CUBIC), u8c1 / u8c3: resize_long_side,
+ * DocScanner.py:27-36 (the whole-photo fallback taken at :313).  INTER_AREA is implemented for shrinking (bit-exact
+ * with cv2); INTER_CUBIC follows OpenCV's own code path — bit-exact with cv2 when IPP is off, within 1 LSB of the
+ * IPP-enabled wheels (IPP substitutes its own float cubic there).  cv_tail_compat as in docscan_adaptive_threshold:
+ * != 0 reproduces the fixed-point arithmetic cv2's SIMD build uses in the last (width*channels) % 8 elements of a row. */
+#define DOCSCAN_INTER_CUBIC 2
+#define DOCSCAN_INTER_AREA 3
+DOCSCAN_API int docscan_resize(docscan_ctx*, const docscan_image* src, docscan_image* dst, int interpolation, int cv_tail_compat);
+
 /* ---- fused reference stage functions ----------------------------------------------------------- */
 /* illumination_correction(gray, method, blur_frac)                       DocScanner.py:147-160
  * method 0 = subtract, 1 = divide; k = the odd kernel size the reference derives from blur_frac. */
@@ -167,6 +176,9 @@ typedef struct docscan_page {
     double angle_deg;                /* deskew angle from the control path (Canny+HoughLines) */
     docscan_image warped;            /* out: u8c3, size = target size of the page (docscan_target_size) */
     docscan_image binary;            /* out: u8c1, same size */
+    int32_t use_whole;               /* != 0: no usable quad — `warped` = resize_long_side(src) (DocScanner.py:313): the
+                                        photo resized to warped's size, INTER_AREA when that shrinks its long side,
+                                        INTER_CUBIC otherwise; `quad` is ignored */
 } docscan_page;
 
 DOCSCAN_API void docscan_default_params(docscan_params* p);                 /* CLI defaults, DocScanner.py:262-276 */

@@ -327,7 +327,9 @@ def hot_path(color, quad, angle_deg, *, page="A4", scale_long=1600, illum_method
     """Per-pixel part of process_document (DocScanner.py:310-346) with the control-path outputs
     (quad, deskew angle) supplied.  Returns every stage image keyed like the reference's dumps."""
     out = {}
-    out["warped"] = perspective_warp(color, quad, page=page, scale_long=scale_long)
+    # DocScanner.py:310-313: no usable quad -> the whole photo through resize_long_side
+    out["warped"] = (perspective_warp(color, quad, page=page, scale_long=scale_long) if quad is not None
+                     else resize_long_side(color, scale_long))
     out["gray"] = bgr2gray(out["warped"])
     out["illum"] = illumination_correction(out["gray"], method=illum_method, blur_frac=illum_blur_frac)
     out["stretch"] = contrast_stretch(out["illum"])
@@ -343,6 +345,43 @@ def hot_path(color, quad, angle_deg, *, page="A4", scale_long=1600, illum_method
 
 
 # --------------------------------------------------------------------------- morph_seq (pyc only)
+
+def resize_area(img, dsize):
+    """cv2.resize(img, dsize, interpolation=cv2.INTER_AREA) for a shrink (DocScanner.py:35-36)."""
+    img = _img(img)
+    dw, dh = dsize
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty((dh, dw) if img.ndim == 2 else (dh, dw, cn), np.uint8)
+    rc = lib().orc_resize_area_u8(_p(img), img.shape[0], img.shape[1], img.strides[0], cn, _p(out), dh, dw, out.strides[0])
+    if rc != 0:
+        raise ValueError("resize_area: destination must not be larger than the source")
+    return out
+
+
+def resize_cubic(img, dsize, simd_tail=True):
+    """cv2.resize(img, dsize, interpolation=cv2.INTER_CUBIC) as OpenCV's own code (IPP off) computes it."""
+    img = _img(img)
+    dw, dh = dsize
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty((dh, dw) if img.ndim == 2 else (dh, dw, cn), np.uint8)
+    rc = lib().orc_resize_cubic_u8(_p(img), img.shape[0], img.shape[1], img.strides[0], cn, _p(out), dh, dw, out.strides[0],
+                                   int(bool(simd_tail)))
+    if rc != 0:
+        raise ValueError("resize_cubic: empty image")
+    return out
+
+
+def resize_long_side(img, scale_long: int):
+    """DocScanner.py:27-36."""
+    h, w = img.shape[:2]
+    if scale_long <= 0:
+        return img
+    long = max(h, w)
+    sf = scale_long / float(long)
+    new_w = int(round(w * sf))
+    new_h = int(round(h * sf))
+    return resize_area(img, (new_w, new_h)) if sf < 1.0 else resize_cubic(img, (new_w, new_h))
+
 
 def to_grayscale(rgb):
     """morph_seq.to_grayscale (pyc src l.46-47): cv2.cvtColor(RGB2GRAY)."""

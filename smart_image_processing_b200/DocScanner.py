@@ -23,7 +23,7 @@ from . import _capi, ops
 from ._capi import Page, Params, image_of
 
 __all__ = [
-    "perspective_warp", "illumination_correction", "adaptive_binarize", "contrast_stretch", "_compute_ink_mask",
+    "resize_long_side", "perspective_warp", "illumination_correction", "adaptive_binarize", "contrast_stretch", "_compute_ink_mask",
     "deskew", "rotate", "morph_cleanup", "process_document", "process_pages", "hot_path", "target_size",
 ]
 
@@ -57,6 +57,19 @@ def target_size(quad: np.ndarray, page: str = "A4", scale_long: int = 1600):
         target_w = scale_long
         target_h = int(round(target_w * ratio))
     return target_w, target_h
+
+
+def resize_long_side(img: np.ndarray, scale_long: int) -> np.ndarray:
+    """DocScanner.py:27-36: the whole-photo fallback (INTER_AREA when the long side shrinks, INTER_CUBIC otherwise;
+    returns its argument when scale_long <= 0, like the reference)."""
+    h, w = img.shape[:2]
+    if scale_long <= 0:
+        return img
+    long = max(h, w)
+    sf = scale_long / float(long)
+    new_w = int(round(w * sf))
+    new_h = int(round(h * sf))
+    return ops.resize(img, (new_w, new_h), _capi.INTER_AREA if sf < 1.0 else _capi.INTER_CUBIC)
 
 
 def perspective_warp(img: np.ndarray, quad: np.ndarray, page: str = "A4", scale_long: int = 1600) -> np.ndarray:
@@ -178,6 +191,7 @@ def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], ang
     """The per-pixel part of process_document (DocScanner.py:310-346) for a batch of independent pages in one
     C-ABI call: warp -> gray -> illumination -> stretch -> ink mask || adaptive threshold -> blend -> rotate ->
     close.  `images` are HxWx3 uint8 BGR numpy arrays (host); returns (warped list, binary list).
+    A quad of None sends that page through the whole-photo fallback (resize_long_side) instead of the warp.
     `out_warped` / `out_binary` may hold preallocated (e.g. pinned) arrays of the right shapes."""
     ctx = _ctx(ctx)
     n = len(images)
@@ -188,8 +202,16 @@ def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], ang
         img = np.ascontiguousarray(images[i])
         if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
             raise TypeError("process_pages: images must be HxWx3 uint8 (BGR)")
-        q = np.asarray(quads[i], np.float32).reshape(4, 2)
-        tw, th = target_size(q, page, scale_long)
+        whole = quads[i] is None                       # no usable quad: resize_long_side (DocScanner.py:313)
+        if whole:
+            if scale_long <= 0:
+                raise ValueError("process_pages: scale_long must be positive for whole-photo pages")
+            sf = scale_long / float(max(img.shape[:2]))
+            tw, th = int(round(img.shape[1] * sf)), int(round(img.shape[0] * sf))
+            q = np.zeros((4, 2), np.float32)
+        else:
+            q = np.asarray(quads[i], np.float32).reshape(4, 2)
+            tw, th = target_size(q, page, scale_long)
         w_arr = out_warped[i] if out_warped is not None else np.empty((th, tw, 3), np.uint8)
         b_arr = out_binary[i] if out_binary is not None else np.empty((th, tw), np.uint8)
         if w_arr.shape != (th, tw, 3) or b_arr.shape != (th, tw):
@@ -199,6 +221,7 @@ def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], ang
         pages[i].angle_deg = float(angles[i])
         pages[i].warped = image_of(w_arr)
         pages[i].binary = image_of(b_arr)
+        pages[i].use_whole = int(whole)
         keep.append(img)
         warped.append(w_arr)
         binary.append(b_arr)
@@ -214,7 +237,8 @@ def hot_path(color: np.ndarray, quad: np.ndarray, angle_deg: float, *, page="A4"
              mask_thresh_offset=8, morph_ksize=3, morph_iters=1)
     t.update(tunables)
     out = {}
-    out["warped"] = perspective_warp(color, quad, page=page, scale_long=scale_long)
+    out["warped"] = (perspective_warp(color, quad, page=page, scale_long=scale_long) if quad is not None
+                     else resize_long_side(color, scale_long))
     out["gray"] = ops.bgr2gray(out["warped"])
     out["illum"] = illumination_correction(out["gray"], method=t["illum_method"], blur_frac=t["illum_blur_frac"])
     out["stretch"] = contrast_stretch(out["illum"])
@@ -264,18 +288,17 @@ def process_document(input_path: str, out_dir: str = "outputs", page: str = "A4"
             use_whole = True
     if use_whole and not fallback_use_whole:
         raise RuntimeError("Quad too small or missing, and fallback disabled.")
-    if use_whole:
-        # DocScanner.py:313 falls back to resize_long_side (INTER_AREA / INTER_CUBIC): SURVEY.md §8(f) next-3
-        raise NotImplementedError("whole-image fallback (resize_long_side) is outside the accelerated path; "
-                                  "pass a quad or use the reference for this image")
+    if use_whole and scale_long <= 0:
+        raise ValueError("scale_long must be positive")        # the reference would hand the full photo on unchanged
     tun = dict(illum_method=illum_method, illum_blur_frac=illum_blur_frac, block_size=block_size, C=C,
                thresh_method=thresh_method, mask_blur_ksize=mask_blur_ksize, blackhat_ksize=blackhat_ksize,
                blackhat_vertical_ratio=blackhat_vertical_ratio, ink_dilate_iters=ink_dilate_iters,
                mask_thresh_offset=mask_thresh_offset, morph_ksize=morph_ksize, morph_iters=morph_iters)
-    quad = np.asarray(quad, np.float32)
+    quad = np.asarray(quad, np.float32) if quad is not None else None
+    warp_quad = None if use_whole else quad                    # DocScanner.py:310-313
     if angle is None or save_stages:
         # the skew estimate needs the blended binary (DocScanner.py:342), so the chain is split there
-        st = hot_path(color, quad, 0.0, page=page, scale_long=scale_long, **tun)
+        st = hot_path(color, warp_quad, 0.0, page=page, scale_long=scale_long, **tun)
         if angle is None:
             angle = control.estimate_skew_angle(st["weighted"], canny_low, canny_high, max_rotate)
         st["deskew"] = rotate(st["weighted"], angle)
@@ -284,7 +307,7 @@ def process_document(input_path: str, out_dir: str = "outputs", page: str = "A4"
         if save_stages:
             control.save_stage_dumps(out_dir, st)
     else:
-        w, b = process_pages([color], [quad], [angle], page=page, scale_long=scale_long, **tun)
+        w, b = process_pages([color], [warp_quad], [angle], page=page, scale_long=scale_long, **tun)
         warped, clean = w[0], b[0]
     result = {"quad": quad, "warped": warped, "binary": clean}
     if do_ocr:

@@ -15,6 +15,7 @@ HOST, DEVICE = 0, 1
 OP_SUB, OP_DIV255, OP_MAX, OP_MASK_SELECT = 0, 1, 2, 3
 MORPH_ERODE, MORPH_DILATE, MORPH_CLOSE, MORPH_BLACKHAT, MORPH_OPEN = 0, 1, 2, 3, 4
 ADAPTIVE_MEAN, ADAPTIVE_GAUSSIAN = 0, 1
+INTER_CUBIC, INTER_AREA = 2, 3
 
 
 class DocscanError(RuntimeError):
@@ -35,7 +36,8 @@ class Params(C.Structure):
 
 
 class Page(C.Structure):
-    _fields_ = [("src", Image), ("quad", C.c_float * 8), ("angle_deg", C.c_double), ("warped", Image), ("binary", Image)]
+    _fields_ = [("src", Image), ("quad", C.c_float * 8), ("angle_deg", C.c_double), ("warped", Image), ("binary", Image),
+                ("use_whole", C.c_int32)]
 
 
 _lib = None
@@ -75,6 +77,7 @@ _SIGS = {
     "docscan_morph_rect": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_adaptive_threshold": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_warp_affine": (C.c_int, [C.c_void_p, C.POINTER(Image), C.POINTER(C.c_double), C.POINTER(Image)]),
+    "docscan_resize": (C.c_int, [C.c_void_p, C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_int]),
     "docscan_illumination_correction": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_ink_mask": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_default_params": (None, [C.POINTER(Params)]),

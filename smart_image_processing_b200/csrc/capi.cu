@@ -394,6 +394,20 @@ extern "C" int docscan_warp_affine(docscan_ctx* ctx, const docscan_image* src, c
     return ds_finish(ctx, is_host(src) || is_host(dst));
 }
 
+extern "C" int docscan_resize(docscan_ctx* ctx, const docscan_image* src, docscan_image* dst, int interpolation, int cv_tail_compat) {
+    if (!ctx) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, src, 0, "resize: src"));
+    DS_TRY(ds_check_image(ctx, dst, src->channels, "resize: dst"));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst) + 64 * ((size_t)src->width + src->height + dst->width + dst->height) + 4096));
+    ArenaScope scope(ctx);
+    DImg s, d;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    DS_TRY(k_resize(ctx, s, d, interpolation, cv_tail_compat));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
 // =====================================================================================================
 // fused reference stage functions
 // =====================================================================================================
@@ -439,7 +453,8 @@ namespace {
 
 size_t page_scratch(const docscan_page& pg) {
     const int w = pg.binary.width, h = pg.binary.height;
-    return 16 * plane_bytes(w, h) + 4096;
+    size_t tables = pg.use_whole ? 64 * ((size_t)pg.src.width + pg.src.height + w + h) + 4096 : 0;    // resize tables
+    return 16 * plane_bytes(w, h) + 4096 + tables;
 }
 
 size_t page_staging(const docscan_page& pg) {
@@ -488,8 +503,18 @@ int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params
     std::vector<WarpPJob> wj(n);
     DS_TRY(alloc_planes(ctx, binary, &gray));
     int mw, mh; max_dims(binary, &mw, &mh);
-    // a1 + a2: perspective warp with fused BGR2GRAY
+    // a1 + a2: perspective warp with fused BGR2GRAY; pages without a usable quad take resize_long_side + BGR2GRAY
+    std::vector<WarpPJob> wj_quad;
+    int qw = 0, qh = 0;
     for (int i = 0; i < n; i++) {
+        if (pages[i].use_whole) {
+            if (regions && (regions[i].x0 != 0 || regions[i].y0 != 0 || regions[i].x1 != pages[i].src.width || regions[i].y1 != pages[i].src.height))
+                return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "internal: whole-photo page with a partial upload");
+            const int long_src = std::max(src[i].w, src[i].h), long_dst = std::max(warped[i].w, warped[i].h);
+            DS_TRY(k_resize(ctx, src[i], warped[i], long_dst < long_src ? DOCSCAN_INTER_AREA : DOCSCAN_INTER_CUBIC, P.cv_tail_compat));
+            DS_TRY(k_bgr2gray(ctx, warped[i], gray[i], 0));
+            continue;
+        }
         WarpPJob& j = wj[i];
         j = WarpPJob{};
         j.src = src[i].p; j.src_pitch = src[i].pitch; j.sw = pages[i].src.width; j.sh = pages[i].src.height; j.ch = 3;
@@ -502,8 +527,10 @@ int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params
         double m[9];
         DS_TRY(docscan_get_perspective_transform(pages[i].quad, dstq, m));
         hm_invert3x3(m, j.m);
+        wj_quad.push_back(j);
+        qw = std::max(qw, j.dw); qh = std::max(qh, j.dh);
     }
-    DS_TRY(k_warp_perspective_jobs(ctx, wj.data(), n, mw, mh));
+    if (!wj_quad.empty()) DS_TRY(k_warp_perspective_jobs(ctx, wj_quad.data(), (int)wj_quad.size(), qw, qh));
 
     // a3 + a4: illumination correction; its MINMAX LUT and contrast_stretch's fold into one LUT
     PageScalars* sc = nullptr;
@@ -665,7 +692,8 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
     std::vector<SrcRegion> regions(n);
     size_t max_stage = 0;
     for (int i = 0; i < n; i++) {
-        regions[i] = is_host(&pages[i].src) ? warp_footprint(pages[i]) : SrcRegion{0, 0, pages[i].src.width, pages[i].src.height};
+        regions[i] = (is_host(&pages[i].src) && !pages[i].use_whole) ? warp_footprint(pages[i])
+                                                                      : SrcRegion{0, 0, pages[i].src.width, pages[i].src.height};
         const size_t src_stage = is_host(&pages[i].src) ? ds_image_bytes(regions[i].x1 - regions[i].x0, regions[i].y1 - regions[i].y0, 3) : 0;
         max_stage = std::max(max_stage, src_stage + host_bytes(&pages[i].warped) + host_bytes(&pages[i].binary) + 1024);
     }

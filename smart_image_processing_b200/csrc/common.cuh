@@ -208,6 +208,8 @@ struct WarpAJob {
     int2* delta;          // per-column fixed-point increments (filled by k_warp_affine_jobs)
 };
 int k_warp_affine_jobs(docscan_ctx*, const WarpAJob* jobs_host, int n, int max_w, int max_h);
+// resize.cu : cv2.resize INTER_AREA (shrink) / INTER_CUBIC
+int k_resize(docscan_ctx*, const DImg& src, const DImg& dst, int interpolation, int cv_tail_compat);
 // synth.cu
 int k_synth_page(docscan_ctx*, uint64_t seed, const DImg& dst, float quad_out[8]);
 

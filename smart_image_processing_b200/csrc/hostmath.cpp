@@ -243,3 +243,24 @@ extern "C" int docscan_target_size(const float quad[8], int page_kind, int scale
     }
     return DOCSCAN_OK;
 }
+
+// cv::resize INTER_CUBIC tables: fx in fp32, cv::interpolateCubic (A = -0.75) in fp32, taps quantised to 11 bits with
+// cvRound, source indices clamped to the image (DocScanner.py:35-36 through resize_long_side).
+void hm_cubic_taps(int ssize, int dsize, int d, int idx[4], short w[4]) {
+    const double scale = (double)ssize / dsize;
+    float fx = (float)((d + 0.5) * scale - 0.5);
+    const int sx = (int)std::floor(fx);
+    fx -= (float)sx;
+    const float A = -0.75f;
+    float c[4];
+    c[0] = ((A * (fx + 1) - 5 * A) * (fx + 1) + 8 * A) * (fx + 1) - 4 * A;
+    c[1] = ((A + 2) * fx - (A + 3)) * fx * fx + 1;
+    c[2] = ((A + 2) * (1 - fx) - (A + 3)) * (1 - fx) * (1 - fx) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+    for (int k = 0; k < 4; k++) {
+        long v = std::lrintf(c[k] * 2048.f);
+        w[k] = (short)(v < -32768 ? -32768 : (v > 32767 ? 32767 : v));
+        const int s = sx - 1 + k;
+        idx[k] = s < 0 ? 0 : (s > ssize - 1 ? ssize - 1 : s);
+    }
+}

@@ -215,3 +215,17 @@ def warp_affine(gray, m, dsize, ctx=None):
     s, d = image_of(gray), image_of(out)
     _ctx(ctx).call("docscan_warp_affine", C.byref(s), _dptr(m, C.c_double), C.byref(d))
     return out
+
+
+def resize(img, dsize, interpolation, cv_tail_compat=True, ctx=None):
+    """cv2.resize(img, dsize, interpolation=...) for INTER_AREA (shrink) and INTER_CUBIC (DocScanner.py:35-36)."""
+    img = np.ascontiguousarray(img)
+    if img.dtype != np.uint8 or img.ndim not in (2, 3):
+        raise TypeError("resize: expected uint8 HxW or HxWx3")
+    dw, dh = int(dsize[0]), int(dsize[1])
+    if dw <= 0 or dh <= 0:
+        raise ValueError("resize: empty destination")
+    out = np.empty((dh, dw) + img.shape[2:], np.uint8)
+    s, d = image_of(img), image_of(out)
+    _ctx(ctx).call("docscan_resize", C.byref(s), C.byref(d), int(interpolation), int(bool(cv_tail_compat)))
+    return out

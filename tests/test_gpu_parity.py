@@ -294,6 +294,57 @@ def test_footprint_upload_matches_whole_photo():
             assert sent < 0.5 * img.nbytes, "only the rows/columns under the quad should travel"
 
 
+def test_resize_area_and_cubic():
+    """cv2.resize as resize_long_side uses it (DocScanner.py:27-36): CUDA vs oracle, ragged and degenerate shapes."""
+    from smart_image_processing_b200 import _capi
+    rng = np.random.default_rng(23)
+    for (H, W, nh, nw) in [(300, 400, 187, 250), (301, 403, 150, 201), (90, 120, 45, 60), (90, 120, 30, 40), (90, 120, 30, 60),
+                           (97, 131, 48, 65), (35, 60, 7, 12), (50, 50, 50, 50), (64, 48, 1, 1), (700, 1000, 280, 400)]:
+        for cn in (1, 3):
+            src = rng.integers(0, 256, (H, W, cn) if cn == 3 else (H, W), dtype=np.uint8)
+            eq(ops.resize(src, (nw, nh), _capi.INTER_AREA), O.resize_area(src, (nw, nh)), f"area {H}x{W}->{nh}x{nw} c{cn}")
+    for (H, W, nh, nw) in [(300, 400, 375, 500), (60, 80, 75, 100), (97, 131, 200, 333), (5, 3, 17, 9), (1, 50, 2, 80),
+                           (100, 77, 100, 77), (40, 30, 41, 30), (333, 250, 640, 481)]:
+        for cn in (1, 3):
+            src = rng.integers(0, 256, (H, W, cn) if cn == 3 else (H, W), dtype=np.uint8)
+            eq(ops.resize(src, (nw, nh), _capi.INTER_CUBIC), O.resize_cubic(src, (nw, nh)), f"cubic {H}x{W}->{nh}x{nw} c{cn}")
+            eq(ops.resize(src, (nw, nh), _capi.INTER_CUBIC, cv_tail_compat=False), O.resize_cubic(src, (nw, nh), simd_tail=False),
+               f"cubic all-fp32 {H}x{W}->{nh}x{nw} c{cn}")
+    with pytest.raises(_capi.DocscanError):
+        ops.resize(np.zeros((8, 8), np.uint8), (16, 16), _capi.INTER_AREA)          # enlarging INTER_AREA is not on the path
+    with pytest.raises(_capi.DocscanError):
+        ops.resize(np.zeros((8, 8), np.uint8), (4, 4), 1)                           # INTER_LINEAR is not on the path
+
+
+def test_resize_long_side_golden():
+    meta = json.load(open(os.path.join(GOLDEN, "resize_golden.json")))
+    z = load_npz("resize.npz")
+    for case in meta["cases"]:
+        tag, sl = case.rsplit("_", 1)
+        eq(DS.resize_long_side(z[f"in_{tag}"], int(sl)), z[f"out_{case}"], f"resize_long_side {case}")
+    img = z["sample3_bgr"]
+    for name in ("sample3_1600", "sample3_1200"):
+        out = DS.resize_long_side(img, int(name.split("_")[1]))
+        assert sha(out) == meta["full"][name]["sha256"], name
+    assert DS.resize_long_side(img, 0) is img
+
+
+def test_whole_photo_fallback_pages():
+    """process_document's branch without a usable quad (DocScanner.py:313): resize_long_side instead of the warp, then the
+    same chain; mixed with warped pages in one batch."""
+    rng = np.random.default_rng(29)
+    H, W = 400, 300
+    base = page_like(rng, H, W)
+    img = np.stack([np.clip(base * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1)
+    quad = np.array([[20, 15], [280, 22], [285, 380], [12, 372]], np.float32)
+    for sl in (250, 520):                                   # shrink (INTER_AREA) and enlarge (INTER_CUBIC)
+        w, b = DS.process_pages([img, img, img], [None, quad, None], [0.5, -1.0, 0.0], scale_long=sl)
+        for i, (q, a) in enumerate(((None, 0.5), (quad, -1.0), (None, 0.0))):
+            ref = O.hot_path(img, q, a, scale_long=sl)
+            eq(w[i], ref["warped"], f"whole-photo batch warped {i} sl={sl}")
+            eq(b[i], ref["clean"], f"whole-photo batch binary {i} sl={sl}")
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
