@@ -140,6 +140,21 @@ DOCSCAN_API int docscan_adaptive_threshold(docscan_ctx*, const docscan_image* sr
 /* cv2.warpAffine(gray, M, (w,h), INTER_LINEAR, BORDER_REPLICATE) u8c1    DocScanner.py:235 */
 DOCSCAN_API int docscan_warp_affine(docscan_ctx*, const docscan_image* src, const double m_fwd[6], docscan_image* dst);
 
+/* ---- the skew estimate of deskew() (DocScanner.py:218-231), on the device ---------------------------- */
+/* cv2.Canny(gray, low, high) (aperture 3, L1 gradient) u8c1 -> {0,255}           DocScanner.py:218 (and :78) */
+DOCSCAN_API int docscan_canny(docscan_ctx*, const docscan_image* src, double low, double high, docscan_image* dst);
+/* cv2.HoughLines(edges, 1, pi/180, threshold): every non-zero pixel votes.  Writes up to max_lines (rho, theta) float
+ * pairs in OpenCV's order (votes descending, then accumulator index) and the total number of lines to *n_lines;
+ * per_angle (may be NULL) receives the number of lines per angle index 0..179.       DocScanner.py:219 */
+DOCSCAN_API int docscan_hough_lines(docscan_ctx*, const docscan_image* edges, int threshold, float* rho_theta, int max_lines,
+                                    int32_t* n_lines, int32_t per_angle[180]);
+/* np.median of the folded line angles in numpy's float32 arithmetic, 0 beyond max_rotate (host arithmetic)
+ *                                                                                   DocScanner.py:221-231 */
+DOCSCAN_API int docscan_median_angle(const int32_t per_angle[180], double max_rotate, double* angle_deg);
+/* Canny -> HoughLines(1, pi/180, 150) -> median angle: the angle deskew() rotates by      DocScanner.py:218-231 */
+DOCSCAN_API int docscan_skew_angle(docscan_ctx*, const docscan_image* gray, double canny_low, double canny_high,
+                                   double max_rotate, double* angle_deg);
+
 /* cv2.resize(img, (dst.width, dst.height), interpolation=INTER_AREA | INTER_CUBIC), u8c1 / u8c3: resize_long_side,
  * DocScanner.py:27-36 (the whole-photo fallback taken at :313).  INTER_AREA is implemented for shrinking (bit-exact
  * with cv2); INTER_CUBIC follows OpenCV's own code path — bit-exact with cv2 when IPP is off, within 1 LSB of the
@@ -168,12 +183,16 @@ typedef struct docscan_params {      /* process_document tunables that touch pix
     int32_t ink_dilate_iters, mask_thresh_offset;
     int32_t morph_ksize, morph_iters;
     int32_t cv_tail_compat;
+    /* deskew()'s own estimate, used for pages whose angle_deg is NaN (DocScanner.py:218-231, :342) */
+    double canny_low, canny_high, max_rotate;
 } docscan_params;
 
 typedef struct docscan_page {
     docscan_image src;               /* photo, u8c3 BGR */
     float quad[8];                   /* TL,TR,BR,BL from the control path (localize_document) */
-    double angle_deg;                /* deskew angle from the control path (Canny+HoughLines) */
+    double angle_deg;                /* deskew angle from the control path; NaN = estimate it on the device from the
+                                        blended page exactly like deskew() (Canny + HoughLines median); read the
+                                        result with docscan_last_angles */
     docscan_image warped;            /* out: u8c3, size = target size of the page (docscan_target_size) */
     docscan_image binary;            /* out: u8c1, same size */
     int32_t use_whole;               /* != 0: no usable quad — `warped` = resize_long_side(src) (DocScanner.py:313): the
@@ -187,6 +206,8 @@ DOCSCAN_API int docscan_target_size(const float quad[8], int page_kind, int scal
 /* warp -> gray -> illumination -> stretch -> ink mask || adaptive threshold -> blend -> rotate -> close
  * (DocScanner.py:310-346 without the PNG dumps) for n independent pages. */
 DOCSCAN_API int docscan_process_pages(docscan_ctx*, int n, docscan_page* pages, const docscan_params* params);
+/* the deskew angle each page of the last docscan_process_pages call was rotated by (supplied or estimated); syncs */
+DOCSCAN_API int docscan_last_angles(docscan_ctx*, double* angles, int n);
 
 /* ---- bench support: deterministic synthetic page photos rendered on the device ------------------- */
 /* Renders a width x height u8c3 photo of a text page (seeded) into `dst` (DEVICE space) and returns

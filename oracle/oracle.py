@@ -383,6 +383,43 @@ def resize_long_side(img, scale_long: int):
     return resize_area(img, (new_w, new_h)) if sf < 1.0 else resize_cubic(img, (new_w, new_h))
 
 
+def canny(gray, low, high):
+    """cv2.Canny(gray, low, high) (DocScanner.py:218)."""
+    gray = _img(gray)
+    out = np.empty_like(gray)
+    lib().orc_canny(_p(gray), gray.shape[0], gray.shape[1], gray.strides[0], C.c_double(low), C.c_double(high), _p(out), out.strides[0])
+    return out
+
+
+def hough_lines(edges, threshold=150, max_lines=1 << 20):
+    """cv2.HoughLines(edges, 1, np.pi / 180, threshold) (DocScanner.py:219): (lines (N, 1, 2) float32 or None, lines per angle)."""
+    edges = _img(edges)
+    per_angle = np.zeros(180, np.int32)
+    buf = np.zeros((max_lines, 2), np.float32)
+    n = lib().orc_hough_lines(_p(edges), edges.shape[0], edges.shape[1], edges.strides[0], int(threshold),
+                              buf.ctypes.data_as(_f32p), max_lines, per_angle.ctypes.data_as(_i32p))
+    return (buf[:min(n, max_lines)].reshape(-1, 1, 2).copy() if n else None), per_angle
+
+
+def median_angle(per_angle, max_rotate=10.0) -> float:
+    """DocScanner.py:221-231 from the number of Hough lines per angle index."""
+    per_angle = np.ascontiguousarray(per_angle, np.int32)
+    fn = lib().orc_median_angle
+    fn.restype = C.c_double
+    return float(fn(per_angle.ctypes.data_as(_i32p), C.c_double(max_rotate)))
+
+
+def estimate_skew_angle(gray, canny_low=50, canny_high=150, max_rotate=10.0) -> float:
+    """The control half of deskew (DocScanner.py:218-231)."""
+    _, per_angle = hough_lines(canny(gray, canny_low, canny_high), 150, max_lines=0 or 1)
+    return median_angle(per_angle, max_rotate)
+
+
+def deskew(gray, canny_low=50, canny_high=150, max_rotate=10.0):
+    """DocScanner.py:217-236."""
+    return rotate(gray, estimate_skew_angle(gray, canny_low, canny_high, max_rotate))
+
+
 def to_grayscale(rgb):
     """morph_seq.to_grayscale (pyc src l.46-47): cv2.cvtColor(RGB2GRAY)."""
     return bgr2gray(rgb, swap_rb=True)

@@ -6,9 +6,9 @@ runs as a CUDA kernel of libdocscan.so (B200, sm_100a) through the C ABI in incl
 
     import smart_image_processing_b200.DocScanner as DS     # instead of: import DocScanner as DS
 
-What is NOT here: the reference's control path (quad detection, Hough skew estimate), file I/O and OCR.
-`process_document` calls them through `control.py`, which uses OpenCV on the host when it is installed;
-pass `quad=` / `angle=` to skip it.  There is no CPU fallback for the pixel path.
+What is NOT here: the reference's quad detection (localize_document), file I/O and OCR.  `process_document` calls
+them through `control.py`, which uses OpenCV on the host when it is installed; pass `quad=` to skip it.  The skew
+estimate of deskew() (Canny + HoughLines median) runs on the device.  There is no CPU fallback for the pixel path.
 """
 from __future__ import annotations
 
@@ -143,11 +143,10 @@ def rotate(gray: np.ndarray, angle_deg: float) -> np.ndarray:
 
 def deskew(gray: np.ndarray, canny_low: int = 50, canny_high: int = 150, max_rotate: float = 10.0,
            angle: Optional[float] = None) -> np.ndarray:
-    """DocScanner.py:217-236.  The skew estimate (Canny + HoughLines median) is the reference's control
-    path and runs on the host (control.py); pass `angle=` to supply it."""
+    """DocScanner.py:217-236: Canny + HoughLines median skew estimate and the rotation, both on the device;
+    pass `angle=` to supply the angle instead."""
     if angle is None:
-        from . import control
-        angle = control.estimate_skew_angle(gray, canny_low, canny_high, max_rotate)
+        angle = ops.skew_angle(gray, canny_low, canny_high, max_rotate)
     return rotate(gray, angle)
 
 
@@ -167,7 +166,8 @@ _PIXEL_KEYS = ("illum_method", "illum_blur_frac", "block_size", "C", "thresh_met
 
 def make_params(illum_method="subtract", illum_blur_frac=0.02, block_size=35, C=10, thresh_method="gaussian",
                 mask_blur_ksize=51, blackhat_ksize=9, blackhat_vertical_ratio=2.0, ink_dilate_iters=1,
-                mask_thresh_offset=8, morph_ksize=3, morph_iters=1, cv_tail_compat=True) -> Params:
+                mask_thresh_offset=8, morph_ksize=3, morph_iters=1, cv_tail_compat=True,
+                canny_low=50, canny_high=150, max_rotate=10.0) -> Params:
     """process_document's pixel tunables (DocScanner.py:268-273) as a docscan_params struct."""
     p = Params()
     p.illum_method = 1 if str(illum_method).lower() == "divide" else 0
@@ -183,15 +183,19 @@ def make_params(illum_method="subtract", illum_blur_frac=0.02, block_size=35, C=
     p.morph_ksize = int(morph_ksize)
     p.morph_iters = int(morph_iters)
     p.cv_tail_compat = int(bool(cv_tail_compat))
+    p.canny_low, p.canny_high, p.max_rotate = float(canny_low), float(canny_high), float(max_rotate)
     return p
 
 
 def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], angles: Sequence[float], *,
-                  page: str = "A4", scale_long: int = 1600, ctx=None, out_warped=None, out_binary=None, **tunables):
+                  page: str = "A4", scale_long: int = 1600, ctx=None, out_warped=None, out_binary=None,
+                  return_angles: bool = False, **tunables):
     """The per-pixel part of process_document (DocScanner.py:310-346) for a batch of independent pages in one
     C-ABI call: warp -> gray -> illumination -> stretch -> ink mask || adaptive threshold -> blend -> rotate ->
     close.  `images` are HxWx3 uint8 BGR numpy arrays (host); returns (warped list, binary list).
-    A quad of None sends that page through the whole-photo fallback (resize_long_side) instead of the warp.
+    A quad of None sends that page through the whole-photo fallback (resize_long_side) instead of the warp; an
+    angle of None makes the library estimate the skew on the device exactly like deskew() (canny_low, canny_high,
+    max_rotate tunables).  return_angles=True appends the list of angles the pages were rotated by.
     `out_warped` / `out_binary` may hold preallocated (e.g. pinned) arrays of the right shapes."""
     ctx = _ctx(ctx)
     n = len(images)
@@ -218,7 +222,7 @@ def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], ang
             raise ValueError("process_pages: preallocated outputs have the wrong shape")
         pages[i].src = image_of(img)
         pages[i].quad = (_ct.c_float * 8)(*q.reshape(8).tolist())
-        pages[i].angle_deg = float(angles[i])
+        pages[i].angle_deg = float("nan") if angles[i] is None else float(angles[i])
         pages[i].warped = image_of(w_arr)
         pages[i].binary = image_of(b_arr)
         pages[i].use_whole = int(whole)
@@ -226,6 +230,10 @@ def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], ang
         warped.append(w_arr)
         binary.append(b_arr)
     ctx.call("docscan_process_pages", n, pages, _ct.byref(params))
+    if return_angles:
+        out = (_ct.c_double * max(n, 1))()
+        ctx.call("docscan_last_angles", out, n)
+        return warped, binary, [float(out[i]) for i in range(n)]
     return warped, binary
 
 
@@ -296,18 +304,19 @@ def process_document(input_path: str, out_dir: str = "outputs", page: str = "A4"
                mask_thresh_offset=mask_thresh_offset, morph_ksize=morph_ksize, morph_iters=morph_iters)
     quad = np.asarray(quad, np.float32) if quad is not None else None
     warp_quad = None if use_whole else quad                    # DocScanner.py:310-313
-    if angle is None or save_stages:
-        # the skew estimate needs the blended binary (DocScanner.py:342), so the chain is split there
+    if save_stages:
         st = hot_path(color, warp_quad, 0.0, page=page, scale_long=scale_long, **tun)
         if angle is None:
-            angle = control.estimate_skew_angle(st["weighted"], canny_low, canny_high, max_rotate)
+            angle = ops.skew_angle(st["weighted"], canny_low, canny_high, max_rotate)     # DocScanner.py:342
         st["deskew"] = rotate(st["weighted"], angle)
         st["clean"] = morph_cleanup(st["deskew"], ksize=morph_ksize, iterations=morph_iters)
         warped, clean = st["warped"], st["clean"]
         if save_stages:
             control.save_stage_dumps(out_dir, st)
     else:
-        w, b = process_pages([color], [warp_quad], [angle], page=page, scale_long=scale_long, **tun)
+        # one C-ABI call; without a supplied angle the skew estimate runs on the device between blend and rotate
+        w, b = process_pages([color], [warp_quad], [angle], page=page, scale_long=scale_long, canny_low=canny_low,
+                             canny_high=canny_high, max_rotate=max_rotate, **tun)
         warped, clean = w[0], b[0]
     result = {"quad": quad, "warped": warped, "binary": clean}
     if do_ocr:

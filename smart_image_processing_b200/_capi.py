@@ -32,7 +32,8 @@ class Params(C.Structure):
                 ("C", C.c_int32), ("thresh_method", C.c_int32), ("mask_blur_ksize", C.c_int32),
                 ("blackhat_ksize", C.c_int32), ("blackhat_vertical_ratio", C.c_double),
                 ("ink_dilate_iters", C.c_int32), ("mask_thresh_offset", C.c_int32), ("morph_ksize", C.c_int32),
-                ("morph_iters", C.c_int32), ("cv_tail_compat", C.c_int32)]
+                ("morph_iters", C.c_int32), ("cv_tail_compat", C.c_int32),
+                ("canny_low", C.c_double), ("canny_high", C.c_double), ("max_rotate", C.c_double)]
 
 
 class Page(C.Structure):
@@ -77,6 +78,12 @@ _SIGS = {
     "docscan_morph_rect": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_adaptive_threshold": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_warp_affine": (C.c_int, [C.c_void_p, C.POINTER(Image), C.POINTER(C.c_double), C.POINTER(Image)]),
+    "docscan_canny": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_double, C.c_double, C.POINTER(Image)]),
+    "docscan_hough_lines": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32)]),
+    "docscan_median_angle": (C.c_int, [C.POINTER(C.c_int32), C.c_double, C.POINTER(C.c_double)]),
+    "docscan_skew_angle": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]),
+    "docscan_last_angles": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_int]),
     "docscan_resize": (C.c_int, [C.c_void_p, C.POINTER(Image), C.POINTER(Image), C.c_int, C.c_int]),
     "docscan_illumination_correction": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_ink_mask": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Image)]),

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libdocscan.so")
 
-CU_SOURCES = ["ctx.cu", "pointwise.cu", "scalars.cu", "blur.cu", "morph.cu", "adaptive.cu", "warp.cu", "resize.cu", "synth.cu", "capi.cu"]
+CU_SOURCES = ["ctx.cu", "pointwise.cu", "scalars.cu", "blur.cu", "morph.cu", "adaptive.cu", "warp.cu", "resize.cu", "deskew.cu", "synth.cu", "capi.cu"]
 CPP_SOURCES = ["hostmath.cpp"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

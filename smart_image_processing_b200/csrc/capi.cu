@@ -394,6 +394,71 @@ extern "C" int docscan_warp_affine(docscan_ctx* ctx, const docscan_image* src, c
     return ds_finish(ctx, is_host(src) || is_host(dst));
 }
 
+extern "C" int docscan_canny(docscan_ctx* ctx, const docscan_image* src, double low, double high, docscan_image* dst) {
+    DS_ARGS2(src, dst, 1, 1, "canny");
+    DS_TRY(same_size(ctx, src, dst, "canny"));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst) + k_skew_scratch_bytes(src->width, src->height, false)));
+    ArenaScope scope(ctx);
+    DImg s, d;
+    DS_TRY(ds_stage_in(ctx, src, &s));
+    DS_TRY(ds_stage_out_begin(ctx, dst, &d));
+    DS_TRY(k_skew_estimate(ctx, &s, 1, low, high, 0, 0.0, &d, nullptr, nullptr));
+    DS_TRY(ds_stage_out_end(ctx, dst, d));
+    return ds_finish(ctx, is_host(src) || is_host(dst));
+}
+
+extern "C" int docscan_hough_lines(docscan_ctx* ctx, const docscan_image* edges, int threshold, float* rho_theta, int max_lines,
+                                   int32_t* n_lines, int32_t per_angle[180]) {
+    if (!ctx || !n_lines || max_lines < 0 || (max_lines && !rho_theta)) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, edges, 1, "hough_lines: edges"));
+    const size_t numrho = 2 * ((size_t)edges->width + edges->height) + 1;
+    DS_TRY(begin_call(ctx, host_bytes(edges) + 4 * (size_t)edges->width * edges->height + 182 * (numrho + 2) * 4 + 180 * numrho * 8 + 8192));
+    ArenaScope scope(ctx);
+    DImg e;
+    DS_TRY(ds_stage_in(ctx, edges, &e));
+    std::vector<uint2> lines;
+    int nr = 0;
+    DS_TRY(k_hough_lines(ctx, e, threshold, &lines, &nr));
+    // cv::HoughLinesStandard sorts by votes (descending), ties by accumulator index (ascending)
+    std::sort(lines.begin(), lines.end(), [](const uint2& a, const uint2& b) { return a.y > b.y || (a.y == b.y && a.x < b.x); });
+    if (per_angle) for (int n = 0; n < 180; n++) per_angle[n] = 0;
+    const float theta = (float)(3.1415926535897932384626433832795 / 180);
+    for (size_t k = 0; k < lines.size(); k++) {
+        const int n = (int)lines[k].x / (nr + 2) - 1, r = (int)lines[k].x - (n + 1) * (nr + 2) - 1;
+        if (per_angle) per_angle[n]++;
+        if ((int)k < max_lines) {
+            rho_theta[2 * k] = ((float)r - (float)(nr - 1) * 0.5f) * 1.0f;
+            rho_theta[2 * k + 1] = 0.f + (float)n * theta;
+        }
+    }
+    *n_lines = (int32_t)lines.size();
+    return DOCSCAN_OK;
+}
+
+extern "C" int docscan_skew_angle(docscan_ctx* ctx, const docscan_image* gray, double canny_low, double canny_high,
+                                  double max_rotate, double* angle_deg) {
+    if (!ctx || !angle_deg) return DOCSCAN_ERR_BAD_ARG;
+    DS_TRY(ds_check_image(ctx, gray, 1, "skew_angle: gray"));
+    DS_TRY(begin_call(ctx, host_bytes(gray) + k_skew_scratch_bytes(gray->width, gray->height, true)));
+    ArenaScope scope(ctx);
+    DImg g;
+    DS_TRY(ds_stage_in(ctx, gray, &g));
+    void* a = nullptr;
+    DS_TRY(ds_arena_alloc(ctx, sizeof(double), &a));
+    double* ad = (double*)a;
+    DS_TRY(k_skew_estimate(ctx, &g, 1, canny_low, canny_high, 150, max_rotate, nullptr, &ad, nullptr));
+    return read_back(ctx, angle_deg, ad, sizeof(double));
+}
+
+extern "C" int docscan_last_angles(docscan_ctx* ctx, double* angles, int n) {
+    if (!ctx || !angles || n < 0) return DOCSCAN_ERR_BAD_ARG;
+    if (n > ctx->angles_n) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "last_angles: the last batch had %d pages", ctx->angles_n);
+    DS_CUDA(ctx, cudaSetDevice(ctx->device));
+    DS_CUDA(ctx, cudaMemcpyAsync(angles, ctx->angles_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DOCSCAN_OK;
+}
+
 extern "C" int docscan_resize(docscan_ctx* ctx, const docscan_image* src, docscan_image* dst, int interpolation, int cv_tail_compat) {
     if (!ctx) return DOCSCAN_ERR_BAD_ARG;
     DS_TRY(ds_check_image(ctx, src, 0, "resize: src"));
@@ -453,6 +518,8 @@ namespace {
 
 size_t page_scratch(const docscan_page& pg) {
     const int w = pg.binary.width, h = pg.binary.height;
+    if (std::isnan(pg.angle_deg)) return 16 * plane_bytes(w, h) + 8192 + k_skew_scratch_bytes(w, h, true) + 4096 +
+                                         (pg.use_whole ? 64 * ((size_t)pg.src.width + pg.src.height + w + h) + 4096 : 0);
     size_t tables = pg.use_whole ? 64 * ((size_t)pg.src.width + pg.src.height + w + h) + 4096 : 0;    // resize tables
     return 16 * plane_bytes(w, h) + 4096 + tables;
 }
@@ -497,7 +564,7 @@ SrcRegion warp_footprint(const docscan_page& pg) {
 
 // `regions` (may be null = whole photos): src[i] then views only that part of page i's photo.
 int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params& P, const std::vector<DImg>& src,
-              const std::vector<DImg>& warped, const std::vector<DImg>& binary, const SrcRegion* regions = nullptr) {
+              const std::vector<DImg>& warped, const std::vector<DImg>& binary, int page0, const SrcRegion* regions = nullptr) {
     ArenaScope scope(ctx);
     std::vector<DImg> gray;
     std::vector<WarpPJob> wj(n);
@@ -586,19 +653,35 @@ int run_group(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params
     }
     // a7: mask combine + 2x2 dilate + masked blend
     DS_TRY(blend_batch(ctx, std::max(P.ink_dilate_iters, 0), 0, ink_sub, bh, &base, blend_dst, sc));
-    // a8: deskew rotation
+    // a8: deskew.  Pages without a supplied angle get deskew()'s own estimate (Canny + HoughLines median on the blended
+    // page, DocScanner.py:218-231) on the device; the finishing kernel writes their rotation matrices into the jobs.
     {
         std::vector<WarpAJob> aj(n);
+        std::vector<double> given(n);
+        std::vector<DImg> est_gray;
+        std::vector<int> est_idx;
         for (int i = 0; i < n; i++) {
             WarpAJob& j = aj[i];
             j = WarpAJob{};
             j.src = blend_dst[i].p; j.src_pitch = blend_dst[i].pitch; j.sw = blend_dst[i].w; j.sh = blend_dst[i].h;
             j.dst = rot_dst[i].p; j.dst_pitch = rot_dst[i].pitch; j.dw = rot_dst[i].w; j.dh = rot_dst[i].h;
+            given[i] = pages[i].angle_deg;
+            if (std::isnan(pages[i].angle_deg)) { est_gray.push_back(blend_dst[i]); est_idx.push_back(i); given[i] = 0.0; continue; }
             double m[6];
             DS_TRY(docscan_get_rotation_matrix(blend_dst[i].w / 2.0, blend_dst[i].h / 2.0, pages[i].angle_deg, m));
             hm_invert_affine(m, j.m);
         }
-        DS_TRY(k_warp_affine_jobs(ctx, aj.data(), n, mw, mh));
+        DS_CUDA(ctx, cudaMemcpyAsync(ctx->angles_dev + page0, given.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        WarpAJob* aj_dev = nullptr;
+        DS_TRY(k_warp_affine_upload(ctx, aj.data(), n, &aj_dev));
+        if (!est_idx.empty()) {
+            std::vector<double*> ang(est_idx.size());
+            std::vector<WarpAJob*> rot(est_idx.size());
+            for (size_t k = 0; k < est_idx.size(); k++) { ang[k] = ctx->angles_dev + page0 + est_idx[k]; rot[k] = aj_dev + est_idx[k]; }
+            DS_TRY(k_skew_estimate(ctx, est_gray.data(), (int)est_gray.size(), P.canny_low, P.canny_high, 150, P.max_rotate, nullptr,
+                                   ang.data(), rot.data()));
+        }
+        DS_TRY(k_warp_affine_launch(ctx, aj_dev, aj.data(), n, mw, mh));
     }
     // a9: morph_cleanup (close)
     if (do_close) DS_TRY(morph_op_batch(ctx, DOCSCAN_MORPH_CLOSE, P.morph_ksize, P.morph_ksize, P.morph_iters, rot_dst, binary, nullptr, 0));
@@ -637,6 +720,14 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         any_host = any_host || is_host(&pg.src) || is_host(&pg.warped) || is_host(&pg.binary);
         max_page = std::max(max_page, page_scratch(pg));
     }
+    DS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->angles_cap < n) {
+        // an earlier batch may still be reading the old buffer: it is tiny, so simply keep it until the context dies
+        if (ctx->angles_dev) ctx->user_allocs.push_back(ctx->angles_dev);
+        DS_CUDA(ctx, cudaMalloc((void**)&ctx->angles_dev, sizeof(double) * (size_t)n));
+        ctx->angles_cap = n;
+    }
+    ctx->angles_n = n;
     // pages per launch group: enough 128-column strips to give every SM a few CTAs without cutting pages
     // into short vertical segments (each segment repeats a 2r-row warm-up in the stencil kernels)
     const int strips_per_page = (pages[0].binary.width + 127) / 128;
@@ -674,7 +765,7 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
             const int k = g % ns;
             ctx->stream = k ? ctx->aux[k] : main_stream;
             ctx->arena_off = base + (size_t)k * region;
-            rc = run_group(ctx, m, pages + i, *params, src, warped, binary);
+            rc = run_group(ctx, m, pages + i, *params, src, warped, binary, i);
         }
         ctx->stream = main_stream;
         ctx->arena_off = base;
@@ -752,7 +843,7 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         DS_CUDA(ctx, cudaEventRecord(in_done[sset], ctx->copy_in));
         DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, in_done[sset], 0));
         if (g >= 2) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, out_done[sset], 0));       // set's outputs drained
-        DS_TRY(run_group(ctx, m, pages + i, *params, src, warped, binary, regions.data() + i));
+        DS_TRY(run_group(ctx, m, pages + i, *params, src, warped, binary, i, regions.data() + i));
         DS_CUDA(ctx, cudaEventRecord(comp_done[sset], ctx->stream));
         DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, comp_done[sset], 0));
         for (int j = 0; j < m; j++) {

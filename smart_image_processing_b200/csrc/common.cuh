@@ -32,6 +32,8 @@ struct docscan_ctx {
     bool own_stream = false;
     std::string err;
     int64_t launches = 0;
+    double* angles_dev = nullptr;             // deskew angles of the last docscan_process_pages call
+    int angles_cap = 0, angles_n = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;     // bytes this context has moved between host and device buffers
     int sm_count = DS_SM_COUNT_FALLBACK;
     size_t l2_bytes = 0;
@@ -208,6 +210,14 @@ struct WarpAJob {
     int2* delta;          // per-column fixed-point increments (filled by k_warp_affine_jobs)
 };
 int k_warp_affine_jobs(docscan_ctx*, const WarpAJob* jobs_host, int n, int max_w, int max_h);
+// the same in two steps, so that a device kernel (deskew.cu) can fill in the matrices in between
+int k_warp_affine_upload(docscan_ctx*, const WarpAJob* jobs_host, int n, WarpAJob** jobs_dev);
+int k_warp_affine_launch(docscan_ctx*, const WarpAJob* jobs_dev, const WarpAJob* jobs_host, int n, int max_w, int max_h);
+// deskew.cu : cv2.Canny, cv2.HoughLines(1, pi/180), the median line angle and the rotation matrix, on the device
+size_t k_skew_scratch_bytes(int w, int h, bool want_list);
+int k_skew_estimate(docscan_ctx*, const DImg* gray, int n, double canny_low, double canny_high, int hough_threshold,
+                    double max_rotate, const DImg* edges_out, double* const* angles_dev, WarpAJob* const* rot_jobs);
+int k_hough_lines(docscan_ctx*, const DImg& edges, int threshold, std::vector<uint2>* lines, int* numrho_out);
 // resize.cu : cv2.resize INTER_AREA (shrink) / INTER_CUBIC
 int k_resize(docscan_ctx*, const DImg& src, const DImg& dst, int interpolation, int cv_tail_compat);
 // synth.cu
@@ -231,6 +241,8 @@ int ds_upload(docscan_ctx* ctx, const void* host, size_t bytes, void** dev_out);
 void hm_invert3x3(const double S[9], double T[9]);
 void hm_invert_affine(const double Min[6], double M[6]);
 void hm_gaussian_kernel_f64(int k, double* c);
+void hm_hough_trig_table(float c[180], float s[180]);
+void hm_folded_angles(float out[180]);
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------

@@ -73,6 +73,7 @@ extern "C" int docscan_destroy(docscan_ctx* ctx) {
     free_retired(ctx);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
     for (void* p : ctx->user_allocs) cudaFree(p);
+    if (ctx->angles_dev) cudaFree(ctx->angles_dev);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->copy_in) {

@@ -1,6 +1,7 @@
 // Host-side parameter preparation, bit-exact with the OpenCV helpers the reference calls.
 // Compiled with -ffp-contract=off: every rounding below is where OpenCV's (non-FMA baseline) code rounds.
 #include <cfloat>
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -205,6 +206,7 @@ extern "C" void docscan_default_params(docscan_params* p) {
     p->blackhat_vertical_ratio = 2.0;
     p->ink_dilate_iters = 1;
     p->mask_thresh_offset = 8;
+    p->canny_low = 50; p->canny_high = 150; p->max_rotate = 10.0;
     p->morph_ksize = 3;
     p->morph_iters = 1;
     p->cv_tail_compat = 1;
@@ -263,4 +265,57 @@ void hm_cubic_taps(int ssize, int dsize, int d, int idx[4], short w[4]) {
         const int s = sx - 1 + k;
         idx[k] = s < 0 ? 0 : (s > ssize - 1 ? ssize - 1 : s);
     }
+}
+
+// cv::HoughLines' trig tables for rho = 1, theta = pi/180 (cv::createTrigTable): the angle is accumulated in fp32.
+void hm_hough_trig_table(float c[180], float s[180]) {
+    float ang = 0.f;
+    const double step = 3.1415926535897932384626433832795 / 180;
+    for (int n = 0; n < 180; n++) {
+        s[n] = (float)std::sin((double)ang);
+        c[n] = (float)std::cos((double)ang);
+        ang += (float)step;
+    }
+}
+
+// DocScanner.py:223-226 for the line angle of Hough index n, in the arithmetic numpy >= 2 gives it: theta is np.float32
+// (cv::HoughLines returns min_theta + n * theta in fp32), so theta*180.0/np.pi and (ang + 90.0) % 180.0 - 90.0 stay fp32.
+void hm_folded_angles(float out[180]) {
+    const float step = (float)(3.1415926535897932384626433832795 / 180), pi_f = (float)3.1415926535897932384626433832795;
+    for (int n = 0; n < 180; n++) {
+        const float theta = 0.f + (float)n * step;
+        float ang = theta * 180.0f;
+        ang = ang / pi_f;
+        out[n] = std::fmod(ang + 90.0f, 180.0f) - 90.0f;       // the operand is >= 0, where Python's % is fmod
+    }
+}
+
+// np.median of the folded angles (mean of the middle two in fp32 for an even count), 0 beyond max_rotate or without
+// lines — DocScanner.py:227-231.  per_angle[n] = number of Hough lines with angle index n.
+extern "C" int docscan_median_angle(const int32_t per_angle[180], double max_rotate, double* angle_deg) {
+    if (!per_angle || !angle_deg) return DOCSCAN_ERR_BAD_ARG;
+    float folded[180];
+    hm_folded_angles(folded);
+    int order[180];
+    for (int i = 0; i < 180; i++) order[i] = i;
+    std::stable_sort(order, order + 180, [&](int a, int b) { return folded[a] < folded[b]; });
+    int64_t total = 0;
+    for (int n = 0; n < 180; n++) {
+        if (per_angle[n] < 0) return DOCSCAN_ERR_BAD_ARG;
+        total += per_angle[n];
+    }
+    *angle_deg = 0.0;
+    if (total == 0) return DOCSCAN_OK;
+    const int64_t k_lo = (total - 1) / 2, k_hi = total / 2;
+    int i_lo = -1, i_hi = -1;
+    int64_t run = 0;
+    for (int i = 0; i < 180; i++) {
+        run += per_angle[order[i]];
+        if (i_lo < 0 && run > k_lo) i_lo = i;
+        if (i_hi < 0 && run > k_hi) { i_hi = i; break; }
+    }
+    const float a = folded[order[i_lo]], b = folded[order[i_hi]];
+    const float med = (total & 1) ? a : (a + b) / 2.0f;
+    if (!(std::fabs((double)med) > max_rotate)) *angle_deg = (double)med;
+    return DOCSCAN_OK;
 }

@@ -292,26 +292,36 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     return DOCSCAN_OK;
 }
 
-int k_warp_affine_jobs(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, int max_w, int max_h) {
+int k_warp_affine_upload(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, WarpAJob** jobs_dev) {
     std::vector<WarpAJob> jobs(jobs_in, jobs_in + n);
     for (int i = 0; i < n; i++) {
         void* t = nullptr;
         DS_TRY(ds_arena_alloc(ctx, sizeof(int2) * ((size_t)jobs[i].dw + 4), &t));
         jobs[i].delta = (int2*)t;
     }
-    const WarpAJob* jobs_host = jobs.data();
     void* dev = nullptr;
-    DS_TRY(ds_upload(ctx, jobs_host, sizeof(WarpAJob) * n, &dev));
+    DS_TRY(ds_upload(ctx, jobs.data(), sizeof(WarpAJob) * n, &dev));
+    *jobs_dev = (WarpAJob*)dev;
+    return DOCSCAN_OK;
+}
+
+int k_warp_affine_launch(docscan_ctx* ctx, const WarpAJob* jobs_dev, const WarpAJob* jobs_host, int n, int max_w, int max_h) {
     {
         ProfScope prof(ctx, "warp_affine_deltas", 0);
-        affine_delta_kernel<<<dim3((max_w + 127) / 128, n), 128, 0, ctx->stream>>>((const WarpAJob*)dev);
+        affine_delta_kernel<<<dim3((max_w + 127) / 128, n), 128, 0, ctx->stream>>>(jobs_dev);
         DS_CHECK_LAUNCH(ctx);
     }
     dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
     double px = 0;
     for (int i = 0; i < n; i++) px += (double)jobs_host[i].dw * jobs_host[i].dh;
     ProfScope prof(ctx, "warp_affine", 2.0 * px);
-    warp_affine_kernel<<<grid, block, 0, ctx->stream>>>((const WarpAJob*)dev);
+    warp_affine_kernel<<<grid, block, 0, ctx->stream>>>(jobs_dev);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
+}
+
+int k_warp_affine_jobs(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, int max_w, int max_h) {
+    WarpAJob* dev = nullptr;
+    DS_TRY(k_warp_affine_upload(ctx, jobs_in, n, &dev));
+    return k_warp_affine_launch(ctx, dev, jobs_in, n, max_w, max_h);
 }

@@ -229,3 +229,51 @@ def resize(img, dsize, interpolation, cv_tail_compat=True, ctx=None):
     s, d = image_of(img), image_of(out)
     _ctx(ctx).call("docscan_resize", C.byref(s), C.byref(d), int(interpolation), int(bool(cv_tail_compat)))
     return out
+
+
+def canny(gray, low, high, ctx=None):
+    """cv2.Canny(gray, low, high) (DocScanner.py:218)."""
+    gray = _gray(gray)
+    out = np.empty_like(gray)
+    s, d = image_of(gray), image_of(out)
+    _ctx(ctx).call("docscan_canny", C.byref(s), float(low), float(high), C.byref(d))
+    return out
+
+
+def hough_lines(edges, threshold=150, max_lines=None, return_per_angle=False, ctx=None):
+    """cv2.HoughLines(edges, 1, np.pi / 180, threshold) (DocScanner.py:219): (N, 1, 2) float32 (rho, theta) in OpenCV's
+    order, or None when no line clears the threshold."""
+    edges = _gray(edges)
+    e = image_of(edges)
+    n = C.c_int32()
+    per = np.zeros(180, np.int32)
+    cap = 4096 if max_lines is None else int(max_lines)
+    while True:
+        buf = np.zeros((max(cap, 1), 2), np.float32)
+        _ctx(ctx).call("docscan_hough_lines", C.byref(e), int(threshold), _dptr(buf, C.c_float), cap, C.byref(n), _dptr(per, C.c_int32))
+        if max_lines is not None or n.value <= cap:
+            break
+        cap = n.value
+    k = min(n.value, cap)
+    lines = buf[:k].reshape(-1, 1, 2).copy() if k else None
+    return (lines, per) if return_per_angle else lines
+
+
+def median_angle(per_angle, max_rotate=10.0):
+    """DocScanner.py:221-231 from the number of Hough lines per angle index (host arithmetic of libdocscan)."""
+    per = np.ascontiguousarray(per_angle, np.int32)
+    a = C.c_double()
+    rc = _capi.lib().docscan_median_angle(_dptr(per, C.c_int32), float(max_rotate), C.byref(a))
+    if rc:
+        raise _capi.DocscanError("docscan_median_angle failed")
+    return float(a.value)
+
+
+def skew_angle(gray, canny_low=50, canny_high=150, max_rotate=10.0, ctx=None):
+    """The angle deskew() rotates by: Canny -> HoughLines(1, pi/180, 150) -> median of the folded line angles
+    (DocScanner.py:218-231), all on the device."""
+    gray = _gray(gray)
+    s = image_of(gray)
+    a = C.c_double()
+    _ctx(ctx).call("docscan_skew_angle", C.byref(s), float(canny_low), float(canny_high), float(max_rotate), C.byref(a))
+    return float(a.value)

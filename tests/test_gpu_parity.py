@@ -345,6 +345,73 @@ def test_whole_photo_fallback_pages():
             eq(b[i], ref["clean"], f"whole-photo batch binary {i} sl={sl}")
 
 
+def _binary_page(rng, h, w, ang=0.0):
+    im = np.full((h, w), 255, np.uint8)
+    for i in range(max(1, h // 14)):
+        y, x = 4 + 14 * i, 4
+        while x < w - 12:
+            ww = int(rng.integers(4, 40))
+            im[y:y + 7, x:x + ww] = 0
+            x += ww + int(rng.integers(3, 14))
+    return O.rotate(im, ang) if ang else im
+
+
+def test_canny_hough_skew_angle():
+    """deskew()'s skew estimate on the device (DocScanner.py:218-231): Canny, HoughLines and the angle vs the oracle."""
+    rng = np.random.default_rng(31)
+    for (h, w, ang) in [(400, 300, 0.0), (500, 380, 2.0), (300, 500, -3.5), (700, 520, 1.5), (64, 64, 0.0), (5, 7, 0.0), (1, 40, 0.0),
+                        (40, 1, 0.0), (130, 1031, 0.5)]:
+        g = _binary_page(rng, h, w, ang) if min(h, w) > 10 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+        noisy = np.clip(g.astype(np.int32) + rng.integers(-40, 41, g.shape), 0, 255).astype(np.uint8)
+        for img in (g, noisy, page_like(rng, h, w)):
+            for lo, hi in ((50, 150), (30, 100)):
+                e = O.canny(img, lo, hi)
+                eq(ops.canny(img, lo, hi), e, f"canny {h}x{w} {lo}/{hi}")
+                assert ops.skew_angle(img, lo, hi, 10.0) == O.estimate_skew_angle(img, lo, hi, 10.0), f"skew angle {h}x{w}"
+            e = O.canny(img, 50, 150)
+            for thr in (150, 40):
+                ref, per = O.hough_lines(e, thr)
+                out, per_gpu = ops.hough_lines(e, thr, return_per_angle=True)
+                assert (ref is None) == (out is None), f"hough {h}x{w} thr {thr}"
+                assert np.array_equal(per, per_gpu)
+                if ref is not None:
+                    assert np.array_equal(ref, out), f"hough lines {h}x{w} thr {thr}"
+        eq(DS.deskew(g), O.deskew(g), f"deskew {h}x{w}")
+
+
+def test_sample_jpg_skew_angles_from_the_reference():
+    meta = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
+    for preset in ("cli", "gui"):
+        p = meta["presets"][preset]
+        weighted = load_npz(f"sample_{preset}_bin.npz")["weighted"]
+        a = ops.skew_angle(weighted, p["params"]["canny_low"], p["params"]["canny_high"], p["params"]["max_rotate"])
+        assert a == float.fromhex(p["angle_hex"]), (preset, a, p["angle"])
+
+
+def test_pages_with_device_side_skew_estimate():
+    """angle=None: the estimate runs between blend and rotate inside docscan_process_pages; mixed with supplied angles."""
+    rng = np.random.default_rng(37)
+    imgs, quads = [], []
+    for i in range(4):
+        H, W = int(rng.integers(380, 520)), int(rng.integers(300, 420))
+        base = O.rotate(page_like(rng, H, W), float(rng.integers(-4, 5)))
+        imgs.append(np.stack([np.clip(base * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1))
+        quads.append((np.array([[0.06 * W, 0.05 * H], [0.94 * W, 0.07 * H], [0.95 * W, 0.95 * H], [0.05 * W, 0.93 * H]])
+                      + rng.uniform(-5, 5, (4, 2))).astype(np.float32))
+    given = [None, 1.5, None, None]
+    for kw in (dict(scale_long=520), dict(scale_long=450, canny_low=30, canny_high=100, max_rotate=4.0, morph_ksize=1, morph_iters=0)):
+        w, b, used = DS.process_pages(imgs, quads, given, return_angles=True, **kw)
+        for i in range(len(imgs)):
+            pix = {k: v for k, v in kw.items() if k not in ("canny_low", "canny_high", "max_rotate")}
+            st = O.hot_path(imgs[i], quads[i], 0.0, **pix)
+            a = given[i] if given[i] is not None else O.estimate_skew_angle(st["weighted"], kw.get("canny_low", 50), kw.get("canny_high", 150),
+                                                                           kw.get("max_rotate", 10.0))
+            assert used[i] == a, f"page {i}: device angle {used[i]} vs oracle {a}"
+            ref = O.hot_path(imgs[i], quads[i], a, **pix)
+            eq(w[i], ref["warped"], f"skew batch warped {i}")
+            eq(b[i], ref["clean"], f"skew batch binary {i}")
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
@@ -369,13 +436,16 @@ def test_process_document_drop_in(tmp_path):
     quad = control.localize_document(img)
     assert quad is not None and np.array_equal(res["quad"], quad)
     st = O.hot_path(img, quad, 0.0, scale_long=800)
-    angle = control.estimate_skew_angle(st["weighted"])
-    ref = O.hot_path(img, quad, angle, scale_long=800)
+    angle = control.estimate_skew_angle(st["weighted"])              # cv2 on the host ...
+    assert angle == O.estimate_skew_angle(st["weighted"])            # ... the oracle ...
+    ref = O.hot_path(img, quad, angle, scale_long=800)               # ... and the device (inside process_document) agree
     eq(res["warped"], ref["warped"], "process_document warped")
     eq(res["binary"], ref["clean"], "process_document binary")
     assert os.path.exists(tmp_path / "out" / "scan_08_clean.png")
     # supplying the control-path outputs takes the single fused C-ABI call
     res2 = DS.process_document(path, scale_long=800, quad=quad, angle=angle)
     eq(res2["binary"], ref["clean"], "process_document (fused) binary")
+    res3 = DS.process_document(path, scale_long=800)                 # one fused call, skew estimated on the device
+    eq(res3["binary"], ref["clean"], "process_document (fused, device-side skew estimate) binary")
     with pytest.raises(FileNotFoundError):
         DS.process_document(str(tmp_path / "missing.png"))
