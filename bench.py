@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--ref-pages", type=int, default=96, help="page-jobs per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-skew", action="store_true", help="skip the extra leg with the device-side skew estimate")
     return ap.parse_args()
 
 
@@ -295,6 +296,37 @@ def run_ours(args):
                 "kernels": {k: {"launches": v[0], "ms": round(v[1], 4), "GB/s": (round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None)}
                             for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
 
+    # ---- the same batch with deskew()'s own skew estimate (Canny + HoughLines median) computed on the device for every
+    # page instead of a supplied angle; reported beside the headline, not as it
+    skew = None
+    if not args.no_skew:
+        nan = float("nan")
+        for i in range(P):
+            pages[i].angle_deg = nan
+        step(); step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ssteps = max(1, min(args.steps, 3))
+        s0.record(stream)
+        for _ in range(ssteps):
+            step()
+        s1.record(stream)
+        barrier()
+        sms = sharding.max_over_ranks(s0.elapsed_time(s1), dev)
+        ctx.profile(True)
+        step()
+        sprof = ctx.profile_dump()
+        ctx.profile(False)
+        est = (C.c_double * P)()
+        ctx.call("docscan_last_angles", est, P)
+        skew = {"value": world * P * PAGE_MP * ssteps / (sms / 1e3), "unit": "MP/s", "ms_per_step": sms / ssteps, "steps": ssteps,
+                "what": "angle_deg = NaN for every page: Canny + HoughLines(1, pi/180, 150) + median angle on the device between blend and rotate",
+                "kernels_ms": {k: round(v[1], 4) for k, v in sorted(sprof.items(), key=lambda kv: -kv[1][1])
+                               if k.startswith(("canny", "hough", "skew"))},
+                "angles_estimated_sample": [float(est[i]) for i in range(min(P, 4))]}
+        for i in range(P):
+            pages[i].angle_deg = angles[i]
+
     # ---- e2e: host (pinned) buffers through the same C-ABI call, copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -358,7 +390,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "pages_per_gpu": P, "page": f"{PAGE_H}x{PAGE_W}x3", "warped": f"{th}x{tw}",
                        "scale_long": SCALE_LONG, "parallelism": f"pages sharded over {world} GPU(s), no collective",
                        "l2": f"inputs larger than L2 ({P * PAGE_H * PAGE_W * 3 / 1e9:.1f} GB read per step per GPU)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "with_skew_estimate": skew, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

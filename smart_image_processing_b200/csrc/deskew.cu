@@ -36,6 +36,34 @@ struct SkewJob {
     uint2* cand; uint32_t* n_cand; int max_cand;     // optional (accumulator index, votes) of every line
 };
 
+// ---- hysteresis as connected components (atomic union-find) --------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int* L, int x) {
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+// find with path halving for the merge phase: every visited node is re-pointed at its grandparent.  Racing writers only
+// ever store an ancestor of the node, so the forest stays valid.
+__device__ __forceinline__ int uf_find_halve(int* L, int x) {
+    int p = L[x];
+    while (p != x) {
+        const int gp = L[p];
+        if (gp != p) L[x] = gp;
+        x = p; p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    while (true) {
+        a = uf_find_halve(L, a); b = uf_find_halve(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }      // the larger root is linked under the smaller one
+        const int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
 // ---- Canny: gradient, non-maximum suppression, double threshold -------------------------------------------------
 constexpr int CT_W = 64, CT_H = 16;
 
@@ -70,9 +98,11 @@ __global__ void __launch_bounds__(256) canny_nms_kernel(const SkewJob* __restric
         s_mag[ly][lx] = (short)m;
     }
     __syncthreads();
+    __shared__ int s_lab[CT_H * CT_W];               // tile-local union-find parents (-1 = no candidate)
     for (int i = tid; i < CT_H * CT_W; i += 256) {
         const int ly = i / CT_W, lx = i - ly * CT_W;
         const int y = y0 + ly, x = x0 + lx;
+        s_lab[i] = -1;
         if (y >= J.h || x >= J.w) continue;
         int xs, ys;
         sobel(ly + 2, lx + 2, xs, ys);
@@ -93,25 +123,28 @@ __global__ void __launch_bounds__(256) canny_nms_kernel(const SkewJob* __restric
         }
         const int p = y * J.w + x;
         J.map[p] = cand ? (m > high ? 2 : 0) : 1;
-        J.label[p] = cand ? p : -1;
-        J.rootflag[p] = 0;
+        if (cand) { s_lab[i] = i; J.rootflag[p] = 0; }       // only candidates are ever looked up
     }
-}
-
-// ---- hysteresis as connected components (atomic union-find) --------------------------------------------------------
-__device__ __forceinline__ int uf_find(const int* L, int x) {
-    int p = L[x];
-    while (p != x) { x = p; p = L[x]; }
-    return x;
-}
-__device__ __forceinline__ void uf_union(int* L, int a, int b) {
-    while (true) {
-        a = uf_find(L, a); b = uf_find(L, b);
-        if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }      // the larger root is linked under the smaller one
-        const int old = atomicMin(&L[a], b);
-        if (old == a) return;
-        a = old;
+    // Connected components inside the tile, in shared memory (the dependent loads and atomics of a union-find cost tens
+    // of cycles here instead of hundreds in L2); ccl_merge_kernel then only stitches the tile borders together.
+    __syncthreads();
+    for (int i = tid; i < CT_H * CT_W; i += 256) {
+        if (s_lab[i] < 0) continue;
+        const int ly = i / CT_W, lx = i - ly * CT_W;
+        if (lx > 0 && s_lab[i - 1] >= 0) uf_union(s_lab, i, i - 1);
+        if (ly > 0) {
+            const int q = i - CT_W;
+            if (lx > 0 && s_lab[q - 1] >= 0) uf_union(s_lab, i, q - 1);
+            if (s_lab[q] >= 0) uf_union(s_lab, i, q);
+            if (lx + 1 < CT_W && s_lab[q + 1] >= 0) uf_union(s_lab, i, q + 1);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < CT_H * CT_W; i += 256) {
+        if (s_lab[i] < 0) continue;
+        const int root = uf_find(s_lab, i);
+        const int ly = i / CT_W, lx = i - ly * CT_W, ry = root / CT_W, rx = root - ry * CT_W;
+        J.label[(y0 + ly) * J.w + x0 + lx] = (y0 + ry) * J.w + x0 + rx;
     }
 }
 
@@ -119,14 +152,18 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(const SkewJob* __restric
     const SkewJob J = jobs[blockIdx.z];
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= J.w || y >= J.h) return;
+    // canny_nms_kernel has already joined everything inside its CT_W x CT_H tiles: only neighbour pairs that straddle a
+    // tile border are left
+    const bool left = (x % CT_W) == 0, right = (x % CT_W) == CT_W - 1, top = (y % CT_H) == 0;
+    if (!(left || right || top)) return;
     const int p = y * J.w + x;
-    if (J.label[p] < 0) return;
-    if (x > 0 && J.map[p - 1] != 1) uf_union(J.label, p, p - 1);
+    if (J.map[p] == 1) return;                       // most pixels are no candidates: decide on the byte plane
+    if (left && x > 0 && J.map[p - 1] != 1) uf_union(J.label, p, p - 1);
     if (y > 0) {
         const int q = p - J.w;
-        if (x > 0 && J.map[q - 1] != 1) uf_union(J.label, p, q - 1);
-        if (J.map[q] != 1) uf_union(J.label, p, q);
-        if (x + 1 < J.w && J.map[q + 1] != 1) uf_union(J.label, p, q + 1);
+        if ((left || top) && x > 0 && J.map[q - 1] != 1) uf_union(J.label, p, q - 1);
+        if (top && J.map[q] != 1) uf_union(J.label, p, q);
+        if ((right || top) && x + 1 < J.w && J.map[q + 1] != 1) uf_union(J.label, p, q + 1);
     }
 }
 
@@ -135,10 +172,11 @@ __global__ void __launch_bounds__(256) ccl_flag_kernel(const SkewJob* __restrict
     const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
     if (x >= J.w || y >= J.h) return;
     const int p = y * J.w + x;
-    if (J.label[p] < 0) return;
+    const int mv = J.map[p];
+    if (mv == 1) return;
     const int root = uf_find(J.label, p);
     J.label[p] = root;                               // path compression (roots keep pointing at themselves)
-    if (J.map[p] == 2) J.rootflag[root] = 1;
+    if (mv == 2) J.rootflag[root] = 1;
 }
 
 __global__ void __launch_bounds__(256) ccl_emit_kernel(const SkewJob* __restrict__ jobs) {
@@ -147,18 +185,23 @@ __global__ void __launch_bounds__(256) ccl_emit_kernel(const SkewJob* __restrict
     bool edge = false;
     if (x < J.w && y < J.h) {
         const int p = y * J.w + x;
-        if (J.label[p] >= 0) edge = J.rootflag[uf_find(J.label, p)] != 0;
+        if (J.map[p] != 1) edge = J.rootflag[uf_find(J.label, p)] != 0;
         if (J.edges) J.edges[(size_t)y * J.edges_pitch + x] = edge ? 255 : 0;
     }
     if (J.list) {
+        // one global atomic per CTA: warps publish their counts, the first warp reserves the block's range
+        __shared__ uint32_t s_cnt[8], s_base;
         const uint32_t ballot = __ballot_sync(0xffffffffu, edge);
-        if (ballot) {
-            const int lane = threadIdx.x & 31;
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(J.count, __popc(ballot));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (edge) J.list[base + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)x | ((uint32_t)y << 16);
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+        if (lane == 0) s_cnt[wrp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+            for (int k = 0; k < 8; k++) { const uint32_t c = s_cnt[k]; s_cnt[k] = total; total += c; }
+            s_base = total ? atomicAdd(J.count, total) : 0u;
         }
+        __syncthreads();
+        if (edge) J.list[s_base + s_cnt[wrp] + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)x | ((uint32_t)y << 16);
     }
 }
 
@@ -179,27 +222,35 @@ __global__ void __launch_bounds__(256) edge_list_kernel(const SkewJob* __restric
 // ---- standard Hough transform: one CTA per (angle, page), votes in shared memory ----------------------------------
 struct TrigTable { float c[NANG], s[NANG]; };
 
+// VOTE_NA angles share one pass over the edge list (the list is streamed from L2 by every CTA of a page, so the number
+// of passes is what the kernel costs); each angle has its own accumulator row in shared memory.
+template <int VOTE_NA>
 __global__ void __launch_bounds__(512) hough_vote_kernel(const SkewJob* __restrict__ jobs, const __grid_constant__ TrigTable T) {
     const SkewJob J = jobs[blockIdx.z];
-    const int n = blockIdx.x;
+    const int n0 = blockIdx.x * VOTE_NA;
     extern __shared__ int s_acc[];
     const int width = J.numrho + 2;
-    for (int i = threadIdx.x; i < width; i += 512) s_acc[i] = 0;
+    for (int i = threadIdx.x; i < VOTE_NA * width; i += 512) s_acc[i] = 0;
     __syncthreads();
-    const float tc = T.c[n], ts = T.s[n];
+    float tc[VOTE_NA], ts[VOTE_NA];
+#pragma unroll
+    for (int a = 0; a < VOTE_NA; a++) { tc[a] = T.c[n0 + a]; ts[a] = T.s[n0 + a]; }
     const int half = (J.numrho - 1) / 2;
     const uint32_t cnt = *J.count;
     for (uint32_t e = threadIdx.x; e < cnt; e += 512) {
         const uint32_t v = J.list[e];
         const float fj = (float)(v & 0xffffu), fi = (float)(v >> 16);
-        const int r = __float2int_rn(__fadd_rn(__fmul_rn(fj, tc), __fmul_rn(fi, ts))) + half;
-        atomicAdd(&s_acc[r + 1], 1);
+#pragma unroll
+        for (int a = 0; a < VOTE_NA; a++) {
+            const int r = __float2int_rn(__fadd_rn(__fmul_rn(fj, tc[a]), __fmul_rn(fi, ts[a]))) + half;
+            atomicAdd(&s_acc[a * width + r + 1], 1);
+        }
     }
     __syncthreads();
-    int* row = J.accum + (size_t)(n + 1) * width;
-    for (int i = threadIdx.x; i < width; i += 512) row[i] = s_acc[i];
-    if (n == 0) for (int i = threadIdx.x; i < width; i += 512) J.accum[i] = 0;                                   // border rows
-    if (n == NANG - 1) for (int i = threadIdx.x; i < width; i += 512) J.accum[(size_t)(NANG + 1) * width + i] = 0;
+    int* rows = J.accum + (size_t)(n0 + 1) * width;
+    for (int i = threadIdx.x; i < VOTE_NA * width; i += 512) rows[i] = s_acc[i];
+    if (n0 == 0) for (int i = threadIdx.x; i < width; i += 512) J.accum[i] = 0;                                   // border rows
+    if (n0 == NANG - VOTE_NA) for (int i = threadIdx.x; i < width; i += 512) J.accum[(size_t)(NANG + 1) * width + i] = 0;
 }
 
 __global__ void __launch_bounds__(256) hough_peaks_kernel(const SkewJob* __restrict__ jobs, int threshold) {
@@ -276,6 +327,25 @@ __global__ void skew_finish_kernel(const SkewJob* __restrict__ jobs, const SkewO
         I[2] = __dsub_rn(__dmul_rn(-I[0], F[2]), __dmul_rn(I[1], F[5]));
         I[5] = __dsub_rn(__dmul_rn(-I[3], F[2]), __dmul_rn(I[4], F[5]));
     }
+}
+
+template <int NA>
+int launch_vote_t(docscan_ctx* ctx, const SkewJob* jd, int n, size_t smem, const TrigTable& T) {
+    if (smem > 48 * 1024) DS_CUDA(ctx, cudaFuncSetAttribute(hough_vote_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hough_vote_kernel<NA><<<dim3(NANG / NA, 1, n), 512, smem, ctx->stream>>>(jd, T);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}
+
+// as many angles per CTA (4, 2 or 1) as the accumulator rows of the largest page leave room for in shared memory
+int launch_vote(docscan_ctx* ctx, const SkewJob* jd, int n, int max_rho) {
+    TrigTable T;
+    hm_hough_trig_table(T.c, T.s);
+    const size_t row = sizeof(int) * (size_t)(max_rho + 2), cap = 100 * 1024;      // <= 100 KB: two CTAs per SM
+    if (4 * row <= cap) return launch_vote_t<4>(ctx, jd, n, 4 * row, T);
+    if (2 * row <= 2 * cap) return launch_vote_t<2>(ctx, jd, n, 2 * row, T);
+    if (row <= 220 * 1024) return launch_vote_t<1>(ctx, jd, n, row, T);
+    return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "Hough transform: image too large for an accumulator row in shared memory");
 }
 
 int get_skew_tables(docscan_ctx* ctx, SkewTables* T) {
@@ -363,24 +433,24 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
     }
     const dim3 pgrid((mw + 63) / 64, (mh + 3) / 4, n);
     {
-        ProfScope prof(ctx, "canny_hysteresis", 12.0 * px);
+        ProfScope prof(ctx, "canny_hyst_merge", 0);
         ccl_merge_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
         DS_CHECK_LAUNCH(ctx);
+    }
+    {
+        ProfScope prof(ctx, "canny_hyst_flag", 0);
         ccl_flag_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
         DS_CHECK_LAUNCH(ctx);
+    }
+    {
+        ProfScope prof(ctx, "canny_hyst_emit", 0);
         ccl_emit_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
         DS_CHECK_LAUNCH(ctx);
     }
     if (!want_angle) return DOCSCAN_OK;
-    TrigTable T;
-    hm_hough_trig_table(T.c, T.s);
-    const size_t smem = sizeof(int) * (size_t)(max_rho + 2);
-    if (smem > 200 * 1024) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "skew estimate: image too large for the Hough accumulator row");
-    if (smem > 48 * 1024) DS_CUDA(ctx, cudaFuncSetAttribute(hough_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope prof(ctx, "hough_vote", 0);
-        hough_vote_kernel<<<dim3(NANG, 1, n), 512, smem, ctx->stream>>>(jd, T);
-        DS_CHECK_LAUNCH(ctx);
+        DS_TRY(launch_vote(ctx, jd, n, max_rho));
     }
     {
         ProfScope prof(ctx, "hough_peaks", 0);
@@ -419,13 +489,7 @@ int k_hough_lines(docscan_ctx* ctx, const DImg& edges, int threshold, std::vecto
     const SkewJob* jd = (const SkewJob*)dev;
     edge_list_kernel<<<dim3((w + 63) / 64, (h + 3) / 4, 1), 256, 0, ctx->stream>>>(jd);
     DS_CHECK_LAUNCH(ctx);
-    TrigTable T;
-    hm_hough_trig_table(T.c, T.s);
-    const size_t smem = sizeof(int) * (size_t)(j.numrho + 2);
-    if (smem > 200 * 1024) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "hough_lines: image too large for the accumulator row");
-    if (smem > 48 * 1024) DS_CUDA(ctx, cudaFuncSetAttribute(hough_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hough_vote_kernel<<<dim3(NANG, 1, 1), 512, smem, ctx->stream>>>(jd, T);
-    DS_CHECK_LAUNCH(ctx);
+    DS_TRY(launch_vote(ctx, jd, 1, j.numrho));
     hough_peaks_kernel<<<dim3((j.numrho + 255) / 256, NANG, 1), 256, 0, ctx->stream>>>(jd, threshold);
     DS_CHECK_LAUNCH(ctx);
     uint32_t n_cand = 0;
