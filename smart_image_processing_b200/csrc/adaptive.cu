@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
     // columns cv2's AVX2 build evaluates without fma (k <= 9: the taps are dyadic, every order is exact)
     const int tail = (L.tail_compat && L.k >= 11) ? (J.w & 7) : 0;
     const int xt_col = J.w - tail;                                  // column filter: mul+add from here on
-    const int xt_row = xt_col + (tail >= 4 ? 4 : 0);                // row filter: scalar code from here on
 
     for (int hb = 0; hb < n_vb + D; hb++) {
         {
@@ -105,33 +104,9 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
             if (row_identity) {
 #pragma unroll
                 for (int o = 0; o < 16; o++) acc[o] = sp[RMAX + o];
-            } else if (xt_row < J.w && x0 + c0 + 15 >= xt_row && x0 + c0 < J.w) {
-                // cv2's row filter leaves the last w % 4 columns (w % 8 >= 4: the last w % 8 - 4) to scalar code: mul+add per
-                // tap, except that the (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9).  At most 3 columns per
-                // row; their chains run side by side so the thread that owns them does not hold up its CTA.
-                const int o_first = max(0, xt_row - (x0 + c0));
-                const int nt = min(16, J.w - (x0 + c0)) - o_first;                  // 1..3 columns
-                const float* in = sp + o_first + RMAX - L.r;                        // tap 0 of the first tail column
-                const int first_fused = L.k - ((L.k - 1) & 3);
-                const float g0 = L.gh[L.r];
-                float a0 = __fmul_rn(g0, in[0]), a1 = __fmul_rn(g0, in[1]), a2 = __fmul_rn(g0, in[2]);
-                int i = 1;
-#pragma unroll 4
-                for (; i < first_fused; i++) {
-                    const float gi = L.gh[abs(i - L.r)];
-                    a0 = __fadd_rn(a0, __fmul_rn(gi, in[i])); a1 = __fadd_rn(a1, __fmul_rn(gi, in[i + 1])); a2 = __fadd_rn(a2, __fmul_rn(gi, in[i + 2]));
-                }
-                for (; i < L.k; i++) {
-                    const float gi = L.gh[abs(i - L.r)];
-                    a0 = __fmaf_rn(in[i], gi, a0); a1 = __fmaf_rn(in[i + 1], gi, a1); a2 = __fmaf_rn(in[i + 2], gi, a2);
-                }
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    if (q == o_first) acc[q] = a0;
-                    if (q == o_first + 1 && nt > 1) acc[q] = a1;
-                    if (q == o_first + 2 && nt > 2) acc[q] = a2;
-                }
             }
+            // (the few columns cv2's row filter evaluates with scalar code are redone by adaptive_tail_kernel afterwards:
+            // their serial tap chains would otherwise hold up the whole CTA of the last strip)
             float4* dst = reinterpret_cast<float4*>(s_ring + ((hb * BR + hr) % RR) * RPF + c0);
             dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -197,6 +172,50 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
                 dp += J.dst_pitch;
             }
         }
+    }
+}
+
+// cv2's row filter leaves the last w % 4 columns (w % 8 >= 4: the last w % 8 - 4) to scalar code: mul+add per tap,
+// except that the (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9); its column filter is unfused from
+// column w - w % 8 on.  This kernel recomputes those <= 3 columns of every page after the main kernel: a CTA takes
+// TAIL_ROWS output rows, evaluates the row-filter chains of the rows it needs into shared memory, then the columns.
+constexpr int TAIL_ROWS = 64;
+__global__ void __launch_bounds__(128) adaptive_tail_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L) {
+    const AdaptJob J = jobs[blockIdx.y];
+    const int tail = J.w & 7;
+    const int nt = tail >= 4 ? tail - 4 : tail;                     // scalar-row columns
+    const int y0 = blockIdx.x * TAIL_ROWS;
+    if (nt == 0 || y0 >= J.h) return;
+    const int xt = J.w - nt, r = L.r, k = L.k;
+    __shared__ float s_row[(TAIL_ROWS + 2 * 32) * 3];
+    const int nrows = min(TAIL_ROWS, J.h - y0), nv = nrows + 2 * r;
+    const bool row_identity = J.w == 1, col_identity = J.h == 1;
+    const int first_fused = k - ((k - 1) & 3);
+    for (int t = threadIdx.x; t < nv * nt; t += 128) {
+        const int v = t / nt, c = t - v * nt;
+        const uint8_t* rowp = J.src + (size_t)ds_clamp(y0 - r + v, 0, J.h - 1) * J.src_pitch;
+        const int xc = xt + c;
+        float a;
+        if (row_identity) a = (float)rowp[xc];
+        else {
+            a = __fmul_rn(L.gh[r], (float)rowp[ds_clamp(xc - r, 0, J.w - 1)]);
+            int i = 1;
+            for (; i < first_fused; i++) a = __fadd_rn(a, __fmul_rn(L.gh[abs(i - r)], (float)rowp[ds_clamp(xc - r + i, 0, J.w - 1)]));
+            for (; i < k; i++) a = __fmaf_rn((float)rowp[ds_clamp(xc - r + i, 0, J.w - 1)], L.gh[abs(i - r)], a);
+        }
+        s_row[v * 3 + c] = a;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nrows * nt; t += 128) {
+        const int o = t / nt, c = t - o * nt;
+        float m = s_row[(o + r) * 3 + c];
+        if (!col_identity) {
+            m = __fmul_rn(L.gh[0], m);
+            for (int j = 1; j <= r; j++) m = __fadd_rn(m, __fmul_rn(L.gh[j], __fadd_rn(s_row[(o + r + j) * 3 + c], s_row[(o + r - j) * 3 + c])));
+        }
+        const int mean = min(max(__float2int_rn(m), 0), 255);
+        const int y = y0 + o, x = xt + c;
+        J.dst[(size_t)y * J.dst_pitch + x] = ((int)J.src[(size_t)y * J.src_pitch + x] - mean > -L.c_param) ? 255 : 0;
     }
 }
 
@@ -388,6 +407,15 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     else rc = launch_adaptive<32>(ctx, jd, L, G, smem);
     }
     DS_TRY(rc);
+    if (cv_tail_compat && k >= 11) {
+        bool any = false;
+        for (int i = 0; i < n; i++) any = any || (jobs_host[i].w & 3) != 0;
+        if (any) {
+            ProfScope prof(ctx, "adaptive_gauss_tail", 0);
+            adaptive_tail_kernel<<<dim3((max_h + TAIL_ROWS - 1) / TAIL_ROWS, n), 128, 0, ctx->stream>>>(jd, L);
+            DS_CHECK_LAUNCH(ctx);
+        }
+    }
     return DOCSCAN_OK;
 }
 

@@ -733,6 +733,7 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
     const int strips_per_page = (pages[0].binary.width + 127) / 128;
     int group = (2 * ctx->sm_count + strips_per_page - 1) / strips_per_page;
     group = std::max(4, std::min(group, 32));
+    if (n >= 4 * 64) group = 64;                       // big resident batches: one 64-page group per stream measured best
     if (const char* e = getenv("DOCSCAN_GROUP")) group = std::max(1, atoi(e));
     if (any_host) group = std::min(group, 8);          // finer pipeline granularity: copies overlap compute
     group = std::min(group, n);
@@ -740,7 +741,7 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         // Device-resident batch.  Consecutive groups rotate over the context's stream and up to DS_MAX_STREAMS-1 extra
         // compute streams (own scratch region each): the small serial kernels of one group (Otsu scan, LUTs) and its wave tails
         // overlap the big kernels of the other.  With per-kernel profiling on, a single stream keeps timings clean.
-        int ns = ctx->prof_on ? 1 : std::min(3, (n + group - 1) / group);      // 3 measured best on B200 (profiles/README.md)
+        int ns = ctx->prof_on ? 1 : std::min(DS_MAX_STREAMS, (n + group - 1) / group);   // 4 measured best on B200 (profiles/README.md)
         if (const char* e = getenv("DOCSCAN_STREAMS")) ns = std::max(1, std::min(std::min(DS_MAX_STREAMS, (n + group - 1) / group), atoi(e)));
         DS_TRY(begin_call(ctx, max_page * group * ns));
         for (int k = 1; k < ns; k++)
