@@ -212,6 +212,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     ctx = _capi.Context(local, stream=stream.cuda_stream)
@@ -286,7 +287,10 @@ def run_ours(args):
     achieved = nbytes / n_l / (t_ms / n_l * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top[0].split("_k")[0])
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj["dram_bytes_per_launch"].get(top[0].split("_k")[0])
+        if traffic is not None:            # ncu captured launches of tj["pages_per_launch"] pages: scale to this run's launches
+            traffic = traffic * (P / n_l) / tj["pages_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Regenerates the tables of profiles/README.md from the raw ncu outputs.
 
-    python profiles/summarize.py profiles/r1_launches.csv gpurun_out/prof_r1_final.ncu-rep
+    python profiles/summarize.py profiles/r1_launches.csv gpurun_out/prof_r1f.ncu-rep
 
 (1) launch list -> per-kernel share; (2) `ncu --set full` report -> one line per captured kernel
 (profiles/r1_ncu_full.txt) and profiles/traffic.json (DRAM read+write bytes per launch, used by bench.py's
@@ -47,7 +47,7 @@ KEEP = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu
 
 
 def key_of(name):
-    for pat, key in (("adaptive", "adaptive_gauss"), ("warp_persp", "warp_perspective_c3"), ("blur", "blur_gauss"),
+    for pat, key in (("adaptive_tail", "adaptive_gauss_tail"), ("adaptive", "adaptive_gauss"), ("lut16", "pw_lut"), ("otsu", "scalars_otsu"), ("warp_persp", "warp_perspective_c3"), ("blur", "blur_gauss"),
                      ("morph_march", "morph_march"), ("mask_blend", "mask_blend"), ("warp_affine", "warp_affine")):
         if pat in name:
             return key
@@ -72,7 +72,8 @@ def full_report(rep):
                   f"dram {t / 1e6:8.1f} MB  issue {float(r[hdr.index('smsp__issue_active.avg.pct_of_peak_sustained_active')]):5.1f} %  "
                   f"warps {float(r[hdr.index('sm__warps_active.avg.pct_of_peak_sustained_active')]):5.1f} %")
     path = os.path.join(HERE, "traffic.json")
-    json.dump(traffic, open(path, "w"), indent=1)
+    # the capture command runs bench.py --pages 32: one launch = 32 pages; bench.py scales to its own launch size
+    json.dump({"pages_per_launch": 32, "dram_bytes_per_launch": traffic}, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":
