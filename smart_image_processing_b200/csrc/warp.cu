@@ -235,15 +235,23 @@ __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __rest
         if (x >= J.dw) break;
         const int2 dl = __ldg(J.delta + x);
         const int X = (X0 + dl.x) >> 5, Y = (Y0 + dl.y) >> 5;
-        const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+        // (OpenCV keeps sx, sy as saturated shorts; with sources below 32767 px the replicate clamp gives the same taps)
+        const int sx = X >> 5, sy = Y >> 5;
         const int ax = X & 31, ay = Y & 31;
-        const int xa = ds_clamp(sx, 0, sw - 1), xb = ds_clamp(sx + 1, 0, sw - 1);
-        const int ya = ds_clamp(sy, 0, sh - 1), yb = ds_clamp(sy + 1, 0, sh - 1);
-        const uint8_t* r0 = src + (size_t)ya * sp;
-        const uint8_t* r1 = src + (size_t)yb * sp;
+        int h0, h1;
         // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) * ((32-ax) p00 + ax p01) + ay * ((32-ax) p10 + ax p11)] exactly
-        const int h0 = (32 - ax) * __ldg(r0 + xa) + ax * __ldg(r0 + xb);
-        const int h1 = (32 - ax) * __ldg(r1 + xa) + ax * __ldg(r1 + xb);
+        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {      // interior: no clamping
+            const uint8_t* r0 = src + (size_t)sy * sp + sx;
+            h0 = (32 - ax) * __ldg(r0) + ax * __ldg(r0 + 1);
+            h1 = (32 - ax) * __ldg(r0 + sp) + ax * __ldg(r0 + sp + 1);
+        } else {
+            const int xa = ds_clamp(sx, 0, sw - 1), xb = ds_clamp(sx + 1, 0, sw - 1);
+            const int ya = ds_clamp(sy, 0, sh - 1), yb = ds_clamp(sy + 1, 0, sh - 1);
+            const uint8_t* r0 = src + (size_t)ya * sp;
+            const uint8_t* r1 = src + (size_t)yb * sp;
+            h0 = (32 - ax) * __ldg(r0 + xa) + ax * __ldg(r0 + xb);
+            h1 = (32 - ax) * __ldg(r1 + xa) + ax * __ldg(r1 + xb);
+        }
         drow[x] = (uint8_t)(((32 - ay) * h0 + ay * h1 + 512) >> 10);
     }
 }
@@ -295,6 +303,8 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
 int k_warp_affine_upload(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, WarpAJob** jobs_dev) {
     std::vector<WarpAJob> jobs(jobs_in, jobs_in + n);
     for (int i = 0; i < n; i++) {
+        if (jobs[i].sw >= 32767 || jobs[i].sh >= 32767)      // cv::remap's own limit (coordinates are shorts)
+            return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "warp source larger than 32766 px");
         void* t = nullptr;
         DS_TRY(ds_arena_alloc(ctx, sizeof(int2) * ((size_t)jobs[i].dw + 4), &t));
         jobs[i].delta = (int2*)t;
