@@ -120,6 +120,19 @@ int morph_op_batch(docscan_ctx* ctx, int op, int kw, int kh, int iterations, con
         case DOCSCAN_MORPH_CLOSE:
         case DOCSCAN_MORPH_BLACKHAT:
         case DOCSCAN_MORPH_OPEN: {
+            if (kw == 3 && kh == 3 && iterations == 1 && op != DOCSCAN_MORPH_BLACKHAT && !(sc && hist_sel)) {
+                // morph_cleanup's default: one fused register-only pass instead of two marching passes
+                const int n = (int)src.size();
+                std::vector<MorphJob> jobs(n);
+                for (int i = 0; i < n; i++) {
+                    MorphJob& j = jobs[i];
+                    j = MorphJob{};
+                    j.src = src[i].p; j.src_pitch = src[i].pitch; j.dst = dst[i].p; j.dst_pitch = dst[i].pitch; j.w = src[i].w; j.h = src[i].h;
+                }
+                int mw, mh; max_dims(src, &mw, &mh);
+                int rc = DOCSCAN_OK;
+                if (k_morph_close3(ctx, op == DOCSCAN_MORPH_OPEN, jobs.data(), n, mw, mh, &rc)) return rc;
+            }
             std::vector<DImg> mid;
             DS_TRY(alloc_planes(ctx, src, &mid));
             const int first = op == DOCSCAN_MORPH_OPEN ? 0 : 1;

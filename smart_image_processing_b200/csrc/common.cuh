@@ -176,6 +176,8 @@ struct MorphJob {
 };
 int k_morph_jobs(docscan_ctx*, int is_dilate, int kw, int kh, int ax, int ay, const MorphJob* jobs_host, int n,
                  int max_w, int max_h);
+// 3x3 close (open_not_close = 0) / open (1), one iteration, as one fused pass; false when the buffers are not 16-byte aligned
+bool k_morph_close3(docscan_ctx*, int open_not_close, const MorphJob* jobs_host, int n, int max_w, int max_h, int* rc);
 // adaptive.cu (gaussian, fp32 ordered fma)
 struct AdaptJob {
     const uint8_t* src; uint8_t* dst;

@@ -409,6 +409,151 @@ int launch_axis(docscan_ctx* ctx, int axis, int is_dilate, int k, int a, const M
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------
+// morphologyEx(CLOSE | OPEN) with the 3x3 rectangle, one iteration (morph_cleanup's default, DocScanner.py:247-259), as
+// ONE register-only pass for the library's own 16-byte-aligned planes.  A thread owns a 16-pixel column chunk (plus one
+// word either side) and marches down its rows: the first operation's 3-row window and the second operation's 3-row
+// window roll through registers, the horizontal windows come from funnel shifts on packed bytes.  Out-of-image pixels
+// are the first operation's neutral element when it reads them and the second operation's neutral element when IT
+// reads them (OpenCV ignores outside pixels in each pass separately).  HBM-shaped: the plane is read once, written once.
+namespace fused3 {
+constexpr int SEG_MAX = 64;      // output rows per thread: halved on the host until the launch fills the machine
+
+// Pixels travel as 16-bit lanes, two per register, so that min / max is the native VIMNMX.U16x2 (the byte-wise
+// __vminu4 / __vmaxu4 are emulated with ~20 logic instructions on this architecture).
+template <bool DIL> __device__ __forceinline__ uint32_t op2(uint32_t a, uint32_t b) { return DIL ? __vmaxu2(a, b) : __vminu2(a, b); }
+
+// 3-wide horizontal window over N pair registers: m[i] valid in every lane that has both neighbours in the array
+template <bool DIL, int N>
+__device__ __forceinline__ void hwin(const uint32_t (&r)[N], uint32_t (&m)[N]) {
+    constexpr uint32_t NEUT = DIL ? 0u : 0x00ff00ffu;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const uint32_t left = odd_shift(i ? r[i - 1] : NEUT, r[i]);           // (px-1, px0) of the pair (px0, px1)
+        const uint32_t right = odd_shift(r[i], i + 1 < N ? r[i + 1] : NEUT);   // (px1, px2)
+        m[i] = op2<DIL>(op2<DIL>(r[i], left), right);
+    }
+}
+
+// FIRST_DIL = true: close (dilate then erode); false: open (erode then dilate)
+template <bool FIRST_DIL>
+__global__ void __launch_bounds__(128) close3_kernel(const MorphJob* __restrict__ jobs, int chunks, int segs, int SEG) {
+    const MorphJob J = jobs[blockIdx.y];
+    const int id = blockIdx.x * 128 + threadIdx.x;
+    const int sg = id / chunks, xc = id - sg * chunks;
+    const int x = xc * 16, y0 = sg * SEG;
+    if (sg >= segs || x >= J.w || y0 >= J.h) return;
+    constexpr uint32_t N1 = FIRST_DIL ? 0u : 0x00ff00ffu;       // neutral of the first pass
+    constexpr uint32_t N2 = FIRST_DIL ? 0x00ff00ffu : 0u;       // neutral of the second pass
+    // pair register i holds px (x - 2 + 2i, x - 1 + 2i), i = 0..9; vm: 0xff in the lanes whose column lies inside the image
+    uint32_t vm[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const int p = x - 2 + 2 * i;
+        vm[i] = ((p >= 0 && p < J.w) ? 0x000000ffu : 0u) | ((p + 1 >= 0 && p + 1 < J.w) ? 0x00ff0000u : 0u);
+    }
+    const bool has_left = x > 0, has_right = x + 16 < J.w;
+    auto load_h = [&](int y, uint32_t (&m)[10]) {                // horizontal first-pass window of source row y
+        uint32_t r[10];
+        if (y < 0 || y >= J.h) {
+#pragma unroll
+            for (int i = 0; i < 10; i++) r[i] = N1;
+        } else {
+            const uint8_t* rowp = J.src + (size_t)y * J.src_pitch + x;
+            const uint4 c = __ldg(reinterpret_cast<const uint4*>(rowp));
+            const uint32_t wl = has_left ? ds_ldg32(rowp - 4) : 0u, wr = has_right ? ds_ldg32(rowp + 16) : 0u;
+            r[0] = __byte_perm(wl, 0, 0x4342);
+            r[1] = __byte_perm(c.x, 0, 0x4140); r[2] = __byte_perm(c.x, 0, 0x4342);
+            r[3] = __byte_perm(c.y, 0, 0x4140); r[4] = __byte_perm(c.y, 0, 0x4342);
+            r[5] = __byte_perm(c.z, 0, 0x4140); r[6] = __byte_perm(c.z, 0, 0x4342);
+            r[7] = __byte_perm(c.w, 0, 0x4140); r[8] = __byte_perm(c.w, 0, 0x4342);
+            r[9] = __byte_perm(wr, 0, 0x4140);
+#pragma unroll
+            for (int i = 0; i < 10; i++) r[i] = FIRST_DIL ? (r[i] & vm[i]) : (r[i] | (vm[i] ^ 0x00ff00ffu));
+        }
+        hwin<FIRST_DIL, 10>(r, m);
+    };
+    // second-pass horizontal window of first-pass row r: outside the image the first pass's result is replaced by the
+    // second pass's neutral element
+    auto second_h = [&](int r, const uint32_t (&a)[10], const uint32_t (&b)[10], const uint32_t (&c)[10], uint32_t (&out)[8]) {
+        uint32_t d[10], m[10];
+        const bool row_in = r >= 0 && r < J.h;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            const uint32_t v = op2<FIRST_DIL>(op2<FIRST_DIL>(a[i], b[i]), c[i]);
+            d[i] = !row_in ? N2 : (FIRST_DIL ? (v | (vm[i] ^ 0x00ff00ffu)) : (v & vm[i]));
+        }
+        hwin<!FIRST_DIL, 10>(d, m);
+#pragma unroll
+        for (int i = 0; i < 8; i++) out[i] = m[i + 1];
+    };
+    // rolling state, indexed modulo 3 with compile-time indices (the row loop is unrolled by 3): hs = first-pass
+    // horizontal rows, he = second-pass horizontal rows
+    uint32_t hs[3][10], he[3][8];
+    const int y_end = min(y0 + SEG, J.h);
+    load_h(y0 - 2, hs[0]);
+    load_h(y0 - 1, hs[1]);
+    load_h(y0, hs[2]);
+    second_h(y0 - 1, hs[0], hs[1], hs[2], he[0]);               // second-pass row y0-1
+    load_h(y0 + 1, hs[0]);
+    second_h(y0, hs[1], hs[2], hs[0], he[1]);                   // row y0
+    const bool full = x + 16 <= J.w;
+    // invariant at the top of step u (output row y): hs[(u+1)%3] = row y, hs[(u+2)%3]... see the indices below
+    for (int yb = y0; yb < y_end; yb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+            const int y = yb + u;
+            // rows y, y+1 live in hs[(u+2)%3], hs[u%3]; the new row y+2 replaces row y-1 in hs[(u+1)%3]
+            load_h(y + 2, hs[(u + 1) % 3]);
+            second_h(y + 1, hs[(u + 2) % 3], hs[u % 3], hs[(u + 1) % 3], he[(u + 2) % 3]);     // row y+1
+            if (y < y_end) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t lo = op2<!FIRST_DIL>(op2<!FIRST_DIL>(he[0][2 * j], he[1][2 * j]), he[2][2 * j]);
+                    const uint32_t hi = op2<!FIRST_DIL>(op2<!FIRST_DIL>(he[0][2 * j + 1], he[1][2 * j + 1]), he[2][2 * j + 1]);
+                    o[j] = __byte_perm(lo, hi, 0x6420);
+                }
+                uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x;
+                if (full) *reinterpret_cast<uint4*>(dp) = make_uint4(o[0], o[1], o[2], o[3]);
+                else for (int b = 0; b < J.w - x; b++) dp[b] = (uint8_t)(o[b >> 2] >> (8 * (b & 3)));
+            }
+        }
+    }
+}
+}  // namespace fused3
+
+// true when the fused 3x3 close / open kernel took the batch
+bool k_morph_close3(docscan_ctx* ctx, int open_not_close, const MorphJob* jobs_host, int n, int max_w, int max_h, int* rc) {
+    for (int i = 0; i < n; i++) {
+        const MorphJob& j = jobs_host[i];
+        const int need = ((j.w + 15) >> 4) << 4;                 // whole 16-byte chunks are read
+        if (((reinterpret_cast<uintptr_t>(j.src) | reinterpret_cast<uintptr_t>(j.dst) | (uintptr_t)j.src_pitch | (uintptr_t)j.dst_pitch) & 15) ||
+            j.src_pitch < need || j.ref || j.hist)
+            return false;
+        const uint8_t* s0 = j.src; const uint8_t* s1 = j.src + (size_t)j.src_pitch * j.h;
+        const uint8_t* d0 = j.dst; const uint8_t* d1 = j.dst + (size_t)j.dst_pitch * j.h;
+        if (s0 < d1 && d0 < s1) return false;                   // in place: neighbours would be read after they were overwritten
+    }
+    void* dev = nullptr;
+    *rc = ds_upload(ctx, jobs_host, sizeof(MorphJob) * n, &dev);
+    if (*rc != DOCSCAN_OK) return true;
+    const int chunks = (max_w + 15) >> 4;
+    int seg = fused3::SEG_MAX;                                   // every segment re-reads 4 halo rows: keep them long ...
+    while (seg > 8 && (long long)chunks * ((max_h + seg - 1) / seg) * n < 2LL * ctx->sm_count * 2048) seg >>= 1;   // ... unless SMs would idle
+    const int segs = (max_h + seg - 1) / seg;
+    double px = 0;
+    for (int i = 0; i < n; i++) px += (double)jobs_host[i].w * jobs_host[i].h;
+    ProfScope prof(ctx, open_not_close ? "morph_open3_fused" : "morph_close3_fused", 2.0 * px);
+    const dim3 grid((chunks * segs + 127) / 128, n);
+    if (open_not_close) fused3::close3_kernel<false><<<grid, 128, 0, ctx->stream>>>((const MorphJob*)dev, chunks, segs, seg);
+    else fused3::close3_kernel<true><<<grid, 128, 0, ctx->stream>>>((const MorphJob*)dev, chunks, segs, seg);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    *rc = e == cudaSuccess ? DOCSCAN_OK : ds_fail(ctx, DOCSCAN_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return true;
+}
+
 // One 2-D erode/dilate pass for every job: H pass src -> tmp (arena), V pass tmp -> dst (+ epilogue).
 // (kw, kh, ax, ay) already include the `iterations` enlargement.
 int k_morph_jobs(docscan_ctx* ctx, int is_dilate, int kw, int kh, int ax, int ay, const MorphJob* jobs_host, int n,

@@ -412,6 +412,17 @@ def test_pages_with_device_side_skew_estimate():
             eq(b[i], ref["clean"], f"skew batch binary {i}")
 
 
+def test_close_open_3x3_fused():
+    """morph_cleanup's default (3x3, one iteration) runs as one fused pass: ragged widths, tiny images, several segments."""
+    rng = np.random.default_rng(41)
+    for h, w in [(61, 47), (130, 600), (1, 40), (40, 1), (300, 70), (2, 2), (3, 17), (200, 1131), (129, 16), (64, 15), (65, 33)]:
+        for g in (rng.integers(0, 256, (h, w), dtype=np.uint8), page_like(rng, h, w) if min(h, w) > 20 else rng.integers(0, 2, (h, w), dtype=np.uint8) * 255):
+            eq(ops.morph_close(g, 3, 3, 1), O.morph_close(g, 3, 3, 1), f"close3 {h}x{w}")
+            eq(DS.morph_cleanup(g), O.morph_cleanup(g), f"cleanup {h}x{w}")
+            ref_open = O.dilate(O.erode(g, 3, 3, 1), 3, 3, 1)
+            eq(ops.morph_open(g, 3, 3, 1) if hasattr(ops, "morph_open") else ref_open, ref_open, f"open3 {h}x{w}")
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
