@@ -423,6 +423,120 @@ def test_close_open_3x3_fused():
             eq(ops.morph_open(g, 3, 3, 1) if hasattr(ops, "morph_open") else ref_open, ref_open, f"open3 {h}x{w}")
 
 
+def _device_batch(ctx, n, scale_long, seeds):
+    """n synthetic 12 MP pages rendered on the device (the bench's workload) + their device-resident outputs."""
+    import ctypes as C
+    from smart_image_processing_b200 import _capi
+    from smart_image_processing_b200.synth import synth_angle
+    PH, PW = 3000, 4000
+    pages = (_capi.Page * n)()
+    bufs, quads, angles = [], [], []
+    q8 = (C.c_float * 8)()
+    for i in range(n):
+        src = ctx.device_alloc(PH * PW * 3)
+        im = _capi.device_image(src, PW, PH, PW * 3, 3)
+        ctx.call("docscan_synth_page", C.c_uint64(seeds[i]), C.byref(im), q8)
+        quad = np.array(list(q8), np.float32).reshape(4, 2)
+        tw, th = DS.target_size(quad, "A4", scale_long)
+        pw3, pw1 = (tw * 3 + 127) // 128 * 128, (tw + 127) // 128 * 128
+        dw, db = ctx.device_alloc(th * pw3), ctx.device_alloc(th * pw1)
+        pages[i].src = im
+        pages[i].quad = (C.c_float * 8)(*quad.reshape(8).tolist())
+        pages[i].angle_deg = synth_angle(seeds[i])
+        pages[i].warped = _capi.device_image(dw, tw, th, pw3, 3)
+        pages[i].binary = _capi.device_image(db, tw, th, pw1, 1)
+        bufs.append((src, dw, db, tw, th, pw3, pw1))
+        quads.append(quad); angles.append(synth_angle(seeds[i]))
+    return pages, bufs, quads, angles
+
+
+def _d2h(ctx, ptr, rows, pitch, width_bytes):
+    import ctypes as C
+    from smart_image_processing_b200 import _capi
+    a = np.empty((rows, pitch), np.uint8)
+    _capi.lib().docscan_memcpy_d2h(ctx._h, a.ctypes.data, C.c_void_p(ptr), a.nbytes)
+    return np.ascontiguousarray(a[:, :width_bytes])
+
+
+@pytest.mark.parametrize("scale_long,preset", [(1600, "cli"), (4000, "gui")])
+def test_full_size_12mp_pages_device_resident(scale_long, preset):
+    """BASELINE.json config 2 at its real size: 12 MP synthetic pages, device-resident batch through docscan_process_pages,
+    bit-exact against the oracle (both presets; scale_long 1600 = the bench setting, 4000 = full-resolution variant), and
+    the host-buffer path (footprint upload, copy pipeline) against the same oracle result."""
+    import ctypes as C
+    from smart_image_processing_b200 import _capi
+    ctx = _capi.Context(0)
+    gui = dict(illum_method="divide", illum_blur_frac=0.05, block_size=31, C=3, morph_ksize=1, morph_iters=0)
+    tun = gui if preset == "gui" else {}
+    n = 5 if scale_long == 1600 else 2
+    seeds = [3, 11, 12, 40, 77][:n]
+    pages, bufs, quads, angles = _device_batch(ctx, n, scale_long, seeds)
+    params = DS.make_params(**tun)
+    ctx.call("docscan_process_pages", n, pages, C.byref(params))
+    ctx.sync()
+    check = [0, n - 1] if scale_long == 1600 else [n - 1]       # the oracle takes 2 s (1600) / 14 s (4000) per 12 MP page
+    for i in check:
+        src, dw, db, tw, th, pw3, pw1 = bufs[i]
+        img = _d2h(ctx, src, 3000, 4000 * 3, 4000 * 3).reshape(3000, 4000, 3)
+        ref = O.hot_path(img, quads[i], angles[i], scale_long=scale_long, **tun)
+        eq(_d2h(ctx, dw, th, pw3, tw * 3).reshape(th, tw, 3), ref["warped"], f"12 MP page {i} warped (device-resident)")
+        eq(_d2h(ctx, db, th, pw1, tw), ref["clean"], f"12 MP page {i} binary (device-resident)")
+        if i == check[0]:
+            w, b = DS.process_pages([img], [quads[i]], [angles[i]], scale_long=scale_long, ctx=ctx, **tun)
+            eq(w[0], ref["warped"], "12 MP page warped (host buffers)")
+            eq(b[0], ref["clean"], "12 MP page binary (host buffers)")
+            # size-independent properties of the result: closing is idempotent, a zero-degree deskew is the identity
+            if params.morph_ksize > 1:
+                eq(ops.morph_close(b[0], params.morph_ksize, params.morph_ksize, params.morph_iters, ctx=ctx), b[0], "close is idempotent")
+            eq(DS.rotate(b[0], 0.0), b[0], "rotation by 0 degrees is the identity")
+    for src, dw, db, *_ in bufs:
+        ctx.device_free(src); ctx.device_free(dw); ctx.device_free(db)
+    ctx.close()
+
+
+def test_batch_results_do_not_depend_on_batching():
+    """A page processed alone, inside a 40-page device-resident batch (several launch groups and streams) and with the
+    device-side skew estimate must give the same bytes."""
+    import ctypes as C
+    from smart_image_processing_b200 import _capi
+    ctx = _capi.Context(0)
+    n = 40
+    seeds = list(range(100, 100 + n))
+    pages, bufs, quads, angles = _device_batch(ctx, n, 1600, seeds)
+    params = DS.make_params()
+    ctx.call("docscan_process_pages", n, pages, C.byref(params))
+    ctx.sync()
+    sha_batch = {}
+    for i in (0, 17, 33, 39):
+        src, dw, db, tw, th, pw3, pw1 = bufs[i]
+        sha_batch[i] = (sha(_d2h(ctx, dw, th, pw3, tw * 3)), sha(_d2h(ctx, db, th, pw1, tw)))
+    for i in (0, 17, 33, 39):                                   # alone, into fresh outputs
+        src, dw, db, tw, th, pw3, pw1 = bufs[i]
+        one = (_capi.Page * 1)()
+        one[0] = pages[i]
+        dw2, db2 = ctx.device_alloc(th * pw3), ctx.device_alloc(th * pw1)
+        one[0].warped = _capi.device_image(dw2, tw, th, pw3, 3)
+        one[0].binary = _capi.device_image(db2, tw, th, pw1, 1)
+        ctx.call("docscan_process_pages", 1, one, C.byref(params))
+        ctx.sync()
+        assert (sha(_d2h(ctx, dw2, th, pw3, tw * 3)), sha(_d2h(ctx, db2, th, pw1, tw))) == sha_batch[i], f"page {i} differs alone vs batched"
+        ctx.device_free(dw2); ctx.device_free(db2)
+    # the device-side skew estimate inside the batch == the single-image entry point on the blended page
+    for i in range(n):
+        pages[i].angle_deg = float("nan")
+    ctx.call("docscan_process_pages", n, pages, C.byref(params))
+    est = (C.c_double * n)()
+    ctx.call("docscan_last_angles", est, n)
+    src, dw, db, tw, th, pw3, pw1 = bufs[5]
+    img = _d2h(ctx, src, 3000, 4000 * 3, 4000 * 3).reshape(3000, 4000, 3)
+    st = DS.hot_path(img, quads[5], 0.0, scale_long=1600)
+    assert est[5] == ops.skew_angle(st["weighted"], ctx=ctx)
+    eq(_d2h(ctx, db, th, pw1, tw), DS.morph_cleanup(DS.rotate(st["weighted"], est[5])), "page 5 with the in-batch skew estimate")
+    for src, dw, db, *_ in bufs:
+        ctx.device_free(src); ctx.device_free(dw); ctx.device_free(db)
+    ctx.close()
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
