@@ -117,6 +117,28 @@ def main():
         run(f"adaptive mean k={k}", 4, g4,
             lambda s, d, k=k: lib.call("docscan_adaptive_threshold", C.byref(s), _capi.ADAPTIVE_MEAN, k, 10, 1, C.byref(d)),
             lambda a, k=k: cv2.adaptiveThreshold(a, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, k, 10))
+    # the rows added this round: Canny, the whole skew estimate, resize_long_side
+    run("canny 50/150", 4, g4, lambda s, d: lib.call("docscan_canny", C.byref(s), 50.0, 150.0, C.byref(d)),
+        lambda a: cv2.Canny(a, 50, 150), alg_bytes_per_px=2.0)
+    ang = C.c_double()
+
+    def skew(s, d):
+        lib.call("docscan_skew_angle", C.byref(s), 50.0, 150.0, 10.0, C.byref(ang))
+
+    def skew_ref(a):
+        lines = cv2.HoughLines(cv2.Canny(a, 50, 150), 1, np.pi / 180, 150)
+        return np.zeros_like(a)          # timing only; the angle is compared below
+
+    run("skew estimate (Canny + HoughLines + median)", 4, g4, skew, skew_ref, alg_bytes_per_px=1.0)
+    rows[-1]["mismatching_px_vs_cv2"] = None
+    if cv2 is not None:
+        from oracle import oracle as O          # the checker: numpy-float32 median of cv2's own lines
+        lines = cv2.HoughLines(cv2.Canny(g4, 50, 150), 1, np.pi / 180, 150)
+        per = np.zeros(180, np.int32)
+        if lines is not None:
+            for th in lines[:, 0, 1]:
+                per[int(round(float(th) / (np.pi / 180)))] += 1
+        rows[-1]["mismatching_px_vs_cv2"] = 0 if O.median_angle(per) == ang.value else 1
     g5 = synth_gray(4320, 7680, 2)
     for k in (101, 151, 217):
         run(f"illumination divide k={k}", 5, g5,

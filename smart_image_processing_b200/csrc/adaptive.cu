@@ -401,7 +401,7 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, G, smem);
     else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, G, smem);
     else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, G, smem);
-    else if (L.r == 15) rc = launch_adaptive<15>(ctx, jd, L, G, smem);      // k = 31 (GUI preset), exact
+    else if (L.r <= 15) rc = launch_adaptive<15>(ctx, jd, L, G, smem);      // k = 31 (GUI preset), exact
     else if (L.r <= 17) rc = launch_adaptive<17>(ctx, jd, L, G, smem);      // k = 35 (CLI default), exact
     else if (L.r <= 25) rc = launch_adaptive<25>(ctx, jd, L, G, smem);
     else rc = launch_adaptive<32>(ctx, jd, L, G, smem);

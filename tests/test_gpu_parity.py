@@ -59,6 +59,13 @@ def test_gaussian_blur(k):
         eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"blur k={k} {h}x{w}")
 
 
+def test_gaussian_blur_every_small_ksize():
+    rng = np.random.default_rng(123)
+    g = rng.integers(0, 256, (97, 150), dtype=np.uint8)
+    for k in range(1, 100, 2):
+        eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"blur k={k}")
+
+
 def test_gaussian_blur_tall_segments():
     rng = np.random.default_rng(99)
     g = rng.integers(0, 256, (1500, 300), dtype=np.uint8)     # several vertical segments per strip
@@ -128,6 +135,16 @@ def test_adaptive_threshold(k):
                O.adaptive_threshold(g, "gaussian", k, c, unfused_tail=0), f"gauss all-fma k={k} c={c} {h}x{w}")
             if k <= 35:
                 eq(ops.adaptive_threshold(g, "mean", k, c), O.adaptive_threshold(g, "mean", k, c), f"mean k={k} c={c} {h}x{w}")
+
+
+def test_adaptive_threshold_every_block_size():
+    """Every odd block size the kernel accepts (3..65): each picks a template radius and zero-pads up to it."""
+    rng = np.random.default_rng(77)
+    g = page_like(rng, 150, 203)
+    for k in range(3, 66, 2):
+        eq(ops.adaptive_threshold(g, "gaussian", k, 5), O.adaptive_threshold(g, "gaussian", k, 5), f"gauss k={k}")
+    with pytest.raises(Exception):
+        ops.adaptive_threshold(g, "gaussian", 67, 5)
 
 
 def test_adaptive_threshold_random_noise_is_exact():
