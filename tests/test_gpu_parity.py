@@ -554,6 +554,73 @@ def test_batch_results_do_not_depend_on_batching():
     ctx.close()
 
 
+def test_fuzz_ops_random_shapes_and_parameters():
+    """Randomised sweep over shapes and parameter values no hand-written case pins (a block size of 29 once slipped
+    through the listed cases): every op against the oracle."""
+    from smart_image_processing_b200 import _capi
+    rng = np.random.default_rng(2026)
+    for t in range(60):
+        h, w = int(rng.integers(1, 260)), int(rng.integers(1, 340))
+        g = rng.integers(0, 256, (h, w), dtype=np.uint8) if t % 3 else page_like(rng, max(h, 16), max(w, 16))
+        h, w = g.shape
+        k = int(rng.integers(0, 80)) * 2 + 1
+        eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"fuzz blur k={k} {h}x{w}")
+        kw, kh, it = int(rng.integers(1, 40)), int(rng.integers(1, 40)), int(rng.integers(1, 4))
+        eq(ops.erode(g, kw, kh, it), O.erode(g, kw, kh, it), f"fuzz erode {kw}x{kh} it{it} {h}x{w}")
+        eq(ops.dilate(g, kw, kh, it), O.dilate(g, kw, kh, it), f"fuzz dilate {kw}x{kh} it{it} {h}x{w}")
+        eq(ops.morph_close(g, kw, kh, it), O.morph_close(g, kw, kh, it), f"fuzz close {kw}x{kh} it{it} {h}x{w}")
+        eq(ops.blackhat(g, kw, kh), O.blackhat(g, kw, kh), f"fuzz blackhat {kw}x{kh} {h}x{w}")
+        ka, c = int(rng.integers(1, 33)) * 2 + 1, int(rng.integers(-5, 16))
+        eq(ops.adaptive_threshold(g, "gaussian", ka, c), O.adaptive_threshold(g, "gaussian", ka, c), f"fuzz gauss k={ka} c={c} {h}x{w}")
+        km = int(rng.integers(1, 18)) * 2 + 1
+        eq(ops.adaptive_threshold(g, "mean", km, c), O.adaptive_threshold(g, "mean", km, c), f"fuzz mean k={km} c={c} {h}x{w}")
+        ang = float(rng.uniform(-30, 30))
+        eq(DS.rotate(g, ang), O.rotate(g, ang), f"fuzz rotate {ang} {h}x{w}")
+        lo, hi = sorted(rng.uniform(0, 300, 2).tolist())
+        eq(ops.canny(g, lo, hi), O.canny(g, lo, hi), f"fuzz canny {lo}/{hi} {h}x{w}")
+        nh, nw = int(rng.integers(1, h + 1)), int(rng.integers(1, w + 1))
+        eq(ops.resize(g, (nw, nh), _capi.INTER_AREA), O.resize_area(g, (nw, nh)), f"fuzz area {h}x{w}->{nh}x{nw}")
+        uh, uw = int(rng.integers(h, 2 * h + 2)), int(rng.integers(w, 2 * w + 2))
+        eq(ops.resize(g, (uw, uh), _capi.INTER_CUBIC), O.resize_cubic(g, (uw, uh)), f"fuzz cubic {h}x{w}->{uh}x{uw}")
+        if min(h, w) >= 16:
+            frac = float(rng.uniform(0.01, 0.4))
+            m = "divide" if t % 2 else "subtract"
+            eq(DS.illumination_correction(g, m, frac), O.illumination_correction(g, m, frac), f"fuzz illum {m} {frac} {h}x{w}")
+            mk, bk, ratio, dil, off = int(rng.integers(3, 90)), int(rng.integers(1, 16)), float(rng.uniform(0.5, 3.0)), int(rng.integers(0, 3)), int(rng.integers(0, 20))
+            eq(DS._compute_ink_mask(g, mk, bk, ratio, dil, off), O._compute_ink_mask(g, mk, bk, ratio, dil, off),
+               f"fuzz ink mask {mk},{bk},{ratio},{dil},{off} {h}x{w}")
+
+
+def test_fuzz_pipeline_random_tunables():
+    """docscan_process_pages with random process_document tunables (even block sizes, iterations, both methods, page kinds,
+    whole-photo pages, device-side skew) against the oracle chain."""
+    rng = np.random.default_rng(4242)
+    for t in range(14):
+        H, W = int(rng.integers(200, 420)), int(rng.integers(160, 360))
+        base = page_like(rng, H, W)
+        img = np.stack([np.clip(base * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1)
+        quad = (np.array([[0.08 * W, 0.06 * H], [0.93 * W, 0.08 * H], [0.95 * W, 0.94 * H], [0.05 * W, 0.92 * H]])
+                + rng.uniform(-10, 10, (4, 2))).astype(np.float32)
+        kw = dict(scale_long=int(rng.integers(150, 500)), page=["A4", "Letter", "custom", "A3"][t % 4],
+                  illum_method=["subtract", "divide"][t % 2], illum_blur_frac=float(rng.uniform(0.01, 0.2)),
+                  block_size=int(rng.integers(3, 60)), C=int(rng.integers(-3, 15)), thresh_method=["gaussian", "mean"][(t // 2) % 2],
+                  mask_blur_ksize=int(rng.integers(3, 80)), blackhat_ksize=int(rng.integers(1, 14)),
+                  blackhat_vertical_ratio=float(rng.uniform(0.5, 3.0)), ink_dilate_iters=int(rng.integers(0, 3)),
+                  mask_thresh_offset=int(rng.integers(0, 16)), morph_ksize=int(rng.integers(0, 6)), morph_iters=int(rng.integers(0, 3)))
+        if kw["thresh_method"] == "mean":
+            kw["block_size"] = min(kw["block_size"], 35)
+        q = None if t % 5 == 4 else quad
+        a = None if t % 3 == 2 else float(rng.integers(-8, 9)) * 0.5
+        w, b, used = DS.process_pages([img], [q], [a], return_angles=True, **kw)
+        pix = dict(kw)
+        st = O.hot_path(img, q, 0.0, **pix)
+        angle = a if a is not None else O.estimate_skew_angle(st["weighted"])
+        assert used[0] == angle, f"fuzz {t}: angle {used[0]} vs {angle}"
+        ref = O.hot_path(img, q, angle, **pix)
+        eq(w[0], ref["warped"], f"fuzz pipeline {t} warped {kw}")
+        eq(b[0], ref["clean"], f"fuzz pipeline {t} binary {kw}")
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
