@@ -3,7 +3,8 @@ estimate, optional stage dumps.  These parts of the reference (DocScanner.py:15-
 282-346) produce a handful of scalars per page from irregular, sequential algorithms (contours, Hough
 peaks) and are out of scope for the CUDA path (SURVEY.md §8f lists them as the next rows).  They run on
 the host with OpenCV when it is installed; every function raises if it is not, so callers can instead
-supply `quad=` / `angle=` themselves.
+supply `quad=` / `angle=` themselves.  Since the skew estimate moved to the device (deskew.cu), what is left here is
+localize_document's sequential half, decode and the dumps; its gray conversion and Canny already use the device kernels.
 """
 from __future__ import annotations
 
@@ -43,7 +44,10 @@ def localize_document(img, canny_low=50, canny_high=150, min_area_ratio=0.2, max
     """Largest 4-gon among the external contours of (Canny edges OR their probabilistic-Hough segments);
     same recipe as DocScanner.py:76-109.  Returns TL, TR, BR, BL as float32 (4, 2), or None."""
     cv2 = _cv2()
-    edges = cv2.Canny(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), canny_low, canny_high)
+    # BGR2GRAY + Canny (DocScanner.py:78-79) run on the device (bit-exact with cv2: tests/test_gpu_parity.py); the
+    # probabilistic Hough transform, contour tracing and polygon fitting that follow are sequential and stay on the host
+    from . import ops
+    edges = ops.canny(ops.bgr2gray(img), canny_low, canny_high)
     segments = cv2.HoughLinesP(edges, 1, np.pi / 180, threshold=80, minLineLength=80, maxLineGap=10)
     strokes = np.zeros_like(edges)
     for seg in ([] if segments is None else segments):

@@ -644,6 +644,8 @@ def test_process_document_drop_in(tmp_path):
     assert set(res) == {"quad", "warped", "binary"}
     quad = control.localize_document(img)
     assert quad is not None and np.array_equal(res["quad"], quad)
+    # localize_document's gray + Canny run on the device: the edge map, hence the quad, must equal the all-cv2 recipe
+    assert np.array_equal(ops.canny(ops.bgr2gray(img), 50, 150), cv2.Canny(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), 50, 150))
     st = O.hot_path(img, quad, 0.0, scale_long=800)
     angle = control.estimate_skew_angle(st["weighted"])              # cv2 on the host ...
     assert angle == O.estimate_skew_angle(st["weighted"])            # ... the oracle ...
