@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
 // coordinates -> loads -> filter + stores.  Interior pixels fetch the 6 bytes of a row's two taps through a 16-byte
 // window (two 64-bit loads at the enclosing 8-byte boundary); pixels whose taps touch the left/right image border take the
 // per-byte path of the generic kernel afterwards.  Requires a resident width of at least 9 px.
+// SAFE_RCP: the host has checked that the denominator W keeps one sign and stays within [1e-290, 1e290] over the whole
+// destination rectangle (it is affine in (x, y), so its extremes sit at the corners).  32 is a power of two, so the
+// correctly rounded quotient 32 / W is then exactly 32 * RN(1 / W) — the reciprocal sequence is half as long as the division.
+template <bool SAFE_RCP>
 __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* __restrict__ jobs) {
     const WarpPJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
             }
             const double x1 = (double)(x - xb);
             double W = __dadd_rn(W0, __dmul_rn(m6, x1));
-            W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+            if (SAFE_RCP) W = __dmul_rn(__drcp_rn(W), 32.0);
+            else W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
             Xs[i] = round_clamped(__dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W));
             Ys[i] = round_clamped(__dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W));
         }
@@ -153,9 +158,12 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int sx = ds_clamp(Xs[i] >> 5, J.rx0 + 3, J.rx1 - 6) - J.rx0, sy = Ys[i] >> 5;
+        const int cy0 = ds_clamp(sy, J.ry0, J.ry1 - 1);
+        const uintptr_t A0 = reinterpret_cast<uintptr_t>(src + (size_t)(cy0 - J.ry0) * sp + 3 * sx);
+        const uintptr_t A1 = A0 + ((sy >= J.ry0 && sy + 1 < J.ry1) ? (uintptr_t)sp : 0);         // row clamp(sy + 1)
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
-            const uintptr_t A = reinterpret_cast<uintptr_t>(src + (size_t)(ds_clamp(sy + rr, J.ry0, J.ry1 - 1) - J.ry0) * sp + 3 * sx);
+            const uintptr_t A = rr ? A1 : A0;
             const uint2* base = reinterpret_cast<const uint2*>(A & ~(uintptr_t)7);
             lo[i][rr] = __ldg(base); hi[i][rr] = __ldg(base + 1);
             sft[i][rr] = (uint32_t)(A & 7);
@@ -293,7 +301,21 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     ProfScope prof(ctx, ch == 3 ? "warp_perspective_c3" : "warp_perspective_c1", bytes);
     bool wide = ch == 3;
     for (int i = 0; i < n; i++) wide = wide && jobs_host[i].rx1 - jobs_host[i].rx0 >= 9;
-    if (wide) warp_perspective3_kernel<<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    bool safe_rcp = wide;
+    for (int i = 0; i < n && safe_rcp; i++) {
+        const WarpPJob& j = jobs_host[i];
+        double lo = 1e308, hi = -1e308;
+        const double cx[2] = {0.0, (double)(((j.dw + 127) / 128) * 128)}, cy[2] = {0.0, (double)j.dh};     // lanes past dw compute too
+        for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++) {
+                const double w = j.m[6] * cx[a] + j.m[7] * cy[b] + j.m[8];
+                lo = fmin(lo, w); hi = fmax(hi, w);
+            }
+        const bool finite = std::isfinite(lo) && std::isfinite(hi);
+        safe_rcp = finite && ((lo > 1e-290 && hi < 1e290) || (hi < -1e-290 && lo > -1e290));
+    }
+    if (wide && safe_rcp) warp_perspective3_kernel<true><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    else if (wide) warp_perspective3_kernel<false><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else warp_perspective_kernel<1><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     DS_CHECK_LAUNCH(ctx);
