@@ -206,6 +206,10 @@ DOCSCAN_API int docscan_target_size(const float quad[8], int page_kind, int scal
 /* warp -> gray -> illumination -> stretch -> ink mask || adaptive threshold -> blend -> rotate -> close
  * (DocScanner.py:310-346 without the PNG dumps) for n independent pages. */
 DOCSCAN_API int docscan_process_pages(docscan_ctx*, int n, docscan_page* pages, const docscan_params* params);
+/* The part of a page's photo docscan_process_pages uploads when `src` is a HOST image: a box [x0, x1) x [y0, y1) that
+ * holds every source pixel the perspective warp of that page can read (the whole photo when that cannot be bounded, or
+ * for use_whole pages).  region = {x0, y0, x1, y1}.  Host arithmetic only. */
+DOCSCAN_API int docscan_warp_footprint(const docscan_page* page, int32_t region[4]);
 /* the deskew angle each page of the last docscan_process_pages call was rotated by (supplied or estimated); syncs */
 DOCSCAN_API int docscan_last_angles(docscan_ctx*, double* angles, int n);
 

@@ -411,7 +411,7 @@ def median_angle(per_angle, max_rotate=10.0) -> float:
 
 def estimate_skew_angle(gray, canny_low=50, canny_high=150, max_rotate=10.0) -> float:
     """The control half of deskew (DocScanner.py:218-231)."""
-    _, per_angle = hough_lines(canny(gray, canny_low, canny_high), 150, max_lines=0 or 1)
+    _, per_angle = hough_lines(canny(gray, canny_low, canny_high), 150, max_lines=1)   # only the per-angle counts matter
     return median_angle(per_angle, max_rotate)
 
 

@@ -89,6 +89,7 @@ _SIGS = {
     "docscan_ink_mask": (C.c_int, [C.c_void_p, C.POINTER(Image), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Image)]),
     "docscan_default_params": (None, [C.POINTER(Params)]),
     "docscan_target_size": (C.c_int, [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "docscan_warp_footprint": (C.c_int, [C.POINTER(Page), C.POINTER(C.c_int32)]),
     "docscan_process_pages": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Page), C.POINTER(Params)]),
     "docscan_synth_page": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Image), C.POINTER(C.c_float)]),
 }

@@ -719,6 +719,14 @@ int copy_2d(docscan_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t 
 
 }  // namespace
 
+extern "C" int docscan_warp_footprint(const docscan_page* page, int32_t region[4]) {
+    if (!page || !region || page->src.width <= 0 || page->src.height <= 0 || page->warped.width <= 0 || page->warped.height <= 0)
+        return DOCSCAN_ERR_BAD_ARG;
+    const SrcRegion r = page->use_whole ? SrcRegion{0, 0, page->src.width, page->src.height} : warp_footprint(*page);
+    region[0] = r.x0; region[1] = r.y0; region[2] = r.x1; region[3] = r.y1;
+    return DOCSCAN_OK;
+}
+
 extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* pages, const docscan_params* params) {
     if (!ctx || n < 0 || (n && !pages) || !params) return DOCSCAN_ERR_BAD_ARG;
     if (n == 0) return DOCSCAN_OK;

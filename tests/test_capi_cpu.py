@@ -109,3 +109,49 @@ def test_signatures_mirror_the_reference():
     assert names[:5] == ["input_path", "out_dir", "page", "scale_long", "do_ocr"] and names[-1] == "min_quad_area_ratio"
     assert pd["mask_blur_ksize"].default == 51 and inspect.signature(DS._compute_ink_mask).parameters["mask_blur_ksize"].default == 61
     assert list(inspect.signature(DS.deskew).parameters)[:4] == ["gray", "canny_low", "canny_high", "max_rotate"]
+
+
+def test_warp_footprint_bounds_every_source_pixel_the_warp_reads():
+    """The host pipeline uploads only docscan_warp_footprint's box of each photo.  For random quads (inside, touching and
+    partly outside the photo, strong perspective) every bilinear tap the warp takes — computed here with the oracle's
+    matrices in float64 — must lie inside the box, with the margin the kernel's 16-byte load window needs."""
+    import ctypes as C
+    from oracle import oracle as O
+    rng = np.random.default_rng(99)
+    lib = _capi.lib()
+    for t in range(300):
+        W, H = int(rng.integers(40, 900)), int(rng.integers(40, 900))
+        spread = [0.05, 0.2, 0.6][t % 3] * min(W, H)
+        quad = (np.array([[0.1 * W, 0.1 * H], [0.9 * W, 0.1 * H], [0.9 * W, 0.9 * H], [0.1 * W, 0.9 * H]])
+                + rng.uniform(-spread, spread, (4, 2))).astype(np.float32)
+        tw, th = int(rng.integers(2, 400)), int(rng.integers(2, 400))
+        page = _capi.Page()
+        page.src = _capi.Image(1, W, H, W * 3, 3, _capi.HOST)
+        page.warped = _capi.Image(1, tw, th, tw * 3, 3, _capi.HOST)
+        page.binary = _capi.Image(1, tw, th, tw, 1, _capi.HOST)
+        page.quad = (C.c_float * 8)(*quad.reshape(8).tolist())
+        reg = (C.c_int32 * 4)()
+        assert lib.docscan_warp_footprint(C.byref(page), reg) == 0
+        x0, y0, x1, y1 = list(reg)
+        assert 0 <= x0 < x1 <= W and 0 <= y0 < y1 <= H
+        dst = np.array([[0, 0], [tw - 1, 0], [tw - 1, th - 1], [0, th - 1]], np.float32)
+        m = O.get_perspective_transform(quad, dst)
+        inv = np.linalg.inv(m)
+        xs, ys = np.meshgrid(np.arange(tw, dtype=np.float64), np.arange(th, dtype=np.float64))
+        wv = inv[2, 0] * xs + inv[2, 1] * ys + inv[2, 2]
+        if (x0, y0, x1, y1) == (0, 0, W, H):
+            continue                                         # whole photo: nothing to prove
+        assert (wv > 0).all() or (wv < 0).all()
+        sx = np.floor((inv[0, 0] * xs + inv[0, 1] * ys + inv[0, 2]) / wv + 1.0 / 64).astype(np.int64)
+        sy = np.floor((inv[1, 0] * xs + inv[1, 1] * ys + inv[1, 2]) / wv + 1.0 / 64).astype(np.int64)
+        # taps (sx, sx + 1) x (sy, sy + 1) that fall inside the photo must be resident
+        for dx in (0, 1):
+            for dy in (0, 1):
+                tx, ty = sx + dx, sy + dy
+                inside = (tx >= 0) & (tx < W) & (ty >= 0) & (ty < H)
+                assert ((tx[inside] >= x0) & (tx[inside] < x1) & (ty[inside] >= y0) & (ty[inside] < y1)).all(), (t, quad.tolist())
+        # interior pixels keep the kernel's fast path: 3 px of slack on the left, 5 on the right, unless the photo ends there
+        inside = (sx >= 0) & (sx + 1 < W) & (sy >= 0) & (sy + 1 < H)
+        if inside.any():
+            assert x0 == 0 or sx[inside].min() - x0 >= 3
+            assert x1 == W or x1 - sx[inside].max() >= 6
