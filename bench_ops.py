@@ -157,7 +157,52 @@ def main():
         run(f"close+divide+normalize k={k}", 5, g5, close_divide,
             lambda a, k=k: cv2.normalize(cv2.divide(a, cv2.morphologyEx(a, cv2.MORPH_CLOSE, cv2.getStructuringElement(cv2.MORPH_RECT, (k, k))),
                                                     scale=255), None, 0, 255, cv2.NORM_MINMAX))
+    # ---- config 1: public/sample.jpg (committed as tests/golden/sample_bgr.npz), whole per-pixel path, single-image latency
+    # through the numpy drop-in (ordinary pageable arrays in and out), with the reference's quad / angle and with the
+    # device-side skew estimate; cv2 chain of DocScanner.py on the host beside it (all cores / one core)
+    lat = []
+    try:
+        from smart_image_processing_b200 import DocScanner as DS
+        from oracle import ref_cv2
+        img = np.load(os.path.join(ROOT, "tests", "golden", "sample_bgr.npz"))["bgr"]
+        meta = json.load(open(os.path.join(ROOT, "tests", "golden", "sample_golden.json")))
+        for preset in ("cli", "gui"):
+            p = meta["presets"][preset]
+            quad = np.frombuffer(bytes.fromhex(p["quad_f32_hex"]), np.float32).reshape(4, 2)
+            angle = float.fromhex(p["angle_hex"])
+            tun = {k: v for k, v in p["params"].items() if k not in ("canny_low", "canny_high", "max_rotate")}
+            skew = {k: p["params"][k] for k in ("canny_low", "canny_high", "max_rotate")}
+
+            def t_ms(fn, n=20):
+                fn(); fn()
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    fn()
+                return (time.perf_counter() - t0) / n * 1e3
+
+            ms_given = t_ms(lambda: DS.process_pages([img], [quad], [angle], **tun))
+            ms_est = t_ms(lambda: DS.process_pages([img], [quad], [None], **tun, **skew))
+            w, b, used = DS.process_pages([img], [quad], [None], return_angles=True, **tun, **skew)
+            row = {"config": 1, "preset": preset, "image": "public/sample.jpg 1280x963", "gpu_ms_angle_given": round(ms_given, 3),
+                   "gpu_ms_angle_estimated_on_device": round(ms_est, 3), "angle_used": used[0], "angle_reference": angle}
+            if cv2 is not None:
+                cpu = ref_cv2.hot_path(img, quad, angle, **tun)
+                row["mismatching_px_vs_cv2"] = int(np.count_nonzero(cpu[1] != DS.process_pages([img], [quad], [angle], **tun)[1][0]))
+                row["cv2_ms_angle_given_all_cores"] = round(t_ms(lambda: ref_cv2.hot_path(img, quad, angle, **tun), 10), 2)
+
+                def cv_skew():
+                    st = ref_cv2.hot_path(img, quad, 0.0, keep_stages=True, **tun)
+                    lines = cv2.HoughLines(cv2.Canny(st["weighted"], skew["canny_low"], skew["canny_high"]), 1, np.pi / 180, 150)
+                    return lines
+
+                row["cv2_ms_with_its_own_skew_estimate"] = round(t_ms(cv_skew, 5), 2)
+            lat.append(row)
+            print(json.dumps(row), flush=True)
+    except Exception as e:          # the sweep tables above do not depend on this block
+        print(json.dumps({"config": 1, "error": repr(e)}), flush=True)
     if args.write:
+        with open(os.path.join(ROOT, "profiles", "latency_sample_jpg.json"), "w") as f:
+            json.dump(lat, f, indent=1)
         path = os.path.join(ROOT, "profiles", "ops_sweep.md")
         with open(path, "w") as f:
             f.write("# Stage-level sweeps (BASELINE.json configs 4 and 5), one B200, device-resident, CUDA events\n\n")
