@@ -228,7 +228,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = _capi.Context(local, stream=stream.cuda_stream)
     P = args.pages
-    params = DS.make_params(cv_tail_compat=not os.environ.get("DOCSCAN_BENCH_NO_TAIL"))
+    params = DS.make_params()
 
     # ---- device-resident synthetic batch (generated on the device; not timed)
     src = torch.empty((P, PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
