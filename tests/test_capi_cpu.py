@@ -155,3 +155,22 @@ def test_warp_footprint_bounds_every_source_pixel_the_warp_reads():
         if inside.any():
             assert x0 == 0 or sx[inside].min() - x0 >= 3
             assert x1 == W or x1 - sx[inside].max() >= 6
+
+
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
+    """include/docscan.h must compile as C99 and libdocscan.so must be usable without Python or C++."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "smart_image_processing_b200")
+    exe = str(tmp_path / "abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c_abi", "abi_check.c"), "-o", exe, "-L", libdir, "-l:libdocscan.so",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert "version 100" in out and "block 35 canny 50/150" in out
+    import torch
+    if not torch.cuda.is_available():
+        assert "create rc -1" in out          # no device: the library refuses, it has no CPU fallback
