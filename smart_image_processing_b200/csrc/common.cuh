@@ -225,15 +225,29 @@ int k_resize(docscan_ctx*, const DImg& src, const DImg& dst, int interpolation, 
 // synth.cu
 int k_synth_page(docscan_ctx*, uint64_t seed, const DImg& dst, float quad_out[8]);
 
-// Segment height for the marching kernels: as many vertical segments as fit in ONE wave of resident CTAs
-// (strips * segs <= SMs * CTAs/SM).  More segments than that run as a partial second wave whose tail idles most of
-// the machine; fewer leave SMs empty.  Each segment repeats a warm-up of ~2r rows, hence the lower bound.
+// Segment height for the marching kernels.  A strip is cut into vertical segments, one CTA each; every segment repeats a
+// warm-up of ~2r rows, hence `min_rows`.  All CTAs of a launch do the same work, so what matters is how full the waves of
+// resident CTAs are: strips * segs CTAs run in ceil(strips * segs / resident) waves, and a partial last wave idles the
+// rest of the machine for a whole CTA lifetime.  Pick the segment count (at most 4 waves) that fills its waves best; on
+// ties the fewer, longer segments win.
 static inline int ds_pick_seg_rows(int resident_ctas, int strips, int max_h, int min_rows, int quantum) {
-    int segs = strips > 0 ? resident_ctas / strips : 1;
-    if (segs < 1) segs = 1;
-    int seg = (max_h + segs - 1) / segs;
-    if (seg < min_rows) seg = min_rows;
-    return (seg + quantum - 1) / quantum * quantum;
+    if (strips < 1) strips = 1;
+    if (resident_ctas < 1) resident_ctas = 1;
+    int best_seg = (max_h + quantum - 1) / quantum * quantum;
+    double best_fill = -1.0;
+    for (int segs = 1; segs <= 64; segs++) {
+        int seg = (max_h + segs - 1) / segs;
+        if (seg < min_rows) seg = min_rows;
+        seg = (seg + quantum - 1) / quantum * quantum;
+        const int actual = (max_h + seg - 1) / seg;                       // segments this height really gives
+        const long long ctas = (long long)strips * actual;
+        const long long waves = (ctas + resident_ctas - 1) / resident_ctas;
+        if (waves > 4 && best_fill >= 0) break;
+        const double fill = (double)ctas / (double)(waves * resident_ctas);
+        if (fill > best_fill + 0.02) { best_fill = fill; best_seg = seg; }
+        if (seg <= min_rows) break;
+    }
+    return best_seg;
 }
 
 // upload a host job array into arena memory (stream ordered); returns the device pointer
