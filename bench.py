@@ -195,6 +195,30 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def _bind_to_gpu_numa_node(torch, local):
+    """With several ranks on one box every rank's pinned host buffers should live on the NUMA node its GPU hangs off
+    (first touch decides), otherwise the H2D / D2H copies of the e2e leg cross the socket interconnect.  Pins this process
+    to the GPU's local CPUs before anything is allocated; returns the cpulist string, or None when sysfs does not say."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        cpulist = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpulist
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -210,6 +234,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # stdout carries exactly one JSON line: NCCL prints its version banner with printf while the communicator is
@@ -404,7 +429,8 @@ def run_ours(args):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pages_per_gpu": P, "page": f"{PAGE_H}x{PAGE_W}x3", "warped": f"{th}x{tw}",
                        "scale_long": SCALE_LONG, "parallelism": f"pages sharded over {world} GPU(s), no collective",
-                       "l2": f"inputs larger than L2 ({P * PAGE_H * PAGE_W * 3 / 1e9:.1f} GB read per step per GPU)"},
+                       "l2": f"inputs larger than L2 ({P * PAGE_H * PAGE_W * 3 / 1e9:.1f} GB read per step per GPU)",
+                       "rank0_cpu_affinity": numa},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "with_skew_estimate": skew, "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
