@@ -314,7 +314,9 @@ int launch(docscan_ctx* ctx, const BlurJob* jobs_dev, BlurLaunch L, const BlurGr
 
 int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const BlurJob* jobs_host, int n,
                 int max_w, int max_h) {
-    if (k < 1 || (k & 1) == 0 || k > 255) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "blur ksize must be odd and in 1..255 (got %d)", k);
+    if (k < 1 || (k & 1) == 0) return ds_fail(ctx, DOCSCAN_ERR_BAD_ARG, "blur ksize must be odd and positive (got %d)", k);
+    // box sums travel through the ring as 16-bit values: 255 * k must fit (the 8.8 Gaussian sums to 256 for every k)
+    if (kind == 1 && k > 255) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "box mean block size must be at most 255 (got %d)", k);
     if (kind == 0 && k == 1) kind = 1;             // 1x1 Gaussian is the identity; so is the 1x1 box mean
     BlurLaunch L{};
     DS_TRY(get_table(ctx, kind, k, &L.t));
@@ -328,6 +330,8 @@ int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const B
     const size_t smem = sizeof(uint4) * (L.t.M + 6) + sizeof(uint32_t) * 2 * (4 * L.t.nb + 8) +
                         sizeof(uint32_t) * BR * L.spw + 16 + sizeof(uint32_t) * (L.ring_rows / 2) * RP2 +
                         (stats ? 4 * 256 * sizeof(uint32_t) : 0);
+    if (smem > 220 * 1024)
+        return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "blur ksize %d needs %zu bytes of shared memory for its row ring (limit 220 KB: k up to about 900)", k, smem);
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, jobs_host, sizeof(BlurJob) * n, &dev));
     const BlurJob* jd = (const BlurJob*)dev;
