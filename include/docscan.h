@@ -131,6 +131,7 @@ DOCSCAN_API int docscan_threshold_binary(docscan_ctx*, const docscan_image* src,
 DOCSCAN_API int docscan_morph_rect(docscan_ctx*, int op, const docscan_image* src, int kw, int kh, int iterations,
                        docscan_image* dst);
 /* cv2.adaptiveThreshold(gray, 255, MEAN_C|GAUSSIAN_C, THRESH_BINARY, k, C)   DocScanner.py:167
+ * Block sizes: GAUSSIAN_C odd 3..257, MEAN_C odd 3..255.
  * cv_tail_compat != 0 reproduces the unfused arithmetic cv2's AVX2 build uses in the last
  * width % 8 columns of GAUSSIAN_C; 0 = fma in every column. */
 #define DOCSCAN_ADAPTIVE_MEAN 0

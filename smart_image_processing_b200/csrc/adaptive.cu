@@ -14,7 +14,7 @@ namespace {
 
 constexpr int TW = 128, BR = 16, NT = 128;
 constexpr int RPF = 132;      // ring row pitch in floats
-constexpr int GMAX = 33;      // half-kernel table size (k <= 65)
+constexpr int GMAX = 129;     // half-kernel table size (k <= 257)
 
 // The half kernel travels in the launch parameters: every tap index below is a compile-time constant, so the
 // coefficient of each fma is a constant-bank operand (no register, no shared-memory load).
@@ -175,6 +175,108 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
     }
 }
 
+// Block sizes beyond the unrolled kernels (radius 33 .. GMAX - 1): same marching layout and the same operation order, but
+// with run-time loops — the taps come from shared memory and the column window is read from the ring instead of living in
+// registers.  About three times the instructions per pixel of the unrolled kernels; it exists so that every block size
+// cv2 accepts up to 257 works, not for speed.
+__global__ void __launch_bounds__(NT) adaptive_gauss_generic_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L,
+                                                                    int ring_rows) {
+    const AdaptJob J = jobs[blockIdx.z];
+    const int x0 = blockIdx.x * TW;
+    const int y_begin = blockIdx.y * L.seg_rows;
+    if (x0 >= J.w || y_begin >= J.h) return;
+    const int y_end = min(J.h, y_begin + L.seg_rows);
+    const int tid = threadIdx.x, r = L.r, k = L.k;
+    const int delta = (4 - (r & 3)) & 3;
+    const int stage_words = (TW + 2 * r + delta + 3) >> 2;
+    const int D = (2 * r + BR - 1) / BR;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* s_g = reinterpret_cast<float*>(smem_raw);               // k taps in order, padded to a multiple of 4
+    float* s_stage = s_g + ((k + 3) & ~3);                         // BR * spf
+    float* s_ring = s_stage + BR * L.spf;                          // ring_rows * RPF
+    for (int i = tid; i < k; i += NT) s_g[i] = L.gh[abs(i - r)];
+    const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
+    const int n_vb = (y_end - y_begin + BR - 1) / BR;
+    const bool row_identity = J.w == 1, col_identity = J.h == 1;
+    const int tail = L.tail_compat ? (J.w & 7) : 0;                // k >= 67 here: cv2's unfused tail columns always apply
+    const int xt_col = J.w - tail;
+    for (int hb = 0; hb < n_vb + D; hb++) {
+        {
+            const int srow_id = tid >> 3;
+            const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - r + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
+            float* sp = s_stage + srow_id * L.spf;
+            for (int wi = tid & 7; wi < stage_words; wi += 8) {
+                const int gx = x0 - r - delta + 4 * wi;
+                const uint32_t wv = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
+#pragma unroll
+                for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(__byte_perm(wv, 0x4B000000u, 0x7440 + b)), 8388608.0f);
+            }
+        }
+        __syncthreads();
+        {   // row pass: taps in increasing order, one fma each (the first tap starts from 0: fma(f, g0, 0) == f * g0)
+            const int lane = tid & 31, wrp = tid >> 5;
+            const int hr = lane & 15;
+            const int c0 = 16 * (2 * wrp + (lane >> 4));
+            const float* sp = s_stage + hr * L.spf + delta + c0;      // sp[u] <-> column x0 + c0 + u - r
+            float acc[16];
+#pragma unroll
+            for (int o = 0; o < 16; o++) acc[o] = 0.0f;
+            if (row_identity) {
+#pragma unroll
+                for (int o = 0; o < 16; o++) acc[o] = sp[r + o];
+            } else {
+                for (int i = 0; i < k; i++) {
+                    const float gi = s_g[i];
+#pragma unroll
+                    for (int o = 0; o < 16; o++) acc[o] = __fmaf_rn(sp[o + i], gi, acc[o]);
+                }
+            }
+            float4* dst = reinterpret_cast<float4*>(s_ring + ((hb * BR + hr) % ring_rows) * RPF + c0);
+            dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            dst[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+            dst[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
+        }
+        __syncthreads();
+        if (hb < D) continue;
+        const int vb = hb - D;
+        const int col = tid, x = x0 + col;
+        const float* colp = s_ring + col;
+        const int base = vb * BR;                                      // ring row of window index 0 (virtual row vb * BR)
+        float acc[BR];
+        const float g0 = s_g[r];
+#pragma unroll
+        for (int o = 0; o < BR; o++) acc[o] = colp[((base + o + r) % ring_rows) * RPF];       // centre values
+        if (!col_identity) {
+#pragma unroll
+            for (int o = 0; o < BR; o++) acc[o] = __fmul_rn(g0, acc[o]);
+            const bool fused = x < xt_col;
+            for (int j = 1; j <= r; j++) {
+                const float gj = s_g[r + j];
+                int up = (base + r + j) % ring_rows, dn = (base + r - j) % ring_rows;
+#pragma unroll
+                for (int o = 0; o < BR; o++) {
+                    const float pair = __fadd_rn(colp[up * RPF], colp[dn * RPF]);
+                    acc[o] = fused ? __fmaf_rn(pair, gj, acc[o]) : __fadd_rn(acc[o], __fmul_rn(gj, pair));
+                    if (++up == ring_rows) up = 0;
+                    if (++dn == ring_rows) dn = 0;
+                }
+            }
+        }
+        if (x < J.w) {
+            const int y0 = y_begin + vb * BR;
+            const int rows = min(BR, y_end - y0);
+#pragma unroll
+            for (int o = 0; o < BR; o++) {
+                if (o >= rows) break;
+                const int mean = min(max(__float2int_rn(acc[o]), 0), 255);
+                const int c = J.src[(size_t)(y0 + o) * J.src_pitch + x];
+                J.dst[(size_t)(y0 + o) * J.dst_pitch + x] = (c - mean > -L.c_param) ? 255 : 0;
+            }
+        }
+    }
+}
+
 // cv2's row filter leaves the last w % 4 columns (w % 8 >= 4: the last w % 8 - 4) to scalar code: mul+add per tap,
 // except that the (k-1) % 4 remainder taps are fma (oracle/docscan_oracle.c, A.9); its column filter is unfused from
 // column w - w % 8 on.  This kernel recomputes those <= 3 columns of every page after the main kernel: a CTA takes
@@ -187,7 +289,7 @@ __global__ void __launch_bounds__(128) adaptive_tail_kernel(const AdaptJob* __re
     const int y0 = blockIdx.x * TAIL_ROWS;
     if (nt == 0 || y0 >= J.h) return;
     const int xt = J.w - nt, r = L.r, k = L.k;
-    __shared__ float s_row[(TAIL_ROWS + 2 * 32) * 3];
+    __shared__ float s_row[(TAIL_ROWS + 2 * (GMAX - 1)) * 3];
     const int nrows = min(TAIL_ROWS, J.h - y0), nv = nrows + 2 * r;
     const bool row_identity = J.w == 1, col_identity = J.h == 1;
     const int first_fused = k - ((k - 1) & 3);
@@ -375,11 +477,12 @@ int launch_adaptive(docscan_ctx* ctx, const AdaptJob* jd, AdaptLaunch L, const A
 
 int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, const AdaptJob* jobs_host, int n,
                           int max_w, int max_h) {
-    if (k < 3 || (k & 1) == 0 || k > 65)
-        return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "adaptive GAUSSIAN_C block size must be odd and in 3..65 (got %d)", k);
+    if (k < 3 || (k & 1) == 0 || k > 2 * (GMAX - 1) + 1)
+        return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "adaptive GAUSSIAN_C block size must be odd and in 3..%d (got %d)", 2 * (GMAX - 1) + 1, k);
     AdaptLaunch L{};
     L.k = k; L.r = k / 2; L.c_param = c; L.tail_compat = cv_tail_compat;
-    const int rmax = L.r <= 5 ? 5 : L.r <= 9 ? 9 : L.r <= 13 ? 13 : L.r <= 15 ? 15 : L.r <= 17 ? 17 : L.r <= 25 ? 25 : 32;
+    const bool generic = L.r > 32;
+    const int rmax = L.r <= 5 ? 5 : L.r <= 9 ? 9 : L.r <= 13 ? 13 : L.r <= 15 ? 15 : L.r <= 17 ? 17 : L.r <= 25 ? 25 : L.r <= 32 ? 32 : L.r;
     const int delta = (4 - (rmax & 3)) & 3;
     L.spf = TW + 2 * rmax + delta + 4;
     L.spf += (33 - (L.spf & 31)) & 31;                 // pitch == 1 (mod 32): lanes of a warp read different banks
@@ -398,7 +501,19 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     int rc;
     {
     ProfScope prof(ctx, "adaptive_gauss_k" + std::to_string(k), 2.0 * px);
-    if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, G, smem);
+    if (generic) {
+        const size_t gsmem = smem + sizeof(float) * ((k + 3) & ~3);
+        if (gsmem > 220 * 1024) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "adaptive GAUSSIAN_C block size %d needs too much shared memory", k);
+        DS_CUDA(ctx, cudaFuncSetAttribute(adaptive_gauss_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        int per_sm = 1;
+        DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_gauss_generic_kernel, NT, gsmem));
+        L.seg_rows = ds_pick_seg_rows(per_sm * ctx->sm_count, G.strips, G.max_h, G.seg_min, BR);
+        dim3 grid((G.max_w + TW - 1) / TW, (G.max_h + L.seg_rows - 1) / L.seg_rows, G.n);
+        adaptive_gauss_generic_kernel<<<grid, NT, gsmem, ctx->stream>>>(jd, L, ring_rows);
+        ctx->launches++;
+        rc = cudaGetLastError() == cudaSuccess ? DOCSCAN_OK : ds_fail(ctx, DOCSCAN_ERR_CUDA, "adaptive generic kernel launch failed");
+    }
+    else if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, G, smem);
     else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, G, smem);
     else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, G, smem);
     else if (L.r <= 15) rc = launch_adaptive<15>(ctx, jd, L, G, smem);      // k = 31 (GUI preset), exact

@@ -143,8 +143,15 @@ def test_adaptive_threshold_every_block_size():
     g = page_like(rng, 150, 203)
     for k in range(3, 66, 2):
         eq(ops.adaptive_threshold(g, "gaussian", k, 5), O.adaptive_threshold(g, "gaussian", k, 5), f"gauss k={k}")
+    # beyond the unrolled kernels: the run-time-loop kernel (radius 33..128), with and without cv2's tail columns
+    for k in (67, 81, 101, 151, 257):
+        for h, w in ((150, 203), (90, 260), (300, 131), (40, 64)):
+            g2 = page_like(rng, h, w)
+            eq(ops.adaptive_threshold(g2, "gaussian", k, 5), O.adaptive_threshold(g2, "gaussian", k, 5), f"gauss k={k} {h}x{w}")
+            eq(ops.adaptive_threshold(g2, "gaussian", k, 5, cv_tail_compat=False),
+               O.adaptive_threshold(g2, "gaussian", k, 5, unfused_tail=0), f"gauss all-fma k={k} {h}x{w}")
     with pytest.raises(Exception):
-        ops.adaptive_threshold(g, "gaussian", 67, 5)
+        ops.adaptive_threshold(g, "gaussian", 259, 5)
 
 
 def test_adaptive_threshold_random_noise_is_exact():
@@ -571,7 +578,7 @@ def test_fuzz_ops_random_shapes_and_parameters():
         eq(ops.dilate(g, kw, kh, it), O.dilate(g, kw, kh, it), f"fuzz dilate {kw}x{kh} it{it} {h}x{w}")
         eq(ops.morph_close(g, kw, kh, it), O.morph_close(g, kw, kh, it), f"fuzz close {kw}x{kh} it{it} {h}x{w}")
         eq(ops.blackhat(g, kw, kh), O.blackhat(g, kw, kh), f"fuzz blackhat {kw}x{kh} {h}x{w}")
-        ka, c = int(rng.integers(1, 33)) * 2 + 1, int(rng.integers(-5, 16))
+        ka, c = int(rng.integers(1, 129 if t % 4 == 0 else 33)) * 2 + 1, int(rng.integers(-5, 16))
         eq(ops.adaptive_threshold(g, "gaussian", ka, c), O.adaptive_threshold(g, "gaussian", ka, c), f"fuzz gauss k={ka} c={c} {h}x{w}")
         km = int(rng.integers(1, 18)) * 2 + 1
         eq(ops.adaptive_threshold(g, "mean", km, c), O.adaptive_threshold(g, "mean", km, c), f"fuzz mean k={km} c={c} {h}x{w}")
