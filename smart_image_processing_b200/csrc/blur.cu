@@ -25,6 +25,7 @@ constexpr int RP2 = 132;      // ring pitch in 32-bit words per ROW PAIR (one wo
 struct BlurTable {
     int k_eff, r_eff, delta, M, nb;
     uint32_t kk;              // k*k (box) or 0
+    float inv_kk;             // (float)(1.0 / (k*k)) for the box mean
     const uint4* qH;          // M + 6 entries (3 zero entries each side)
     const uint32_t* qV;       // 2 * (4*nb + 8) entries: even-aligned tap pairs, then odd-aligned tap pairs (dp2a operands)
 };
@@ -202,7 +203,8 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
                 const int y = y_begin + vbase + o;
                 if (o >= rows_here) break;
                 uint32_t b0, b1;
-                if (T.kk) { b0 = (2 * a0[o] + T.kk) / (2 * T.kk); b1 = (2 * a1[o] + T.kk) / (2 * T.kk); }
+                // cv::boxFilter scales the integer box sum in fp32: cvRound((float)sum * (float)(1.0 / k^2))
+                if (T.kk) { b0 = (uint32_t)__float2int_rn(__fmul_rn((float)a0[o], T.inv_kk)); b1 = (uint32_t)__float2int_rn(__fmul_rn((float)a1[o], T.inv_kk)); }
                 else { b0 = (a0[o] + 32768u) >> 16; b1 = (a1[o] + 32768u) >> 16; }
                 uint32_t v0 = b0, v1 = b1;
                 if (EPI != DS_EPI_BLUR) {
@@ -263,6 +265,7 @@ int get_table(docscan_ctx* ctx, int kind, int k, BlurTable* out) {
     const int nb = ((k_eff + 7 + 1) / 2 + 3) / 4;          // V pass: blocks of 4 row pairs covering 8 outputs + k_eff - 1 rows
     out->k_eff = k_eff; out->r_eff = r_eff; out->delta = delta; out->M = M; out->nb = nb;
     out->kk = kind == 1 ? (uint32_t)k * (uint32_t)k : 0;
+    out->inv_kk = (float)(1.0 / ((double)k * (double)k));
     const uint64_t key = ((uint64_t)(kind + 1) << 32) | (uint32_t)k;
     const int nqv = 4 * nb + 8;
     const size_t qh_bytes = sizeof(uint4) * (M + 6), qv_bytes = sizeof(uint32_t) * 2 * nqv;

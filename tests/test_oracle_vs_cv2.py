@@ -118,3 +118,20 @@ def test_warps_random():
         m2 = cv2.getRotationMatrix2D((W / 2.0, H / 2.0), ang, 1.0)
         assert np.array_equal(cv2.warpAffine(g, m2, (W, H), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE),
                               O.warp_affine(g, m2, (W, H)))
+
+
+def test_mean_c_large_blocks_follow_cv2s_fp32_scale():
+    """cv::boxFilter scales the box sum in fp32; from k = 165 on that differs from the exactly rounded quotient for some
+    sums.  A checkerboard of n / n+1 puts every window mean within 1 / (2 k^2) of a tie."""
+    yy, xx = np.mgrid[0:120, 0:173]
+    for k in (35, 101, 163, 165, 201, 255):
+        for n in (7, 100, 254):
+            g = (n + ((yy + xx) & 1)).astype(np.uint8)
+            for c in (0, 1):
+                ref = cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, k, c)
+                assert np.array_equal(O.adaptive_threshold(g, "mean", k, c), ref), (k, n, c)
+    rng = np.random.default_rng(12)
+    g = rng.integers(0, 256, (150, 211), dtype=np.uint8)
+    for k in (51, 151, 255):
+        assert np.array_equal(O.adaptive_threshold(g, "mean", k, 3),
+                              cv2.adaptiveThreshold(g, 255, cv2.ADAPTIVE_THRESH_MEAN_C, cv2.THRESH_BINARY, k, 3))
