@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-skew", action="store_true", help="skip the extra leg with the device-side skew estimate")
+    ap.add_argument("--scale-long", type=int, default=SCALE_LONG,
+                    help="long side of the rectified page; 1600 = CLI default = the headline workload, 4000 = SURVEY config 2's full-resolution variant")
+    ap.add_argument("--preset", choices=["cli", "gui"], default="cli", help="process_document tunables: CLI defaults or the GUI's call")
     return ap.parse_args()
 
 
@@ -105,7 +108,10 @@ class ClockSampler:
 _W = {}
 
 
-def _cpu_worker_init(path, quads, angles):
+GUI_TUNABLES = dict(illum_method="divide", illum_blur_frac=0.05, block_size=31, C=3, morph_ksize=1, morph_iters=0)   # AI_classification.py:646-663
+
+
+def _cpu_worker_init(path, quads, angles, scale_long=SCALE_LONG, tunables=None):
     """Worker process: one cv2 thread, pages memory-mapped from a scratch file."""
     from oracle import ref_cv2
     if ref_cv2.HAVE_CV2:
@@ -113,6 +119,7 @@ def _cpu_worker_init(path, quads, angles):
         cv2.setNumThreads(1)
     _W["pages"] = np.load(path, mmap_mode="r")
     _W["quads"], _W["angles"] = quads, angles
+    _W["scale_long"], _W["tun"] = scale_long, dict(tunables or {})
     _W["fn"] = ref_cv2.hot_path if ref_cv2.HAVE_CV2 else None
 
 
@@ -120,10 +127,10 @@ def _cpu_worker_job(j):
     i = j % len(_W["quads"])
     page = np.asarray(_W["pages"][i])
     if _W["fn"] is not None:
-        _W["fn"](page, _W["quads"][i], _W["angles"][i], scale_long=SCALE_LONG)
+        _W["fn"](page, _W["quads"][i], _W["angles"][i], scale_long=_W["scale_long"], **_W["tun"])
     else:
         from oracle import oracle as O
-        O.hot_path(page, _W["quads"][i], _W["angles"][i], scale_long=SCALE_LONG)
+        O.hot_path(page, _W["quads"][i], _W["angles"][i], scale_long=_W["scale_long"], **_W["tun"])
     return 0
 
 
@@ -132,7 +139,7 @@ class CpuReference:
     every host core: os.cpu_count() spawned worker processes with one cv2 thread each (SURVEY.md 8d mode B, the
     faster of the two modes the survey measured).  Never forks after cv2/CUDA have been initialised."""
 
-    def __init__(self, pages, quads, angles):
+    def __init__(self, pages, quads, angles, scale_long=SCALE_LONG, tunables=None):
         import multiprocessing as mp
         import tempfile
         from oracle import ref_cv2
@@ -145,7 +152,7 @@ class CpuReference:
         self.how = (f"cv2 call chain of DocScanner.py (oracle/ref_cv2.py), {self.cores} worker processes x 1 cv2 thread"
                     if ref_cv2.HAVE_CV2 else f"C oracle (cv2 not installed), {self.cores} worker processes")
         self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_worker_init,
-                                                 initargs=(self.path, [np.asarray(q) for q in quads], list(angles)))
+                                                 initargs=(self.path, [np.asarray(q) for q in quads], list(angles), scale_long, tunables))
         self.run(2 * self.cores)                                   # imports + first-touch, not timed
 
     def run(self, jobs: int):
@@ -163,6 +170,12 @@ class CpuReference:
             pass
 
 
+def _workload(args):
+    if args.scale_long == SCALE_LONG and args.preset == "cli":
+        return WORKLOAD
+    return WORKLOAD.replace("CLI defaults, scale_long=1600", f"{'GUI preset' if args.preset == 'gui' else 'CLI defaults'}, scale_long={args.scale_long}")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -173,7 +186,8 @@ def run_reference_arm(args):
     for s in range(distinct):
         img, quad = synth_page_numpy(s, PAGE_W, PAGE_H)
         pages.append(img); quads.append(quad); angles.append(synth_angle(s))
-    ref = CpuReference(pages, quads, angles)
+    tun = GUI_TUNABLES if args.preset == "gui" else {}
+    ref = CpuReference(pages, quads, angles, args.scale_long, tun)
     for _ in range(args.warmup):
         ref.run(max(ref.cores, 8))
     total = 0.0
@@ -186,7 +200,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "page": f"{PAGE_H}x{PAGE_W}x3", "scale_long": SCALE_LONG, "pages_per_step": args.ref_pages},
+        "config": {"workload": _workload(args), "page": f"{PAGE_H}x{PAGE_W}x3", "scale_long": args.scale_long, "pages_per_step": args.ref_pages},
         "cpu_baseline": {"value": value, "unit": "MP/s", "cores": ref.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -253,7 +267,8 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     ctx = _capi.Context(local, stream=stream.cuda_stream)
     P = args.pages
-    params = DS.make_params()
+    tun = GUI_TUNABLES if args.preset == "gui" else {}
+    params = DS.make_params(**tun)
 
     # ---- device-resident synthetic batch (generated on the device; not timed)
     src = torch.empty((P, PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
@@ -266,7 +281,7 @@ def run_ours(args):
         ctx.call("docscan_synth_page", C.c_uint64(seed), C.byref(im), q8)
         quads.append(np.array(list(q8), np.float32).reshape(4, 2))
         angles.append(synth_angle(seed))
-    sizes = [DS.target_size(q, "A4", SCALE_LONG) for q in quads]
+    sizes = [DS.target_size(q, "A4", args.scale_long) for q in quads]
     tw, th = sizes[0]
     assert all(s == (tw, th) for s in sizes)
     pw3, pw1 = (tw * 3 + 127) // 128 * 128, (tw + 127) // 128 * 128
@@ -414,7 +429,7 @@ def run_ours(args):
         hp = [np.empty((PAGE_H, PAGE_W, 3), np.uint8) for _ in range(D)]
         for i in range(D):
             _capi.lib().docscan_memcpy_d2h(ctx._h, hp[i].ctypes.data, C.c_void_p(src[i].data_ptr()), hp[i].nbytes)
-        ref = CpuReference(hp, quads[:D], angles[:D])
+        ref = CpuReference(hp, quads[:D], angles[:D], args.scale_long, tun)
         _, dt1 = ref.run(2 * ref.cores)
         jobs = int(max(2 * ref.cores, min(4096, 12.0 / max(dt1 / (2 * ref.cores), 1e-6))))
         v, dt = ref.run(jobs)
@@ -427,8 +442,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pages_per_gpu": P, "page": f"{PAGE_H}x{PAGE_W}x3", "warped": f"{th}x{tw}",
-                       "scale_long": SCALE_LONG, "parallelism": f"pages sharded over {world} GPU(s), no collective",
+            "config": {"workload": _workload(args), "pages_per_gpu": P, "page": f"{PAGE_H}x{PAGE_W}x3", "warped": f"{th}x{tw}",
+                       "scale_long": args.scale_long, "parallelism": f"pages sharded over {world} GPU(s), no collective",
                        "l2": f"inputs larger than L2 ({P * PAGE_H * PAGE_W * 3 / 1e9:.1f} GB read per step per GPU)",
                        "rank0_cpu_affinity": numa},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "with_skew_estimate": skew, "gpu_launches": int(launches),

@@ -754,7 +754,7 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
     const int strips_per_page = (pages[0].binary.width + 127) / 128;
     int group = (2 * ctx->sm_count + strips_per_page - 1) / strips_per_page;
     group = std::max(4, std::min(group, 32));
-    if (n >= 4 * 64) group = 64;                       // big resident batches: one 64-page group per stream measured best
+    if (n >= 4 * 64 && strips_per_page <= 12) group = 64;   // big resident batches of ordinary pages: one 64-page group per stream measured best
     if (const char* e = getenv("DOCSCAN_GROUP")) group = std::max(1, atoi(e));
     if (any_host) group = std::min(group, 8);          // finer pipeline granularity: copies overlap compute
     group = std::min(group, n);
