@@ -50,8 +50,15 @@ __device__ __noinline__ uint32_t fetch_word_slow(const uint8_t* rowp, int gx, in
 
 constexpr int SB = 7;         // staging loads a thread keeps in flight (7 x 8 words covers k <= 63 in one go)
 
-template <int EPI, bool STATS>
+// KEFF > 0: a kernel instance for one effective tap count (the sizes the pipeline uses all day).  Loop bounds, the
+// coefficient windows and — above all — which (input word, output) combinations carry only zero taps are then known at
+// compile time: both passes are fully unrolled and issue only the dot products that can contribute (k = 23: 18 instead of
+// 26 per pixel).  KEFF == 0 is the general kernel with run-time loops.
+template <int EPI, bool STATS, int KEFF>
 __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restrict__ jobs, const BlurLaunch L) {
+    constexpr bool FIXED = KEFF > 0;
+    constexpr int FR = KEFF / 2, FDELTA = (4 - (FR & 3)) & 3, FM = (FDELTA + KEFF + 2) / 4 + 1;      // as get_table() derives them
+    constexpr int FNP = (KEFF + 6) / 2 + 1;                                                          // row pairs 8 outputs reach over
     const BlurJob J = jobs[blockIdx.z];
     const int x0 = blockIdx.x * TW;
     const int y_begin = blockIdx.y * L.seg_rows;
@@ -108,8 +115,27 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
             uint32_t acc[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) acc[i] = 0;
+            if (FIXED) {
+                // acc[4g + s] += dp4a(word wi, coefficient word (m = wi - g, shift s)); word (m, s) holds taps 4m + b - s - delta
+#pragma unroll
+                for (int wi = 0; wi < FM + 3; wi++) {
+                    const uint32_t W = srow[wi];
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const int m = wi - g;
+                        if (m < 0 || m >= FM) continue;
+                        const uint4 Q = s_qH[m + 3];
+                        const uint32_t qs[4] = {Q.x, Q.y, Q.z, Q.w};
+#pragma unroll
+                        for (int sft = 0; sft < 4; sft++) {
+                            const int lo = 4 * m - sft - FDELTA, hi = lo + 3;               // tap range of this word
+                            if (hi >= 0 && lo < KEFF) acc[4 * g + sft] = __dp4a(W, qs[sft], acc[4 * g + sft]);
+                        }
+                    }
+                }
+            }
             uint4 q0 = s_qH[0], q1 = s_qH[1], q2 = s_qH[2], q3;    // zero entries: q[wi + 3 - g], g = 3,2,1
-            for (int wi = 0; wi < T.M + 3; wi++) {
+            for (int wi = 0; !FIXED && wi < T.M + 3; wi++) {
                 q3 = s_qH[wi + 3];
                 const uint32_t W = srow[wi];
                 // group g uses coefficient word m = wi - g  -> table entry m + 3
@@ -163,7 +189,28 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
         const int ring_pairs = L.ring_rows >> 1;
         const uint32_t* rp = s_ring + ((vbase >> 1) % ring_pairs) * RP2 + 2 * cp;
         const uint32_t* const rend = s_ring + ring_pairs * RP2 + 2 * cp;
-        for (int b = 0; b < T.nb; b++) {
+        if (FIXED) {
+            // pair step p feeds output o through the even-aligned coefficient pair m = p - o/2 (even o) or the odd-aligned
+            // pair m = p - (o+1)/2 (odd o); pairs whose two taps both fall outside [0, KEFF) are skipped
+#pragma unroll
+            for (int p = 0; p < FNP; p++) {
+                if (p && (p & 3) == 0) {
+                    rp += 4 * RP2;
+                    if (rp >= rend) rp -= ring_pairs * RP2;
+                }
+                const uint2 w = *reinterpret_cast<const uint2*>(rp + (p & 3) * RP2);
+#pragma unroll
+                for (int o = 0; o < 8; o++) {
+                    const int m = (o & 1) ? p - (o + 1) / 2 : p - o / 2;
+                    const bool nz = (o & 1) ? (m >= -1 && 2 * m + 1 < KEFF) : (m >= 0 && 2 * m < KEFF);
+                    if (!nz) continue;
+                    const uint32_t c = (o & 1) ? s_qO[m + 4] : s_qE[m + 4];
+                    a0[o] = __dp2a_lo(w.x, c, a0[o]);
+                    a1[o] = __dp2a_lo(w.y, c, a1[o]);
+                }
+            }
+        }
+        for (int b = 0; !FIXED && b < T.nb; b++) {
 #pragma unroll
             for (int i = 0; i < 4; i++) { E[i] = E[i + 4]; O[i] = O[i + 4]; }
             {
@@ -300,17 +347,33 @@ int get_table(docscan_ctx* ctx, int kind, int k, BlurTable* out) {
 
 struct BlurGridInfo { int strips, max_w, max_h, n, seg_min; };
 
-template <int EPI, bool STATS>
-int launch(docscan_ctx* ctx, const BlurJob* jobs_dev, BlurLaunch L, const BlurGridInfo& G, size_t smem) {
+template <int EPI, bool STATS, int KEFF>
+int launch_k(docscan_ctx* ctx, const BlurJob* jobs_dev, BlurLaunch L, const BlurGridInfo& G, size_t smem) {
     if (smem > 48 * 1024)
-        DS_CUDA(ctx, cudaFuncSetAttribute(blur_march_kernel<EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA(ctx, cudaFuncSetAttribute(blur_march_kernel<EPI, STATS, KEFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blur_march_kernel<EPI, STATS>, NT, smem));
+    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, blur_march_kernel<EPI, STATS, KEFF>, NT, smem));
     L.seg_rows = ds_pick_seg_rows(per_sm * ctx->sm_count, G.strips, G.max_h, G.seg_min, BR);
     dim3 grid((G.max_w + TW - 1) / TW, (G.max_h + L.seg_rows - 1) / L.seg_rows, G.n);
-    blur_march_kernel<EPI, STATS><<<grid, NT, smem, ctx->stream>>>(jobs_dev, L);
+    blur_march_kernel<EPI, STATS, KEFF><<<grid, NT, smem, ctx->stream>>>(jobs_dev, L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
+}
+
+template <int EPI, bool STATS>
+int launch(docscan_ctx* ctx, const BlurJob* jobs_dev, BlurLaunch L, const BlurGridInfo& G, size_t smem) {
+    // fixed-size instances for the epilogues of the page pipeline (background subtract / divide with min-max, ink branch
+    // with histogram) at the tap counts its default and GUI presets produce: k = 23, 43, 51, 57
+    if (STATS && (EPI == DS_EPI_SUB || EPI == DS_EPI_RSUB || EPI == DS_EPI_DIV)) {
+        switch (L.t.k_eff) {
+            case 21: return launch_k<EPI, STATS, 21>(ctx, jobs_dev, L, G, smem);
+            case 39: return launch_k<EPI, STATS, 39>(ctx, jobs_dev, L, G, smem);
+            case 45: return launch_k<EPI, STATS, 45>(ctx, jobs_dev, L, G, smem);
+            case 51: return launch_k<EPI, STATS, 51>(ctx, jobs_dev, L, G, smem);
+            default: break;
+        }
+    }
+    return launch_k<EPI, STATS, 0>(ctx, jobs_dev, L, G, smem);
 }
 
 }  // namespace

@@ -639,6 +639,23 @@ def test_fuzz_pipeline_random_tunables():
         eq(b[0], ref["clean"], f"fuzz pipeline {t} binary {kw}")
 
 
+def test_fixed_size_blur_instances():
+    """k = 23, 43, 51, 57 (effective taps 21, 39, 45, 51) run the fully unrolled blur instances with zero-tap skipping when
+    they feed the pipeline's epilogues (subtract / divide + min-max, ink branch + histogram): ragged shapes, images smaller
+    than the kernel, several vertical segments."""
+    rng = np.random.default_rng(53)
+    shapes = [(200, 333), (97, 131), (64, 128), (33, 260), (1500, 300), (20, 15), (130, 1031), (257, 129)]
+    for k in (23, 43, 51, 57):
+        for h, w in shapes:
+            g = page_like(rng, h, w) if min(h, w) >= 16 else rng.integers(0, 256, (h, w), dtype=np.uint8)
+            frac = (k - 0.4) / min(h, w)                       # round(min(h, w) * frac) == k (or k - 1 -> forced odd)
+            assert DS._illum_ksize(h, w, frac) == k
+            for method in ("subtract", "divide"):
+                eq(DS.illumination_correction(g, method, frac), O.illumination_correction(g, method, frac), f"illum k={k} {method} {h}x{w}")
+            eq(DS._compute_ink_mask(g, mask_blur_ksize=k), O._compute_ink_mask(g, mask_blur_ksize=k), f"ink mask blur k={k} {h}x{w}")
+            eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"plain blur k={k} {h}x{w}")
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
