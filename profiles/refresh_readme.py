@@ -28,7 +28,8 @@ def main():
         "| `e2e` (pinned host buffers":
             f"| `e2e` (pinned host buffers through the C ABI, H2D ∥ kernels ∥ D2H) | **{d['e2e']['value'] / 1e3:.1f} k MP/s** — "
             f"{d['e2e']['h2d_bytes_per_step'] / 1e9:.2f} GB in (only the part of each photo under its quad; 9.22 GB before) + "
-            f"{d['e2e']['d2h_bytes_per_step'] / 1e9:.2f} GB out per step ≈ 52 GB/s over PCIe: link-bound | `r1_bench_1gpu.json` |",
+            f"{d['e2e']['d2h_bytes_per_step'] / 1e9:.2f} GB out per step ≈ 52 GB/s over PCIe: link-bound (raw contiguous pinned copies on the same "
+            f"box: 52–56 GB/s up, 56–57 GB/s down, `tools/pcie_bandwidth.py`) | `r1_bench_1gpu.json` |",
         "| `with_skew_estimate`":
             f"| `with_skew_estimate` (every page's deskew angle estimated on the device: Canny + HoughLines + median) | "
             f"{sk['value'] / 1e3:.1f} k MP/s, {sk['ms_per_step']:.1f} ms per step; kernels (ms per 256 pages): {skrows} | `r1_bench_1gpu.json` |",
