@@ -656,6 +656,46 @@ def test_fixed_size_blur_instances():
             eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"plain blur k={k} {h}x{w}")
 
 
+def test_two_threads_with_their_own_contexts():
+    """The reference calls the path from a worker thread (AI_classification.py:855); contexts are per thread and the
+    library keeps no global mutable state: two threads running different work at once must both get exact results."""
+    import threading
+    rng = np.random.default_rng(61)
+    H, W = 360, 280
+    base = page_like(rng, H, W)
+    img = np.stack([np.clip(base * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1)
+    quad = np.array([[18, 14], [262, 20], [266, 344], [12, 338]], np.float32)
+    g = page_like(rng, 300, 411)
+    ref_a = O.hot_path(img, quad, 1.0, scale_long=400)
+    ref_b = (O.adaptive_binarize(g), O._compute_ink_mask(g, mask_blur_ksize=51), O.deskew(g))
+    errors = []
+
+    def worker_a():
+        try:
+            for _ in range(12):
+                w, b = DS.process_pages([img], [quad], [1.0], scale_long=400)
+                eq(w[0], ref_a["warped"], "thread A warped")
+                eq(b[0], ref_a["clean"], "thread A binary")
+        except Exception as e:          # surfaced in the main thread below
+            errors.append(e)
+
+    def worker_b():
+        try:
+            for _ in range(12):
+                eq(DS.adaptive_binarize(g), ref_b[0], "thread B adaptive")
+                eq(DS._compute_ink_mask(g, mask_blur_ksize=51), ref_b[1], "thread B ink mask")
+                eq(DS.deskew(g), ref_b[2], "thread B deskew")
+        except Exception as e:
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker_a), threading.Thread(target=worker_b)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[0]
+
+
 def test_errors_are_loud():
     from smart_image_processing_b200._capi import DocscanError
     with pytest.raises(DocscanError):
