@@ -149,8 +149,11 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
             double W = __dadd_rn(W0, __dmul_rn(m6, x1));
             if (SAFE_RCP) W = __dmul_rn(__drcp_rn(W), 32.0);
             else W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
-            Xs[i] = round_clamped(__dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W));
-            Ys[i] = round_clamped(__dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W));
+            const double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(m0, x1)), W), fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(m3, x1)), W);
+            // SAFE_RCP: finite matrix and a bounded, non-zero denominator — the products cannot be NaN, and the conversion
+            // instruction saturates like OpenCV's clamp
+            Xs[i] = SAFE_RCP ? __double2int_rn(fX) : round_clamped(fX);
+            Ys[i] = SAFE_RCP ? __double2int_rn(fY) : round_clamped(fY);
         }
     }
     uint2 lo[4][2], hi[4][2];
@@ -311,7 +314,8 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
                 const double w = j.m[6] * cx[a] + j.m[7] * cy[b] + j.m[8];
                 lo = fmin(lo, w); hi = fmax(hi, w);
             }
-        const bool finite = std::isfinite(lo) && std::isfinite(hi);
+        bool finite = std::isfinite(lo) && std::isfinite(hi);
+        for (int e = 0; e < 9; e++) finite = finite && std::isfinite(j.m[e]) && std::fabs(j.m[e]) < 1e150;
         safe_rcp = finite && ((lo > 1e-290 && hi < 1e290) || (hi < -1e-290 && lo > -1e290));
     }
     if (wide && safe_rcp) warp_perspective3_kernel<true><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
