@@ -136,9 +136,10 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int x = xt + 32 * i + threadIdx.x;
-            // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows))
-            const int xbi = J.block_w == 64 ? (x & ~63) : x - x % J.block_w;
-            if (xbi != xb) {
+            // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows)); the
+            // SAFE_RCP instances are only launched for 64-px blocks, where a thread's pixels 0,1 / 2,3 share an origin
+            const int xbi = SAFE_RCP ? xt + 64 * (i >> 1) : (J.block_w == 64 ? (x & ~63) : x - x % J.block_w);
+            if (SAFE_RCP ? (i & 1) == 0 : xbi != xb) {
                 xb = xbi;
                 const double dxb = (double)xb;
                 X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
@@ -316,7 +317,7 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
             }
         bool finite = std::isfinite(lo) && std::isfinite(hi);
         for (int e = 0; e < 9; e++) finite = finite && std::isfinite(j.m[e]) && std::fabs(j.m[e]) < 1e150;
-        safe_rcp = finite && ((lo > 1e-290 && hi < 1e290) || (hi < -1e-290 && lo > -1e290));
+        safe_rcp = finite && j.block_w == 64 && ((lo > 1e-290 && hi < 1e290) || (hi < -1e-290 && lo > -1e290));
     }
     if (wide && safe_rcp) warp_perspective3_kernel<true><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else if (wide) warp_perspective3_kernel<false><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
