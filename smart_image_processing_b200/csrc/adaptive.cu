@@ -157,19 +157,28 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
         }
         if (x < J.w) {
             const int y0 = y_begin + vb * BR;
-            const uint8_t* sp = J.src + (size_t)y0 * J.src_pitch + x;
-            uint8_t* dp = J.dst + (size_t)y0 * J.dst_pitch + x;
             const int rows = min(BR, y_end - y0);
+            // 32-bit offsets from the (warp-uniform) plane pointers; the mean of uint8 data under a kernel that sums to 1 lies
+            // in [0, 255.0001], so the conversion needs no clamp
+            const uint32_t so = (uint32_t)y0 * (uint32_t)J.src_pitch + (uint32_t)x, d_o = (uint32_t)y0 * (uint32_t)J.dst_pitch + (uint32_t)x;
             int cpx[BR];                                   // centre pixels, loaded up front
+            if (rows == BR) {
 #pragma unroll
-            for (int o = 0; o < BR; o++) { cpx[o] = o < rows ? (int)*sp : 0; sp += J.src_pitch; }
+                for (int o = 0; o < BR; o++) cpx[o] = J.src[so + (uint32_t)o * (uint32_t)J.src_pitch];
 #pragma unroll
-            for (int o = 0; o < BR; o++) {
-                if (o >= rows) break;
-                const float m = col_identity ? Wn[o + RMAX] : acc[o];
-                const int mean = min(max(__float2int_rn(m), 0), 255);
-                *dp = (cpx[o] - mean > -L.c_param) ? 255 : 0;
-                dp += J.dst_pitch;
+                for (int o = 0; o < BR; o++) {
+                    const int mean = __float2int_rn(col_identity ? Wn[o + RMAX] : acc[o]);
+                    J.dst[d_o + (uint32_t)o * (uint32_t)J.dst_pitch] = (cpx[o] - mean > -L.c_param) ? 255 : 0;
+                }
+            } else {
+#pragma unroll
+                for (int o = 0; o < BR; o++) cpx[o] = o < rows ? (int)J.src[so + (uint32_t)o * (uint32_t)J.src_pitch] : 0;
+#pragma unroll
+                for (int o = 0; o < BR; o++) {
+                    if (o >= rows) break;
+                    const int mean = __float2int_rn(col_identity ? Wn[o + RMAX] : acc[o]);
+                    J.dst[d_o + (uint32_t)o * (uint32_t)J.dst_pitch] = (cpx[o] - mean > -L.c_param) ? 255 : 0;
+                }
             }
         }
     }

@@ -166,6 +166,18 @@ def test_mean_c_large_blocks():
         eq(ops.adaptive_threshold(g, "mean", k, 4), O.adaptive_threshold(g, "mean", k, 4), f"mean page k={k}")
 
 
+def test_adaptive_threshold_extreme_images():
+    """All-255 / all-0 / checkerboard 0-255 pages: the local mean touches both ends of the uint8 range."""
+    yy, xx = np.mgrid[0:90, 0:203]
+    imgs = [np.full((90, 203), 255, np.uint8), np.zeros((90, 203), np.uint8), (((yy + xx) & 1) * 255).astype(np.uint8),
+            (((yy // 7 + xx // 5) & 1) * 255).astype(np.uint8)]
+    for g in imgs:
+        for k in (3, 11, 31, 35, 51, 101):
+            for c in (0, 10, -3):
+                eq(ops.adaptive_threshold(g, "gaussian", k, c), O.adaptive_threshold(g, "gaussian", k, c), f"extreme gauss k={k} c={c}")
+                eq(ops.adaptive_threshold(g, "mean", k, c), O.adaptive_threshold(g, "mean", k, c), f"extreme mean k={k} c={c}")
+
+
 def test_adaptive_threshold_random_noise_is_exact():
     # pure noise puts many local means next to rounding ties: the ordered fp32 evaluation must still match
     rng = np.random.default_rng(5)
