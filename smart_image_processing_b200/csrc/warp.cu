@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
 // SAFE_RCP: the host has checked that the denominator W keeps one sign and stays within [1e-290, 1e290] over the whole
 // destination rectangle (it is affine in (x, y), so its extremes sit at the corners).  32 is a power of two, so the
 // correctly rounded quotient 32 / W is then exactly 32 * RN(1 / W) — the reciprocal sequence is half as long as the division.
-template <bool SAFE_RCP>
+// P8: every source pitch is a multiple of 8 bytes, so the two rows of a pixel share their offset inside the 8-byte window.
+template <bool SAFE_RCP, bool P8>
 __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* __restrict__ jobs) {
     const WarpPJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
@@ -163,15 +164,13 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
     for (int i = 0; i < 4; i++) {
         const int sx = ds_clamp(Xs[i] >> 5, J.rx0 + 3, J.rx1 - 6) - J.rx0, sy = Ys[i] >> 5;
         const int cy0 = ds_clamp(sy, J.ry0, J.ry1 - 1);
-        const uintptr_t A0 = reinterpret_cast<uintptr_t>(src + (size_t)(cy0 - J.ry0) * sp + 3 * sx);
-        const uintptr_t A1 = A0 + ((sy >= J.ry0 && sy + 1 < J.ry1) ? (uintptr_t)sp : 0);         // row clamp(sy + 1)
-#pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-            const uintptr_t A = rr ? A1 : A0;
-            const uint2* base = reinterpret_cast<const uint2*>(A & ~(uintptr_t)7);
-            lo[i][rr] = __ldg(base); hi[i][rr] = __ldg(base + 1);
-            sft[i][rr] = (uint32_t)(A & 7);
-        }
+        const uintptr_t A0 = reinterpret_cast<uintptr_t>(src + ((uint32_t)(cy0 - J.ry0) * (uint32_t)sp + 3u * (uint32_t)sx));      // < 2^32: checked by the host
+        const uint32_t step = (sy >= J.ry0 && sy + 1 < J.ry1) ? (uint32_t)sp : 0u;               // row clamp(sy + 1)
+        const uintptr_t B0 = A0 & ~(uintptr_t)7, B1 = P8 ? B0 + step : (A0 + step) & ~(uintptr_t)7;
+        lo[i][0] = __ldg(reinterpret_cast<const uint2*>(B0)); hi[i][0] = __ldg(reinterpret_cast<const uint2*>(B0) + 1);
+        lo[i][1] = __ldg(reinterpret_cast<const uint2*>(B1)); hi[i][1] = __ldg(reinterpret_cast<const uint2*>(B1) + 1);
+        sft[i][0] = (uint32_t)(A0 & 7);
+        sft[i][1] = P8 ? sft[i][0] : (uint32_t)((A0 + step) & 7);
     }
     uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
     uint8_t* grow = J.gray ? J.gray + (size_t)y * J.gray_pitch : nullptr;
@@ -184,20 +183,23 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
         int acc[3];
         if (sx >= J.rx0 + 3 && sx <= J.rx1 - 6) {
             // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) h0 + ay h1] exactly, so (.. + 2^14) >> 15 == (v + 512) >> 10
-            const uint32_t wx = (uint32_t)(32 - ax) | ((uint32_t)ax << 8);
-            const int wy0 = y0in ? 32 - ay : 0, wy1 = y1in ? ay : 0;         // rows outside the image: BORDER_CONSTANT 0
-            int h[2][3];
+            // The four weights / 32 are at most 1024: they ride as 16-bit pairs (left, right) of one word per source row and
+            // dp2a applies a pair to two pixel bytes — 6 dot products and 3 byte permutes per pixel, no separate vertical pass.
+            const uint32_t wxx = 32u + 0xffffu * (uint32_t)ax;              // (32 - ax) | ax << 16
+            const uint32_t wt = (y0in ? 32u - (uint32_t)ay : 0u) * wxx;      // rows outside the image: BORDER_CONSTANT 0
+            const uint32_t wb = (y1in ? (uint32_t)ay : 0u) * wxx;
+            uint32_t b0[2], gr[2];
 #pragma unroll
             for (int rr = 0; rr < 2; rr++) {
                 const bool up = sft[i][rr] >= 4;
-                const uint32_t wa = up ? lo[i][rr].y : lo[i][rr].x, wb = up ? hi[i][rr].x : lo[i][rr].y, wc = up ? hi[i][rr].y : hi[i][rr].x;
-                const uint32_t b0 = __funnelshift_r(wa, wb, 8 * sft[i][rr]), b1 = __funnelshift_r(wb, wc, 8 * sft[i][rr]);   // shift mod 32
-                h[rr][0] = __dp4a(__byte_perm(b0, b1, 0x0030), wx, 0u);      // (B0, B1)
-                h[rr][1] = __dp4a(__byte_perm(b0, b1, 0x0041), wx, 0u);      // (G0, G1)
-                h[rr][2] = __dp4a(__byte_perm(b0, b1, 0x0052), wx, 0u);      // (R0, R1)
+                const uint32_t wa = up ? lo[i][rr].y : lo[i][rr].x, wm = up ? hi[i][rr].x : lo[i][rr].y, wc = up ? hi[i][rr].y : hi[i][rr].x;
+                b0[rr] = __funnelshift_r(wa, wm, 8 * sft[i][rr]);                                     // B0 G0 R0 B1   (shift mod 32)
+                gr[rr] = __byte_perm(b0[rr], __funnelshift_r(wm, wc, 8 * sft[i][rr]), 0x5241);       // G0 G1 R0 R1
             }
-#pragma unroll
-            for (int c = 0; c < 3; c++) acc[c] = (wy0 * h[0][c] + wy1 * h[1][c] + 512) >> 10;
+            const uint32_t bb = __byte_perm(b0[0], b0[1], 0x7430);                                    // B0 B1 of row 0, B0 B1 of row 1
+            acc[0] = (int)(__dp2a_hi(wb, bb, __dp2a_lo(wt, bb, 512u)) >> 10);
+            acc[1] = (int)(__dp2a_lo(wb, gr[1], __dp2a_lo(wt, gr[0], 512u)) >> 10);
+            acc[2] = (int)(__dp2a_hi(wb, gr[1], __dp2a_hi(wt, gr[0], 512u)) >> 10);
         } else {
             const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
             const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
@@ -239,13 +241,14 @@ __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __rest
     const int Y0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[4], dy), J.m[5]), 1024.0)) + 16;
     const uint8_t* __restrict__ src = J.src;
     const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
-    uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
+    uint8_t* const dpx = J.dst + (size_t)y * J.dst_pitch + (xt + threadIdx.x);
+    const int2* const dlp = J.delta + (xt + threadIdx.x);
     // lane-interleaved pixels (see warp_perspective_kernel): compact gathers, coalesced byte stores
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int x = xt + 32 * i + threadIdx.x;
         if (x >= J.dw) break;
-        const int2 dl = __ldg(J.delta + x);
+        const int2 dl = __ldg(dlp + 32 * i);
         const int X = (X0 + dl.x) >> 5, Y = (Y0 + dl.y) >> 5;
         // (OpenCV keeps sx, sy as saturated shorts; with sources below 32767 px the replicate clamp gives the same taps)
         const int sx = X >> 5, sy = Y >> 5;
@@ -253,9 +256,10 @@ __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __rest
         int h0, h1;
         // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) * ((32-ax) p00 + ax p01) + ay * ((32-ax) p10 + ax p11)] exactly
         if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {      // interior: no clamping
-            const uint8_t* r0 = src + (size_t)sy * sp + sx;
+            const uint8_t* r0 = src + ((uint32_t)sy * (uint32_t)sp + (uint32_t)sx);          // < 2^32: checked by the host
+            const uint8_t* r1 = r0 + (uint32_t)sp;
             h0 = (32 - ax) * __ldg(r0) + ax * __ldg(r0 + 1);
-            h1 = (32 - ax) * __ldg(r0 + sp) + ax * __ldg(r0 + sp + 1);
+            h1 = (32 - ax) * __ldg(r1) + ax * __ldg(r1 + 1);
         } else {
             const int xa = ds_clamp(sx, 0, sw - 1), xb = ds_clamp(sx + 1, 0, sw - 1);
             const int ya = ds_clamp(sy, 0, sh - 1), yb = ds_clamp(sy + 1, 0, sh - 1);
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __rest
             h0 = (32 - ax) * __ldg(r0 + xa) + ax * __ldg(r0 + xb);
             h1 = (32 - ax) * __ldg(r1 + xa) + ax * __ldg(r1 + xb);
         }
-        drow[x] = (uint8_t)(((32 - ay) * h0 + ay * h1 + 512) >> 10);
+        dpx[32 * i] = (uint8_t)(((32 - ay) * h0 + ay * h1 + 512) >> 10);
     }
 }
 
@@ -304,7 +308,9 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     }
     ProfScope prof(ctx, ch == 3 ? "warp_perspective_c3" : "warp_perspective_c1", bytes);
     bool wide = ch == 3;
-    for (int i = 0; i < n; i++) wide = wide && jobs_host[i].rx1 - jobs_host[i].rx0 >= 9;
+    for (int i = 0; i < n; i++)      // the fast kernel keeps byte offsets inside the resident region in 32 bits
+        wide = wide && jobs_host[i].rx1 - jobs_host[i].rx0 >= 9 && jobs_host[i].src_pitch > 0 &&
+               (unsigned long long)(jobs_host[i].ry1 - jobs_host[i].ry0) * (unsigned long long)jobs_host[i].src_pitch < 0xffff0000ull;
     bool safe_rcp = wide;
     for (int i = 0; i < n && safe_rcp; i++) {
         const WarpPJob& j = jobs_host[i];
@@ -319,8 +325,11 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
         for (int e = 0; e < 9; e++) finite = finite && std::isfinite(j.m[e]) && std::fabs(j.m[e]) < 1e150;
         safe_rcp = finite && j.block_w == 64 && ((lo > 1e-290 && hi < 1e290) || (hi < -1e-290 && lo > -1e290));
     }
-    if (wide && safe_rcp) warp_perspective3_kernel<true><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
-    else if (wide) warp_perspective3_kernel<false><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    bool p8 = true;
+    for (int i = 0; i < n; i++) p8 = p8 && jobs_host[i].src_pitch % 8 == 0;
+    if (wide && safe_rcp && p8) warp_perspective3_kernel<true, true><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    else if (wide && safe_rcp) warp_perspective3_kernel<true, false><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    else if (wide) warp_perspective3_kernel<false, false><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else warp_perspective_kernel<1><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     DS_CHECK_LAUNCH(ctx);
@@ -332,6 +341,8 @@ int k_warp_affine_upload(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, WarpA
     for (int i = 0; i < n; i++) {
         if (jobs[i].sw >= 32767 || jobs[i].sh >= 32767)      // cv::remap's own limit (coordinates are shorts)
             return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "warp source larger than 32766 px");
+        if (jobs[i].src_pitch <= 0 || (unsigned long long)jobs[i].sh * (unsigned long long)jobs[i].src_pitch >= 0xffff0000ull)
+            return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "warp source plane of 4 GiB or more");
         void* t = nullptr;
         DS_TRY(ds_arena_alloc(ctx, sizeof(int2) * ((size_t)jobs[i].dw + 4), &t));
         jobs[i].delta = (int2*)t;

@@ -217,6 +217,55 @@ def test_warp_affine():
     eq(DS.rotate(g, 0.0), g, "angle 0 is an exact copy")
 
 
+def test_warps_on_caller_device_buffers_with_odd_pitches():
+    """Device-resident sources whose pitch / base address are not multiples of 8 (or of 4) take the kernel instances that
+    work out the load-window offset per source row; results must not depend on where the caller put the bytes."""
+    import ctypes as C
+    from smart_image_processing_b200 import _capi
+    ctx = _capi.Context(0)
+    rng = np.random.default_rng(66)
+    H, W, tw, th = 211, 301, 250, 170
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    quad = np.array([[20, 12], [280, 25], [290, 200], [8, 190]], np.float32)
+    m = O.get_perspective_transform(quad, np.array([[0, 0], [tw - 1, 0], [tw - 1, th - 1], [0, th - 1]], np.float32))
+    ref = O.warp_perspective(img, m, (tw, th))
+    mm = np.ascontiguousarray(m, np.float64).reshape(9)
+    g = img[:, :, 1].copy()
+    ma = np.ascontiguousarray(O.rotation_matrix((W / 2.0, H / 2.0), 3.5), np.float64).reshape(6)
+    refa = O.warp_affine(g, ma.reshape(2, 3), (W, H))
+    for pitch3, off in ((W * 3, 0), (W * 3 + 5, 3), (W * 3 + 13, 1), (W * 3 + 8, 16)):
+        host = np.zeros((H, pitch3), np.uint8)
+        host[:, :W * 3] = img.reshape(H, W * 3)
+        raw = ctx.device_alloc(H * pitch3 + 64)
+        _capi.lib().docscan_memcpy_h2d(ctx._h, C.c_void_p(raw + off), host.ctypes.data, host.nbytes)
+        dpitch = tw * 3 + 7
+        draw = ctx.device_alloc(th * dpitch + 64)
+        gpitch = tw + 3
+        graw = ctx.device_alloc(th * gpitch + 64)
+        s = _capi.device_image(raw + off, W, H, pitch3, 3)
+        d = _capi.device_image(draw + 1, tw, th, dpitch, 3)
+        gi = _capi.device_image(graw + 2, tw, th, gpitch, 1)
+        ctx.call("docscan_warp_perspective", C.byref(s), mm.ctypes.data_as(C.POINTER(C.c_double)), C.byref(d), C.byref(gi))
+        ctx.sync()
+        eq(_d2h(ctx, draw + 1, th, dpitch, tw * 3).reshape(th, tw, 3), ref, f"warp, source pitch {pitch3} offset {off}")
+        eq(_d2h(ctx, graw + 2, th, gpitch, tw), O.bgr2gray(ref), f"fused gray, source pitch {pitch3} offset {off}")
+        # one channel: rotate a plane that lives at an odd pitch
+        pitch1 = W + (pitch3 - W * 3)
+        host1 = np.zeros((H, pitch1), np.uint8)
+        host1[:, :W] = g
+        raw1 = ctx.device_alloc(H * pitch1 + 64)
+        _capi.lib().docscan_memcpy_h2d(ctx._h, C.c_void_p(raw1 + off), host1.ctypes.data, host1.nbytes)
+        out1 = ctx.device_alloc(H * (W + 1) + 64)
+        s1 = _capi.device_image(raw1 + off, W, H, pitch1, 1)
+        d1 = _capi.device_image(out1 + 1, W, H, W + 1, 1)
+        ctx.call("docscan_warp_affine", C.byref(s1), ma.ctypes.data_as(C.POINTER(C.c_double)), C.byref(d1))
+        ctx.sync()
+        eq(_d2h(ctx, out1 + 1, H, W + 1, W), refa, f"rotate, source pitch {pitch1} offset {off}")
+        for ptr in (raw, draw, graw, raw1, out1):
+            ctx.device_free(ptr)
+    ctx.close()
+
+
 def test_reference_stage_functions():
     rng = np.random.default_rng(8)
     for h, w in [(240, 170), (333, 500), (64, 64), (700, 495)]:
