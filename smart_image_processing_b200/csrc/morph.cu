@@ -205,11 +205,13 @@ __device__ __forceinline__ void windows_h(uint32_t (&r)[N]) {           // r[i] 
 struct MarchLaunch { int seg_rows, spw, ring_rows; };
 
 template <int KW, int KH, bool DIL>
-__global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __restrict__ jobs, const MarchLaunch L) {
+// small windows: capped at 6 CTAs' worth of registers (72; the prefetch registers would otherwise push it to 96)
+__global__ void __launch_bounds__(NTm, (KH <= 19 ? 6 : 1)) morph_march_kernel(const MorphJob* __restrict__ jobs, const MarchLaunch L) {
     constexpr int AX = KW / 2, AY = KH / 2;
     constexpr int AXW = ((AX + 3) / 4) * 4, OFF = AXW - AX;
     constexpr int NWH = (OFF + 31 + KW + 3) / 4, NH = 2 * NWH;         // words / registers a thread needs per row (H)
     constexpr int NRW = 8 + KH - 1;                                     // ring rows a thread needs (V)
+    constexpr int SPW = (24 + NWH + 1) | 1;                             // staged words per row == L.spw (launch_t)
     constexpr int PV = 1 << ilog2_floor(KH);
     constexpr int D = (KH - 1 + BRm - 1) / BRm;                         // V step lags the H step by D steps
     constexpr uint32_t NEUTRAL_W = DIL ? 0u : 0xffffffffu;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __rest
     const int tid = threadIdx.x;
     extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t* s_stage = smem_u32;                                        // BRm * spw
-    uint32_t* s_ring = s_stage + BRm * L.spw;                            // ring_rows * RPW
+    uint32_t* s_ring = s_stage + BRm * SPW;                            // ring_rows * RPW
     s_ring = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_ring) + 15) & ~(uintptr_t)15);
     uint32_t* s_hist = s_ring + L.ring_rows * RPW;                       // 4 x 256 when J.hist
     if (J.hist) for (int i = tid; i < 4 * 256; i += NTm) s_hist[i] = 0;
@@ -229,23 +231,45 @@ __global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __rest
     const bool dst_al = ((reinterpret_cast<uintptr_t>(J.dst) | (uintptr_t)J.dst_pitch) & 3) == 0;
     const int n_vb = (y_end - y_begin + BRm - 1) / BRm;
     uint32_t zero_count = 0;
+    // Staging is software-pipelined through registers in the strips whose staged rows lie inside the image and are
+    // word-aligned (all but the first and last strip of a page): the words of step hb + 1 are requested right after step
+    // hb's have been parked in shared memory, so their latency hides behind the H and V passes instead of stalling the STS.
+    constexpr int NPF = (SPW + 3) / 4;
+    const bool pipelined = src_al && x0 - AXW >= 0 && x0 - AXW + 4 * SPW <= J.w;
+    uint32_t pf[NPF];
+    auto fetch = [&](int hb) {   // virtual row v <-> source row y_begin - AY + v (neutral outside the image)
+        const int gy = y_begin - AY + hb * BRm + (tid >> 2);
+        const bool row_in = gy >= 0 && gy < J.h;
+        const uint8_t* rowp = J.src + (size_t)(row_in ? gy : 0) * J.src_pitch + (x0 - AXW + 4 * (tid & 3));
+#pragma unroll
+        for (int j = 0; j < NPF; j++) {
+            pf[j] = NEUTRAL_W;
+            if (row_in && (tid & 3) + 4 * j < SPW) pf[j] = ds_ldg32(rowp + 16 * j);
+        }
+    };
+    if (pipelined) fetch(0);
     for (int hb = 0; hb < n_vb + D; hb++) {
-        {   // ---- stage 32 source rows: virtual row v <-> source row y_begin - AY + v (neutral outside the image)
+        if (pipelined) {   // ---- park the 32 staged source rows
+            uint32_t* srow_w = s_stage + (tid >> 2) * SPW + (tid & 3);
+#pragma unroll
+            for (int j = 0; j < NPF; j++) if ((tid & 3) + 4 * j < SPW) srow_w[4 * j] = pf[j];
+        } else {           // ---- stage 32 source rows, any alignment, neutral outside the image
             const int srow = tid >> 2;
             const int gy = y_begin - AY + hb * BRm + srow;
             const bool row_in = gy >= 0 && gy < J.h;
             const uint8_t* rowp = J.src + (size_t)(row_in ? gy : 0) * J.src_pitch;
-            for (int wi = tid & 3; wi < L.spw; wi += 4) {
+            for (int wi = tid & 3; wi < SPW; wi += 4) {
                 const int gx = x0 - AXW + 4 * wi;
                 uint32_t word = NEUTRAL_W;
                 if (row_in) word = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : load_word_slow(rowp, gx, J.w, NEUTRAL_W & 255u);
-                s_stage[srow * L.spw + wi] = word;
+                s_stage[srow * SPW + wi] = word;
             }
         }
         __syncthreads();
+        if (pipelined && hb + 1 < n_vb + D) fetch(hb + 1);
         {   // ---- H pass: thread = (row, 32 consecutive outputs)
             const int hr = tid >> 2, cg = tid & 3;
-            const uint32_t* sp = s_stage + hr * L.spw + cg * 8;
+            const uint32_t* sp = s_stage + hr * SPW + cg * 8;
             uint32_t r[NH];
 #pragma unroll
             for (int j = 0; j < NWH; j++) { const uint32_t w = sp[j]; r[2 * j] = __byte_perm(w, 0, 0x4140); r[2 * j + 1] = __byte_perm(w, 0, 0x4342); }
@@ -287,16 +311,23 @@ __global__ void __launch_bounds__(NTm) morph_march_kernel(const MorphJob* __rest
         if (x < J.w) {
             const int nvalid = min(4, J.w - x);
             const int yb = y_begin + vb * BRm + rg * 8;
+            uint32_t rw[8];                                           // black-hat: the 8 reference words, requested together
+            if (J.ref) {
+                const uint8_t* rp = J.ref + (size_t)yb * J.ref_pitch + x;
+                const bool fast = nvalid == 4 && ((reinterpret_cast<uintptr_t>(rp) | (uintptr_t)J.ref_pitch) & 3) == 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    rw[i] = 0;
+                    if (yb + i < y_end) rw[i] = fast ? ds_ldg32(rp) : load_word_slow(rp - x, x, J.w, 0);
+                    rp += J.ref_pitch;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int y = yb + i;
                 if (y >= y_end) break;
                 uint32_t res = __byte_perm(va[i], vbq[i], 0x6420);
-                if (J.ref) {                                          // black-hat: sat(close(src) - src)
-                    const uint8_t* rp = J.ref + (size_t)y * J.ref_pitch + x;
-                    const uint32_t rw = (nvalid == 4 && (reinterpret_cast<uintptr_t>(rp) & 3) == 0) ? ds_ldg32(rp) : load_word_slow(rp - x, x, J.w, 0);
-                    res = __vsubus4(res, rw);
-                }
+                if (J.ref) res = __vsubus4(res, rw[i]);               // sat(close(src) - src)
                 if (J.hist) {
                     // a black-hat page is mostly zeros: count those in a register instead of 32 lanes hammering bin 0
                     if (res == 0) zero_count += nvalid;

@@ -11,6 +11,10 @@
 
 #include "common.cuh"
 
+#ifndef WP3_MINB
+#define WP3_MINB 8      // resident CTAs per SM the 3-channel perspective kernel is compiled for: 64 registers (measured: 7 -> 2.81 ms, 8 -> 2.65, 9 -> 2.92, 10 -> 3.09)
+#endif
+
 namespace {
 
 __device__ __forceinline__ uint8_t gray15(int b, int g, int r) {
@@ -121,7 +125,7 @@ __global__ void __launch_bounds__(128) warp_perspective_kernel(const WarpPJob* _
 // correctly rounded quotient 32 / W is then exactly 32 * RN(1 / W) — the reciprocal sequence is half as long as the division.
 // P8: every source pitch is a multiple of 8 bytes, so the two rows of a pixel share their offset inside the 8-byte window.
 template <bool SAFE_RCP, bool P8>
-__global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(128, WP3_MINB) warp_perspective3_kernel(const WarpPJob* __restrict__ jobs) {
     const WarpPJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int xt = blockIdx.x * 128;                 // a warp covers 128 consecutive destination pixels of one row
@@ -220,36 +224,43 @@ __global__ void __launch_bounds__(128) warp_perspective3_kernel(const WarpPJob* 
 }
 
 // cv::warpAffine precomputes adelta[x] = saturate_cast<int>(M[0]*x*1024), bdelta[x] = saturate_cast<int>(M[3]*x*1024)
-// once per call; so do we (one tiny kernel), which keeps fp64 out of the per-pixel loop.
+// once per call; so do we (one tiny kernel), which keeps fp64 out of the per-pixel loop.  The same kernel tabulates the
+// row origins X0[y] = saturate_cast<int>((M[1]*y + M[2])*1024) + 16 (and Y0) behind the column table: rows start at
+// delta[dw + 4].
 __global__ void affine_delta_kernel(const WarpAJob* __restrict__ jobs) {
     const WarpAJob& J = jobs[blockIdx.y];
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= J.dw) return;
-    const double dx = (double)x;
-    J.delta[x] = make_int2(round_clamped(__dmul_rn(__dmul_rn(J.m[0], dx), 1024.0)),
-                           round_clamped(__dmul_rn(__dmul_rn(J.m[3], dx), 1024.0)));
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double dt = (double)t;
+    if (t < J.dw)
+        J.delta[t] = make_int2(round_clamped(__dmul_rn(__dmul_rn(J.m[0], dt), 1024.0)),
+                               round_clamped(__dmul_rn(__dmul_rn(J.m[3], dt), 1024.0)));
+    if (t < J.dh)
+        J.delta[J.dw + 4 + t] = make_int2(round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[1], dt), J.m[2]), 1024.0)) + 16,
+                                          round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[4], dt), J.m[5]), 1024.0)) + 16);
 }
 
+// One warp = 128 destination pixels of a row, lane-interleaved (see warp_perspective_kernel): compact gathers, coalesced
+// byte stores.  The kernel runs at 90 % occupancy, so the per-pixel chain table -> address -> taps -> filter is hidden by
+// the other warps; batching a thread's 16 gathers ahead of the filter (as warp_perspective3_kernel does) only costs
+// registers here (measured: 1.05 -> 1.10 ms).  Interior pixels skip the replicate clamps.
 __global__ void __launch_bounds__(128) warp_affine_kernel(const WarpAJob* __restrict__ jobs) {
     const WarpAJob& J = jobs[blockIdx.z];
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int xt = blockIdx.x * 128;
-    if (y >= J.dh || xt >= J.dw) return;
-    const double dy = (double)y;
-    // cv::warpAffine: X0 = saturate_cast<int>((M[1]*y + M[2])*1024) + 16
-    const int X0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[1], dy), J.m[2]), 1024.0)) + 16;
-    const int Y0 = round_clamped(__dmul_rn(__dadd_rn(__dmul_rn(J.m[4], dy), J.m[5]), 1024.0)) + 16;
+    const int dw = J.dw;
+    if (y >= J.dh || xt >= dw) return;
+    const int2* __restrict__ tab = J.delta;
+    const int2 org = __ldg(tab + dw + 4 + y);          // cv::warpAffine's X0, Y0 of this row
     const uint8_t* __restrict__ src = J.src;
     const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
-    uint8_t* const dpx = J.dst + (size_t)y * J.dst_pitch + (xt + threadIdx.x);
-    const int2* const dlp = J.delta + (xt + threadIdx.x);
-    // lane-interleaved pixels (see warp_perspective_kernel): compact gathers, coalesced byte stores
+    const int xl = xt + threadIdx.x;
+    uint8_t* const dpx = J.dst + (size_t)y * J.dst_pitch + xl;
+    const int2* const dlp = tab + xl;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int x = xt + 32 * i + threadIdx.x;
-        if (x >= J.dw) break;
+        if (xl + 32 * i >= dw) break;
         const int2 dl = __ldg(dlp + 32 * i);
-        const int X = (X0 + dl.x) >> 5, Y = (Y0 + dl.y) >> 5;
+        const int X = (org.x + dl.x) >> 5, Y = (org.y + dl.y) >> 5;
         // (OpenCV keeps sx, sy as saturated shorts; with sources below 32767 px the replicate clamp gives the same taps)
         const int sx = X >> 5, sy = Y >> 5;
         const int ax = X & 31, ay = Y & 31;
@@ -344,7 +355,7 @@ int k_warp_affine_upload(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, WarpA
         if (jobs[i].src_pitch <= 0 || (unsigned long long)jobs[i].sh * (unsigned long long)jobs[i].src_pitch >= 0xffff0000ull)
             return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "warp source plane of 4 GiB or more");
         void* t = nullptr;
-        DS_TRY(ds_arena_alloc(ctx, sizeof(int2) * ((size_t)jobs[i].dw + 4), &t));
+        DS_TRY(ds_arena_alloc(ctx, sizeof(int2) * ((size_t)jobs[i].dw + 4 + (size_t)jobs[i].dh), &t));      // columns, then rows
         jobs[i].delta = (int2*)t;
     }
     void* dev = nullptr;
@@ -356,7 +367,7 @@ int k_warp_affine_upload(docscan_ctx* ctx, const WarpAJob* jobs_in, int n, WarpA
 int k_warp_affine_launch(docscan_ctx* ctx, const WarpAJob* jobs_dev, const WarpAJob* jobs_host, int n, int max_w, int max_h) {
     {
         ProfScope prof(ctx, "warp_affine_deltas", 0);
-        affine_delta_kernel<<<dim3((max_w + 127) / 128, n), 128, 0, ctx->stream>>>(jobs_dev);
+        affine_delta_kernel<<<dim3((std::max(max_w, max_h) + 127) / 128, n), 128, 0, ctx->stream>>>(jobs_dev);
         DS_CHECK_LAUNCH(ctx);
     }
     dim3 grid((max_w + 127) / 128, (max_h + 3) / 4, n), block(32, 4);
