@@ -8,6 +8,7 @@
 // (per 64-pixel block origin, no fma contraction), the affine ones in OpenCV's 10-bit fixed point.
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -223,6 +224,164 @@ __global__ void __launch_bounds__(128, WP3_MINB) warp_perspective3_kernel(const 
     }
 }
 
+// ---- 1-D bulk copies global -> shared (the TMA unit's cp.async.bulk) completing on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// Tile-staged variant of warp_perspective3_kernel<true, true> for 16-byte aligned sources: a CTA owns a 64 x 8 destination
+// tile (one OpenCV coordinate block wide).  After the coordinates are known the CTA reduces the bounding box of its source
+// taps, warp 0 requests the box row by row with bulk copies (no per-byte instructions, full-line requests instead of
+// 8-byte gathers) and every thread filters its 4 pixels out of shared memory with the same 16-byte-window arithmetic.  The
+// gathers then see shared-memory latency instead of L2 / HBM latency.  A box that does not fit `cap` bytes (steep
+// perspective) or would run past the last resident row is read straight from global memory with the same code: the
+// loads are generic, only their base and pitch change.  Arithmetic identical to the other instances.
+constexpr int TILE_W = 64, TILE_H = 8;
+__global__ void __launch_bounds__(128, 8) warp_perspective3_tile_kernel(const WarpPJob* __restrict__ jobs, const int cap) {
+    extern __shared__ __align__(128) uint8_t s_tile[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_box[4][4];
+    const WarpPJob& J = jobs[blockIdx.z];
+    const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+    if (x0 >= J.dw || y0 >= J.dh) return;
+    const int lane = threadIdx.x, wp = threadIdx.y;
+    if (lane == 0 && wp == 0) mbar_init(&s_bar, 1);
+    const int sh = J.sh, sp = J.src_pitch;
+    const uint8_t* __restrict__ src = J.src;
+    // pixel k of a thread: row y0 + wp + 4 (k >> 1), column x0 + lane + 32 (k & 1)
+    int Xs[4], Ys[4];
+    {
+        const double m0 = J.m[0], m1 = J.m[1], m2 = J.m[2], m3 = J.m[3], m4 = J.m[4], m5 = J.m[5], m6 = J.m[6], m7 = J.m[7], m8 = J.m[8];
+        const double dxb = (double)x0;
+        const double xa = (double)lane, xb = (double)(lane + 32);
+        const double ax0 = __dmul_rn(m0, xa), ax1 = __dmul_rn(m0, xb), ay0 = __dmul_rn(m3, xa), ay1 = __dmul_rn(m3, xb);
+        const double aw0 = __dmul_rn(m6, xa), aw1 = __dmul_rn(m6, xb);
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+            const double dy = (double)(y0 + wp + 4 * rr);
+            const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
+            const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(m3, dxb), __dmul_rn(m4, dy)), m5);
+            const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(m6, dxb), __dmul_rn(m7, dy)), m8);
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const double W = __dmul_rn(__drcp_rn(__dadd_rn(W0, c ? aw1 : aw0)), 32.0);      // == 32 / W (host-proved safe)
+                Xs[2 * rr + c] = __double2int_rn(__dmul_rn(__dadd_rn(X0, c ? ax1 : ax0), W));
+                Ys[2 * rr + c] = __double2int_rn(__dmul_rn(__dadd_rn(Y0, c ? ay1 : ay0), W));
+            }
+        }
+    }
+    // clamped tap origin of every pixel (byte offset inside the resident row, resident row indices) and their bounding box
+    int ao[4], c0[4], c1[4];
+    int amin = INT_MAX, amax = INT_MIN, rmin = INT_MAX, rmax = INT_MIN;
+    const int nres = J.ry1 - J.ry0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool valid = y0 + wp + 4 * (k >> 1) < J.dh && x0 + lane + 32 * (k & 1) < J.dw;
+        ao[k] = 3 * (ds_clamp(Xs[k] >> 5, J.rx0 + 3, J.rx1 - 6) - J.rx0);
+        const int sy = Ys[k] >> 5;
+        c0[k] = ds_clamp(sy, J.ry0, J.ry1 - 1) - J.ry0;
+        c1[k] = ds_clamp(sy + 1, J.ry0, J.ry1 - 1) - J.ry0;
+        if (valid) { amin = min(amin, ao[k]); amax = max(amax, ao[k]); rmin = min(rmin, c0[k]); rmax = max(rmax, c1[k]); }
+    }
+    amin = __reduce_min_sync(0xffffffffu, amin); amax = __reduce_max_sync(0xffffffffu, amax);
+    rmin = __reduce_min_sync(0xffffffffu, rmin); rmax = __reduce_max_sync(0xffffffffu, rmax);
+    if (lane == 0) { s_box[wp][0] = amin; s_box[wp][1] = amax; s_box[wp][2] = rmin; s_box[wp][3] = rmax; }
+    __syncthreads();                                   // also publishes the initialised barrier
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        amin = min(amin, s_box[w][0]); amax = max(amax, s_box[w][1]); rmin = min(rmin, s_box[w][2]); rmax = max(rmax, s_box[w][3]);
+    }
+    // box in bytes [bx0, bx1) x rows [rmin, rmax]: every 16-byte load window [(a & ~7), +16) of the tile lies inside
+    const int bx0 = amin & ~15, bx1 = ((amax & ~7) + 16 + 15) & ~15;
+    const int pitch_s = bx1 - bx0, nrows = rmax - rmin + 1;
+    const bool staged = (long long)nrows * pitch_s <= cap && (bx1 <= 3 * (J.rx1 - J.rx0) || rmax + 1 < nres);
+    uintptr_t gbase;
+    uint32_t gpitch;
+    if (staged) {
+        if (wp == 0) {
+            if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(nrows * pitch_s));
+            __syncwarp();
+            for (int r = lane; r < nrows; r += 32)
+                bulk_g2s(s_tile + r * pitch_s, src + (size_t)(rmin + r) * sp + bx0, (uint32_t)pitch_s, &s_bar);
+        }
+        gbase = reinterpret_cast<uintptr_t>(s_tile) - (uintptr_t)(rmin * pitch_s + bx0);
+        gpitch = (uint32_t)pitch_s;
+        mbar_wait(&s_bar, 0);
+    } else {
+        gbase = reinterpret_cast<uintptr_t>(src);
+        gpitch = (uint32_t)sp;
+    }
+    uint2 lo[4][2], hi[4][2];
+    uint32_t sft[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool valid = y0 + wp + 4 * (k >> 1) < J.dh && x0 + lane + 32 * (k & 1) < J.dw;
+        const int a = valid ? ao[k] : amin, r0 = valid ? c0[k] : rmin, r1 = valid ? c1[k] : rmin;      // lanes past the page read a harmless tap
+        const uintptr_t A0 = gbase + ((uint32_t)r0 * gpitch + (uint32_t)a);
+        const uintptr_t B0 = A0 & ~(uintptr_t)7, B1 = B0 + (r1 != r0 ? gpitch : 0u);                     // both pitches are multiples of 16
+        lo[k][0] = *reinterpret_cast<const uint2*>(B0); hi[k][0] = *(reinterpret_cast<const uint2*>(B0) + 1);
+        lo[k][1] = *reinterpret_cast<const uint2*>(B1); hi[k][1] = *(reinterpret_cast<const uint2*>(B1) + 1);
+        sft[k] = (uint32_t)(A0 & 7);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int y = y0 + wp + 4 * (k >> 1), x = x0 + lane + 32 * (k & 1);
+        if (y >= J.dh || x >= J.dw) continue;
+        const int sx = Xs[k] >> 5, sy = Ys[k] >> 5, ax = Xs[k] & 31, ay = Ys[k] & 31;
+        const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
+        int acc[3];
+        if (sx >= J.rx0 + 3 && sx <= J.rx1 - 6) {
+            const uint32_t wxx = 32u + 0xffffu * (uint32_t)ax;              // (32 - ax) | ax << 16
+            const uint32_t wt = (y0in ? 32u - (uint32_t)ay : 0u) * wxx;      // rows outside the image: BORDER_CONSTANT 0
+            const uint32_t wb = (y1in ? (uint32_t)ay : 0u) * wxx;
+            uint32_t b0[2], gr[2];
+            const bool up = sft[k] >= 4;
+#pragma unroll
+            for (int rr = 0; rr < 2; rr++) {
+                const uint32_t wa = up ? lo[k][rr].y : lo[k][rr].x, wm = up ? hi[k][rr].x : lo[k][rr].y, wc = up ? hi[k][rr].y : hi[k][rr].x;
+                b0[rr] = __funnelshift_r(wa, wm, 8 * sft[k]);                                     // B0 G0 R0 B1   (shift mod 32)
+                gr[rr] = __byte_perm(b0[rr], __funnelshift_r(wm, wc, 8 * sft[k]), 0x5241);       // G0 G1 R0 R1
+            }
+            const uint32_t bb = __byte_perm(b0[0], b0[1], 0x7430);                                // B0 B1 of row 0, B0 B1 of row 1
+            acc[0] = (int)(__dp2a_hi(wb, bb, __dp2a_lo(wt, bb, 512u)) >> 10);
+            acc[1] = (int)(__dp2a_lo(wb, gr[1], __dp2a_lo(wt, gr[0], 512u)) >> 10);
+            acc[2] = (int)(__dp2a_hi(wb, gr[1], __dp2a_hi(wt, gr[0], 512u)) >> 10);
+        } else {
+            const int sw = J.sw;
+            const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+            const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
+            const int cx0 = ds_clamp(sx, J.rx0, J.rx1 - 1) - J.rx0, cx1 = ds_clamp(sx + 1, J.rx0, J.rx1 - 1) - J.rx0;
+            const int v00 = (x0in && y0in) ? w00 : 0, v01 = (x1in && y0in) ? w01 : 0;
+            const int v10 = (x0in && y1in) ? w10 : 0, v11 = (x1in && y1in) ? w11 : 0;
+            const uint8_t* r0 = src + (size_t)c0[k] * sp;
+            const uint8_t* r1 = src + (size_t)c1[k] * sp;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                acc[c] = (16384 + v00 * __ldg(r0 + cx0 * 3 + c) + v01 * __ldg(r0 + cx1 * 3 + c) +
+                          v10 * __ldg(r1 + cx0 * 3 + c) + v11 * __ldg(r1 + cx1 * 3 + c)) >> 15;
+        }
+        uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + (size_t)x * 3;
+        dp[0] = (uint8_t)acc[0]; dp[1] = (uint8_t)acc[1]; dp[2] = (uint8_t)acc[2];      // <= 255 by construction
+        if (J.gray) J.gray[(size_t)y * J.gray_pitch + x] = gray15(acc[0], acc[1], acc[2]);
+    }
+}
+
 // cv::warpAffine precomputes adelta[x] = saturate_cast<int>(M[0]*x*1024), bdelta[x] = saturate_cast<int>(M[3]*x*1024)
 // once per call; so do we (one tiny kernel), which keeps fp64 out of the per-pixel loop.  The same kernel tabulates the
 // row origins X0[y] = saturate_cast<int>((M[1]*y + M[2])*1024) + 16 (and Y0) behind the column table: rows start at
@@ -326,7 +485,7 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     for (int i = 0; i < n && safe_rcp; i++) {
         const WarpPJob& j = jobs_host[i];
         double lo = 1e308, hi = -1e308;
-        const double cx[2] = {0.0, (double)(((j.dw + 127) / 128) * 128)}, cy[2] = {0.0, (double)j.dh};     // lanes past dw compute too
+        const double cx[2] = {0.0, (double)(((j.dw + 127) / 128) * 128)}, cy[2] = {0.0, (double)(((j.dh + 7) / 8) * 8)};     // lanes past dw / dh compute too
         for (int a = 0; a < 2; a++)
             for (int b = 0; b < 2; b++) {
                 const double w = j.m[6] * cx[a] + j.m[7] * cy[b] + j.m[8];
@@ -338,7 +497,15 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     }
     bool p8 = true;
     for (int i = 0; i < n; i++) p8 = p8 && jobs_host[i].src_pitch % 8 == 0;
-    if (wide && safe_rcp && p8) warp_perspective3_kernel<true, true><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
+    bool a16 = p8;                                   // bulk copies: 16-byte aligned source rows
+    for (int i = 0; i < n; i++)
+        a16 = a16 && jobs_host[i].src_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(jobs_host[i].src) & 15) == 0;
+    static const int tile_mode = getenv("DOCSCAN_WARP_TILE") ? atoi(getenv("DOCSCAN_WARP_TILE")) : 1;
+    if (wide && safe_rcp && a16 && tile_mode) {
+        constexpr int cap = 24 * 1024;
+        dim3 tgrid((max_w + TILE_W - 1) / TILE_W, (max_h + TILE_H - 1) / TILE_H, n);
+        warp_perspective3_tile_kernel<<<tgrid, block, cap, ctx->stream>>>((const WarpPJob*)dev, cap);
+    } else if (wide && safe_rcp && p8) warp_perspective3_kernel<true, true><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else if (wide && safe_rcp) warp_perspective3_kernel<true, false><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else if (wide) warp_perspective3_kernel<false, false><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);
     else if (ch == 3) warp_perspective_kernel<3><<<grid, block, 0, ctx->stream>>>((const WarpPJob*)dev);

@@ -217,6 +217,30 @@ def test_warp_affine():
     eq(DS.rotate(g, 0.0), g, "angle 0 is an exact copy")
 
 
+def test_warp_perspective_tile_staging_and_its_fallbacks():
+    """The tile-staged kernel copies the bounding box of a 64x8 tile's taps into shared memory when it fits; strong
+    shrinks / steep perspective (box too large), tiles on the last source row and quads outside the photo take the
+    direct path inside the same kernel.  All must give the oracle's bytes."""
+    rng = np.random.default_rng(99)
+    cases = [
+        (900, 1200, 160, 120, 0.02),     # shrink 7.5x: boxes of ~1.4 KB x 62 rows do not fit
+        (900, 1200, 700, 500, 0.02),     # shrink 1.7x: staged
+        (300, 400, 640, 480, 0.02),      # enlargement: tiny boxes
+        (600, 800, 333, 250, 0.45),      # steep perspective, corners outside the photo
+        (257, 263, 130, 129, 0.0),       # quad = whole photo: tiles touch the last row / column
+    ]
+    for H, W, tw, th, spread in cases:
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        quad = np.array([[0, 0], [W - 1, 0], [W - 1, H - 1], [0, H - 1]], np.float64)
+        quad = (quad + rng.uniform(-spread, spread, (4, 2)) * min(W, H)).astype(np.float32)
+        dst = np.array([[0, 0], [tw - 1, 0], [tw - 1, th - 1], [0, th - 1]], np.float32)
+        m = O.get_perspective_transform(quad, dst)
+        ref = O.warp_perspective(img, m, (tw, th))
+        out, gray = ops.warp_perspective(img, m, (tw, th), return_gray=True)
+        eq(out, ref, f"tile warp {H}x{W}->{th}x{tw} spread {spread}")
+        eq(gray, O.bgr2gray(ref), "fused gray")
+
+
 def test_warps_on_caller_device_buffers_with_odd_pitches():
     """Device-resident sources whose pitch / base address are not multiples of 8 (or of 4) take the kernel instances that
     work out the load-window offset per source row; results must not depend on where the caller put the bytes."""
