@@ -245,7 +245,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!done);
 }
 
-// Tile-staged variant of warp_perspective3_kernel<true, true> for 16-byte aligned sources: a CTA owns a 64 x 8 destination
+// Tile-staged variant of warp_perspective3_kernel<true, true> for 16-byte aligned sources with 8-byte-multiple pitches: a CTA owns a 64 x 8 destination
 // tile (one OpenCV coordinate block wide).  After the coordinates are known the CTA reduces the bounding box of its source
 // taps, warp 0 requests the box row by row with bulk copies (no per-byte instructions, full-line requests instead of
 // 8-byte gathers) and every thread filters its 4 pixels out of shared memory with the same 16-byte-window arithmetic.  The
@@ -307,34 +307,37 @@ __global__ void __launch_bounds__(128, 8) warp_perspective3_tile_kernel(const Wa
     for (int w = 0; w < 4; w++) {
         amin = min(amin, s_box[w][0]); amax = max(amax, s_box[w][1]); rmin = min(rmin, s_box[w][2]); rmax = max(rmax, s_box[w][3]);
     }
-    // box in bytes [bx0, bx1) x rows [rmin, rmax]: every 16-byte load window [(a & ~7), +16) of the tile lies inside
+    // box in bytes [bx0, bx1) x rows [rmin, rmax]: every 16-byte load window [(a & ~7), +16) of the tile lies inside.
+    // A bulk copy needs a 16-byte aligned source: the source base is (host-checked), its pitch only a multiple of 8, so row
+    // r starts `(src + r * pitch) & 15` (0 or 8) bytes into its shared-memory row and 16 bytes more are copied per row.
     const int bx0 = amin & ~15, bx1 = ((amax & ~7) + 16 + 15) & ~15;
-    const int pitch_s = bx1 - bx0, nrows = rmax - rmin + 1;
-    const bool staged = (long long)nrows * pitch_s <= cap && (bx1 <= 3 * (J.rx1 - J.rx0) || rmax + 1 < nres);
-    uintptr_t gbase;
-    uint32_t gpitch;
+    const int pitch_s = bx1 - bx0 + 16, nrows = rmax - rmin + 1;
+    const bool staged = (long long)nrows * pitch_s <= cap && (bx1 + 16 <= 3 * (J.rx1 - J.rx0) || rmax + 1 < nres);
+    const uint32_t src_lo = (uint32_t)reinterpret_cast<uintptr_t>(src);
     if (staged) {
         if (wp == 0) {
             if (lane == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)(nrows * pitch_s));
             __syncwarp();
-            for (int r = lane; r < nrows; r += 32)
-                bulk_g2s(s_tile + r * pitch_s, src + (size_t)(rmin + r) * sp + bx0, (uint32_t)pitch_s, &s_bar);
+            for (int r = lane; r < nrows; r += 32) {
+                const uintptr_t g = reinterpret_cast<uintptr_t>(src + (size_t)(rmin + r) * sp + bx0) & ~(uintptr_t)15;
+                bulk_g2s(s_tile + r * pitch_s, reinterpret_cast<const void*>(g), (uint32_t)pitch_s, &s_bar);
+            }
         }
-        gbase = reinterpret_cast<uintptr_t>(s_tile) - (uintptr_t)(rmin * pitch_s + bx0);
-        gpitch = (uint32_t)pitch_s;
         mbar_wait(&s_bar, 0);
-    } else {
-        gbase = reinterpret_cast<uintptr_t>(src);
-        gpitch = (uint32_t)sp;
     }
+    const uintptr_t gbase = staged ? reinterpret_cast<uintptr_t>(s_tile) - (uintptr_t)bx0 : reinterpret_cast<uintptr_t>(src);
+    // byte offset of resident row r from gbase
+    auto row_off = [&](int r) -> uint32_t {
+        return staged ? (uint32_t)((r - rmin) * pitch_s) + ((src_lo + (uint32_t)r * (uint32_t)sp) & 15u) : (uint32_t)r * (uint32_t)sp;
+    };
     uint2 lo[4][2], hi[4][2];
     uint32_t sft[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const bool valid = y0 + wp + 4 * (k >> 1) < J.dh && x0 + lane + 32 * (k & 1) < J.dw;
         const int a = valid ? ao[k] : amin, r0 = valid ? c0[k] : rmin, r1 = valid ? c1[k] : rmin;      // lanes past the page read a harmless tap
-        const uintptr_t A0 = gbase + ((uint32_t)r0 * gpitch + (uint32_t)a);
-        const uintptr_t B0 = A0 & ~(uintptr_t)7, B1 = B0 + (r1 != r0 ? gpitch : 0u);                     // both pitches are multiples of 16
+        const uintptr_t A0 = gbase + (row_off(r0) + (uint32_t)a);
+        const uintptr_t B0 = A0 & ~(uintptr_t)7, B1 = (gbase + (row_off(r1) + (uint32_t)a)) & ~(uintptr_t)7;   // same offset mod 8 in both rows
         lo[k][0] = *reinterpret_cast<const uint2*>(B0); hi[k][0] = *(reinterpret_cast<const uint2*>(B0) + 1);
         lo[k][1] = *reinterpret_cast<const uint2*>(B1); hi[k][1] = *(reinterpret_cast<const uint2*>(B1) + 1);
         sft[k] = (uint32_t)(A0 & 7);
@@ -497,10 +500,13 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     }
     bool p8 = true;
     for (int i = 0; i < n; i++) p8 = p8 && jobs_host[i].src_pitch % 8 == 0;
-    bool a16 = p8;                                   // bulk copies: 16-byte aligned source rows
-    for (int i = 0; i < n; i++)
-        a16 = a16 && jobs_host[i].src_pitch % 16 == 0 && (reinterpret_cast<uintptr_t>(jobs_host[i].src) & 15) == 0;
-    static const int tile_mode = getenv("DOCSCAN_WARP_TILE") ? atoi(getenv("DOCSCAN_WARP_TILE")) : 1;
+    bool a16 = p8;                                   // bulk copies: 16-byte aligned source base (rows may start 8 bytes off)
+    for (int i = 0; i < n; i++) a16 = a16 && (reinterpret_cast<uintptr_t>(jobs_host[i].src) & 15) == 0;
+    // Opt-in (DOCSCAN_WARP_TILE=1): measured 3.58 ms against 2.65 ms for the gather kernel on the benchmark batch — one
+    // ~0.5 KB bulk copy per source row and CTA (22 per 512 pixels) plus the CTA-wide wait cost more than the gathers' latency
+    // did, which 32 resident warps already hide.  Kept, parity-tested, as the starting point for a 2-D tensor-map version.
+    const char* tile_env = getenv("DOCSCAN_WARP_TILE");
+    const int tile_mode = tile_env ? atoi(tile_env) : 0;
     if (wide && safe_rcp && a16 && tile_mode) {
         constexpr int cap = 24 * 1024;
         dim3 tgrid((max_w + TILE_W - 1) / TILE_W, (max_h + TILE_H - 1) / TILE_H, n);

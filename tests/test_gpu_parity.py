@@ -222,12 +222,54 @@ def test_warp_perspective_tile_staging_and_its_fallbacks():
     shrinks / steep perspective (box too large), tiles on the last source row and quads outside the photo take the
     direct path inside the same kernel.  All must give the oracle's bytes."""
     rng = np.random.default_rng(99)
+    os.environ["DOCSCAN_WARP_TILE"] = "1"        # the instance is opt-in (the gather kernel is faster on the benchmark batch)
+    try:
+        _tile_cases(rng)
+        # ... and a whole page through the pipeline with it
+        g = page_like(rng, 420, 320)
+        img = np.stack([g, g, g], -1)
+        quad = np.array([[22, 18], [300, 25], [305, 400], [15, 392]], np.float32)
+        w, b = DS.process_pages([img], [quad], [1.5], scale_long=480)
+        ref = O.hot_path(img, quad, 1.5, scale_long=480)
+        eq(w[0], ref["warped"], "pipeline warped (tile-staged warp)")
+        eq(b[0], ref["clean"], "pipeline binary (tile-staged warp)")
+        # a caller's device buffer whose pitch is 8 mod 16 (like the 9000-byte rows of a 3000-px-wide photo): every other row
+        # sits 8 bytes into its shared-memory row
+        import ctypes as C
+        from smart_image_processing_b200 import _capi
+        ctx = _capi.Context(0)
+        H, W, tw, th = 240, 333, 300, 200
+        pitch3 = W * 3 + 9                                   # 1008 = 16 * 63: aligned rows
+        for pitch3 in (W * 3 + 9, W * 3 + 17):               # 1008 (rows 16-byte aligned), 1016 (8 mod 16)
+            img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+            host = np.zeros((H, pitch3), np.uint8)
+            host[:, :W * 3] = img.reshape(H, W * 3)
+            raw = ctx.device_alloc(H * pitch3)
+            _capi.lib().docscan_memcpy_h2d(ctx._h, C.c_void_p(raw), host.ctypes.data, host.nbytes)
+            dpitch = tw * 3
+            draw = ctx.device_alloc(th * dpitch)
+            quad = np.array([[10, 8], [320, 14], [325, 230], [6, 226]], np.float32)
+            m = O.get_perspective_transform(quad, np.array([[0, 0], [tw - 1, 0], [tw - 1, th - 1], [0, th - 1]], np.float32))
+            mm = np.ascontiguousarray(m, np.float64).reshape(9)
+            sdev = _capi.device_image(raw, W, H, pitch3, 3)
+            ddev = _capi.device_image(draw, tw, th, dpitch, 3)
+            ctx.call("docscan_warp_perspective", C.byref(sdev), mm.ctypes.data_as(C.POINTER(C.c_double)), C.byref(ddev), None)
+            ctx.sync()
+            eq(_d2h(ctx, draw, th, dpitch, tw * 3).reshape(th, tw, 3), O.warp_perspective(img, m, (tw, th)), f"tile warp, device source pitch {pitch3}")
+            ctx.device_free(raw); ctx.device_free(draw)
+        ctx.close()
+    finally:
+        del os.environ["DOCSCAN_WARP_TILE"]
+
+
+def _tile_cases(rng):
     cases = [
         (900, 1200, 160, 120, 0.02),     # shrink 7.5x: boxes of ~1.4 KB x 62 rows do not fit
         (900, 1200, 700, 500, 0.02),     # shrink 1.7x: staged
         (300, 400, 640, 480, 0.02),      # enlargement: tiny boxes
         (600, 800, 333, 250, 0.45),      # steep perspective, corners outside the photo
         (257, 263, 130, 129, 0.0),       # quad = whole photo: tiles touch the last row / column
+        (301, 403, 200, 150, 0.05),      # staged source pitch 1280: rows 16-byte aligned
     ]
     for H, W, tw, th, spread in cases:
         img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
