@@ -502,9 +502,9 @@ int k_warp_perspective_jobs(docscan_ctx* ctx, const WarpPJob* jobs_host, int n, 
     for (int i = 0; i < n; i++) p8 = p8 && jobs_host[i].src_pitch % 8 == 0;
     bool a16 = p8;                                   // bulk copies: 16-byte aligned source base (rows may start 8 bytes off)
     for (int i = 0; i < n; i++) a16 = a16 && (reinterpret_cast<uintptr_t>(jobs_host[i].src) & 15) == 0;
-    // Opt-in (DOCSCAN_WARP_TILE=1): measured 3.58 ms against 2.65 ms for the gather kernel on the benchmark batch — one
-    // ~0.5 KB bulk copy per source row and CTA (22 per 512 pixels) plus the CTA-wide wait cost more than the gathers' latency
-    // did, which 32 resident warps already hide.  Kept, parity-tested, as the starting point for a 2-D tensor-map version.
+    // Opt-in (DOCSCAN_WARP_TILE=1): measured 3.58 ms against 2.65 ms for the gather kernel on the benchmark batch.  Same DRAM
+    // traffic, higher issue rate, but 47 % more instructions (bounding-box reduction, per-row offsets, the barrier wait) than
+    // the gathers' latency costs, which 32 resident warps already hide (profiles/r1_ncu_tile_warp.txt).  Kept, parity-tested.
     const char* tile_env = getenv("DOCSCAN_WARP_TILE");
     const int tile_mode = tile_env ? atoi(tile_env) : 0;
     if (wide && safe_rcp && a16 && tile_mode) {
