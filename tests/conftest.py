@@ -13,6 +13,16 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # A fresh checkout has no built artefacts (they are git-ignored): build the C-ABI library (nvcc cross-compiles without
+    # a GPU) and the C oracle once, exactly as __graft_entry__.build() does.  On the GPU box the prebuilt files travel
+    # with the snapshot and nothing is rebuilt.
+    if os.environ.get("PYTEST_XDIST_WORKER"):
+        return
+    from smart_image_processing_b200 import build as _b
+    if not os.path.exists(_b.LIB):
+        _b.build_library()
+    from oracle import oracle as _o
+    _o.build()
 
 
 def pytest_collection_modifyitems(config, items):
