@@ -54,7 +54,11 @@ def parse():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--pages", type=int, default=256, help="pages per GPU per step")
     ap.add_argument("--e2e-distinct", type=int, default=16, help="distinct pinned host pages the e2e leg cycles through")
-    ap.add_argument("--ref-pages", type=int, default=96, help="page-jobs per step of the CPU reference arm")
+    ap.add_argument("--ref-pages", type=int, default=0, help="page-jobs per step of the CPU reference arm (0 = --pages, the same step as the GPU arm)")
+    ap.add_argument("--total-pages", type=int, default=0,
+                    help="BASELINE config 3 as written: this many page ids per step, sharded over the ranks by page id (strong scaling); "
+                         "0 = the weak-scaling default of --pages per GPU")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run check of 2 pages per rank against the oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-skew", action="store_true", help="skip the extra leg with the device-side skew estimate")
@@ -106,6 +110,21 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- CPU arm
 _W = {}
+
+
+# what holds each kernel family below the HBM roof today, from the ncu captures under profiles/ (reported as roofline.limiter)
+KERNEL_LIMITER = {
+    "warp_perspective_c3": "instruction issue + L1 gather (fp64 coordinate chain, 4 scattered 8-byte loads per pixel)",
+    "warp_affine": "instruction issue + L1 gather",
+    "adaptive_gauss": "fp32 pipe: the parity-fixed ordered fma chain",
+    "blur_gauss": "instruction issue (integer MACs on CUDA cores)",
+    "tc_blur": "TMEM read-out + epilogue issue (the banded contraction itself runs on the tensor cores)",
+    "tc_adaptive": "TMEM read-out + epilogue issue",
+    "morph_march": "shared-memory staging + barrier latency",
+    "morph_close3_fused": "L2/HBM latency at 1 load per 16 px",
+    "mask_blend": "HBM",
+    "pw_lut": "HBM",
+}
 
 
 GUI_TUNABLES = dict(illum_method="divide", illum_blur_frac=0.05, block_size=31, C=3, morph_ksize=1, morph_iters=0)   # AI_classification.py:646-663
@@ -176,6 +195,19 @@ def _workload(args):
     return WORKLOAD.replace("CLI defaults, scale_long=1600", f"{'GUI preset' if args.preset == 'gui' else 'CLI defaults'}, scale_long={args.scale_long}")
 
 
+def _config(args, n_gpus):
+    """The `config` object: identical in both arms for the same command line (the driver compares them)."""
+    from smart_image_processing_b200 import DocScanner as DS
+    from smart_image_processing_b200.synth import synth_quad
+    tw, th = DS.target_size(synth_quad(0, PAGE_W, PAGE_H), "A4", args.scale_long)
+    cfg = {"workload": _workload(args), "pages_per_gpu": args.pages, "page": f"{PAGE_H}x{PAGE_W}x3", "warped": f"{th}x{tw}",
+           "scale_long": args.scale_long, "parallelism": f"pages sharded over {n_gpus} GPU(s) by page id, no collective",
+           "l2": f"inputs larger than L2 ({args.pages * PAGE_H * PAGE_W * 3 / 1e9:.1f} GB read per step per GPU)"}
+    if args.total_pages:
+        cfg["total_pages"] = args.total_pages
+    return cfg
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -188,19 +220,28 @@ def run_reference_arm(args):
         pages.append(img); quads.append(quad); angles.append(synth_angle(s))
     tun = GUI_TUNABLES if args.preset == "gui" else {}
     ref = CpuReference(pages, quads, angles, args.scale_long, tun)
+    # a step of the reference arm is the GPU arm's step (args.pages page-jobs), bounded so that the run ends within minutes:
+    # a first probe measures the rate, and steps that would take more than ~6 s each are cut to a sample of the batch
+    ref_pages = args.ref_pages or args.pages
+    _, dt1 = ref.run(2 * ref.cores)
+    per_job = dt1 / (2 * ref.cores)
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    if ref_pages * per_job > budget_s:
+        ref_pages = max(ref.cores, int(budget_s / per_job))
     for _ in range(args.warmup):
         ref.run(max(ref.cores, 8))
     total = 0.0
     for _ in range(args.steps):
-        total += ref.run(args.ref_pages)[1]
+        total += ref.run(ref_pages)[1]
     ref.close()
-    value = args.steps * args.ref_pages * PAGE_MP / total
-    sample = f"{args.ref_pages} page-jobs per step over {distinct} distinct synthetic 12 MP pages; {ref.how}"
+    value = args.steps * ref_pages * PAGE_MP / total
+    sample = f"{ref_pages} page-jobs per step over {distinct} distinct synthetic 12 MP pages; {ref.how}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "strong" if args.total_pages else "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": _workload(args), "page": f"{PAGE_H}x{PAGE_W}x3", "scale_long": args.scale_long, "pages_per_step": args.ref_pages},
+        "config": _config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "MP/s", "cores": ref.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -266,16 +307,25 @@ def run_ours(args):
             os.close(saved_stdout)
     stream = torch.cuda.Stream(device=dev)
     ctx = _capi.Context(local, stream=stream.cuda_stream)
-    P = args.pages
     tun = GUI_TUNABLES if args.preset == "gui" else {}
     params = DS.make_params(**tun)
 
     # ---- device-resident synthetic batch (generated on the device; not timed)
-    src = torch.empty((P, PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
+    # weak scaling (default): every rank owns args.pages pages (seeds rank*P ...).  --total-pages T (BASELINE config 3):
+    # page ids 0..T-1 are sharded by id (sharding.page_ids); a rank keeps the first args.pages of its ids resident (T photos
+    # would be 147 GB) and runs its other page-jobs on them again, each job writing outputs of its own.
+    if args.total_pages:
+        ids = sharding.page_ids(args.total_pages, rank, world)
+        P = len(ids)                                   # page-jobs of this rank per step
+        D = min(args.pages, P)
+        seeds = list(ids[:D])
+    else:
+        P = D = args.pages
+        seeds = list(sharding.weak_batch_seeds(P, rank))
+    src = torch.empty((D, PAGE_H, PAGE_W, 3), dtype=torch.uint8, device=dev)
     quads, angles = [], []
     q8 = (C.c_float * 8)()
-    seeds = sharding.weak_batch_seeds(P, rank)
-    for i in range(P):
+    for i in range(D):
         seed = seeds[i]
         im = _capi.device_image(src[i].data_ptr(), PAGE_W, PAGE_H, PAGE_W * 3, 3)
         ctx.call("docscan_synth_page", C.c_uint64(seed), C.byref(im), q8)
@@ -289,12 +339,14 @@ def run_ours(args):
     binary = torch.empty((P, th, pw1), dtype=torch.uint8, device=dev)
     pages = (_capi.Page * P)()
     for i in range(P):
-        pages[i].src = _capi.device_image(src[i].data_ptr(), PAGE_W, PAGE_H, PAGE_W * 3, 3)
-        pages[i].quad = (C.c_float * 8)(*quads[i].reshape(8).tolist())
-        pages[i].angle_deg = angles[i]
+        d = i % D
+        pages[i].src = _capi.device_image(src[d].data_ptr(), PAGE_W, PAGE_H, PAGE_W * 3, 3)
+        pages[i].quad = (C.c_float * 8)(*quads[d].reshape(8).tolist())
+        pages[i].angle_deg = angles[d]
         pages[i].warped = _capi.device_image(warped[i].data_ptr(), tw, th, pw3, 3)
         pages[i].binary = _capi.device_image(binary[i].data_ptr(), tw, th, pw1, 1)
     ctx.sync()
+    total_jobs = args.total_pages if args.total_pages else world * P     # page-jobs of the whole job per step
 
     def step():
         ctx.call("docscan_process_pages", P, pages, C.byref(params))
@@ -318,7 +370,31 @@ def run_ours(args):
         barrier()
     launches = ctx.launches - l0
     ms_total = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    value = world * P * PAGE_MP * args.steps / (ms_total / 1e3)
+    value = total_jobs * PAGE_MP * args.steps / (ms_total / 1e3)
+
+    # ---- parity of the timed batch: two pages of every rank (first and last resident page) against the oracle
+    # (oracle/ is the checker here, never the thing measured); all ranks must agree for parity_checked to be true
+    parity = None
+    if not args.no_parity:
+        from oracle import oracle as O
+
+        def _host(t, rows, width_bytes):
+            return np.ascontiguousarray(t.cpu().numpy()[:rows, :width_bytes])
+
+        ok = 1
+        for i in sorted({0, D - 1}):
+            img = src[i].cpu().numpy()
+            ref = O.hot_path(img, quads[i], angles[i], scale_long=args.scale_long, **tun)
+            j = i if i < P else 0
+            got_w = _host(warped[j], th, tw * 3).reshape(th, tw, 3)
+            got_b = _host(binary[j], th, tw)
+            if not (np.array_equal(got_w, ref["warped"]) and np.array_equal(got_b, ref["clean"])):
+                ok = 0
+        if world > 1:
+            t = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = int(t.item())
+        parity = bool(ok)
 
     # ---- per-kernel pass (instrumented; not the number reported as `value`)
     ctx.profile(True)
@@ -347,7 +423,9 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "share_of_step": t_ms / kernel_ms,
                 "algorithmic_bytes_per_launch": nbytes / n_l, "avg_launch_ms": t_ms / n_l,
-                "note": "kernel is instruction-issue bound, not HBM bound (see DESIGN.md); fraction reported as required",
+                "limiter": KERNEL_LIMITER.get(top[0].split("_k")[0], "see profiles/README.md"),
+                "note": "bound = the roof this byte-oriented path is measured against (HBM copy bandwidth; no dense contraction "
+                        "on it); limiter = what ncu shows holding this kernel below that roof today",
                 "kernels": {k: {"launches": v[0], "ms": round(v[1], 4), "GB/s": (round(v[2] / (v[1] * 1e-3) / 1e9, 1) if v[1] > 0 else None)}
                             for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
 
@@ -374,7 +452,7 @@ def run_ours(args):
         ctx.profile(False)
         est = (C.c_double * P)()
         ctx.call("docscan_last_angles", est, P)
-        skew = {"value": world * P * PAGE_MP * ssteps / (sms / 1e3), "unit": "MP/s", "ms_per_step": sms / ssteps, "steps": ssteps,
+        skew = {"value": total_jobs * PAGE_MP * ssteps / (sms / 1e3), "unit": "MP/s", "ms_per_step": sms / ssteps, "steps": ssteps,
                 "what": "angle_deg = NaN for every page: Canny + HoughLines(1, pi/180, 150) + median angle on the device between blend and rotate",
                 "kernels_ms": {k: round(v[1], 4) for k, v in sorted(sprof.items(), key=lambda kv: -kv[1][1])
                                if k.startswith(("canny", "hough", "skew"))},
@@ -382,71 +460,109 @@ def run_ours(args):
         for i in range(P):
             pages[i].angle_deg = angles[i]
 
-    # ---- e2e: host (pinned) buffers through the same C-ABI call, copies inside the timed region
+    # ---- e2e: HOST buffers through the same C-ABI call, copies inside the timed region.  Headline leg: pinned buffers
+    # (docscan_host_alloc), >= 10 steps.  Beside it: the same call with PAGEABLE numpy buffers (what cv2.imread hands a caller),
+    # and the box's raw concurrent pinned H2D + D2H rate measured on every rank at once (the ceiling the leg runs against).
     e2e = None
     if not args.no_e2e:
-        D = min(args.e2e_distinct, P)
-        h_src = [ctx.pinned_empty((PAGE_H, PAGE_W, 3)) for _ in range(D)]
-        h_w = [ctx.pinned_empty((th, tw, 3)) for _ in range(D)]
-        h_b = [ctx.pinned_empty((th, tw)) for _ in range(D)]
-        for i in range(D):
-            _capi.lib().docscan_memcpy_d2h(ctx._h, h_src[i].ctypes.data, C.c_void_p(src[i].data_ptr()), h_src[i].nbytes)
-        hpages = (_capi.Page * P)()
-        for i in range(P):
-            d = i % D
-            hpages[i].src = _capi.image_of(h_src[d])
-            hpages[i].quad = (C.c_float * 8)(*quads[d].reshape(8).tolist())
-            hpages[i].angle_deg = angles[d]
-            hpages[i].warped = _capi.image_of(h_w[d])
-            hpages[i].binary = _capi.image_of(h_b[d])
+        De = min(args.e2e_distinct, D)
 
-        def hstep():
-            ctx.call("docscan_process_pages", P, hpages, C.byref(params))
+        def host_pages(alloc):
+            h_src = [alloc((PAGE_H, PAGE_W, 3)) for _ in range(De)]
+            h_w = [alloc((th, tw, 3)) for _ in range(De)]
+            h_b = [alloc((th, tw)) for _ in range(De)]
+            for i in range(De):
+                _capi.lib().docscan_memcpy_d2h(ctx._h, h_src[i].ctypes.data, C.c_void_p(src[i].data_ptr()), h_src[i].nbytes)
+            hp = (_capi.Page * P)()
+            for i in range(P):
+                d = i % De
+                hp[i].src = _capi.image_of(h_src[d])
+                hp[i].quad = (C.c_float * 8)(*quads[d].reshape(8).tolist())
+                hp[i].angle_deg = angles[d]
+                hp[i].warped = _capi.image_of(h_w[d])
+                hp[i].binary = _capi.image_of(h_b[d])
+            return hp, (h_src, h_w, h_b)
 
-        hstep()
-        barrier()
-        tb0 = ctx.transfer_bytes
-        esteps = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(esteps):
-            hstep()
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        tb1 = ctx.transfer_bytes
-        ems = sharding.max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3), dev)
-        e2e = {"value": world * P * PAGE_MP * esteps / (ems / 1e3), "unit": "MP/s",
-               "h2d_bytes_per_step": (tb1[0] - tb0[0]) // esteps, "d2h_bytes_per_step": (tb1[1] - tb0[1]) // esteps,
-               "steps": esteps,
-               "host_buffers": f"pinned; {D} distinct pages cycled, every page copied every step; the library uploads only the "
+        def timed_host(hp, nsteps):
+            ctx.call("docscan_process_pages", P, hp, C.byref(params))
+            barrier()
+            tb0 = ctx.transfer_bytes
+            t0 = time.perf_counter()
+            e0.record(stream)
+            for _ in range(nsteps):
+                ctx.call("docscan_process_pages", P, hp, C.byref(params))
+            e1.record(stream)
+            barrier()
+            wall = time.perf_counter() - t0
+            tb1 = ctx.transfer_bytes
+            ms = sharding.max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3), dev)
+            return total_jobs * PAGE_MP * nsteps / (ms / 1e3), (tb1[0] - tb0[0]) // nsteps, (tb1[1] - tb0[1]) // nsteps
+
+        hpages, keep_pinned = host_pages(ctx.pinned_empty)
+        esteps = max(10, args.steps)
+        ev, h2d, d2h = timed_host(hpages, esteps)
+        # results of the host path == results of the device-resident path (same page, same bytes)
+        same = bool(np.array_equal(np.asarray(keep_pinned[2][0]), binary[0].cpu().numpy()[:th, :tw]))
+        e2e = {"value": ev, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": esteps,
+               "matches_device_resident": same,
+               "host_buffers": f"pinned; {De} distinct pages cycled, every page copied every step; the library uploads only the "
                                f"rows/columns of each {PAGE_H * PAGE_W * 3} B photo under its quad (bytes counted by the library)"}
+        # raw link rate, all ranks at once, both directions at once
+        n_link = 1 << 30
+        h_up, h_dn = torch.empty(n_link, dtype=torch.uint8).pin_memory(), torch.empty(n_link, dtype=torch.uint8).pin_memory()
+        d_up, d_dn = torch.empty(n_link, dtype=torch.uint8, device=dev), torch.empty(n_link, dtype=torch.uint8, device=dev)
+        s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        for _ in range(2):
+            with torch.cuda.stream(s_up):
+                d_up.copy_(h_up, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_dn.copy_(d_dn, non_blocking=True)
+        barrier()
+        reps = 6
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            with torch.cuda.stream(s_up):
+                d_up.copy_(h_up, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_dn.copy_(d_dn, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        link_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
+        link_gbs = reps * n_link / link_s / 1e9                      # per direction, per rank, with every rank copying
+        del h_up, h_dn, d_up, d_dn
+        floor_s = max(h2d, d2h) / (link_gbs * 1e9)                  # a step cannot beat its larger direction at link rate
+        e2e["pcie"] = {"per_direction_GBps_per_rank_all_ranks_copying": round(link_gbs, 2),
+                       "step_floor_ms": round(floor_s * 1e3, 2),
+                       "e2e_frac_of_link_floor": round((floor_s * 1e3) / (total_jobs * PAGE_MP / ev * 1e3), 3)}
+        del hpages, keep_pinned
+        # pageable buffers (plain numpy arrays)
+        ppages, keep_pageable = host_pages(lambda shape: np.empty(shape, np.uint8))
+        pv, _, _ = timed_host(ppages, 2)
+        e2e["pageable"] = {"value": pv, "unit": "MP/s", "steps": 2, "host_buffers": "plain numpy arrays (pageable), same call"}
+        del ppages, keep_pageable
 
     # ---- CPU baseline beside it (rank 0, single-GPU run only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        D = 4
-        hp = [np.empty((PAGE_H, PAGE_W, 3), np.uint8) for _ in range(D)]
-        for i in range(D):
+        Dc = min(4, D)
+        hp = [np.empty((PAGE_H, PAGE_W, 3), np.uint8) for _ in range(Dc)]
+        for i in range(Dc):
             _capi.lib().docscan_memcpy_d2h(ctx._h, hp[i].ctypes.data, C.c_void_p(src[i].data_ptr()), hp[i].nbytes)
-        ref = CpuReference(hp, quads[:D], angles[:D], args.scale_long, tun)
+        ref = CpuReference(hp, quads[:Dc], angles[:Dc], args.scale_long, tun)
         _, dt1 = ref.run(2 * ref.cores)
         jobs = int(max(2 * ref.cores, min(4096, 12.0 / max(dt1 / (2 * ref.cores), 1e-6))))
         v, dt = ref.run(jobs)
         ref.close()
         cpu = {"value": v, "unit": "MP/s", "cores": ref.cores, "kind": "port",
-               "sample": f"{jobs} page-jobs over {D} distinct pages of this run's batch, {dt:.1f} s; {ref.how}"}
+               "sample": f"{jobs} page-jobs over {Dc} distinct pages of this run's batch, {dt:.1f} s; {ref.how}"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": _workload(args), "pages_per_gpu": P, "page": f"{PAGE_H}x{PAGE_W}x3", "warped": f"{th}x{tw}",
-                       "scale_long": args.scale_long, "parallelism": f"pages sharded over {world} GPU(s), no collective",
-                       "l2": f"inputs larger than L2 ({P * PAGE_H * PAGE_W * 3 / 1e9:.1f} GB read per step per GPU)",
-                       "rank0_cpu_affinity": numa},
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if args.total_pages else "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": _config(args, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "with_skew_estimate": skew, "gpu_launches": int(launches),
+            "parity_checked": parity, "page_jobs_per_step": total_jobs, "rank0_cpu_affinity": numa,
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

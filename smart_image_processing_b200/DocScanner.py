@@ -277,13 +277,21 @@ def process_document(input_path: str, out_dir: str = "outputs", page: str = "A4"
                      fallback_use_whole: bool = True,
                      min_quad_area_ratio: float = 0.15,
                      *, quad: Optional[np.ndarray] = None, angle: Optional[float] = None,
-                     save_stages: bool = False) -> dict:
+                     save_stages: bool = True) -> dict:
     """DocScanner.process_document (DocScanner.py:262-365): same 28 parameters, same result dict
-    {"quad", "warped", "binary"}.  The control path (load, quad localisation, skew angle) runs on the host
-    through control.py unless `quad` / `angle` are supplied; the per-pixel path runs on the GPU.
-    The reference's twelve PNG dumps are written only with save_stages=True."""
+    {"quad", "warped", "binary"}, same twelve PNG dumps in `out_dir` (scan_01_pre ... scan_08_clean).
+    The control path (load, bilateral `preprocess` dump, quad localisation, overlay dump) runs on the host through
+    control.py unless `quad` is supplied; the per-pixel path and deskew()'s angle estimate run on the GPU.
+    Keyword-only extras: `quad=` / `angle=` skip the localisation / the skew estimate; `save_stages=False` drops the
+    dumps and takes the single fused C-ABI call (the reference always dumps, hence the default)."""
     from . import control
+    if out_dir:                                                # ensure_dir(out_dir), DocScanner.py:277
+        os.makedirs(out_dir, exist_ok=True)
     color = control.load_image(input_path)
+    if save_stages:
+        # DocScanner.py:280-282: the denoised image is only ever dumped, nothing downstream reads it
+        control.save_image(os.path.join(out_dir, "scan_01_pre.png"),
+                           control.preprocess(color, bilateral_d, bilateral_sigmaColor, bilateral_sigmaSpace, gaussian_ksize))
     use_whole = False
     if quad is None:
         quad = control.localize_document(color, canny_low=canny_low, canny_high=canny_high,
@@ -296,15 +304,17 @@ def process_document(input_path: str, out_dir: str = "outputs", page: str = "A4"
             use_whole = True
     if use_whole and not fallback_use_whole:
         raise RuntimeError("Quad too small or missing, and fallback disabled.")
-    if use_whole and scale_long <= 0:
-        raise ValueError("scale_long must be positive")        # the reference would hand the full photo on unchanged
+    if save_stages:
+        control.save_image(os.path.join(out_dir, "scan_02_quad.png"), control.quad_overlay(color, None if use_whole else quad))
     tun = dict(illum_method=illum_method, illum_blur_frac=illum_blur_frac, block_size=block_size, C=C,
                thresh_method=thresh_method, mask_blur_ksize=mask_blur_ksize, blackhat_ksize=blackhat_ksize,
                blackhat_vertical_ratio=blackhat_vertical_ratio, ink_dilate_iters=ink_dilate_iters,
                mask_thresh_offset=mask_thresh_offset, morph_ksize=morph_ksize, morph_iters=morph_iters)
     quad = np.asarray(quad, np.float32) if quad is not None else None
     warp_quad = None if use_whole else quad                    # DocScanner.py:310-313
-    if save_stages:
+    # resize_long_side hands the photo on unchanged for scale_long <= 0 (DocScanner.py:29-30); the fused call has no
+    # such page kind, so that case takes the stage-by-stage route as well
+    if save_stages or (use_whole and scale_long <= 0):
         st = hot_path(color, warp_quad, 0.0, page=page, scale_long=scale_long, **tun)
         if angle is None:
             angle = ops.skew_angle(st["weighted"], canny_low, canny_high, max_rotate)     # DocScanner.py:342

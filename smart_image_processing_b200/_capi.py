@@ -134,6 +134,23 @@ def device_image(ptr: int, width: int, height: int, pitch: int, channels: int) -
     return Image(ptr, width, height, pitch, channels, DEVICE)
 
 
+class _PinnedBlock:
+    """Owner of one docscan_host_alloc block; numpy arrays made from it keep it (and its context) alive through `.base`."""
+
+    def __init__(self, ctx: "Context", ptr: int, nbytes: int):
+        self._ctx, self._ptr = ctx, ptr
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            ctx, ptr = self._ctx, self._ptr
+            self._ptr = None
+            if ptr and getattr(ctx, "_h", None) and ctx._h.value:
+                ctx._lib.docscan_host_free(ctx._h, C.c_void_p(ptr))
+        except Exception:
+            pass
+
+
 class Context:
     """One docscan_ctx: a CUDA device + stream + scratch arena.  Not thread-safe; use one per thread."""
 
@@ -195,12 +212,13 @@ class Context:
 
     # pinned numpy arrays for the fast host path
     def pinned_empty(self, shape, dtype=np.uint8) -> np.ndarray:
+        """Page-locked host array (docscan_host_alloc).  The block is owned by the array: it is released with
+        docscan_host_free when the array and every view of it are gone (the block keeps this context alive until then)."""
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = C.c_void_p()
         self.call("docscan_host_alloc", nbytes, C.byref(p))
-        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        return arr
+        block = _PinnedBlock(self, p.value, max(nbytes, 1))
+        return np.asarray(block)[:nbytes].view(dtype).reshape(shape)
 
     def device_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()

@@ -29,10 +29,51 @@ def load_image(path: str) -> np.ndarray:
     return img
 
 
+def save_image(path: str, img: np.ndarray) -> None:
+    d = os.path.dirname(path)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    _cv2().imwrite(path, img)
+
+
+def preprocess(img, bilateral_d=9, bilateral_sigmaColor=75, bilateral_sigmaSpace=75, gaussian_ksize=0) -> np.ndarray:
+    """DocScanner.py:39-45: the bilateral-denoised gray image the reference dumps as scan_01_pre.png and never reads
+    again.  The gray conversion and the optional Gaussian run on the device; cv2.bilateralFilter has no device kernel
+    here (dead output) and runs on the host."""
+    from . import ops
+    gray = ops.bgr2gray(img) if img.ndim == 3 else img
+    den = _cv2().bilateralFilter(gray, bilateral_d, bilateral_sigmaColor, bilateral_sigmaSpace)
+    if gaussian_ksize and gaussian_ksize > 1:
+        den = ops.gaussian_blur(den, gaussian_ksize) if gaussian_ksize % 2 else _cv2().GaussianBlur(den, (gaussian_ksize, gaussian_ksize), 0)
+    return den
+
+
+def quad_overlay(color: np.ndarray, quad) -> np.ndarray:
+    """scan_02_quad.png (DocScanner.py:300-308): the detected quad in green, or the frame in orange for whole-photo pages."""
+    cv2 = _cv2()
+    overlay = color.copy()
+    if quad is not None:
+        pts = np.asarray(quad).astype(np.int32).reshape((-1, 1, 2))
+        cv2.polylines(overlay, [pts], True, (0, 255, 0), 2)
+    else:
+        h, w = color.shape[:2]
+        full = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], dtype=np.int32).reshape((-1, 1, 2))
+        cv2.polylines(overlay, [full], True, (0, 165, 255), 2)
+    return overlay
+
+
 def quad_area(quad) -> float:
-    q = np.asarray(quad, np.float64).reshape(4, 2)
-    x, y = q[:, 0], q[:, 1]
-    return float(abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1))) * 0.5)
+    """cv2.contourArea of the float32 quad (DocScanner.py:291-292).  OpenCV accumulates the shoelace sum in double from
+    float32 coordinates: `a00 += (double)xi_1 * yi - (double)xi * yi_1`, starting from the last point, then
+    `fabs(a00 * 0.5)` -- the products of two float32 values are exact in double, so only the order of the sum matters."""
+    q = np.asarray(quad, np.float32).reshape(4, 2)
+    a00 = 0.0
+    px, py = float(q[3, 0]), float(q[3, 1])
+    for i in range(4):
+        x, y = float(q[i, 0]), float(q[i, 1])
+        a00 += px * y - x * py
+        px, py = x, y
+    return abs(a00 * 0.5)
 
 
 def _ordered(pts: np.ndarray) -> np.ndarray:

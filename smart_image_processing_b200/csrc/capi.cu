@@ -791,12 +791,12 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         }
         ctx->stream = main_stream;
         ctx->arena_off = base;
-        DS_TRY(rc);
+        // join the extra streams first, also when a group failed: their queued kernels still use the arena regions
         for (int k = 1; k < ns; k++) {
             DS_CUDA(ctx, cudaEventRecord(ctx->aux_ev[k], ctx->aux[k]));
             DS_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->aux_ev[k], 0));
         }
-        return DOCSCAN_OK;
+        return rc;
     }
 
     // ---- host buffers: three-stage pipeline over groups (H2D | kernels | D2H) on three streams with two
@@ -835,7 +835,12 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         const int m = std::min(group, n - i);
         const int sset = g & 1;
         std::vector<DImg> src(m), warped(m), binary(m);
-        if (g >= 2) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, comp_done[sset], 0));     // set's inputs consumed
+        if (g >= 2) {
+            // The set is carved per page as [src][warped][binary] with page-dependent sizes, so group g's uploads may land on
+            // bytes group g-2's results are still being read back from: wait for its kernels AND its D2H copies.
+            DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, comp_done[sset], 0));
+            DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, out_done[sset], 0));
+        }
         uint8_t* cur = stage_base[sset];
         auto carve = [&](const docscan_image& im, bool dense) {
             DImg d;

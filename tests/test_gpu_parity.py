@@ -856,9 +856,9 @@ def test_process_document_drop_in(tmp_path):
     eq(res["binary"], ref["clean"], "process_document binary")
     assert os.path.exists(tmp_path / "out" / "scan_08_clean.png")
     # supplying the control-path outputs takes the single fused C-ABI call
-    res2 = DS.process_document(path, scale_long=800, quad=quad, angle=angle)
+    res2 = DS.process_document(path, out_dir=str(tmp_path / "out2"), scale_long=800, quad=quad, angle=angle, save_stages=False)
     eq(res2["binary"], ref["clean"], "process_document (fused) binary")
-    res3 = DS.process_document(path, scale_long=800)                 # one fused call, skew estimated on the device
+    res3 = DS.process_document(path, out_dir=str(tmp_path / "out3"), scale_long=800, save_stages=False)   # one fused call, skew estimated on the device
     eq(res3["binary"], ref["clean"], "process_document (fused, device-side skew estimate) binary")
     with pytest.raises(FileNotFoundError):
-        DS.process_document(str(tmp_path / "missing.png"))
+        DS.process_document(str(tmp_path / "missing.png"), out_dir=str(tmp_path / "out4"))
