@@ -458,7 +458,9 @@ def run_ours(args):
                                if k.startswith(("canny", "hough", "skew"))},
                 "angles_estimated_sample": [float(est[i]) for i in range(min(P, 4))]}
         for i in range(P):
-            pages[i].angle_deg = angles[i]
+            pages[i].angle_deg = angles[i % D]
+        step()                                  # leave the supplied-angle results in the device-resident outputs again
+        barrier()
 
     # ---- e2e: HOST buffers through the same C-ABI call, copies inside the timed region.  Headline leg: pinned buffers
     # (docscan_host_alloc), >= 10 steps.  Beside it: the same call with PAGEABLE numpy buffers (what cv2.imread hands a caller),
