@@ -18,7 +18,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libdocscan.so")
 
-CU_SOURCES = ["ctx.cu", "pointwise.cu", "scalars.cu", "blur.cu", "morph.cu", "adaptive.cu", "warp.cu", "resize.cu", "deskew.cu", "synth.cu", "capi.cu"]
+CU_SOURCES = ["ctx.cu", "pointwise.cu", "scalars.cu", "blur.cu", "tcblur.cu", "morph.cu", "adaptive.cu", "warp.cu", "resize.cu", "deskew.cu", "synth.cu", "capi.cu"]
 CPP_SOURCES = ["hostmath.cpp"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -39,7 +39,7 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "docscan.h"), os.path.abspath(__file__)]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc05.cuh"), os.path.join(INCLUDE, "docscan.h"), os.path.abspath(__file__)]
     jobs = []
     objs = []
     for s in CU_SOURCES:

@@ -384,6 +384,10 @@ int k_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, int c_param, const B
     // box sums travel through the ring as 16-bit values: 255 * k must fit (the 8.8 Gaussian sums to 256 for every k)
     if (kind == 1 && k > 255) return ds_fail(ctx, DOCSCAN_ERR_UNSUPPORTED, "box mean block size must be at most 255 (got %d)", k);
     if (kind == 0 && k == 1) kind = 1;             // 1x1 Gaussian is the identity; so is the 1x1 box mean
+    {
+        int rc = DOCSCAN_OK;                       // the Gaussian as two banded contractions on the tensor cores (tcblur.cu)
+        if (k_tc_blur_jobs(ctx, kind, k, epi, jobs_host, n, &rc)) return rc;
+    }
     BlurLaunch L{};
     DS_TRY(get_table(ctx, kind, k, &L.t));
     L.border = kind == 0 ? 0 : 1;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <array>
 #include <cstring>
 #include <map>
 #include <string>
@@ -46,6 +47,9 @@ struct docscan_ctx {
     size_t pinned_size = 0, pinned_off = 0;
     // cached device coefficient tables, keyed by (kind, k, delta)
     std::map<uint64_t, void*> tables;
+    // band matrices of the tensor-core stencils (tcblur.cu), keyed by (axis, k, near-border distances, tile geometry)
+    std::map<std::array<int, 6>, void*> tc_tables;
+    uint32_t* tc_status = nullptr;            // pinned host words the tensor-core kernels report a timed-out wait into
     std::vector<void*> user_allocs;
     // host-buffer pipeline of docscan_process_pages: copy streams + events (created on first use)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -167,6 +171,8 @@ struct BlurJob {
 // gaussian (REFLECT_101, 8.8 fixed point) for kind 0, box (REPLICATE, ones) for kind 1
 int k_blur_jobs(docscan_ctx*, int kind, int k, int epi, int c_param, const BlurJob* jobs_host, int n,
                 int max_w, int max_h);
+// tcblur.cu : the Gaussian on the tensor cores (tcgen05); false = not applicable, run k_blur_jobs' own kernels
+bool k_tc_blur_jobs(docscan_ctx*, int kind, int k, int epi, const BlurJob* jobs_host, int n, int* rc);
 // morph.cu
 struct MorphJob {
     const uint8_t* src; uint8_t* dst;

@@ -72,10 +72,12 @@ extern "C" int docscan_destroy(docscan_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_retired(ctx);
     for (auto& kv : ctx->tables) cudaFree(kv.second);
+    for (auto& kv : ctx->tc_tables) cudaFree(kv.second);
     for (void* p : ctx->user_allocs) cudaFree(p);
     if (ctx->angles_dev) cudaFree(ctx->angles_dev);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->tc_status) cudaFreeHost(ctx->tc_status);
     if (ctx->copy_in) {
         cudaStreamDestroy(ctx->copy_in);
         cudaStreamDestroy(ctx->copy_out);

@@ -1,0 +1,535 @@
+// cv2.GaussianBlur(u8, 8.8 fixed point, BORDER_REFLECT_101) as two exact-integer banded-Toeplitz contractions on the
+// 5th-generation tensor cores (tcgen05, kind::i8, s32 accumulators in tensor memory), with the same fused epilogues as
+// blur.cu (subtract / divide / reverse subtract, min-max, histogram).  DocScanner.py:153,184.
+//
+// Every sum of the fixed-point blur is an exact integer, so regrouping it into matrix products is bit-exact:
+//
+//   pass 1 (vertical):   D1[y, x']  = sum_y'  Tv[y, y'] * S[y', x']        M = 128 output rows, N = 128 input columns, K = K1 rows
+//   pass 2 (horizontal): D2[y, x ]  = sum_x'  D1[y, x'] * Th[x', x]        M = 128, N = NOUT output columns, K = 128
+//   dst = (D2 + 32768) >> 16
+//
+// S  : the u8 source tile, K1 = 128 + 2R rows (rounded up to 32) x 128 columns, fetched by ONE TMA tensor-map request per
+//      tile (128-byte swizzle, out-of-image elements zero-filled); image rows are contiguous along x, which makes the tile
+//      an MN-major B operand as it lies.
+// Tv : constant band matrix [128 x K1] (u8 coefficients of the quantised kernel), A operand, K-major, in shared memory.
+//      The border rule is folded into the matrix: a top / bottom tile uses a variant in which the taps that REFLECT_101
+//      maps back into the image are added onto the rows they land on — the kernel itself never sees a border.
+// D1 : s32 in tensor memory, values <= 255 * 256.  The epilogue warps read it back (tcgen05.ld), split every value into
+//      its low and high byte, pack four neighbours per 32-bit word and write the two byte planes back to tensor memory
+//      (tcgen05.st) as the A operands of pass 2 — D1 never touches shared or global memory.
+// Th : constant band matrix [NOUT x 128], B operand, K-major (left / right border variants like Tv).
+// D2 : two accumulators, D2lo = A2lo * Th and D2hi = A2hi * Th;  V = D2lo + 256 * D2hi.
+//
+// One CTA = 8 warps, 256 TMEM columns, ~100 KB of shared memory -> two CTAs per SM: while one CTA drains its accumulators
+// the other one's MMAs run.  Tiles are dealt round-robin to a persistent grid of 2 x SMs CTAs.
+// Out-of-scope here (blur.cu keeps them): box sums, radii above 48, buffers that are not 16-byte aligned.
+#include <cuda.h>      // CUtensorMap types; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
+#include <array>
+
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace {
+
+constexpr int TM = 128;          // output rows per tile (MMA M, TMEM lanes)
+constexpr int NIN = 128;         // input columns per tile (pass-1 N, pass-2 K)
+constexpr int NT = 256;
+constexpr int TMEM_COLS = 256;
+constexpr int COL_D1 = 0, COL_D2LO = 0, COL_D2HI = 96, COL_A2LO = 192, COL_A2HI = 224;
+constexpr int T_BYTES = 2 * TM * 128;      // two 128-byte K blocks
+constexpr int TOE_BYTES = 96 * 128;
+constexpr int MAX_R = 48;
+
+struct TcJob {
+    const uint8_t* src; uint8_t* dst;
+    int src_pitch, dst_pitch, w, h;
+    uint32_t* minmax; uint32_t* hist;
+    int tile_base, ntx, nty;
+    int t_off, toe_off;          // this page's first row / column variant pointer in `tabs`
+};
+
+struct TcLaunch {
+    const TcJob* jobs;
+    const CUtensorMap* maps;
+    const uint8_t* const* tabs;
+    uint32_t* dbg;               // debug dump of the first tile (DOCSCAN_TC_DEBUG), else null
+    volatile uint32_t* status;   // pinned host words: [0] = which wait timed out, [1] = progress of CTA 0 (debug runs)
+    int n_jobs, total_tiles;
+    int R, RL, K1, NOUT;         // RL: left margin of the source window (TMA needs its first byte 16-byte aligned)
+    uint32_t idesc1, idesc2;
+};
+
+__device__ __forceinline__ uint32_t epi_px(int epi, uint32_t s, uint32_t b) {
+    switch (epi) {
+        case DS_EPI_SUB: return (uint32_t)max((int)s - (int)b, 0);
+        case DS_EPI_RSUB: return (uint32_t)max((int)b - (int)s, 0);
+        case DS_EPI_DIV: return ds_div255((uint8_t)s, (uint8_t)b);
+        default: return b;
+    }
+}
+
+template <int EPI, bool STATS>
+__global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sT = base;
+    uint8_t* sToe = sT + T_BYTES;
+    uint8_t* sS[2] = {sToe + TOE_BYTES, sToe + TOE_BYTES + L.K1 * 128};
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(sS[1] + L.K1 * 128);       // 8 x 256, only with STATS
+    __shared__ uint64_t bar_s[2], bar_c, bar_d1, bar_d2;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        tc::mbar_init(&bar_s[0], 1); tc::mbar_init(&bar_s[1], 1); tc::mbar_init(&bar_c, 1);
+        tc::mbar_init(&bar_d1, 1); tc::mbar_init(&bar_d2, 1);
+        tc::mbar_init_fence();
+    }
+    if (warp == 1) tc::tmem_alloc(&s_tmem, TMEM_COLS);
+    if (STATS)
+        for (int i = tid; i < 8 * 256; i += NT) s_hist[i] = 0;
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+#define TC_CRUMB(v) do { if (L.dbg && blockIdx.x == 0 && tid == 0) { L.status[1] = (v); __threadfence_system(); } } while (0)
+#define TC_WAIT(bar, par, id) do { if (!tc::mbar_wait_bounded(bar, par)) { L.status[0] = (id); __threadfence_system(); __trap(); } } while (0)
+    TC_CRUMB(1);
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // this warp's quarter of the TMEM lanes
+    const int hf = warp >> 2;                                          // which half of the columns this warp drains
+
+    // tile index -> (job, tx, ty); tiles of a page are numbered row-major so that neighbours share their halo in L2
+    int job = 0;
+    auto locate = [&](int t, int* tx, int* ty) {
+        while (job + 1 < L.n_jobs && t >= L.jobs[job + 1].tile_base) job++;
+        const int idx = t - L.jobs[job].tile_base, ntx = L.jobs[job].ntx;
+        *ty = idx / ntx; *tx = idx - *ty * ntx;
+    };
+
+    // issuing thread's state
+    const uint8_t* cur_t = nullptr; const uint8_t* cur_toe = nullptr;
+    uint32_t ph_c = 0, ph_s[2] = {0, 0};
+    int tx, ty;
+    if (tid == 0 && (int)blockIdx.x < L.total_tiles) {
+        locate(blockIdx.x, &tx, &ty);
+        tc::tmap_acquire(&L.maps[job]);
+        tc::mbar_expect_tx(&bar_s[0], (uint32_t)L.K1 * 128);
+        tc::tma_load_2d(sS[0], &L.maps[job], tx * L.NOUT - L.RL, ty * TM - L.R, &bar_s[0]);
+        TC_CRUMB(12);
+    }
+    uint32_t st_lo = 255, st_hi = 0, zero_count = 0;
+    uint32_t* st_minmax = nullptr; uint32_t* st_hist = nullptr;      // where the running statistics belong (one page at a time)
+
+    auto flush_stats = [&]() {
+        if (!STATS) return;
+        if (st_minmax) {
+            for (int o = 16; o; o >>= 1) {
+                st_lo = min(st_lo, __shfl_xor_sync(0xffffffffu, st_lo, o));
+                st_hi = max(st_hi, __shfl_xor_sync(0xffffffffu, st_hi, o));
+            }
+            if (lane == 0 && st_lo <= st_hi) { atomicMin(&st_minmax[0], st_lo); atomicMax(&st_minmax[1], st_hi); }
+        }
+        if (st_hist) {
+            for (int o = 16; o; o >>= 1) zero_count += __shfl_xor_sync(0xffffffffu, zero_count, o);
+            if (lane == 0 && zero_count) atomicAdd(&s_hist[warp * 256], zero_count);
+            __syncthreads();
+            for (int i = tid; i < 256; i += NT) {
+                uint32_t s = 0;
+#pragma unroll
+                for (int wv = 0; wv < 8; wv++) { s += s_hist[wv * 256 + i]; s_hist[wv * 256 + i] = 0; }
+                if (s) atomicAdd(&st_hist[i], s);
+            }
+            __syncthreads();
+        }
+        st_lo = 255; st_hi = 0; zero_count = 0;
+    };
+
+    int it = 0;
+    for (int t = blockIdx.x; t < L.total_tiles; t += gridDim.x, it++) {
+        const int prev_job = job;
+        locate(t, &tx, &ty);
+        const TcJob J = L.jobs[job];
+        if (STATS && it > 0 && job != prev_job) flush_stats();        // statistics are per page
+        st_minmax = J.minmax; st_hist = J.hist;
+        const int x0 = tx * L.NOUT, y0 = ty * TM;
+        const int stage = it & 1;
+
+        if (tid == 0) {
+            const uint8_t* want_t = L.tabs[J.t_off + ty];
+            const uint8_t* want_toe = L.tabs[J.toe_off + tx];
+            if (want_t != cur_t || want_toe != cur_toe) {
+                // every MMA that read the old matrices has completed (bar_d2 of the previous tile was waited for)
+                uint32_t bytes = 0;
+                if (want_t != cur_t) bytes += T_BYTES;
+                if (want_toe != cur_toe) bytes += (uint32_t)L.NOUT * 128;
+                tc::mbar_expect_tx(&bar_c, bytes);
+                TC_CRUMB(13);
+                if (want_t != cur_t) tc::bulk_load(sT, want_t, T_BYTES, &bar_c);
+                TC_CRUMB(14);
+                if (want_toe != cur_toe) tc::bulk_load(sToe, want_toe, (uint32_t)L.NOUT * 128, &bar_c);
+                cur_t = want_t; cur_toe = want_toe;
+                TC_WAIT(&bar_c, ph_c, 1); ph_c ^= 1;
+                TC_CRUMB(2);
+            }
+            // prefetch the next tile's source window into the other stage (its last reader, MMA1 of the previous tile, is done)
+            const int tn = t + gridDim.x;
+            if (tn < L.total_tiles) {
+                int jn = job, ntx_, nty_;
+                const int keep = job;
+                locate(tn, &ntx_, &nty_);
+                jn = job; job = keep;
+                if (jn != job) tc::tmap_acquire(&L.maps[jn]);
+                tc::mbar_expect_tx(&bar_s[stage ^ 1], (uint32_t)L.K1 * 128);
+                tc::tma_load_2d(sS[stage ^ 1], &L.maps[jn], ntx_ * L.NOUT - L.RL, nty_ * TM - L.R, &bar_s[stage ^ 1]);
+            }
+            TC_WAIT(&bar_s[stage], ph_s[stage], 2); ph_s[stage] ^= 1;
+            TC_CRUMB(3);
+            tc::fence_after_sync();
+            // pass 1: D1[128 x 128] = Tv[128 x K1] * S[K1 x 128]
+            const uint32_t aT = tc::smem_u32(sT), aS = tc::smem_u32(sS[stage]);
+            for (int s = 0; s < L.K1 / 32; s++) {
+                const uint64_t ad = tc::smem_desc_sw128(aT + (s >> 2) * (TM * 128) + (s & 3) * 32, 16, 1024);
+                const uint64_t bd = tc::smem_desc_sw128(aS + s * 4096, (uint32_t)L.K1 * 128, 1024);
+                tc::mma_i8_ss(tmem + COL_D1, ad, bd, L.idesc1, s > 0);
+            }
+            tc::mma_commit(&bar_d1);
+            TC_CRUMB(4);
+        }
+        __syncwarp();
+
+        // ---- D1 -> byte planes (A operands of pass 2): this warp's 32 rows x 64 columns
+        TC_WAIT(&bar_d1, it & 1, 3);
+        tc::fence_after_sync();
+        TC_CRUMB(5);
+        {
+            uint32_t lo[16], hi[16];
+#pragma unroll
+            for (int part = 0; part < 2; part++) {
+                uint32_t v[32];
+                tc::tmem_ld32(tmem + lane_base + COL_D1 + hf * 64 + part * 32, v);
+                tc::tmem_wait_ld();
+                if (L.dbg && t == 0)
+                    for (int i = 0; i < 32; i++) L.dbg[((warp & 3) * 32 + lane) * 128 + hf * 64 + part * 32 + i] = v[i];
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const uint32_t t1 = __byte_perm(v[4 * g], v[4 * g + 1], 0x5140);        // a0 b0 a1 b1
+                    const uint32_t t2 = __byte_perm(v[4 * g + 2], v[4 * g + 3], 0x5140);    // c0 d0 c1 d1
+                    lo[part * 8 + g] = __byte_perm(t1, t2, 0x5410);                         // a0 b0 c0 d0
+                    hi[part * 8 + g] = __byte_perm(t1, t2, 0x7632);                         // a1 b1 c1 d1
+                }
+            }
+            TC_CRUMB(6);
+            tc::tmem_st16(tmem + lane_base + COL_A2LO + hf * 16, lo);
+            tc::tmem_st16(tmem + lane_base + COL_A2HI + hf * 16, hi);
+            tc::tmem_wait_st();
+            TC_CRUMB(7);
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            // pass 2: D2lo / D2hi [128 x NOUT] = A2lo / A2hi [128 x 128] (tensor memory) * Th[128 x NOUT]
+            const uint32_t aToe = tc::smem_u32(sToe);
+            for (int s = 0; s < NIN / 32; s++)
+                tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s * 8, tc::smem_desc_sw128(aToe + s * 32, 16, 1024), L.idesc2, s > 0);
+            for (int s = 0; s < NIN / 32; s++)
+                tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s * 8, tc::smem_desc_sw128(aToe + s * 32, 16, 1024), L.idesc2, s > 0);
+            tc::mma_commit(&bar_d2);
+            TC_CRUMB(8);
+        }
+        __syncwarp();
+
+        // ---- epilogue: this warp's 32 rows x its half of the NOUT columns, 16 columns at a time
+        const int H0 = ((L.NOUT >> 1) + 15) & ~15;
+        const int c_begin = hf ? H0 : 0, c_end = hf ? L.NOUT : H0;
+        const int y = y0 + (warp & 3) * 32 + lane;
+        const bool row_ok = y < J.h;
+        const uint8_t* srow = J.src + (size_t)y * J.src_pitch;
+        uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
+        uint4 cw_next = make_uint4(0, 0, 0, 0);
+        if (EPI != DS_EPI_BLUR && row_ok && c_begin < c_end && x0 + c_begin < J.w)
+            cw_next = __ldg(reinterpret_cast<const uint4*>(srow + x0 + c_begin));
+        TC_WAIT(&bar_d2, it & 1, 4);
+        tc::fence_after_sync();
+        TC_CRUMB(9);
+        for (int c = c_begin; c < c_end; c += 16) {
+            uint32_t lo[16], hi[16];
+            tc::tmem_ld16(tmem + lane_base + COL_D2LO + c, lo);
+            tc::tmem_ld16(tmem + lane_base + COL_D2HI + c, hi);
+            const uint4 cw = cw_next;
+            const int x = x0 + c;
+            if (EPI != DS_EPI_BLUR && row_ok && c + 16 < c_end && x + 16 < J.w)
+                cw_next = __ldg(reinterpret_cast<const uint4*>(srow + x + 16));
+            tc::tmem_wait_ld();
+            if (L.dbg && t == 0)
+                for (int i = 0; i < 16; i++) {
+                    L.dbg[16384 + ((warp & 3) * 32 + lane) * 96 + c + i] = lo[i];
+                    L.dbg[16384 + 12288 + ((warp & 3) * 32 + lane) * 96 + c + i] = hi[i];
+                }
+            if (row_ok && x < J.w) {
+                const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+                uint32_t out[4];
+                const int nvalid = min(16, J.w - x);
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int i = 4 * g + b;
+                        const uint32_t blur = (lo[i] + (hi[i] << 8) + 32768u) >> 16;
+                        const uint32_t s = (cws[g] >> (8 * b)) & 0xFFu;
+                        const uint32_t v = epi_px(EPI, s, blur);
+                        word |= v << (8 * b);
+                        if (STATS && i < nvalid) {
+                            st_lo = min(st_lo, v); st_hi = max(st_hi, v);
+                            if (J.hist) {
+                                if (v) atomicAdd(&s_hist[warp * 256 + v], 1u); else zero_count++;
+                            }
+                        }
+                    }
+                    out[g] = word;
+                }
+                if (nvalid == 16) {
+                    *reinterpret_cast<uint4*>(drow + x) = make_uint4(out[0], out[1], out[2], out[3]);
+                } else {                                    // last columns of the page: never write past its width
+                    for (int i = 0; i < nvalid; i++) drow[x + i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
+                }
+            }
+            __syncwarp();                                   // the tensor-memory loads of the next round are warp-wide
+        }
+        TC_CRUMB(10);
+        tc::fence_before_sync();
+        __syncthreads();                                    // accumulators drained: the next tile may overwrite them
+        tc::fence_after_sync();
+    }
+    flush_stats();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, TMEM_COLS);
+    TC_CRUMB(11);
+#undef TC_CRUMB
+#undef TC_WAIT
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    return p;
+}
+
+// Byte (row, k) of a K-major operand with 128-byte swizzle: 128-byte rows, 16-byte chunks XORed with the row number mod 8;
+// K beyond 128 continues in the next block of `rows` rows.
+size_t sw128_offset(int rows, int row, int k) {
+    const int blk = k >> 7, kk = k & 127;
+    return (size_t)blk * rows * 128 + (size_t)row * 128 + (size_t)(((kk >> 4) ^ (row & 7)) << 4) + (kk & 15);
+}
+
+// Band matrix of one tile row (vertical, A operand [128 x K1]) or tile column (horizontal, B operand [NOUT x 128]):
+// entry (o, slot) = sum of the taps of output o0 + o that the border rule maps onto source index o0 - margin + slot.
+// Returns false when a folded coefficient does not fit 8 bits (images much smaller than the kernel).
+bool build_band(const int32_t* q, int k_eff, int R, int margin, int o0, int len, int n_out, int n_slots, int rows_alloc, uint8_t* img, size_t img_bytes) {
+    std::vector<int> acc((size_t)n_out * n_slots, 0);
+    for (int o = 0; o < n_out; o++) {
+        const int p = o0 + o;
+        if (p >= len) break;
+        for (int t = 0; t < k_eff; t++) {
+            const int sp = reflect101(p + t - R, len);
+            const int slot = sp - (o0 - margin);
+            if (slot < 0 || slot >= n_slots) return false;
+            acc[(size_t)o * n_slots + slot] += q[t];
+        }
+    }
+    memset(img, 0, img_bytes);
+    for (int o = 0; o < n_out; o++)
+        for (int s = 0; s < n_slots; s++) {
+            const int v = acc[(size_t)o * n_slots + s];
+            if (v > 255) return false;
+            if (v) img[sw128_offset(rows_alloc, o, s)] = (uint8_t)v;
+        }
+    return true;
+}
+
+struct Variant { const uint8_t* dev; };
+
+// device copy of one band matrix, cached per context: key = (axis, k, top/left distance or -1, bottom/right distance or -1)
+int get_variant(docscan_ctx* ctx, int axis, int k, const int32_t* q, int k_eff, int R, int RL, int K1, int NOUT, int o0, int len, const uint8_t** out,
+                bool* ok) {
+    const int n_out = axis == 0 ? TM : NOUT, n_slots = axis == 0 ? K1 : NIN;
+    const int a = (o0 - R < 0) ? o0 : -1;
+    const int b = (o0 + n_out - 1 + R > len - 1) ? len - o0 : -1;
+    const std::array<int, 6> key = {axis, k, a, b, NOUT, K1};
+    auto it = ctx->tc_tables.find(key);
+    if (it == ctx->tc_tables.end()) {
+        const size_t bytes = axis == 0 ? (size_t)T_BYTES : (size_t)TOE_BYTES;
+        std::vector<uint8_t> img(bytes);
+        *ok = build_band(q, k_eff, R, axis == 0 ? R : RL, o0, len, n_out, n_slots, axis == 0 ? TM : NOUT, img.data(), bytes);
+        if (!*ok) return DOCSCAN_OK;
+        void* dev = nullptr;
+        DS_CUDA(ctx, cudaMalloc(&dev, bytes));
+        DS_CUDA(ctx, cudaMemcpyAsync(dev, img.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+        DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->tc_tables.emplace(key, dev).first;
+    }
+    *ok = true;
+    *out = reinterpret_cast<const uint8_t*>(it->second);
+    return DOCSCAN_OK;
+}
+
+template <int EPI, bool STATS>
+int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
+    static bool attr_done = false;          // per template instance; the attribute is per function and device
+    (void)attr_done;
+    DS_CUDA(ctx, cudaFuncSetAttribute(tc_blur_kernel<EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = std::min(L.total_tiles, 2 * ctx->sm_count);
+    if (const char* e = getenv("DOCSCAN_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
+    tc_blur_kernel<EPI, STATS><<<grid, NT, smem, ctx->stream>>>(L);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}
+
+}  // namespace
+
+// Returns false when the tensor-core path does not apply (the caller then runs blur.cu); otherwise *rc is the result.
+bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* jobs_host, int n, int* rc) {
+    *rc = DOCSCAN_OK;
+    if (kind != 0 || k < 3 || n <= 0) return false;
+    if (epi != DS_EPI_BLUR && epi != DS_EPI_SUB && epi != DS_EPI_RSUB && epi != DS_EPI_DIV) return false;
+    if (const char* e = getenv("DOCSCAN_TC")) if (atoi(e) == 0) return false;
+    if (!encode_fn()) return false;
+    std::vector<int32_t> q(k);
+    if (docscan_gaussian_kernel_q8(k, q.data()) != DOCSCAN_OK) return false;
+    int z = 0;
+    while (z < k / 2 && q[z] == 0) z++;                 // zero tails of the quantised kernel
+    const int k_eff = k - 2 * z, R = k_eff / 2;
+    if (R < 1 || R > MAX_R) return false;
+    for (int i = 0; i < k_eff; i++) if (q[z + i] > 255) return false;
+    const int K1 = (TM + 2 * R + 31) / 32 * 32;
+    const int RL = (R + 15) & ~15;                      // the window's first column must sit on a 16-byte boundary of its row
+    const int NOUT = std::min(96, (NIN - RL - R) / 16 * 16);
+    if (NOUT < 16 || K1 > 256) return false;
+    bool stats = false;
+    for (int i = 0; i < n; i++) {
+        const BlurJob& j = jobs_host[i];
+        const int w16 = (j.w + 15) & ~15;
+        if (((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)j.src_pitch | (uintptr_t)j.dst_pitch) & 15) return false;
+        if (j.src_pitch < w16 || j.dst_pitch < w16 || j.w < 1 || j.h < 1) return false;
+        stats = stats || j.minmax || j.hist;
+    }
+    // per-page geometry: tile counts, border variants of the two band matrices, tensor map of the source plane
+    std::vector<TcJob> jobs(n);
+    std::vector<const uint8_t*> tabs;
+    std::vector<CUtensorMap> maps(n);
+    std::map<std::pair<int, int>, std::pair<int, int>> geom;          // (w, h) -> (t_off, toe_off)
+    int total = 0;
+    double px = 0;
+    for (int i = 0; i < n; i++) {
+        const BlurJob& b = jobs_host[i];
+        TcJob& j = jobs[i];
+        j.src = b.src; j.dst = b.dst; j.src_pitch = b.src_pitch; j.dst_pitch = b.dst_pitch; j.w = b.w; j.h = b.h;
+        j.minmax = b.minmax; j.hist = b.hist;
+        j.ntx = (b.w + NOUT - 1) / NOUT; j.nty = (b.h + TM - 1) / TM;
+        j.tile_base = total;
+        total += j.ntx * j.nty;
+        px += (double)b.w * b.h;
+        auto g = geom.find({b.w, b.h});
+        if (g == geom.end()) {
+            const int t_off = (int)tabs.size();
+            for (int ty = 0; ty < j.nty; ty++) {
+                const uint8_t* p = nullptr; bool ok = false;
+                *rc = get_variant(ctx, 0, k, q.data() + z, k_eff, R, RL, K1, NOUT, ty * TM, b.h, &p, &ok);
+                if (*rc != DOCSCAN_OK) return true;
+                if (!ok) return false;
+                tabs.push_back(p);
+            }
+            const int toe_off = (int)tabs.size();
+            for (int tx = 0; tx < j.ntx; tx++) {
+                const uint8_t* p = nullptr; bool ok = false;
+                *rc = get_variant(ctx, 1, k, q.data() + z, k_eff, R, RL, K1, NOUT, tx * NOUT, b.w, &p, &ok);
+                if (*rc != DOCSCAN_OK) return true;
+                if (!ok) return false;
+                tabs.push_back(p);
+            }
+            g = geom.emplace(std::make_pair(b.w, b.h), std::make_pair(t_off, toe_off)).first;
+        }
+        j.t_off = g->second.first; j.toe_off = g->second.second;
+        const cuuint64_t dims[2] = {(cuuint64_t)b.w, (cuuint64_t)b.h};
+        const cuuint64_t strides[1] = {(cuuint64_t)b.src_pitch};
+        const cuuint32_t box[2] = {(cuuint32_t)NIN, (cuuint32_t)K1};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult cr = encode_fn()(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)b.src, dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return false;
+    }
+    TcLaunch L{};
+    void* dev = nullptr;
+    // one upload: tensor maps (64-byte aligned) | jobs | variant pointers
+    const size_t off_jobs = sizeof(CUtensorMap) * n, off_tabs = off_jobs + ((sizeof(TcJob) * n + 63) & ~(size_t)63);
+    std::vector<uint8_t> blob(off_tabs + sizeof(void*) * tabs.size());
+    memcpy(blob.data(), maps.data(), sizeof(CUtensorMap) * n);
+    memcpy(blob.data() + off_jobs, jobs.data(), sizeof(TcJob) * n);
+    memcpy(blob.data() + off_tabs, tabs.data(), sizeof(void*) * tabs.size());
+    *rc = ds_upload(ctx, blob.data(), blob.size(), &dev);
+    if (*rc != DOCSCAN_OK) return true;
+    L.maps = reinterpret_cast<const CUtensorMap*>(dev);
+    L.jobs = reinterpret_cast<const TcJob*>((uint8_t*)dev + off_jobs);
+    L.tabs = reinterpret_cast<const uint8_t* const*>((uint8_t*)dev + off_tabs);
+    L.n_jobs = n; L.total_tiles = total; L.R = R; L.RL = RL; L.K1 = K1; L.NOUT = NOUT;
+    L.idesc1 = tc::idesc_i8(TM, NIN, 0, 0, 0, 1);
+    L.idesc2 = tc::idesc_i8(TM, NOUT, 0, 0, 0, 0);
+    if (!ctx->tc_status) {
+        if (cudaHostAlloc((void**)&ctx->tc_status, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+        memset(ctx->tc_status, 0, 64);
+    }
+    L.status = ctx->tc_status;
+    const char* dbg_path = getenv("DOCSCAN_TC_DEBUG");
+    const size_t dbg_words = 16384 + 2 * 12288;
+    if (dbg_path) {
+        void* d = nullptr;
+        *rc = ds_arena_alloc(ctx, dbg_words * 4, &d);
+        if (*rc != DOCSCAN_OK) return true;
+        cudaMemsetAsync(d, 0xEE, dbg_words * 4, ctx->stream);
+        L.dbg = (uint32_t*)d;
+    }
+    const size_t smem = 1024 + T_BYTES + TOE_BYTES + 2 * (size_t)K1 * 128 + (stats ? 8 * 256 * 4 : 0);
+    {
+        ProfScope prof(ctx, std::string("tc_blur_k") + std::to_string(k), 2.0 * px);
+#define DS_TC_CASE(E) case E: *rc = stats ? launch_tc<E, true>(ctx, L, smem) : launch_tc<E, false>(ctx, L, smem); break;
+        switch (epi) {
+            DS_TC_CASE(DS_EPI_BLUR)
+            DS_TC_CASE(DS_EPI_SUB)
+            DS_TC_CASE(DS_EPI_RSUB)
+            DS_TC_CASE(DS_EPI_DIV)
+        }
+#undef DS_TC_CASE
+    }
+    if (dbg_path && *rc == DOCSCAN_OK) {
+        std::vector<uint32_t> host(dbg_words);
+        cudaMemcpyAsync(host.data(), L.dbg, dbg_words * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (FILE* f = fopen(dbg_path, "wb")) {
+            fprintf(stderr, "[tc debug] k=%d k_eff=%d R=%d RL=%d K1=%d NOUT=%d tiles=%d sync=%s timeout_id=%u progress=%u\n", k, k_eff, R, RL, K1, NOUT, total,
+                    cudaGetErrorString(e), ctx->tc_status[0], ctx->tc_status[1]);
+            fwrite(host.data(), 4, dbg_words, f);
+            fclose(f);
+        }
+    }
+    return true;
+}
