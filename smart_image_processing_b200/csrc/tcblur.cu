@@ -40,6 +40,7 @@ constexpr int COL_D1 = 0, COL_D2LO = 0, COL_D2HI = 96, COL_A2LO = 192, COL_A2HI 
 constexpr int T_BYTES = 2 * TM * 128;      // two 128-byte K blocks
 constexpr int TOE_BYTES = 96 * 128;
 constexpr int MAX_R = 48;
+constexpr int MAX_JOBS = 64, MAX_TABS = 256;      // page table / band-matrix pointer table kept in shared memory
 
 struct TcJob {
     const uint8_t* src; uint8_t* dst;
@@ -55,19 +56,14 @@ struct TcLaunch {
     const uint8_t* const* tabs;
     uint32_t* dbg;               // debug dump of the first tile (DOCSCAN_TC_DEBUG), else null
     volatile uint32_t* status;   // pinned host words: [0] = which wait timed out, [1] = progress of CTA 0 (debug runs)
-    int n_jobs, total_tiles;
+    int n_jobs, n_tabs, total_tiles;
+    int crumbs;                  // debug: CTA 0 reports its progress to status[1] (slow: a system-scope fence per phase)
     int R, RL, K1, NOUT;         // RL: left margin of the source window (TMA needs its first byte 16-byte aligned)
     uint32_t idesc1, idesc2;
 };
 
-__device__ __forceinline__ uint32_t epi_px(int epi, uint32_t s, uint32_t b) {
-    switch (epi) {
-        case DS_EPI_SUB: return (uint32_t)max((int)s - (int)b, 0);
-        case DS_EPI_RSUB: return (uint32_t)max((int)b - (int)s, 0);
-        case DS_EPI_DIV: return ds_div255((uint8_t)s, (uint8_t)b);
-        default: return b;
-    }
-}
+// sat(a - b) on four packed bytes
+__device__ __forceinline__ uint32_t sub_sat4(uint32_t a, uint32_t b) { return __vsubus4(a, b); }
 
 template <int EPI, bool STATS>
 __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
@@ -79,6 +75,8 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(sS[1] + L.K1 * 128);       // 8 x 256, only with STATS
     __shared__ uint64_t bar_s[2], bar_c, bar_d1, bar_d2;
     __shared__ uint32_t s_tmem;
+    __shared__ TcJob s_jobs[MAX_JOBS];                   // the launch's page table and band-matrix pointers, read every tile
+    __shared__ const uint8_t* s_tabs[MAX_TABS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -87,114 +85,123 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
         tc::mbar_init_fence();
     }
     if (warp == 1) tc::tmem_alloc(&s_tmem, TMEM_COLS);
+    for (int i = tid; i < L.n_jobs; i += NT) s_jobs[i] = L.jobs[i];
+    for (int i = tid; i < L.n_tabs; i += NT) s_tabs[i] = L.tabs[i];
     if (STATS)
         for (int i = tid; i < 8 * 256; i += NT) s_hist[i] = 0;
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
-#define TC_CRUMB(v) do { if (L.dbg && blockIdx.x == 0 && tid == 0) { L.status[1] = (v); __threadfence_system(); } } while (0)
+#define TC_CRUMB(v) do { if (L.crumbs && blockIdx.x == 0 && warp == 0) { L.status[1] = (v); __threadfence_system(); } } while (0)
 #define TC_WAIT(bar, par, id) do { if (!tc::mbar_wait_bounded(bar, par)) { L.status[0] = (id); __threadfence_system(); __trap(); } } while (0)
+#define TC_STAMP(k) do { if (L.dbg && blockIdx.x == 0 && warp == 0 && it < 64) { long long c_ = clock64(); L.dbg[40960 + it * 32 + 2 * (k)] = (uint32_t)c_; L.dbg[40960 + it * 32 + 2 * (k) + 1] = (uint32_t)(c_ >> 32); } } while (0)
     TC_CRUMB(1);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // this warp's quarter of the TMEM lanes
     const int hf = warp >> 2;                                          // which half of the columns this warp drains
+    const int row = (warp & 3) * 32 + lane;                            // tile row of this thread
 
     // tile index -> (job, tx, ty); tiles of a page are numbered row-major so that neighbours share their halo in L2
-    int job = 0;
-    auto locate = [&](int t, int* tx, int* ty) {
-        while (job + 1 < L.n_jobs && t >= L.jobs[job + 1].tile_base) job++;
-        const int idx = t - L.jobs[job].tile_base, ntx = L.jobs[job].ntx;
-        *ty = idx / ntx; *tx = idx - *ty * ntx;
+    auto locate = [&](int t, int& j, int& tx, int& ty) {
+        while (j + 1 < L.n_jobs && t >= s_jobs[j + 1].tile_base) j++;
+        const int idx = t - s_jobs[j].tile_base, ntx = s_jobs[j].ntx;
+        ty = idx / ntx; tx = idx - ty * ntx;
     };
+
+    // operand descriptors: constant but for the start address (low word)
+    const uint64_t dT = tc::smem_desc_sw128(tc::smem_u32(sT), 16, 1024);
+    const uint64_t dS[2] = {tc::smem_desc_sw128(tc::smem_u32(sS[0]), (uint32_t)L.K1 * 128, 1024),
+                            tc::smem_desc_sw128(tc::smem_u32(sS[1]), (uint32_t)L.K1 * 128, 1024)};
+    const uint64_t dToe = tc::smem_desc_sw128(tc::smem_u32(sToe), 16, 1024);
 
     // issuing thread's state
     const uint8_t* cur_t = nullptr; const uint8_t* cur_toe = nullptr;
     uint32_t ph_c = 0, ph_s[2] = {0, 0};
-    int tx, ty;
-    if (tid == 0 && (int)blockIdx.x < L.total_tiles) {
-        locate(blockIdx.x, &tx, &ty);
+    int job = 0, tx = 0, ty = 0;
+    if ((int)blockIdx.x < L.total_tiles) locate(blockIdx.x, job, tx, ty);
+    if (warp == 0 && (int)blockIdx.x < L.total_tiles && tc::elect_one()) {
         tc::tmap_acquire(&L.maps[job]);
         tc::mbar_expect_tx(&bar_s[0], (uint32_t)L.K1 * 128);
         tc::tma_load_2d(sS[0], &L.maps[job], tx * L.NOUT - L.RL, ty * TM - L.R, &bar_s[0]);
         TC_CRUMB(12);
     }
-    uint32_t st_lo = 255, st_hi = 0, zero_count = 0;
-    uint32_t* st_minmax = nullptr; uint32_t* st_hist = nullptr;      // where the running statistics belong (one page at a time)
+    // running statistics of the current page (flushed when the page changes)
+    uint32_t mn2 = 0x00FF00FFu, mx2 = 0;                 // min / max as two 16-bit lanes
+    uint32_t* st_minmax = nullptr; uint32_t* st_hist = nullptr;
 
     auto flush_stats = [&]() {
         if (!STATS) return;
         if (st_minmax) {
+            uint32_t lo = min(mn2 & 0xFFFFu, mn2 >> 16), hi = max(mx2 & 0xFFFFu, mx2 >> 16);
             for (int o = 16; o; o >>= 1) {
-                st_lo = min(st_lo, __shfl_xor_sync(0xffffffffu, st_lo, o));
-                st_hi = max(st_hi, __shfl_xor_sync(0xffffffffu, st_hi, o));
+                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
             }
-            if (lane == 0 && st_lo <= st_hi) { atomicMin(&st_minmax[0], st_lo); atomicMax(&st_minmax[1], st_hi); }
+            if (lane == 0 && lo <= hi) { atomicMin(&st_minmax[0], lo); atomicMax(&st_minmax[1], hi); }
         }
         if (st_hist) {
-            for (int o = 16; o; o >>= 1) zero_count += __shfl_xor_sync(0xffffffffu, zero_count, o);
-            if (lane == 0 && zero_count) atomicAdd(&s_hist[warp * 256], zero_count);
             __syncthreads();
             for (int i = tid; i < 256; i += NT) {
-                uint32_t s = 0;
+                uint32_t sum = 0;
 #pragma unroll
-                for (int wv = 0; wv < 8; wv++) { s += s_hist[wv * 256 + i]; s_hist[wv * 256 + i] = 0; }
-                if (s) atomicAdd(&st_hist[i], s);
+                for (int wv = 0; wv < 8; wv++) { sum += s_hist[wv * 256 + i]; s_hist[wv * 256 + i] = 0; }
+                if (sum) atomicAdd(&st_hist[i], sum);
             }
             __syncthreads();
         }
-        st_lo = 255; st_hi = 0; zero_count = 0;
+        mn2 = 0x00FF00FFu; mx2 = 0;
     };
 
     int it = 0;
     for (int t = blockIdx.x; t < L.total_tiles; t += gridDim.x, it++) {
-        const int prev_job = job;
-        locate(t, &tx, &ty);
-        const TcJob J = L.jobs[job];
-        if (STATS && it > 0 && job != prev_job) flush_stats();        // statistics are per page
-        st_minmax = J.minmax; st_hist = J.hist;
+        TC_STAMP(11);
+        const TcJob& J = s_jobs[job];
+        if (STATS && (st_minmax != J.minmax || st_hist != J.hist)) {   // statistics are per page
+            if (it > 0) flush_stats();
+            st_minmax = J.minmax; st_hist = J.hist;
+        }
         const int x0 = tx * L.NOUT, y0 = ty * TM;
         const int stage = it & 1;
+        // the tile after this one (every thread keeps the same view)
+        const int tn = t + gridDim.x;
+        int jobn = job, txn = 0, tyn = 0;
+        if (tn < L.total_tiles) locate(tn, jobn, txn, tyn);
+        TC_STAMP(0);
 
-        if (tid == 0) {
-            const uint8_t* want_t = L.tabs[J.t_off + ty];
-            const uint8_t* want_toe = L.tabs[J.toe_off + tx];
+        if (warp == 0 && tc::elect_one()) {
+            const uint8_t* want_t = s_tabs[J.t_off + ty];
+            const uint8_t* want_toe = s_tabs[J.toe_off + tx];
             if (want_t != cur_t || want_toe != cur_toe) {
                 // every MMA that read the old matrices has completed (bar_d2 of the previous tile was waited for)
                 uint32_t bytes = 0;
                 if (want_t != cur_t) bytes += T_BYTES;
                 if (want_toe != cur_toe) bytes += (uint32_t)L.NOUT * 128;
                 tc::mbar_expect_tx(&bar_c, bytes);
-                TC_CRUMB(13);
                 if (want_t != cur_t) tc::bulk_load(sT, want_t, T_BYTES, &bar_c);
-                TC_CRUMB(14);
                 if (want_toe != cur_toe) tc::bulk_load(sToe, want_toe, (uint32_t)L.NOUT * 128, &bar_c);
                 cur_t = want_t; cur_toe = want_toe;
                 TC_WAIT(&bar_c, ph_c, 1); ph_c ^= 1;
                 TC_CRUMB(2);
             }
-            // prefetch the next tile's source window into the other stage (its last reader, MMA1 of the previous tile, is done)
-            const int tn = t + gridDim.x;
-            if (tn < L.total_tiles) {
-                int jn = job, ntx_, nty_;
-                const int keep = job;
-                locate(tn, &ntx_, &nty_);
-                jn = job; job = keep;
-                if (jn != job) tc::tmap_acquire(&L.maps[jn]);
-                tc::mbar_expect_tx(&bar_s[stage ^ 1], (uint32_t)L.K1 * 128);
-                tc::tma_load_2d(sS[stage ^ 1], &L.maps[jn], ntx_ * L.NOUT - L.RL, nty_ * TM - L.R, &bar_s[stage ^ 1]);
-            }
+            TC_STAMP(1);
             TC_WAIT(&bar_s[stage], ph_s[stage], 2); ph_s[stage] ^= 1;
             TC_CRUMB(3);
+            TC_STAMP(2);
             tc::fence_after_sync();
             // pass 1: D1[128 x 128] = Tv[128 x K1] * S[K1 x 128]
-            const uint32_t aT = tc::smem_u32(sT), aS = tc::smem_u32(sS[stage]);
-            for (int s = 0; s < L.K1 / 32; s++) {
-                const uint64_t ad = tc::smem_desc_sw128(aT + (s >> 2) * (TM * 128) + (s & 3) * 32, 16, 1024);
-                const uint64_t bd = tc::smem_desc_sw128(aS + s * 4096, (uint32_t)L.K1 * 128, 1024);
-                tc::mma_i8_ss(tmem + COL_D1, ad, bd, L.idesc1, s > 0);
-            }
+            const int nk = L.K1 >> 5;
+            for (int s = 0; s < nk; s++)
+                tc::mma_i8_ss(tmem + COL_D1, dT + (uint64_t)(((s >> 2) * (TM * 128) + (s & 3) * 32) >> 4), dS[stage] + (uint64_t)((s * 4096) >> 4),
+                              L.idesc1, s > 0);
             tc::mma_commit(&bar_d1);
             TC_CRUMB(4);
+            TC_STAMP(3);
+            // fetch the next tile's source window into the other stage (its last reader, MMA1 of the previous tile, is done)
+            if (tn < L.total_tiles) {
+                if (jobn != job) tc::tmap_acquire(&L.maps[jobn]);
+                tc::mbar_expect_tx(&bar_s[stage ^ 1], (uint32_t)L.K1 * 128);
+                tc::tma_load_2d(sS[stage ^ 1], &L.maps[jobn], txn * L.NOUT - L.RL, tyn * TM - L.R, &bar_s[stage ^ 1]);
+            }
         }
         __syncwarp();
 
@@ -202,6 +209,7 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
         TC_WAIT(&bar_d1, it & 1, 3);
         tc::fence_after_sync();
         TC_CRUMB(5);
+        TC_STAMP(4);
         {
             uint32_t lo[16], hi[16];
 #pragma unroll
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
                 tc::tmem_ld32(tmem + lane_base + COL_D1 + hf * 64 + part * 32, v);
                 tc::tmem_wait_ld();
                 if (L.dbg && t == 0)
-                    for (int i = 0; i < 32; i++) L.dbg[((warp & 3) * 32 + lane) * 128 + hf * 64 + part * 32 + i] = v[i];
+                    for (int i = 0; i < 32; i++) L.dbg[row * 128 + hf * 64 + part * 32 + i] = v[i];
 #pragma unroll
                 for (int g = 0; g < 8; g++) {
                     const uint32_t t1 = __byte_perm(v[4 * g], v[4 * g + 1], 0x5140);        // a0 b0 a1 b1
@@ -219,95 +227,144 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
                     hi[part * 8 + g] = __byte_perm(t1, t2, 0x7632);                         // a1 b1 c1 d1
                 }
             }
+            if (hf) {
+                // columns 126 and 127 carry no tap: they hold the rounding constant instead, 2 x (128 * 128) = 32768,
+                // against the two 128s in the band matrix's last two slots
+                lo[15] = (lo[15] & 0x0000FFFFu) | 0x80800000u;
+                hi[15] &= 0x0000FFFFu;
+            }
             TC_CRUMB(6);
             tc::tmem_st16(tmem + lane_base + COL_A2LO + hf * 16, lo);
             tc::tmem_st16(tmem + lane_base + COL_A2HI + hf * 16, hi);
             tc::tmem_wait_st();
             TC_CRUMB(7);
         }
+        TC_STAMP(5);
         tc::fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        TC_STAMP(6);
+        if (warp == 0 && tc::elect_one()) {
             tc::fence_after_sync();
             // pass 2: D2lo / D2hi [128 x NOUT] = A2lo / A2hi [128 x 128] (tensor memory) * Th[128 x NOUT]
-            const uint32_t aToe = tc::smem_u32(sToe);
-            for (int s = 0; s < NIN / 32; s++)
-                tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s * 8, tc::smem_desc_sw128(aToe + s * 32, 16, 1024), L.idesc2, s > 0);
-            for (int s = 0; s < NIN / 32; s++)
-                tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s * 8, tc::smem_desc_sw128(aToe + s * 32, 16, 1024), L.idesc2, s > 0);
+#pragma unroll
+            for (int s = 0; s < NIN / 32; s++) tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s * 8, dToe + (uint64_t)(s * 2), L.idesc2, s > 0);
+#pragma unroll
+            for (int s = 0; s < NIN / 32; s++) tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s * 8, dToe + (uint64_t)(s * 2), L.idesc2, s > 0);
             tc::mma_commit(&bar_d2);
             TC_CRUMB(8);
+            TC_STAMP(7);
         }
         __syncwarp();
 
         // ---- epilogue: this warp's 32 rows x its half of the NOUT columns, 16 columns at a time
         const int H0 = ((L.NOUT >> 1) + 15) & ~15;
         const int c_begin = hf ? H0 : 0, c_end = hf ? L.NOUT : H0;
-        const int y = y0 + (warp & 3) * 32 + lane;
+        const int y = y0 + row;
         const bool row_ok = y < J.h;
-        const uint8_t* srow = J.src + (size_t)y * J.src_pitch;
         uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
-        uint4 cw_next = make_uint4(0, 0, 0, 0);
-        if (EPI != DS_EPI_BLUR && row_ok && c_begin < c_end && x0 + c_begin < J.w)
-            cw_next = __ldg(reinterpret_cast<const uint4*>(srow + x0 + c_begin));
+        // the centre pixels are in the source tile: row `row + R`, 16-byte chunk (c + RL) / 16, swizzled by the row number
+        const int srow_i = row + L.R;
+        const uint8_t* s_center = sS[stage] + srow_i * 128;
+        const int chunk0 = L.RL >> 4, swz = srow_i & 7;
+        unsigned long long hc = 0;                        // this tile's counts of the values 0..7 (8 bits each)
         TC_WAIT(&bar_d2, it & 1, 4);
         tc::fence_after_sync();
         TC_CRUMB(9);
+        TC_STAMP(8);
         for (int c = c_begin; c < c_end; c += 16) {
             uint32_t lo[16], hi[16];
             tc::tmem_ld16(tmem + lane_base + COL_D2LO + c, lo);
             tc::tmem_ld16(tmem + lane_base + COL_D2HI + c, hi);
-            const uint4 cw = cw_next;
-            const int x = x0 + c;
-            if (EPI != DS_EPI_BLUR && row_ok && c + 16 < c_end && x + 16 < J.w)
-                cw_next = __ldg(reinterpret_cast<const uint4*>(srow + x + 16));
+            uint4 cw = make_uint4(0, 0, 0, 0);
+            if (EPI != DS_EPI_BLUR) cw = *reinterpret_cast<const uint4*>(s_center + ((((c >> 4) + chunk0) ^ swz) << 4));
             tc::tmem_wait_ld();
             if (L.dbg && t == 0)
                 for (int i = 0; i < 16; i++) {
-                    L.dbg[16384 + ((warp & 3) * 32 + lane) * 96 + c + i] = lo[i];
-                    L.dbg[16384 + 12288 + ((warp & 3) * 32 + lane) * 96 + c + i] = hi[i];
+                    L.dbg[16384 + row * 96 + c + i] = lo[i];
+                    L.dbg[16384 + 12288 + row * 96 + c + i] = hi[i];
                 }
+            const int x = x0 + c;
             if (row_ok && x < J.w) {
                 const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
                 uint32_t out[4];
-                const int nvalid = min(16, J.w - x);
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    uint32_t word = 0;
+                    // blurred byte = bits 16..23 of D2lo + 256 * D2hi (the rounding constant is already in the sum)
+                    const uint32_t e0 = lo[4 * g] + (hi[4 * g] << 8), e1 = lo[4 * g + 1] + (hi[4 * g + 1] << 8);
+                    const uint32_t e2 = lo[4 * g + 2] + (hi[4 * g + 2] << 8), e3 = lo[4 * g + 3] + (hi[4 * g + 3] << 8);
+                    const uint32_t bw = __byte_perm(__byte_perm(e0, e1, 0x0062), __byte_perm(e2, e3, 0x0062), 0x5410);
+                    if (EPI == DS_EPI_SUB) out[g] = sub_sat4(cws[g], bw);
+                    else if (EPI == DS_EPI_RSUB) out[g] = sub_sat4(bw, cws[g]);
+                    else if (EPI == DS_EPI_DIV) {
+                        uint32_t word = 0;
 #pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        const int i = 4 * g + b;
-                        const uint32_t blur = (lo[i] + (hi[i] << 8) + 32768u) >> 16;
-                        const uint32_t s = (cws[g] >> (8 * b)) & 0xFFu;
-                        const uint32_t v = epi_px(EPI, s, blur);
-                        word |= v << (8 * b);
-                        if (STATS && i < nvalid) {
-                            st_lo = min(st_lo, v); st_hi = max(st_hi, v);
-                            if (J.hist) {
-                                if (v) atomicAdd(&s_hist[warp * 256 + v], 1u); else zero_count++;
-                            }
-                        }
-                    }
-                    out[g] = word;
+                        for (int b = 0; b < 4; b++) word |= (uint32_t)ds_div255((uint8_t)(cws[g] >> (8 * b)), (uint8_t)(bw >> (8 * b))) << (8 * b);
+                        out[g] = word;
+                    } else out[g] = bw;
                 }
+                const int nvalid = min(16, J.w - x);
                 if (nvalid == 16) {
                     *reinterpret_cast<uint4*>(drow + x) = make_uint4(out[0], out[1], out[2], out[3]);
                 } else {                                    // last columns of the page: never write past its width
                     for (int i = 0; i < nvalid; i++) drow[x + i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
                 }
+                if (STATS) {
+                    if (nvalid < 16) {                      // keep the columns past the width out of the statistics
+                        const uint32_t fill = out[0] & 0xFFu;
+#pragma unroll
+                        for (int i = 1; i < 16; i++)
+                            if (i >= nvalid) out[i >> 2] = (out[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | (fill << (8 * (i & 3)));
+                    }
+                    if (J.minmax) {
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            const uint32_t ev = out[g] & 0x00FF00FFu, od = (out[g] >> 8) & 0x00FF00FFu;
+                            mn2 = __vminu2(__vminu2(mn2, ev), od);
+                            mx2 = __vmaxu2(__vmaxu2(mx2, ev), od);
+                        }
+                    }
+                    if (J.hist) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            if (i >= nvalid) break;
+                            const uint32_t v = (out[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                            if (v < 8) hc += 1ull << (8 * v);
+                            else atomicAdd(&s_hist[warp * 256 + v], 1u);
+                        }
+                    }
+                }
             }
             __syncwarp();                                   // the tensor-memory loads of the next round are warp-wide
         }
+        if (STATS && J.hist) {
+            // the small values of this tile: 8-bit counters -> 16-bit lanes, summed over the warp, 8 atomics per warp
+            uint32_t f0 = (uint32_t)(hc & 0xFF) | ((uint32_t)((hc >> 8) & 0xFF) << 16), f1 = (uint32_t)((hc >> 16) & 0xFF) | ((uint32_t)((hc >> 24) & 0xFF) << 16);
+            uint32_t f2 = (uint32_t)((hc >> 32) & 0xFF) | ((uint32_t)((hc >> 40) & 0xFF) << 16), f3 = (uint32_t)((hc >> 48) & 0xFF) | ((uint32_t)((hc >> 56) & 0xFF) << 16);
+            for (int o = 16; o; o >>= 1) {
+                f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+                f2 += __shfl_xor_sync(0xffffffffu, f2, o); f3 += __shfl_xor_sync(0xffffffffu, f3, o);
+            }
+            if (lane < 8) {
+                const uint32_t f = (lane >> 1) == 0 ? f0 : (lane >> 1) == 1 ? f1 : (lane >> 1) == 2 ? f2 : f3;
+                const uint32_t cnt = (f >> (16 * (lane & 1))) & 0xFFFFu;
+                if (cnt) atomicAdd(&s_hist[warp * 256 + lane], cnt);
+            }
+        }
         TC_CRUMB(10);
+        TC_STAMP(9);
         tc::fence_before_sync();
         __syncthreads();                                    // accumulators drained: the next tile may overwrite them
         tc::fence_after_sync();
+        TC_STAMP(10);
+        job = jobn; tx = txn; ty = tyn;
+        TC_STAMP(12);
     }
     flush_stats();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem, TMEM_COLS);
     TC_CRUMB(11);
 #undef TC_CRUMB
+#undef TC_STAMP
 #undef TC_WAIT
 }
 
@@ -344,7 +401,8 @@ size_t sw128_offset(int rows, int row, int k) {
 // Band matrix of one tile row (vertical, A operand [128 x K1]) or tile column (horizontal, B operand [NOUT x 128]):
 // entry (o, slot) = sum of the taps of output o0 + o that the border rule maps onto source index o0 - margin + slot.
 // Returns false when a folded coefficient does not fit 8 bits (images much smaller than the kernel).
-bool build_band(const int32_t* q, int k_eff, int R, int margin, int o0, int len, int n_out, int n_slots, int rows_alloc, uint8_t* img, size_t img_bytes) {
+bool build_band(const int32_t* q, int k_eff, int R, int margin, int o0, int len, int n_out, int n_slots, int rows_alloc, bool rounding_slots,
+                uint8_t* img, size_t img_bytes) {
     std::vector<int> acc((size_t)n_out * n_slots, 0);
     for (int o = 0; o < n_out; o++) {
         const int p = o0 + o;
@@ -356,6 +414,11 @@ bool build_band(const int32_t* q, int k_eff, int R, int margin, int o0, int len,
             acc[(size_t)o * n_slots + slot] += q[t];
         }
     }
+    if (rounding_slots)
+        for (int o = 0; o < n_out; o++) {
+            if (acc[(size_t)o * n_slots + n_slots - 2] || acc[(size_t)o * n_slots + n_slots - 1]) return false;
+            acc[(size_t)o * n_slots + n_slots - 2] = acc[(size_t)o * n_slots + n_slots - 1] = 128;    // x 128 in the A operand, twice = 32768
+        }
     memset(img, 0, img_bytes);
     for (int o = 0; o < n_out; o++)
         for (int s = 0; s < n_slots; s++) {
@@ -379,7 +442,7 @@ int get_variant(docscan_ctx* ctx, int axis, int k, const int32_t* q, int k_eff, 
     if (it == ctx->tc_tables.end()) {
         const size_t bytes = axis == 0 ? (size_t)T_BYTES : (size_t)TOE_BYTES;
         std::vector<uint8_t> img(bytes);
-        *ok = build_band(q, k_eff, R, axis == 0 ? R : RL, o0, len, n_out, n_slots, axis == 0 ? TM : NOUT, img.data(), bytes);
+        *ok = build_band(q, k_eff, R, axis == 0 ? R : RL, o0, len, n_out, n_slots, axis == 0 ? TM : NOUT, axis == 1, img.data(), bytes);
         if (!*ok) return DOCSCAN_OK;
         void* dev = nullptr;
         DS_CUDA(ctx, cudaMalloc(&dev, bytes));
@@ -409,7 +472,7 @@ int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
 // Returns false when the tensor-core path does not apply (the caller then runs blur.cu); otherwise *rc is the result.
 bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* jobs_host, int n, int* rc) {
     *rc = DOCSCAN_OK;
-    if (kind != 0 || k < 3 || n <= 0) return false;
+    if (kind != 0 || k < 3 || n <= 0 || n > MAX_JOBS) return false;
     if (epi != DS_EPI_BLUR && epi != DS_EPI_SUB && epi != DS_EPI_RSUB && epi != DS_EPI_DIV) return false;
     if (const char* e = getenv("DOCSCAN_TC")) if (atoi(e) == 0) return false;
     if (!encode_fn()) return false;
@@ -422,7 +485,8 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
     for (int i = 0; i < k_eff; i++) if (q[z + i] > 255) return false;
     const int K1 = (TM + 2 * R + 31) / 32 * 32;
     const int RL = (R + 15) & ~15;                      // the window's first column must sit on a 16-byte boundary of its row
-    const int NOUT = std::min(96, (NIN - RL - R) / 16 * 16);
+    // the last two source slots of a tile carry the rounding constant (see the kernel), so the taps must end before them
+    const int NOUT = std::min(96, (NIN - 2 - RL - R) / 16 * 16);
     if (NOUT < 16 || K1 > 256) return false;
     bool stats = false;
     for (int i = 0; i < n; i++) {
@@ -478,6 +542,7 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return false;
     }
+    if (tabs.size() > (size_t)MAX_TABS) return false;
     TcLaunch L{};
     void* dev = nullptr;
     // one upload: tensor maps (64-byte aligned) | jobs | variant pointers
@@ -491,7 +556,7 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
     L.maps = reinterpret_cast<const CUtensorMap*>(dev);
     L.jobs = reinterpret_cast<const TcJob*>((uint8_t*)dev + off_jobs);
     L.tabs = reinterpret_cast<const uint8_t* const*>((uint8_t*)dev + off_tabs);
-    L.n_jobs = n; L.total_tiles = total; L.R = R; L.RL = RL; L.K1 = K1; L.NOUT = NOUT;
+    L.n_jobs = n; L.n_tabs = (int)tabs.size(); L.total_tiles = total; L.R = R; L.RL = RL; L.K1 = K1; L.NOUT = NOUT;
     L.idesc1 = tc::idesc_i8(TM, NIN, 0, 0, 0, 1);
     L.idesc2 = tc::idesc_i8(TM, NOUT, 0, 0, 0, 0);
     if (!ctx->tc_status) {
@@ -500,13 +565,14 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
     }
     L.status = ctx->tc_status;
     const char* dbg_path = getenv("DOCSCAN_TC_DEBUG");
-    const size_t dbg_words = 16384 + 2 * 12288;
+    const size_t dbg_words = 16384 + 2 * 12288 + 64 * 32;      // first tile's accumulators + phase clocks of CTA 0's first 64 tiles
     if (dbg_path) {
         void* d = nullptr;
         *rc = ds_arena_alloc(ctx, dbg_words * 4, &d);
         if (*rc != DOCSCAN_OK) return true;
         cudaMemsetAsync(d, 0xEE, dbg_words * 4, ctx->stream);
         L.dbg = (uint32_t*)d;
+        L.crumbs = getenv("DOCSCAN_TC_CRUMBS") != nullptr;
     }
     const size_t smem = 1024 + T_BYTES + TOE_BYTES + 2 * (size_t)K1 * 128 + (stats ? 8 * 256 * 4 : 0);
     {

@@ -35,7 +35,7 @@ def expected_tile0(img, k):
     keff, R = len(q), len(q) // 2
     K1 = (128 + 2 * R + 31) // 32 * 32
     RL = (R + 15) // 16 * 16
-    NOUT = min(96, (128 - RL - R) // 16 * 16)
+    NOUT = min(96, (128 - 2 - RL - R) // 16 * 16)
     h, w = img.shape
     S = np.zeros((K1, 128), np.int64)
     for j in range(K1):
@@ -55,6 +55,9 @@ def expected_tile0(img, k):
             Th[n, reflect101(n + t - R, w) + RL] += q[t]
     D1 = T @ S
     lo, hi = D1 & 255, D1 >> 8
+    Th[:, 126:128] = 128                   # the rounding constant rides in the last two slots
+    lo[:, 126:128] = 128
+    hi[:, 126:128] = 0
     return D1, lo @ Th.T, hi @ Th.T, NOUT
 
 
@@ -95,7 +98,7 @@ def main():
             D1, D2lo, D2hi, NOUT = expected_tile0(img, k)
             show("D1  ", dbg[:16384].reshape(128, 128), D1)
             show("D2lo", dbg[16384:16384 + 12288].reshape(128, 96)[:, :NOUT], D2lo)
-            show("D2hi", dbg[16384 + 12288:].reshape(128, 96)[:, :NOUT], D2hi)
+            show("D2hi", dbg[16384 + 12288:16384 + 2 * 12288].reshape(128, 96)[:, :NOUT], D2hi)
     # the fused epilogues through the stage functions
     from smart_image_processing_b200 import DocScanner as DS
     g = rng.integers(0, 256, (700, 900), dtype=np.uint8)
