@@ -47,6 +47,13 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// 32-bit left shift with PTX semantics: shift amounts of 32 or more give 0 (undefined in C++)
+__device__ __forceinline__ uint32_t shl32(uint32_t v, uint32_t n) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -62,8 +62,13 @@ struct TcLaunch {
     uint32_t idesc1, idesc2;
 };
 
-// sat(a - b) on four packed bytes
-__device__ __forceinline__ uint32_t sub_sat4(uint32_t a, uint32_t b) { return __vsubus4(a, b); }
+// pass 1 of one tile: NK MMAs of K = 32 source rows each (K-major band matrix in two 128-byte blocks, MN-major source tile)
+template <int NK>
+__device__ __forceinline__ void issue_pass1(uint32_t d_tmem, uint64_t dT, uint64_t dS, uint32_t idesc) {
+#pragma unroll
+    for (int s = 0; s < NK; s++)
+        tc::mma_i8_ss(d_tmem, dT + (uint64_t)(((s >> 2) * (TM * 128) + (s & 3) * 32) >> 4), dS + (uint64_t)((s * 4096) >> 4), idesc, s > 0);
+}
 
 template <int EPI, bool STATS>
 __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
@@ -165,7 +170,6 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
         // the tile after this one (every thread keeps the same view)
         const int tn = t + gridDim.x;
         int jobn = job, txn = 0, tyn = 0;
-        if (tn < L.total_tiles) locate(tn, jobn, txn, tyn);
         TC_STAMP(0);
 
         if (warp == 0 && tc::elect_one()) {
@@ -189,21 +193,26 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
             TC_STAMP(2);
             tc::fence_after_sync();
             // pass 1: D1[128 x 128] = Tv[128 x K1] * S[K1 x 128]
-            const int nk = L.K1 >> 5;
-            for (int s = 0; s < nk; s++)
-                tc::mma_i8_ss(tmem + COL_D1, dT + (uint64_t)(((s >> 2) * (TM * 128) + (s & 3) * 32) >> 4), dS[stage] + (uint64_t)((s * 4096) >> 4),
-                              L.idesc1, s > 0);
+            switch (L.K1 >> 5) {
+                case 5: issue_pass1<5>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
+                case 6: issue_pass1<6>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
+                case 7: issue_pass1<7>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
+                default: issue_pass1<8>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
+            }
             tc::mma_commit(&bar_d1);
             TC_CRUMB(4);
             TC_STAMP(3);
             // fetch the next tile's source window into the other stage (its last reader, MMA1 of the previous tile, is done)
             if (tn < L.total_tiles) {
+                locate(tn, jobn, txn, tyn);
                 if (jobn != job) tc::tmap_acquire(&L.maps[jobn]);
                 tc::mbar_expect_tx(&bar_s[stage ^ 1], (uint32_t)L.K1 * 128);
                 tc::tma_load_2d(sS[stage ^ 1], &L.maps[jobn], txn * L.NOUT - L.RL, tyn * TM - L.R, &bar_s[stage ^ 1]);
             }
         }
         __syncwarp();
+        jobn = job;
+        if (tn < L.total_tiles) locate(tn, jobn, txn, tyn);           // while pass 1 runs
 
         // ---- D1 -> byte planes (A operands of pass 2): this warp's 32 rows x 64 columns
         TC_WAIT(&bar_d1, it & 1, 3);
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
         const int srow_i = row + L.R;
         const uint8_t* s_center = sS[stage] + srow_i * 128;
         const int chunk0 = L.RL >> 4, swz = srow_i & 7;
-        unsigned long long hc = 0;                        // this tile's counts of the values 0..7 (8 bits each)
+        uint32_t hc_ev = 0, hc_od = 0;                    // this tile's counts of the values 0..7 (8 bits each: even / odd bins)
         TC_WAIT(&bar_d2, it & 1, 4);
         tc::fence_after_sync();
         TC_CRUMB(9);
@@ -286,50 +295,64 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
             const int x = x0 + c;
             if (row_ok && x < J.w) {
                 const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
+                const int nvalid = min(16, J.w - x);
                 uint32_t out[4];
+                uint32_t dl[8];                             // results as 16-bit lanes: dl[2g] = (px 4g, px 4g+2), dl[2g+1] = (px 4g+1, px 4g+3)
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    // blurred byte = bits 16..23 of D2lo + 256 * D2hi (the rounding constant is already in the sum)
+                    // blurred byte = bits 16..23 of D2lo + 256 * D2hi (the rounding constant is already in the sum; bits 24.. are 0)
                     const uint32_t e0 = lo[4 * g] + (hi[4 * g] << 8), e1 = lo[4 * g + 1] + (hi[4 * g + 1] << 8);
                     const uint32_t e2 = lo[4 * g + 2] + (hi[4 * g + 2] << 8), e3 = lo[4 * g + 3] + (hi[4 * g + 3] << 8);
-                    const uint32_t bw = __byte_perm(__byte_perm(e0, e1, 0x0062), __byte_perm(e2, e3, 0x0062), 0x5410);
-                    if (EPI == DS_EPI_SUB) out[g] = sub_sat4(cws[g], bw);
-                    else if (EPI == DS_EPI_RSUB) out[g] = sub_sat4(bw, cws[g]);
-                    else if (EPI == DS_EPI_DIV) {
-                        uint32_t word = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; b++) word |= (uint32_t)ds_div255((uint8_t)(cws[g] >> (8 * b)), (uint8_t)(bw >> (8 * b))) << (8 * b);
-                        out[g] = word;
-                    } else out[g] = bw;
+                    const uint32_t b_ev = __byte_perm(e0, e2, 0x7632), b_od = __byte_perm(e1, e3, 0x7632);
+                    uint32_t d_ev = b_ev, d_od = b_od;
+                    if (EPI != DS_EPI_BLUR) {
+                        const uint32_t s_ev = __byte_perm(cws[g], 0u, 0x4240), s_od = __byte_perm(cws[g], 0u, 0x4341);
+                        if (EPI == DS_EPI_SUB) {            // sat(s - b) = max(s, b) - b, lane-wise without borrows
+                            d_ev = __vmaxu2(s_ev, b_ev) - b_ev; d_od = __vmaxu2(s_od, b_od) - b_od;
+                        } else if (EPI == DS_EPI_RSUB) {
+                            d_ev = __vmaxu2(s_ev, b_ev) - s_ev; d_od = __vmaxu2(s_od, b_od) - s_od;
+                        } else {                            // divide(s, b, 255) in fp32, per pixel
+                            d_ev = (uint32_t)ds_div255((uint8_t)s_ev, (uint8_t)b_ev) | ((uint32_t)ds_div255((uint8_t)(s_ev >> 16), (uint8_t)(b_ev >> 16)) << 16);
+                            d_od = (uint32_t)ds_div255((uint8_t)s_od, (uint8_t)b_od) | ((uint32_t)ds_div255((uint8_t)(s_od >> 16), (uint8_t)(b_od >> 16)) << 16);
+                        }
+                    }
+                    dl[2 * g] = d_ev; dl[2 * g + 1] = d_od;
+                    out[g] = __byte_perm(d_ev, d_od, 0x6240);
                 }
-                const int nvalid = min(16, J.w - x);
                 if (nvalid == 16) {
                     *reinterpret_cast<uint4*>(drow + x) = make_uint4(out[0], out[1], out[2], out[3]);
                 } else {                                    // last columns of the page: never write past its width
                     for (int i = 0; i < nvalid; i++) drow[x + i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
                 }
                 if (STATS) {
-                    if (nvalid < 16) {                      // keep the columns past the width out of the statistics
-                        const uint32_t fill = out[0] & 0xFFu;
-#pragma unroll
-                        for (int i = 1; i < 16; i++)
-                            if (i >= nvalid) out[i >> 2] = (out[i >> 2] & ~(0xFFu << (8 * (i & 3)))) | (fill << (8 * (i & 3)));
-                    }
-                    if (J.minmax) {
-#pragma unroll
-                        for (int g = 0; g < 4; g++) {
-                            const uint32_t ev = out[g] & 0x00FF00FFu, od = (out[g] >> 8) & 0x00FF00FFu;
-                            mn2 = __vminu2(__vminu2(mn2, ev), od);
-                            mx2 = __vmaxu2(__vmaxu2(mx2, ev), od);
-                        }
-                    }
-                    if (J.hist) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            if (i >= nvalid) break;
+                    if (nvalid < 16) {                      // rare: keep the columns past the width out of the statistics
+                        for (int i = 0; i < nvalid; i++) {
                             const uint32_t v = (out[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                            if (v < 8) hc += 1ull << (8 * v);
-                            else atomicAdd(&s_hist[warp * 256 + v], 1u);
+                            if (J.minmax) { mn2 = __vminu2(mn2, v | 0x00FF0000u); mx2 = __vmaxu2(mx2, v); }
+                            if (J.hist) atomicAdd(&s_hist[warp * 256 + v], 1u);
+                        }
+                    } else {
+                        if (J.minmax) {
+#pragma unroll
+                            for (int i = 0; i < 8; i++) { mn2 = __vminu2(mn2, dl[i]); mx2 = __vmaxu2(mx2, dl[i]); }
+                        }
+                        if (J.hist) {
+                            // values 0..7: 4-bit counters in two registers (a 32-bit shift by 32 or more gives 0, so larger values
+                            // add nothing here); at most 8 increments per field and chunk
+                            uint32_t h0 = 0, h1 = 0;
+#pragma unroll
+                            for (int i = 0; i < 8; i++) {
+                                const uint32_t d = dl[i];
+                                h0 += tc::shl32(1u, (d << 2) & 0x3FCu);
+                                h1 += tc::shl32(1u, (d >> 14) & 0x3FCu);
+                                if (d & 0x00F800F8u) {      // a value of 8 or more: the shared-memory histogram
+                                    const uint32_t v0 = d & 0xFFu, v1 = d >> 16;
+                                    if (v0 >= 8) atomicAdd(&s_hist[warp * 256 + v0], 1u);
+                                    if (v1 >= 8) atomicAdd(&s_hist[warp * 256 + v1], 1u);
+                                }
+                            }
+                            hc_ev += (h0 & 0x0F0F0F0Fu) + (h1 & 0x0F0F0F0Fu);               // bins 0, 2, 4, 6 (8 bits each)
+                            hc_od += ((h0 >> 4) & 0x0F0F0F0Fu) + ((h1 >> 4) & 0x0F0F0F0Fu);  // bins 1, 3, 5, 7
                         }
                     }
                 }
@@ -338,8 +361,10 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
         }
         if (STATS && J.hist) {
             // the small values of this tile: 8-bit counters -> 16-bit lanes, summed over the warp, 8 atomics per warp
-            uint32_t f0 = (uint32_t)(hc & 0xFF) | ((uint32_t)((hc >> 8) & 0xFF) << 16), f1 = (uint32_t)((hc >> 16) & 0xFF) | ((uint32_t)((hc >> 24) & 0xFF) << 16);
-            uint32_t f2 = (uint32_t)((hc >> 32) & 0xFF) | ((uint32_t)((hc >> 40) & 0xFF) << 16), f3 = (uint32_t)((hc >> 48) & 0xFF) | ((uint32_t)((hc >> 56) & 0xFF) << 16);
+            uint32_t f0 = (hc_ev & 0xFFu) | ((hc_od & 0xFFu) << 16);                       // bins 0, 1
+            uint32_t f1 = ((hc_ev >> 8) & 0xFFu) | (((hc_od >> 8) & 0xFFu) << 16);         // bins 2, 3
+            uint32_t f2 = ((hc_ev >> 16) & 0xFFu) | (((hc_od >> 16) & 0xFFu) << 16);       // bins 4, 5
+            uint32_t f3 = (hc_ev >> 24) | ((hc_od >> 24) << 16);                           // bins 6, 7
             for (int o = 16; o; o >>= 1) {
                 f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o);
                 f2 += __shfl_xor_sync(0xffffffffu, f2, o); f3 += __shfl_xor_sync(0xffffffffu, f3, o);
