@@ -34,9 +34,12 @@ namespace {
 
 constexpr int TM = 128;          // output rows per tile (MMA M, TMEM lanes)
 constexpr int NIN = 128;         // input columns per tile (pass-1 N, pass-2 K)
-constexpr int NT = 256;
-constexpr int TMEM_COLS = 256;
-constexpr int COL_D1 = 0, COL_D2LO = 0, COL_D2HI = 96, COL_A2LO = 192, COL_A2HI = 224;
+constexpr int N_EPI_WARPS = 16;                  // drain / epilogue warps; warp 16 issues TMA and MMAs
+constexpr int NT = (N_EPI_WARPS + 1) * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int COL_D1 = 0, COL_A2LO = 128, COL_A2HI = 160, COL_D2LO = 192, COL_D2HI = 288;
+constexpr int NS = 3;                            // source-window stages: pass 1 of tile i+1 and the centre pixels of tile i are live together
+constexpr int TOE_SLOTS = 3;                     // cached pass-2 band matrices (left / interior / right)
 constexpr int T_BYTES = 2 * TM * 128;      // two 128-byte K blocks
 constexpr int TOE_BYTES = 96 * 128;
 constexpr int MAX_R = 48;
@@ -52,12 +55,15 @@ struct TcJob {
 
 struct TcLaunch {
     const TcJob* jobs;
-    const CUtensorMap* maps;
+    const CUtensorMap* maps;      // source planes (128-byte swizzle, box 128 x K1)
+    const CUtensorMap* dmaps;     // destination planes (no swizzle, box NOUT x 128)
     const uint8_t* const* tabs;
     uint32_t* dbg;               // debug dump of the first tile (DOCSCAN_TC_DEBUG), else null
     volatile uint32_t* status;   // pinned host words: [0] = which wait timed out, [1] = progress of CTA 0 (debug runs)
     int n_jobs, n_tabs, total_tiles;
+    int flags;                   // debug: skip parts of the epilogue (DOCSCAN_TC_FLAGS), for timing experiments only
     int crumbs;                  // debug: CTA 0 reports its progress to status[1] (slow: a system-scope fence per phase)
+    int t_slots;                 // cached pass-1 band matrices (top / interior / bottom): 3 when shared memory allows, else 2
     int R, RL, K1, NOUT;         // RL: left margin of the source window (TMA needs its first byte 16-byte aligned)
     uint32_t idesc1, idesc2;
 };
@@ -70,23 +76,41 @@ __device__ __forceinline__ void issue_pass1(uint32_t d_tmem, uint64_t dT, uint64
         tc::mma_i8_ss(d_tmem, dT + (uint64_t)(((s >> 2) * (TM * 128) + (s & 3) * 32) >> 4), dS + (uint64_t)((s * 4096) >> 4), idesc, s > 0);
 }
 
+// One decoded tile: the issuing warp fills a ring of these 32 at a time (one lane per tile), so that nobody divides or walks
+// the page table on the critical path.
+struct TileRec { int job, tx, ty, pad; const uint8_t* t_mat; const uint8_t* toe_mat; };
+constexpr int REC_RING = 64;
+
+// One CTA per SM: 16 drain / epilogue warps (warp w: TMEM lane quarter w & 3, column group w >> 2) and one issuing warp that
+// runs the TMA loads and both tensor-core passes one tile ahead, so that pass 1 of tile i+1 executes behind the epilogue of
+// tile i.  No CTA-wide barrier inside the loop: the roles meet on mbarriers only.
+//   bar_s[st]  source window of a tile has landed in stage st          (TMA transaction bytes)        issuer waits
+//   bar_c      band matrices have landed                                (bulk-copy transaction bytes)  issuer waits
+//   bar_d1     pass 1 of tile i complete: D1 readable                   (tcgen05.commit)               drain warps wait
+//   bar_a2     all 16 warps have written their part of A2 for tile i (and so are done with D2 and the centre pixels of tile
+//              i-1 and with D1 of tile i)                               (16 arrivals)                  issuer waits
+//   bar_d2     pass 2 of tile i complete: D2lo / D2hi readable          (tcgen05.commit)               epilogue warps wait
 template <int EPI, bool STATS>
-__global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
+__global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sT = base;
-    uint8_t* sToe = sT + T_BYTES;
-    uint8_t* sS[2] = {sToe + TOE_BYTES, sToe + TOE_BYTES + L.K1 * 128};
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(sS[1] + L.K1 * 128);       // 8 x 256, only with STATS
-    __shared__ uint64_t bar_s[2], bar_c, bar_d1, bar_d2;
+    uint8_t* sT = base;                                            // L.t_slots band matrices of pass 1
+    uint8_t* sToe = sT + L.t_slots * T_BYTES;                      // TOE_SLOTS band matrices of pass 2
+    const uint32_t toe_bytes = (uint32_t)L.NOUT * 128;
+    uint8_t* sS = sToe + TOE_SLOTS * toe_bytes;                    // NS source windows
+    uint8_t* s_out = sS + NS * L.K1 * 128;                         // the tile's results, 128 dense rows of NOUT bytes: the source of the TMA store
+    const int out_pitch = L.NOUT;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_out + TM * out_pitch);   // 8 x 256, only with STATS
+    __shared__ uint64_t bar_s[NS], bar_c, bar_d1, bar_d2, bar_a2;
     __shared__ uint32_t s_tmem;
     __shared__ TcJob s_jobs[MAX_JOBS];                   // the launch's page table and band-matrix pointers, read every tile
     __shared__ const uint8_t* s_tabs[MAX_TABS];
+    __shared__ TileRec s_rec[REC_RING];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        tc::mbar_init(&bar_s[0], 1); tc::mbar_init(&bar_s[1], 1); tc::mbar_init(&bar_c, 1);
-        tc::mbar_init(&bar_d1, 1); tc::mbar_init(&bar_d2, 1);
+        for (int i = 0; i < NS; i++) tc::mbar_init(&bar_s[i], 1);
+        tc::mbar_init(&bar_c, 1); tc::mbar_init(&bar_d1, 1); tc::mbar_init(&bar_d2, 1); tc::mbar_init(&bar_a2, N_EPI_WARPS);
         tc::mbar_init_fence();
     }
     if (warp == 1) tc::tmem_alloc(&s_tmem, TMEM_COLS);
@@ -98,299 +122,360 @@ __global__ void __launch_bounds__(NT, 2) tc_blur_kernel(const __grid_constant__ 
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
-#define TC_CRUMB(v) do { if (L.crumbs && blockIdx.x == 0 && warp == 0) { L.status[1] = (v); __threadfence_system(); } } while (0)
+#define TC_CRUMB(v) do { if (L.crumbs && blockIdx.x == 0) { L.status[1] = (v); __threadfence_system(); } } while (0)
+#define TC_STAMP(who, i, k) do { if (L.dbg && blockIdx.x == 0 && (i) < 64) { long long c_ = clock64(); uint32_t* d_ = L.dbg + 40960 + (who) * 2048 + (i) * 32 + 2 * (k); d_[0] = (uint32_t)c_; d_[1] = (uint32_t)(c_ >> 32); } } while (0)
 #define TC_WAIT(bar, par, id) do { if (!tc::mbar_wait_bounded(bar, par)) { L.status[0] = (id); __threadfence_system(); __trap(); } } while (0)
-#define TC_STAMP(k) do { if (L.dbg && blockIdx.x == 0 && warp == 0 && it < 64) { long long c_ = clock64(); L.dbg[40960 + it * 32 + 2 * (k)] = (uint32_t)c_; L.dbg[40960 + it * 32 + 2 * (k) + 1] = (uint32_t)(c_ >> 32); } } while (0)
-    TC_CRUMB(1);
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // this warp's quarter of the TMEM lanes
-    const int hf = warp >> 2;                                          // which half of the columns this warp drains
-    const int row = (warp & 3) * 32 + lane;                            // tile row of this thread
 
-    // tile index -> (job, tx, ty); tiles of a page are numbered row-major so that neighbours share their halo in L2
-    auto locate = [&](int t, int& j, int& tx, int& ty) {
-        while (j + 1 < L.n_jobs && t >= s_jobs[j + 1].tile_base) j++;
-        const int idx = t - s_jobs[j].tile_base, ntx = s_jobs[j].ntx;
-        ty = idx / ntx; tx = idx - ty * ntx;
-    };
-
-    // operand descriptors: constant but for the start address (low word)
-    const uint64_t dT = tc::smem_desc_sw128(tc::smem_u32(sT), 16, 1024);
-    const uint64_t dS[2] = {tc::smem_desc_sw128(tc::smem_u32(sS[0]), (uint32_t)L.K1 * 128, 1024),
-                            tc::smem_desc_sw128(tc::smem_u32(sS[1]), (uint32_t)L.K1 * 128, 1024)};
-    const uint64_t dToe = tc::smem_desc_sw128(tc::smem_u32(sToe), 16, 1024);
-
-    // issuing thread's state
-    const uint8_t* cur_t = nullptr; const uint8_t* cur_toe = nullptr;
-    uint32_t ph_c = 0, ph_s[2] = {0, 0};
-    int job = 0, tx = 0, ty = 0;
-    if ((int)blockIdx.x < L.total_tiles) locate(blockIdx.x, job, tx, ty);
-    if (warp == 0 && (int)blockIdx.x < L.total_tiles && tc::elect_one()) {
-        tc::tmap_acquire(&L.maps[job]);
-        tc::mbar_expect_tx(&bar_s[0], (uint32_t)L.K1 * 128);
-        tc::tma_load_2d(sS[0], &L.maps[job], tx * L.NOUT - L.RL, ty * TM - L.R, &bar_s[0]);
-        TC_CRUMB(12);
-    }
-    // running statistics of the current page (flushed when the page changes)
-    uint32_t mn2 = 0x00FF00FFu, mx2 = 0;                 // min / max as two 16-bit lanes
-    uint32_t* st_minmax = nullptr; uint32_t* st_hist = nullptr;
-
-    auto flush_stats = [&]() {
-        if (!STATS) return;
-        if (st_minmax) {
-            uint32_t lo = min(mn2 & 0xFFFFu, mn2 >> 16), hi = max(mx2 & 0xFFFFu, mx2 >> 16);
-            for (int o = 16; o; o >>= 1) {
-                lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    // this CTA's tiles: a contiguous run of the launch's tile sequence (pages change once or twice per CTA, not every tile:
+    // a page change costs a tensor-map acquire and a flush of the page statistics)
+    const int per_cta = L.total_tiles / (int)gridDim.x, extra = L.total_tiles % (int)gridDim.x;
+    const int n_mine = per_cta + ((int)blockIdx.x < extra ? 1 : 0);
+    const int tile0 = (int)blockIdx.x * per_cta + min((int)blockIdx.x, extra);
+    if (warp == N_EPI_WARPS) {
+        // ================================================ issuing warp ================================================
+        // tile i of this CTA is global tile tile0 + i; tiles of a page are numbered row-major, so consecutive tiles share
+        // their halo columns through L2.  Lane l decodes tile i0 + l into the ring (32 tiles per refill).
+        int jc = 0;                                                // this lane's page cursor (its tiles only move forward)
+        auto refill = [&](int i0) {
+            const int i = i0 + lane;
+            if (i < n_mine) {
+                const int t = tile0 + i;
+                while (jc + 1 < L.n_jobs && t >= s_jobs[jc + 1].tile_base) jc++;
+                const TcJob& J = s_jobs[jc];
+                const int idx = t - J.tile_base;
+                TileRec r;
+                r.job = jc; r.ty = idx / J.ntx; r.tx = idx - r.ty * J.ntx; r.pad = 0;
+                r.t_mat = s_tabs[J.t_off + r.ty]; r.toe_mat = s_tabs[J.toe_off + r.tx];
+                s_rec[i % REC_RING] = r;
             }
-            if (lane == 0 && lo <= hi) { atomicMin(&st_minmax[0], lo); atomicMax(&st_minmax[1], hi); }
-        }
-        if (st_hist) {
-            __syncthreads();
-            for (int i = tid; i < 256; i += NT) {
-                uint32_t sum = 0;
-#pragma unroll
-                for (int wv = 0; wv < 8; wv++) { sum += s_hist[wv * 256 + i]; s_hist[wv * 256 + i] = 0; }
-                if (sum) atomicAdd(&st_hist[i], sum);
-            }
-            __syncthreads();
-        }
-        mn2 = 0x00FF00FFu; mx2 = 0;
-    };
+            __threadfence_block();
+            __syncwarp();
+        };
+        refill(0);
+        refill(32);
+        asm volatile("bar.arrive 2, %0;" ::"n"(NT) : "memory");       // the first records are there (the epilogue warps wait on this)
 
-    int it = 0;
-    for (int t = blockIdx.x; t < L.total_tiles; t += gridDim.x, it++) {
-        TC_STAMP(11);
-        const TcJob& J = s_jobs[job];
-        if (STATS && (st_minmax != J.minmax || st_hist != J.hist)) {   // statistics are per page
-            if (it > 0) flush_stats();
-            st_minmax = J.minmax; st_hist = J.hist;
-        }
-        const int x0 = tx * L.NOUT, y0 = ty * TM;
-        const int stage = it & 1;
-        // the tile after this one (every thread keeps the same view)
-        const int tn = t + gridDim.x;
-        int jobn = job, txn = 0, tyn = 0;
-        TC_STAMP(0);
+        // elected-lane state, all in registers
+        const uint8_t* t_tag0 = nullptr; const uint8_t* t_tag1 = nullptr; const uint8_t* t_tag2 = nullptr;
+        const uint8_t* e_tag0 = nullptr; const uint8_t* e_tag1 = nullptr; const uint8_t* e_tag2 = nullptr;
+        int t_rr = 0, e_rr = 0;                                    // round-robin replacement
+        uint32_t ph_c = 0, ph_s0 = 0, ph_s1 = 0, ph_s2 = 0;
+        int last_map = -1;
+        const uint32_t aT = tc::smem_u32(sT), aToe = tc::smem_u32(sToe), aS = tc::smem_u32(sS);
+        const uint32_t s_bytes = (uint32_t)L.K1 * 128;
+        const uint64_t dT0 = tc::smem_desc_sw128(aT, 16, 1024), dToe0 = tc::smem_desc_sw128(aToe, 16, 1024);
+        const uint64_t dS0 = tc::smem_desc_sw128(aS, s_bytes, 1024);
 
-        if (warp == 0 && tc::elect_one()) {
-            const uint8_t* want_t = s_tabs[J.t_off + ty];
-            const uint8_t* want_toe = s_tabs[J.toe_off + tx];
-            if (want_t != cur_t || want_toe != cur_toe) {
-                // every MMA that read the old matrices has completed (bar_d2 of the previous tile was waited for)
-                uint32_t bytes = 0;
-                if (want_t != cur_t) bytes += T_BYTES;
-                if (want_toe != cur_toe) bytes += (uint32_t)L.NOUT * 128;
-                tc::mbar_expect_tx(&bar_c, bytes);
-                if (want_t != cur_t) tc::bulk_load(sT, want_t, T_BYTES, &bar_c);
-                if (want_toe != cur_toe) tc::bulk_load(sToe, want_toe, (uint32_t)L.NOUT * 128, &bar_c);
-                cur_t = want_t; cur_toe = want_toe;
-                TC_WAIT(&bar_c, ph_c, 1); ph_c ^= 1;
-                TC_CRUMB(2);
-            }
-            TC_STAMP(1);
-            TC_WAIT(&bar_s[stage], ph_s[stage], 2); ph_s[stage] ^= 1;
-            TC_CRUMB(3);
-            TC_STAMP(2);
+        // pass-1 band matrix `want` into a slot (returned); `keep` = slot an unfinished MMA may still be reading
+        auto ensure_t = [&](const uint8_t* want, int keep) {
+            if (want == t_tag0) return 0;
+            if (want == t_tag1) return 1;
+            if (L.t_slots > 2 && want == t_tag2) return 2;
+            int v = t_rr;
+            if (v == keep) v = (v + 1 == L.t_slots) ? 0 : v + 1;
+            t_rr = (v + 1 == L.t_slots) ? 0 : v + 1;
+            tc::mbar_expect_tx(&bar_c, T_BYTES);
+            tc::bulk_load(sT + (size_t)v * T_BYTES, want, T_BYTES, &bar_c);
+            TC_WAIT(&bar_c, ph_c, 1); ph_c ^= 1;
+            if (v == 0) t_tag0 = want; else if (v == 1) t_tag1 = want; else t_tag2 = want;
+            return v;
+        };
+        auto ensure_toe = [&](const uint8_t* want, int keep) {
+            if (want == e_tag0) return 0;
+            if (want == e_tag1) return 1;
+            if (want == e_tag2) return 2;
+            int v = e_rr;
+            if (v == keep) v = (v + 1 == TOE_SLOTS) ? 0 : v + 1;
+            e_rr = (v + 1 == TOE_SLOTS) ? 0 : v + 1;
+            tc::mbar_expect_tx(&bar_c, toe_bytes);
+            tc::bulk_load(sToe + (size_t)v * toe_bytes, want, toe_bytes, &bar_c);
+            TC_WAIT(&bar_c, ph_c, 1); ph_c ^= 1;
+            if (v == 0) e_tag0 = want; else if (v == 1) e_tag1 = want; else e_tag2 = want;
+            return v;
+        };
+        auto load_source = [&](int i) {
+            const TileRec r = s_rec[i % REC_RING];
+            if (r.job != last_map) { tc::tmap_acquire(&L.maps[r.job]); last_map = r.job; }
+            const int st = i % NS;
+            uint64_t* bar = &bar_s[st];
+            tc::mbar_expect_tx(bar, s_bytes);
+            tc::tma_load_2d(sS + (size_t)st * s_bytes, &L.maps[r.job], r.tx * L.NOUT - L.RL, r.ty * TM - L.R, bar);
+        };
+        auto pass1 = [&](int i, int t_slot) {
+            const int st = i % NS;
+            if (st == 0) { TC_WAIT(&bar_s[0], ph_s0, 2); ph_s0 ^= 1; }
+            else if (st == 1) { TC_WAIT(&bar_s[1], ph_s1, 2); ph_s1 ^= 1; }
+            else { TC_WAIT(&bar_s[2], ph_s2, 2); ph_s2 ^= 1; }
             tc::fence_after_sync();
-            // pass 1: D1[128 x 128] = Tv[128 x K1] * S[K1 x 128]
+            const uint64_t dT = dT0 + (uint64_t)((t_slot * T_BYTES) >> 4);
+            const uint64_t dS = dS0 + (uint64_t)((st * s_bytes) >> 4);
             switch (L.K1 >> 5) {
-                case 5: issue_pass1<5>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
-                case 6: issue_pass1<6>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
-                case 7: issue_pass1<7>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
-                default: issue_pass1<8>(tmem + COL_D1, dT, dS[stage], L.idesc1); break;
+                case 5: issue_pass1<5>(tmem + COL_D1, dT, dS, L.idesc1); break;
+                case 6: issue_pass1<6>(tmem + COL_D1, dT, dS, L.idesc1); break;
+                case 7: issue_pass1<7>(tmem + COL_D1, dT, dS, L.idesc1); break;
+                default: issue_pass1<8>(tmem + COL_D1, dT, dS, L.idesc1); break;
             }
             tc::mma_commit(&bar_d1);
-            TC_CRUMB(4);
-            TC_STAMP(3);
-            // fetch the next tile's source window into the other stage (its last reader, MMA1 of the previous tile, is done)
-            if (tn < L.total_tiles) {
-                locate(tn, jobn, txn, tyn);
-                if (jobn != job) tc::tmap_acquire(&L.maps[jobn]);
-                tc::mbar_expect_tx(&bar_s[stage ^ 1], (uint32_t)L.K1 * 128);
-                tc::tma_load_2d(sS[stage ^ 1], &L.maps[jobn], txn * L.NOUT - L.RL, tyn * TM - L.R, &bar_s[stage ^ 1]);
-            }
+        };
+
+        int t_slot = 0, toe_prev = -1;
+        if (n_mine > 0 && tc::elect_one()) {
+            load_source(0);
+            if (n_mine > 1) load_source(1);
+            t_slot = ensure_t(s_rec[0].t_mat, -1);
+            pass1(0, t_slot);
+            TC_CRUMB(2);
         }
         __syncwarp();
-        jobn = job;
-        if (tn < L.total_tiles) locate(tn, jobn, txn, tyn);           // while pass 1 runs
-
-        // ---- D1 -> byte planes (A operands of pass 2): this warp's 32 rows x 64 columns
-        TC_WAIT(&bar_d1, it & 1, 3);
-        tc::fence_after_sync();
-        TC_CRUMB(5);
-        TC_STAMP(4);
-        {
-            uint32_t lo[16], hi[16];
+        for (int i = 0; i < n_mine; i++) {
+            if ((i & 31) == 0 && i > 0) refill(i + 32);          // whole warp: tiles i+32 .. i+63 (their slots were read 32 rounds ago)
+            if (tc::elect_one()) {
+                TC_STAMP(1, i, 0);
+                // matrices this round needs: pass 2 of tile i, pass 1 of tile i+1 (fetched, if missing, while the warps drain D1)
+                const int toe_slot = ensure_toe(s_rec[i % REC_RING].toe_mat, toe_prev);
+                int t_next = t_slot;
+                if (i + 1 < n_mine) t_next = ensure_t(s_rec[(i + 1) % REC_RING].t_mat, t_slot);
+                TC_STAMP(1, i, 1);
+                TC_WAIT(&bar_a2, i & 1, 5);
+                tc::fence_after_sync();
+                TC_STAMP(1, i, 2);
+                // pass 2: D2lo / D2hi [128 x NOUT] = A2lo / A2hi [128 x 128] (tensor memory) * Th[128 x NOUT]
+                const uint64_t dToe = dToe0 + (uint64_t)((toe_slot * toe_bytes) >> 4);
 #pragma unroll
-            for (int part = 0; part < 2; part++) {
-                uint32_t v[32];
-                tc::tmem_ld32(tmem + lane_base + COL_D1 + hf * 64 + part * 32, v);
+                for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+#pragma unroll
+                for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                tc::mma_commit(&bar_d2);
+                TC_STAMP(1, i, 3);
+                if (i + 1 < n_mine) pass1(i + 1, t_next);       // runs behind pass 2 of tile i, under its epilogue
+                TC_STAMP(1, i, 4);
+                // stage (i + 2) % NS held tile i - 1, whose epilogue is over (bar_a2 of tile i): refill it
+                if (i + 2 < n_mine) load_source(i + 2);
+                TC_STAMP(1, i, 5);
+                toe_prev = toe_slot; t_slot = t_next;
+                TC_CRUMB(3);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ============================================= drain / epilogue warps =============================================
+        const int q = warp & 3, cg = warp >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;          // this warp's quarter of the TMEM lanes
+        const int row = q * 32 + lane;                                // tile row of this thread
+        // columns of the epilogue in units of 8, dealt to the four column groups as evenly as possible
+        const int units = L.NOUT >> 3;
+        const int u_begin = (units * cg) >> 2, u_end = (units * (cg + 1)) >> 2;
+        uint32_t mn2 = 0x00FF00FFu, mx2 = 0;                          // running min / max of the current page, two 16-bit lanes
+        uint32_t* st_minmax = nullptr; uint32_t* st_hist = nullptr;
+        uint32_t* my_hist = s_hist + (warp & 7) * 256;
+        int last_dmap = -1;
+        asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");            // the issuing warp has decoded the first tiles
+
+        auto flush_stats = [&]() {
+            if (!STATS) return;
+            if (st_minmax) {
+                uint32_t lo = min(mn2 & 0xFFFFu, mn2 >> 16), hi = max(mx2 & 0xFFFFu, mx2 >> 16);
+                for (int o = 16; o; o >>= 1) {
+                    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                }
+                if (lane == 0 && lo <= hi) { atomicMin(&st_minmax[0], lo); atomicMax(&st_minmax[1], hi); }
+            }
+            if (st_hist) {
+                asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");     // the 16 epilogue warps only
+                for (int i = tid; i < 256; i += N_EPI_WARPS * 32) {
+                    uint32_t sum = 0;
+#pragma unroll
+                    for (int wv = 0; wv < 8; wv++) { sum += s_hist[wv * 256 + i]; s_hist[wv * 256 + i] = 0; }
+                    if (sum) atomicAdd(&st_hist[i], sum);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
+            }
+            mn2 = 0x00FF00FFu; mx2 = 0;
+        };
+
+        for (int i = 0; i < n_mine; i++) {
+            const TileRec tr = s_rec[i % REC_RING];
+            // the page's fields into registers: the shared-memory stores below would otherwise force re-reads of the table
+            const int Jw = s_jobs[tr.job].w, Jh = s_jobs[tr.job].h, Jdp = s_jobs[tr.job].dst_pitch;
+            uint8_t* const Jdst = s_jobs[tr.job].dst;
+            uint32_t* const Jminmax = s_jobs[tr.job].minmax; uint32_t* const Jhist = s_jobs[tr.job].hist;
+            if (STATS && (st_minmax != Jminmax || st_hist != Jhist)) {   // statistics are per page
+                if (i > 0) flush_stats();
+                st_minmax = Jminmax; st_hist = Jhist;
+            }
+            const int x0 = tr.tx * L.NOUT, y0 = tr.ty * TM;
+            const bool first = L.dbg && blockIdx.x == 0 && i == 0;
+
+            if (tid == 0) TC_STAMP(0, i, 0);
+            // ---- D1 -> byte planes (A operands of pass 2): this warp's 32 rows x 32 columns
+            TC_WAIT(&bar_d1, i & 1, 3);
+            tc::fence_after_sync();
+            if (tid == 0) TC_STAMP(0, i, 1);
+            {
+                uint32_t v[32], lo[8], hi[8];
+                tc::tmem_ld32(tmem + lane_base + COL_D1 + cg * 32, v);
                 tc::tmem_wait_ld();
-                if (L.dbg && t == 0)
-                    for (int i = 0; i < 32; i++) L.dbg[row * 128 + hf * 64 + part * 32 + i] = v[i];
+                if (first)
+                    for (int k = 0; k < 32; k++) L.dbg[row * 128 + cg * 32 + k] = v[k];
 #pragma unroll
                 for (int g = 0; g < 8; g++) {
                     const uint32_t t1 = __byte_perm(v[4 * g], v[4 * g + 1], 0x5140);        // a0 b0 a1 b1
                     const uint32_t t2 = __byte_perm(v[4 * g + 2], v[4 * g + 3], 0x5140);    // c0 d0 c1 d1
-                    lo[part * 8 + g] = __byte_perm(t1, t2, 0x5410);                         // a0 b0 c0 d0
-                    hi[part * 8 + g] = __byte_perm(t1, t2, 0x7632);                         // a1 b1 c1 d1
+                    lo[g] = __byte_perm(t1, t2, 0x5410);                                    // a0 b0 c0 d0
+                    hi[g] = __byte_perm(t1, t2, 0x7632);                                    // a1 b1 c1 d1
                 }
+                if (cg == 3) {
+                    // columns 126 and 127 carry no tap: they hold the rounding constant instead, 2 x (128 * 128) = 32768,
+                    // against the two 128s in the band matrix's last two slots
+                    lo[7] = (lo[7] & 0x0000FFFFu) | 0x80800000u;
+                    hi[7] &= 0x0000FFFFu;
+                }
+                tc::tmem_st8(tmem + lane_base + COL_A2LO + cg * 8, lo);
+                tc::tmem_st8(tmem + lane_base + COL_A2HI + cg * 8, hi);
+                tc::tmem_wait_st();
             }
-            if (hf) {
-                // columns 126 and 127 carry no tap: they hold the rounding constant instead, 2 x (128 * 128) = 32768,
-                // against the two 128s in the band matrix's last two slots
-                lo[15] = (lo[15] & 0x0000FFFFu) | 0x80800000u;
-                hi[15] &= 0x0000FFFFu;
-            }
-            TC_CRUMB(6);
-            tc::tmem_st16(tmem + lane_base + COL_A2LO + hf * 16, lo);
-            tc::tmem_st16(tmem + lane_base + COL_A2HI + hf * 16, hi);
-            tc::tmem_wait_st();
-            TC_CRUMB(7);
-        }
-        TC_STAMP(5);
-        tc::fence_before_sync();
-        __syncthreads();
-        TC_STAMP(6);
-        if (warp == 0 && tc::elect_one()) {
-            tc::fence_after_sync();
-            // pass 2: D2lo / D2hi [128 x NOUT] = A2lo / A2hi [128 x 128] (tensor memory) * Th[128 x NOUT]
-#pragma unroll
-            for (int s = 0; s < NIN / 32; s++) tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s * 8, dToe + (uint64_t)(s * 2), L.idesc2, s > 0);
-#pragma unroll
-            for (int s = 0; s < NIN / 32; s++) tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s * 8, dToe + (uint64_t)(s * 2), L.idesc2, s > 0);
-            tc::mma_commit(&bar_d2);
-            TC_CRUMB(8);
-            TC_STAMP(7);
-        }
-        __syncwarp();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_a2);
+            if (tid == 0) TC_STAMP(0, i, 2);
 
-        // ---- epilogue: this warp's 32 rows x its half of the NOUT columns, 16 columns at a time
-        const int H0 = ((L.NOUT >> 1) + 15) & ~15;
-        const int c_begin = hf ? H0 : 0, c_end = hf ? L.NOUT : H0;
-        const int y = y0 + row;
-        const bool row_ok = y < J.h;
-        uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
-        // the centre pixels are in the source tile: row `row + R`, 16-byte chunk (c + RL) / 16, swizzled by the row number
-        const int srow_i = row + L.R;
-        const uint8_t* s_center = sS[stage] + srow_i * 128;
-        const int chunk0 = L.RL >> 4, swz = srow_i & 7;
-        uint32_t hc_ev = 0, hc_od = 0;                    // this tile's counts of the values 0..7 (8 bits each: even / odd bins)
-        TC_WAIT(&bar_d2, it & 1, 4);
-        tc::fence_after_sync();
-        TC_CRUMB(9);
-        TC_STAMP(8);
-        for (int c = c_begin; c < c_end; c += 16) {
-            uint32_t lo[16], hi[16];
-            tc::tmem_ld16(tmem + lane_base + COL_D2LO + c, lo);
-            tc::tmem_ld16(tmem + lane_base + COL_D2HI + c, hi);
-            uint4 cw = make_uint4(0, 0, 0, 0);
-            if (EPI != DS_EPI_BLUR) cw = *reinterpret_cast<const uint4*>(s_center + ((((c >> 4) + chunk0) ^ swz) << 4));
-            tc::tmem_wait_ld();
-            if (L.dbg && t == 0)
-                for (int i = 0; i < 16; i++) {
-                    L.dbg[16384 + row * 96 + c + i] = lo[i];
-                    L.dbg[16384 + 12288 + row * 96 + c + i] = hi[i];
+            // ---- epilogue: 32 rows x this column group's units of 8 columns, the next unit's accumulators in flight
+            const int y = y0 + row;
+            const bool row_ok = y < Jh;
+            // the centre pixels are in the source tile: row `row + R`, byte RL + column, 16-byte chunks swizzled by the row number
+            const int srow_i = row + L.R;
+            const uint8_t* s_center = sS + (size_t)(i % NS) * L.K1 * 128 + srow_i * 128;
+            const int swz = srow_i & 7;
+            uint32_t hc_ev = 0, hc_od = 0;                    // this tile's counts of the values 0..7 (8 bits each: even / odd bins)
+            TC_WAIT(&bar_d2, i & 1, 4);
+            tc::fence_after_sync();
+            if (tid == 0) TC_STAMP(0, i, 3);
+            // one unit of 8 columns: combine the two accumulators, apply the epilogue, store, update the statistics
+            auto work = [&](int u, const uint32_t* lo, const uint32_t* hi) {
+                const int c = u * 8, x = x0 + c;
+                uint2 cw = make_uint2(0, 0);
+                if (EPI != DS_EPI_BLUR && !(L.flags & 2)) {
+                    const int cb = L.RL + c;
+                    cw = *reinterpret_cast<const uint2*>(s_center + ((((cb >> 4) ^ swz) << 4) | (cb & 8)));
                 }
-            const int x = x0 + c;
-            if (row_ok && x < J.w) {
-                const uint32_t cws[4] = {cw.x, cw.y, cw.z, cw.w};
-                const int nvalid = min(16, J.w - x);
-                uint32_t out[4];
-                uint32_t dl[8];                             // results as 16-bit lanes: dl[2g] = (px 4g, px 4g+2), dl[2g+1] = (px 4g+1, px 4g+3)
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    // blurred byte = bits 16..23 of D2lo + 256 * D2hi (the rounding constant is already in the sum; bits 24.. are 0)
-                    const uint32_t e0 = lo[4 * g] + (hi[4 * g] << 8), e1 = lo[4 * g + 1] + (hi[4 * g + 1] << 8);
-                    const uint32_t e2 = lo[4 * g + 2] + (hi[4 * g + 2] << 8), e3 = lo[4 * g + 3] + (hi[4 * g + 3] << 8);
-                    const uint32_t b_ev = __byte_perm(e0, e2, 0x7632), b_od = __byte_perm(e1, e3, 0x7632);
-                    uint32_t d_ev = b_ev, d_od = b_od;
-                    if (EPI != DS_EPI_BLUR) {
-                        const uint32_t s_ev = __byte_perm(cws[g], 0u, 0x4240), s_od = __byte_perm(cws[g], 0u, 0x4341);
-                        if (EPI == DS_EPI_SUB) {            // sat(s - b) = max(s, b) - b, lane-wise without borrows
-                            d_ev = __vmaxu2(s_ev, b_ev) - b_ev; d_od = __vmaxu2(s_od, b_od) - b_od;
-                        } else if (EPI == DS_EPI_RSUB) {
-                            d_ev = __vmaxu2(s_ev, b_ev) - s_ev; d_od = __vmaxu2(s_od, b_od) - s_od;
-                        } else {                            // divide(s, b, 255) in fp32, per pixel
-                            d_ev = (uint32_t)ds_div255((uint8_t)s_ev, (uint8_t)b_ev) | ((uint32_t)ds_div255((uint8_t)(s_ev >> 16), (uint8_t)(b_ev >> 16)) << 16);
-                            d_od = (uint32_t)ds_div255((uint8_t)s_od, (uint8_t)b_od) | ((uint32_t)ds_div255((uint8_t)(s_od >> 16), (uint8_t)(b_od >> 16)) << 16);
-                        }
+                if (first)
+                    for (int k = 0; k < 8; k++) {
+                        L.dbg[16384 + row * 96 + c + k] = lo[k];
+                        L.dbg[16384 + 12288 + row * 96 + c + k] = hi[k];
                     }
-                    dl[2 * g] = d_ev; dl[2 * g + 1] = d_od;
-                    out[g] = __byte_perm(d_ev, d_od, 0x6240);
-                }
-                if (nvalid == 16) {
-                    *reinterpret_cast<uint4*>(drow + x) = make_uint4(out[0], out[1], out[2], out[3]);
-                } else {                                    // last columns of the page: never write past its width
-                    for (int i = 0; i < nvalid; i++) drow[x + i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
-                }
-                if (STATS) {
-                    if (nvalid < 16) {                      // rare: keep the columns past the width out of the statistics
-                        for (int i = 0; i < nvalid; i++) {
-                            const uint32_t v = (out[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                            if (J.minmax) { mn2 = __vminu2(mn2, v | 0x00FF0000u); mx2 = __vmaxu2(mx2, v); }
-                            if (J.hist) atomicAdd(&s_hist[warp * 256 + v], 1u);
-                        }
-                    } else {
-                        if (J.minmax) {
+                if (row_ok && x < Jw) {
+                    const uint32_t cws[2] = {cw.x, cw.y};
+                    const int nvalid = min(8, Jw - x);
+                    uint32_t out[2];
+                    uint32_t dl[4];                         // results as 16-bit lanes: dl[2g] = (px 4g, px 4g+2), dl[2g+1] = (px 4g+1, px 4g+3)
 #pragma unroll
-                            for (int i = 0; i < 8; i++) { mn2 = __vminu2(mn2, dl[i]); mx2 = __vmaxu2(mx2, dl[i]); }
-                        }
-                        if (J.hist) {
-                            // values 0..7: 4-bit counters in two registers (a 32-bit shift by 32 or more gives 0, so larger values
-                            // add nothing here); at most 8 increments per field and chunk
-                            uint32_t h0 = 0, h1 = 0;
-#pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                const uint32_t d = dl[i];
-                                h0 += tc::shl32(1u, (d << 2) & 0x3FCu);
-                                h1 += tc::shl32(1u, (d >> 14) & 0x3FCu);
-                                if (d & 0x00F800F8u) {      // a value of 8 or more: the shared-memory histogram
-                                    const uint32_t v0 = d & 0xFFu, v1 = d >> 16;
-                                    if (v0 >= 8) atomicAdd(&s_hist[warp * 256 + v0], 1u);
-                                    if (v1 >= 8) atomicAdd(&s_hist[warp * 256 + v1], 1u);
-                                }
+                    for (int g = 0; g < 2; g++) {
+                        // blurred byte = bits 16..23 of D2lo + 256 * D2hi (the rounding constant is already in the sum; bits 24.. are 0)
+                        const uint32_t e0 = lo[4 * g] + (hi[4 * g] << 8), e1 = lo[4 * g + 1] + (hi[4 * g + 1] << 8);
+                        const uint32_t e2 = lo[4 * g + 2] + (hi[4 * g + 2] << 8), e3 = lo[4 * g + 3] + (hi[4 * g + 3] << 8);
+                        const uint32_t b_ev = __byte_perm(e0, e2, 0x7632), b_od = __byte_perm(e1, e3, 0x7632);
+                        uint32_t d_ev = b_ev, d_od = b_od;
+                        if (EPI != DS_EPI_BLUR) {
+                            const uint32_t s_ev = __byte_perm(cws[g], 0u, 0x4240), s_od = __byte_perm(cws[g], 0u, 0x4341);
+                            if (EPI == DS_EPI_SUB) {        // sat(s - b) = max(s, b) - b, lane-wise without borrows
+                                d_ev = __vmaxu2(s_ev, b_ev) - b_ev; d_od = __vmaxu2(s_od, b_od) - b_od;
+                            } else if (EPI == DS_EPI_RSUB) {
+                                d_ev = __vmaxu2(s_ev, b_ev) - s_ev; d_od = __vmaxu2(s_od, b_od) - s_od;
+                            } else {                        // divide(s, b, 255) in fp32, per pixel
+                                d_ev = (uint32_t)ds_div255((uint8_t)s_ev, (uint8_t)b_ev) | ((uint32_t)ds_div255((uint8_t)(s_ev >> 16), (uint8_t)(b_ev >> 16)) << 16);
+                                d_od = (uint32_t)ds_div255((uint8_t)s_od, (uint8_t)b_od) | ((uint32_t)ds_div255((uint8_t)(s_od >> 16), (uint8_t)(b_od >> 16)) << 16);
                             }
-                            hc_ev += (h0 & 0x0F0F0F0Fu) + (h1 & 0x0F0F0F0Fu);               // bins 0, 2, 4, 6 (8 bits each)
-                            hc_od += ((h0 >> 4) & 0x0F0F0F0Fu) + ((h1 >> 4) & 0x0F0F0F0Fu);  // bins 1, 3, 5, 7
+                        }
+                        dl[2 * g] = d_ev; dl[2 * g + 1] = d_od;
+                        out[g] = __byte_perm(d_ev, d_od, 0x6240);
+                    }
+                    if (!(L.flags & 8)) *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
+                    if (STATS) {
+                        if (nvalid < 8) {                   // rare: keep the columns past the width out of the statistics
+                            for (int k = 0; k < nvalid; k++) {
+                                const uint32_t v = (out[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                                if (Jminmax) { mn2 = __vminu2(mn2, v | 0x00FF0000u); mx2 = __vmaxu2(mx2, v); }
+                                if (Jhist) atomicAdd(&my_hist[v], 1u);
+                            }
+                        } else {
+                            if (Jminmax && !(L.flags & 1)) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) { mn2 = __vminu2(mn2, dl[k]); mx2 = __vmaxu2(mx2, dl[k]); }
+                            }
+                            if (Jhist && !(L.flags & 4)) {
+                                // values 0..7: 4-bit counters in two registers (a 32-bit shift by 32 or more gives 0, so larger
+                                // values add nothing here); at most 4 increments per field and unit
+                                uint32_t h0 = 0, h1 = 0;
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const uint32_t d = dl[k];
+                                    h0 += tc::shl32(1u, (d << 2) & 0x3FCu);
+                                    h1 += tc::shl32(1u, (d >> 14) & 0x3FCu);
+                                    if (d & 0x00F800F8u) {  // a value of 8 or more: the shared-memory histogram
+                                        const uint32_t v0 = d & 0xFFu, v1 = d >> 16;
+                                        if (v0 >= 8) atomicAdd(&my_hist[v0], 1u);
+                                        if (v1 >= 8) atomicAdd(&my_hist[v1], 1u);
+                                    }
+                                }
+                                hc_ev += (h0 & 0x0F0F0F0Fu) + (h1 & 0x0F0F0F0Fu);               // bins 0, 2, 4, 6 (8 bits each)
+                                hc_od += ((h0 >> 4) & 0x0F0F0F0Fu) + ((h1 >> 4) & 0x0F0F0F0Fu);  // bins 1, 3, 5, 7
+                            }
                         }
                     }
                 }
+            };
+            if (tid == 0) tc::tma_store_wait_read();
+            asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");      // the previous tile has left the staging buffer
+            // both accumulators of this warp's columns in two wide loads (a TMEM load costs about the same whatever its width;
+            // the columns past this group's share belong to a neighbour or to nobody and are ignored)
+            uint32_t lo[32], hi[32];
+            tc::tmem_ld32(tmem + lane_base + COL_D2LO + u_begin * 8, lo);
+            tc::tmem_ld32(tmem + lane_base + COL_D2HI + u_begin * 8, hi);
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (u_begin + k < u_end) work(u_begin + k, lo + 8 * k, hi + 8 * k);
             }
-            __syncwarp();                                   // the tensor-memory loads of the next round are warp-wide
+            __syncwarp();
+            // ---- staging buffer -> global memory: one TMA store per tile (rows / columns outside the page are clipped by the
+            // tensor map, so nothing is ever written past the page's width or height)
+            tc::fence_async_smem();
+            asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
+            if (tid == 0 && !(L.flags & 16)) {
+                if (tr.job != last_dmap) { tc::tmap_acquire(&L.dmaps[tr.job]); last_dmap = tr.job; }
+                tc::tma_store_2d(&L.dmaps[tr.job], x0, y0, s_out);
+            }
+            if (tid == 0) TC_STAMP(0, i, 4);
+            if (STATS && Jhist) {
+                // the small values of this tile: 8-bit counters -> 16-bit lanes, summed over the warp, 8 atomics per warp
+                uint32_t f0 = (hc_ev & 0xFFu) | ((hc_od & 0xFFu) << 16);                       // bins 0, 1
+                uint32_t f1 = ((hc_ev >> 8) & 0xFFu) | (((hc_od >> 8) & 0xFFu) << 16);         // bins 2, 3
+                uint32_t f2 = ((hc_ev >> 16) & 0xFFu) | (((hc_od >> 16) & 0xFFu) << 16);       // bins 4, 5
+                uint32_t f3 = (hc_ev >> 24) | ((hc_od >> 24) << 16);                           // bins 6, 7
+                for (int o = 16; o; o >>= 1) {
+                    f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+                    f2 += __shfl_xor_sync(0xffffffffu, f2, o); f3 += __shfl_xor_sync(0xffffffffu, f3, o);
+                }
+                if (lane < 8) {
+                    const uint32_t f = (lane >> 1) == 0 ? f0 : (lane >> 1) == 1 ? f1 : (lane >> 1) == 2 ? f2 : f3;
+                    const uint32_t cnt = (f >> (16 * (lane & 1))) & 0xFFFFu;
+                    if (cnt) atomicAdd(&my_hist[lane], cnt);
+                }
+            }
+            if (tid == 0) TC_STAMP(0, i, 5);
+            tc::fence_before_sync();
         }
-        if (STATS && J.hist) {
-            // the small values of this tile: 8-bit counters -> 16-bit lanes, summed over the warp, 8 atomics per warp
-            uint32_t f0 = (hc_ev & 0xFFu) | ((hc_od & 0xFFu) << 16);                       // bins 0, 1
-            uint32_t f1 = ((hc_ev >> 8) & 0xFFu) | (((hc_od >> 8) & 0xFFu) << 16);         // bins 2, 3
-            uint32_t f2 = ((hc_ev >> 16) & 0xFFu) | (((hc_od >> 16) & 0xFFu) << 16);       // bins 4, 5
-            uint32_t f3 = (hc_ev >> 24) | ((hc_od >> 24) << 16);                           // bins 6, 7
-            for (int o = 16; o; o >>= 1) {
-                f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o);
-                f2 += __shfl_xor_sync(0xffffffffu, f2, o); f3 += __shfl_xor_sync(0xffffffffu, f3, o);
-            }
-            if (lane < 8) {
-                const uint32_t f = (lane >> 1) == 0 ? f0 : (lane >> 1) == 1 ? f1 : (lane >> 1) == 2 ? f2 : f3;
-                const uint32_t cnt = (f >> (16 * (lane & 1))) & 0xFFFFu;
-                if (cnt) atomicAdd(&s_hist[warp * 256 + lane], cnt);
-            }
-        }
-        TC_CRUMB(10);
-        TC_STAMP(9);
-        tc::fence_before_sync();
-        __syncthreads();                                    // accumulators drained: the next tile may overwrite them
-        tc::fence_after_sync();
-        TC_STAMP(10);
-        job = jobn; tx = txn; ty = tyn;
-        TC_STAMP(12);
+        if (n_mine > 0) flush_stats();
+        if (tid == 0) tc::tma_store_wait_all();
     }
-    flush_stats();
+    tc::fence_before_sync();
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc(tmem, TMEM_COLS);
     TC_CRUMB(11);
 #undef TC_CRUMB
-#undef TC_STAMP
 #undef TC_WAIT
+#undef TC_STAMP
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------------
@@ -485,7 +570,7 @@ int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
     static bool attr_done = false;          // per template instance; the attribute is per function and device
     (void)attr_done;
     DS_CUDA(ctx, cudaFuncSetAttribute(tc_blur_kernel<EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = std::min(L.total_tiles, 2 * ctx->sm_count);
+    int grid = std::min(L.total_tiles, ctx->sm_count);            // one CTA per SM (512 TMEM columns, ~210 KB of shared memory)
     if (const char* e = getenv("DOCSCAN_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
     tc_blur_kernel<EPI, STATS><<<grid, NT, smem, ctx->stream>>>(L);
     DS_CHECK_LAUNCH(ctx);
@@ -516,15 +601,14 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
     bool stats = false;
     for (int i = 0; i < n; i++) {
         const BlurJob& j = jobs_host[i];
-        const int w16 = (j.w + 15) & ~15;
         if (((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)j.src_pitch | (uintptr_t)j.dst_pitch) & 15) return false;
-        if (j.src_pitch < w16 || j.dst_pitch < w16 || j.w < 1 || j.h < 1) return false;
+        if (j.src_pitch < j.w || j.dst_pitch < j.w || j.w < 1 || j.h < 1) return false;
         stats = stats || j.minmax || j.hist;
     }
     // per-page geometry: tile counts, border variants of the two band matrices, tensor map of the source plane
     std::vector<TcJob> jobs(n);
     std::vector<const uint8_t*> tabs;
-    std::vector<CUtensorMap> maps(n);
+    std::vector<CUtensorMap> maps(2 * (size_t)n);          // [0, n): sources, [n, 2n): destinations
     std::map<std::pair<int, int>, std::pair<int, int>> geom;          // (w, h) -> (t_off, toe_off)
     int total = 0;
     double px = 0;
@@ -566,19 +650,26 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (cr != CUDA_SUCCESS) return false;
+        const cuuint64_t dstrides[1] = {(cuuint64_t)b.dst_pitch};
+        const cuuint32_t dbox[2] = {(cuuint32_t)NOUT, (cuuint32_t)TM};
+        const CUresult cr2 = encode_fn()(&maps[n + i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)b.dst, dims, dstrides, dbox, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr2 != CUDA_SUCCESS) return false;
     }
     if (tabs.size() > (size_t)MAX_TABS) return false;
     TcLaunch L{};
     void* dev = nullptr;
     // one upload: tensor maps (64-byte aligned) | jobs | variant pointers
-    const size_t off_jobs = sizeof(CUtensorMap) * n, off_tabs = off_jobs + ((sizeof(TcJob) * n + 63) & ~(size_t)63);
+    const size_t off_jobs = sizeof(CUtensorMap) * 2 * n, off_tabs = off_jobs + ((sizeof(TcJob) * n + 63) & ~(size_t)63);
     std::vector<uint8_t> blob(off_tabs + sizeof(void*) * tabs.size());
-    memcpy(blob.data(), maps.data(), sizeof(CUtensorMap) * n);
+    memcpy(blob.data(), maps.data(), sizeof(CUtensorMap) * 2 * n);
     memcpy(blob.data() + off_jobs, jobs.data(), sizeof(TcJob) * n);
     memcpy(blob.data() + off_tabs, tabs.data(), sizeof(void*) * tabs.size());
     *rc = ds_upload(ctx, blob.data(), blob.size(), &dev);
     if (*rc != DOCSCAN_OK) return true;
     L.maps = reinterpret_cast<const CUtensorMap*>(dev);
+    L.dmaps = L.maps + n;
     L.jobs = reinterpret_cast<const TcJob*>((uint8_t*)dev + off_jobs);
     L.tabs = reinterpret_cast<const uint8_t* const*>((uint8_t*)dev + off_tabs);
     L.n_jobs = n; L.n_tabs = (int)tabs.size(); L.total_tiles = total; L.R = R; L.RL = RL; L.K1 = K1; L.NOUT = NOUT;
@@ -590,7 +681,7 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
     }
     L.status = ctx->tc_status;
     const char* dbg_path = getenv("DOCSCAN_TC_DEBUG");
-    const size_t dbg_words = 16384 + 2 * 12288 + 64 * 32;      // first tile's accumulators + phase clocks of CTA 0's first 64 tiles
+    const size_t dbg_words = 16384 + 2 * 12288 + 2 * 2048;     // first tile's accumulators + phase clocks of CTA 0 (epilogue warp 0, issuer)
     if (dbg_path) {
         void* d = nullptr;
         *rc = ds_arena_alloc(ctx, dbg_words * 4, &d);
@@ -598,8 +689,11 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
         cudaMemsetAsync(d, 0xEE, dbg_words * 4, ctx->stream);
         L.dbg = (uint32_t*)d;
         L.crumbs = getenv("DOCSCAN_TC_CRUMBS") != nullptr;
+        if (const char* f = getenv("DOCSCAN_TC_FLAGS")) L.flags = atoi(f);
     }
-    const size_t smem = 1024 + T_BYTES + TOE_BYTES + 2 * (size_t)K1 * 128 + (stats ? 8 * 256 * 4 : 0);
+    const size_t smem_fixed = 1024 + (size_t)TOE_SLOTS * NOUT * 128 + (size_t)NS * K1 * 128 + (size_t)TM * NOUT + (stats ? 8 * 256 * 4 : 0);
+    L.t_slots = smem_fixed + 3 * (size_t)T_BYTES <= 218 * 1024 ? 3 : 2;      // + ~9 KB of static shared memory <= 227 KB
+    const size_t smem = smem_fixed + (size_t)L.t_slots * T_BYTES;
     {
         ProfScope prof(ctx, std::string("tc_blur_k") + std::to_string(k), 2.0 * px);
 #define DS_TC_CASE(E) case E: *rc = stats ? launch_tc<E, true>(ctx, L, smem) : launch_tc<E, false>(ctx, L, smem); break;

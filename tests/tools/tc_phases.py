@@ -1,5 +1,5 @@
-"""Per-phase clock counts of the tensor-core blur kernel (CTA 0, thread 0) on a big image.  Developer tool, run on a B200:
-    python tests/tools/tc_phases.py [k] [mode]      mode: blur | sub | ink"""
+"""Per-phase clock counts of the tensor-core blur kernel (CTA 0: epilogue warp 0 and the issuing warp) on a big image.
+Developer tool, run on a B200:   python tests/tools/tc_phases.py [k] [mode]      mode: blur | sub | ink"""
 import os
 import sys
 import tempfile
@@ -11,10 +11,24 @@ sys.path.insert(0, ROOT)
 from smart_image_processing_b200 import DocScanner as DS  # noqa: E402
 from smart_image_processing_b200 import ops  # noqa: E402
 
+
+def page_like(rng, h, w):
+    im = np.full((h, w), 205.0, np.float32)
+    for i in range(max(1, h // 14)):
+        y, x = 4 + 14 * i, 4
+        while x < w - 12:
+            ww = int(rng.integers(4, 40))
+            im[y:y + 7, x:x + ww] = rng.integers(15, 95)
+            x += ww + int(rng.integers(3, 14))
+    im = im * (0.55 + 0.45 * np.linspace(0, 1, w)[None, :]) + rng.normal(0, 3, (h, w))
+    return np.clip(im, 0, 255).astype(np.uint8)
+
+
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 23
 mode = sys.argv[2] if len(sys.argv) > 2 else "blur"
 rng = np.random.default_rng(0)
-img = rng.integers(0, 256, (8000, 8000), dtype=np.uint8)
+kind = sys.argv[3] if len(sys.argv) > 3 else "page"
+img = np.tile(page_like(rng, 2000, 2000), (4, 4)) if kind == "page" else np.clip(rng.normal(200, 3, (8000, 8000)), 0, 255).astype(np.uint8)
 ops.gaussian_blur(img, k)                                # warm-up (tables, arena)
 path = tempfile.NamedTemporaryFile(suffix=".bin", delete=False).name
 os.environ["DOCSCAN_TC_DEBUG"] = path
@@ -26,18 +40,14 @@ else:
     DS._compute_ink_mask(img, mask_blur_ksize=k)
 del os.environ["DOCSCAN_TC_DEBUG"]
 d = np.fromfile(path, np.uint32)
-st = d[40960:40960 + 64 * 32].reshape(64, 16, 2).astype(np.uint64)
-clk_all = (st[:, :, 0] | (st[:, :, 1] << np.uint64(32))).astype(np.int64)
-clk = clk_all[:, :11]
-valid = [i for i in range(64) if 0 < clk[i, 0] < clk[i, 10] < (1 << 62)]
-names = ["top->consts", "consts+prefetch->S landed", "S->MMA1 issued", "MMA1 issued->D1 ready", "D1 drain", "sync", "MMA2 issue",
-         "MMA2->D2 ready", "epilogue", "end sync"]
-print(f"k={k} mode={mode} tiles seen by CTA 0: {len(valid)}")
-rows = np.array([np.diff(clk[i]) for i in valid[1:]])
-for j, nm in enumerate(names):
-    print(f"  {nm:28s} mean {rows[:, j].mean():9.0f}  median {int(np.median(rows[:, j])):7d}  min {rows[:, j].min():7d}  max {rows[:, j].max():7d}")
-print(f"  tile total                   mean {np.mean([clk[i, 10] - clk[i, 0] for i in valid[1:]]):9.0f}")
-print(f"  loop top (stamp11) -> stamp0  mean {np.mean([clk_all[i, 0] - clk_all[i, 11] for i in valid[1:]]):9.0f}")
-print(f"  end sync -> loop bottom (12)  mean {np.mean([clk_all[i, 12] - clk_all[i, 10] for i in valid[1:]]):9.0f}")
-print(f"  bottom -> next top            mean {np.mean([clk_all[valid[n + 1], 11] - clk_all[valid[n], 12] for n in range(len(valid) - 1)]):9.0f}")
-print(f"  tile-to-tile                 mean {np.mean(np.diff([clk[i, 0] for i in valid])):9.0f}")
+print(f"k={k} mode={mode} image={kind}")
+for who, names in ((0, ["top->D1 ready", "drain+arrive", "wait D2", "epilogue units", "hist flush"]),
+                   (1, ["ensure matrices", "wait A2 (16 warps)", "pass 2 issue", "wait S + pass 1 issue", "next TMA"])):
+    st = d[40960 + who * 2048:40960 + (who + 1) * 2048].reshape(64, 16, 2).astype(np.uint64)
+    clk = (st[:, :, 0] | (st[:, :, 1] << np.uint64(32))).astype(np.int64)[:, :6]
+    valid = [i for i in range(64) if 0 < clk[i, 0] < clk[i, 5] < (1 << 62)]
+    rows = np.array([np.diff(clk[i]) for i in valid[2:-1]])
+    print(f" {'epilogue warp 0' if who == 0 else 'issuer'}: {len(valid)} tiles")
+    for j, nm in enumerate(names):
+        print(f"  {nm:26s} mean {rows[:, j].mean():8.0f}  median {int(np.median(rows[:, j])):6d}  min {rows[:, j].min():6d}  max {rows[:, j].max():6d}")
+    print(f"  tile-to-tile               mean {np.mean(np.diff([clk[i, 0] for i in valid[2:-1]])):8.0f}")
