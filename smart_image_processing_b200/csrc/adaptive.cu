@@ -8,6 +8,8 @@
 // Same marching layout as blur.cu: 128-column strips, 16 rows per step, fp32 ring of row-filtered
 // rows in shared memory; row pass register-blocked 16 outputs/thread, column pass one column and 16
 // rows per thread with the whole column window held in registers.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace {
@@ -330,6 +332,66 @@ __global__ void __launch_bounds__(128) adaptive_tail_kernel(const AdaptJob* __re
     }
 }
 
+// ---- exact evaluation of single pixels -------------------------------------------------------------------------------------
+// The tensor-core path (tcblur.cu) decides every pixel whose fixed-point mean is further from the rounding boundary than its
+// error bound and lists the others (about one in a thousand).  Those get cv2's exact fp32 value here, in cv2's operation
+// order: the same row chains (fma per tap; the scalar variant in the last w % 4 columns), the same column chain (symmetric pairs,
+// fused before column w - w % 8, mul+add from there on), the same kernel shrinking on 1-pixel axes.
+__device__ float exact_mean_px(const AdaptJob& J, const AdaptLaunch& L, int x, int y) {
+    const int r = L.r, k = L.k;
+    const int tail = (L.tail_compat && k >= 11) ? (J.w & 7) : 0;
+    const int xt_col = J.w - tail;
+    const int nt = tail >= 4 ? tail - 4 : tail;
+    const bool scalar_row = x >= J.w - nt;
+    const int first_fused = k - ((k - 1) & 3);
+    auto row_value = [&](int yy) -> float {
+        const uint8_t* rowp = J.src + (size_t)ds_clamp(yy, 0, J.h - 1) * J.src_pitch;
+        if (J.w == 1) return (float)rowp[x];
+        float a = __fmul_rn(L.gh[r], (float)rowp[ds_clamp(x - r, 0, J.w - 1)]);
+        if (scalar_row) {
+            int i = 1;
+            for (; i < first_fused; i++) a = __fadd_rn(a, __fmul_rn(L.gh[abs(i - r)], (float)rowp[ds_clamp(x - r + i, 0, J.w - 1)]));
+            for (; i < k; i++) a = __fmaf_rn((float)rowp[ds_clamp(x - r + i, 0, J.w - 1)], L.gh[abs(i - r)], a);
+        } else {
+            for (int i = 1; i < k; i++) a = __fmaf_rn((float)rowp[ds_clamp(x - r + i, 0, J.w - 1)], L.gh[abs(i - r)], a);
+        }
+        return a;
+    };
+    float m = row_value(y);
+    if (J.h == 1) return m;
+    m = __fmul_rn(L.gh[0], m);
+    const bool fused = x < xt_col;
+    for (int j = 1; j <= r; j++) {
+        const float pair = __fadd_rn(row_value(y + j), row_value(y - j));
+        m = fused ? __fmaf_rn(pair, L.gh[j], m) : __fadd_rn(m, __fmul_rn(L.gh[j], pair));
+    }
+    return m;
+}
+
+__device__ __forceinline__ void fix_one(const AdaptJob& J, const AdaptLaunch& L, int x, int y) {
+    const int mean = min(max(__float2int_rn(exact_mean_px(J, L, x, y)), 0), 255);
+    J.dst[(size_t)y * J.dst_pitch + x] = ((int)J.src[(size_t)y * J.src_pitch + x] - mean > -L.c_param) ? 255 : 0;
+}
+
+// the listed pixels (entry = job, y << 16 | x)
+__global__ void __launch_bounds__(128) adaptive_fix_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L,
+                                                           const uint2* __restrict__ list, const uint32_t* __restrict__ count, uint32_t cap) {
+    const uint32_t n = *count;
+    if (n > cap) return;                                     // the list overflowed: adaptive_fix_all_kernel redoes whole pages
+    for (uint32_t i = blockIdx.x * 128u + threadIdx.x; i < n; i += gridDim.x * 128u) {
+        const uint2 e = list[i];
+        fix_one(jobs[e.x], L, (int)(e.y & 0xFFFFu), (int)(e.y >> 16));
+    }
+}
+// only when the list overflowed (an image built to sit on the rounding boundary everywhere): every pixel, exactly
+__global__ void __launch_bounds__(128) adaptive_fix_all_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L,
+                                                               const uint32_t* __restrict__ count, uint32_t cap) {
+    if (*count <= cap) return;
+    const AdaptJob J = jobs[blockIdx.y];
+    const int npx = J.w * J.h;
+    for (int i = blockIdx.x * 128 + threadIdx.x; i < npx; i += gridDim.x * 128) fix_one(J, L, i % J.w, i / J.w);
+}
+
 // combined = max(ink_sub_n > t_sub, bh_n > t_bh) -> dilate rect 2x2 x iters (window {x-n..x} x {y-n..y},
 // out-of-image ignored) -> bin = base where combined else 255.  The normalise + threshold of both
 // branches is folded into the raw cut-offs computed by scalars.cu.
@@ -500,6 +562,48 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     docscan_gaussian_kernel_f32(k, g.data());
     for (int j = 0; j <= L.r; j++) L.gh[j] = g[L.r + j];     // the half kernel rides in the launch parameters
 
+    // ---- the tensor-core path: fixed-point mean + guard band, exact evaluation of the listed pixels (see tcblur.cu)
+    if (k <= 65 && n <= 64) {
+        std::vector<int32_t> w16(k);
+        double err = 0;                                      // sum |w / 65536 - g|: bound of the weight quantisation, per pass
+        for (int i = 0; i < k; i++) {
+            w16[i] = (int32_t)std::lround((double)g[i] * 65536.0);
+            err += std::fabs((double)w16[i] / 65536.0 - (double)g[i]);
+        }
+        // |fixed-point mean - cv2's fp32 mean| <= 255 * (2 err + err^2)   weights, both passes
+        //                                        + 2^-9                      row means kept in 8.8
+        //                                        + (2k + 4) * 255 * 2^-23    cv2's own fp32 roundings (k fma + k/2 add + k/2 fma)
+        //                                        + 2^-8                      margin (truncated low product, tie direction)
+        const double eps = 255.0 * (2.0 * err + err * err) + 1.0 / 512 + (2.0 * k + 4) * 255.0 / 8388608.0 + 1.0 / 256;
+        const int band = (int)std::ceil(eps * 65536.0);
+        double px_total = 0;
+        for (int i = 0; i < n; i++) px_total += (double)jobs_host[i].w * jobs_host[i].h;
+        const uint32_t cap = (uint32_t)std::max(4096.0, px_total / 16.0);
+        void* fl = nullptr; void* fc = nullptr;
+        DS_TRY(ds_arena_alloc(ctx, (size_t)cap * sizeof(uint2), &fl));
+        DS_TRY(ds_arena_alloc(ctx, 256, &fc));
+        DS_CUDA(ctx, cudaMemsetAsync(fc, 0, 4, ctx->stream));
+        int rc2 = DOCSCAN_OK;
+        if (k_tc_adaptive_jobs(ctx, k, c, w16.data(), band, jobs_host, n, (uint2*)fl, (uint32_t*)fc, cap, &rc2)) {
+            DS_TRY(rc2);
+            void* devj = nullptr;
+            DS_TRY(ds_upload(ctx, jobs_host, sizeof(AdaptJob) * n, &devj));
+            {
+                ProfScope prof(ctx, "adaptive_gauss_fix", 0);
+                adaptive_fix_kernel<<<4 * ctx->sm_count, 128, 0, ctx->stream>>>((const AdaptJob*)devj, L, (const uint2*)fl, (const uint32_t*)fc, cap);
+                DS_CHECK_LAUNCH(ctx);
+            }
+            adaptive_fix_all_kernel<<<dim3(64, n), 128, 0, ctx->stream>>>((const AdaptJob*)devj, L, (const uint32_t*)fc, cap);
+            DS_CHECK_LAUNCH(ctx);
+            if (getenv("DOCSCAN_TC_DEBUG")) {
+                uint32_t cnt = 0;
+                cudaMemcpyAsync(&cnt, fc, 4, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaStreamSynchronize(ctx->stream);
+                fprintf(stderr, "[tc debug] adaptive k=%d band=%d/65536 (eps %.4f) listed %u of %.0f px (cap %u)\n", k, band, eps, cnt, px_total, cap);
+            }
+            return DOCSCAN_OK;
+        }
+    }
     const AdaptGridInfo G{n * ((max_w + TW - 1) / TW), max_w, max_h, n, max(64, 4 * L.r)};
     const size_t smem = sizeof(float) * ((size_t)BR * L.spf + (size_t)ring_rows * RPF);
     void* dev = nullptr;

@@ -351,7 +351,7 @@ extern "C" int docscan_adaptive_threshold(docscan_ctx* ctx, const docscan_image*
                                           int cv_tail_compat, docscan_image* dst) {
     DS_ARGS2(src, dst, 1, 1, "adaptive_threshold");
     DS_TRY(same_size(ctx, src, dst, "adaptive_threshold"));
-    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst)));
+    DS_TRY(begin_call(ctx, host_bytes(src) + host_bytes(dst) + plane_bytes(src->width, src->height)));   // + the guard-band pixel list
     ArenaScope scope(ctx);
     std::vector<DImg> s(1), d(1);
     DS_TRY(ds_stage_in(ctx, src, &s[0]));
@@ -531,10 +531,10 @@ namespace {
 
 size_t page_scratch(const docscan_page& pg) {
     const int w = pg.binary.width, h = pg.binary.height;
-    if (std::isnan(pg.angle_deg)) return 16 * plane_bytes(w, h) + 8192 + k_skew_scratch_bytes(w, h, true) + 4096 +
+    if (std::isnan(pg.angle_deg)) return 17 * plane_bytes(w, h) + 8192 + k_skew_scratch_bytes(w, h, true) + 4096 +
                                          (pg.use_whole ? 64 * ((size_t)pg.src.width + pg.src.height + w + h) + 4096 : 0);
     size_t tables = pg.use_whole ? 64 * ((size_t)pg.src.width + pg.src.height + w + h) + 4096 : 0;    // resize tables
-    return 16 * plane_bytes(w, h) + 4096 + tables;
+    return 17 * plane_bytes(w, h) + 65536 + tables;
 }
 
 size_t page_staging(const docscan_page& pg) {

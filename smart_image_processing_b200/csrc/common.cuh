@@ -162,6 +162,7 @@ int k_otsu_plain(docscan_ctx*, PageScalars* s, int n, const int32_t* npix_dev);
 #define DS_EPI_RSUB 2      // dst = sat(blur - src)
 #define DS_EPI_DIV 3       // dst = divide(src, blur, 255)
 #define DS_EPI_ATHRESH 4   // box mean: dst = src - mean > -C ? 255 : 0
+#define DS_EPI_AGAUSS 5    // tensor-core path only: Gaussian local mean in 16.16 fixed point, threshold with a guard band
 struct BlurJob {
     const uint8_t* src; uint8_t* dst;
     int src_pitch, dst_pitch, w, h;
@@ -191,6 +192,9 @@ struct AdaptJob {
 };
 int k_adaptive_gauss_jobs(docscan_ctx*, int k, int c, int cv_tail_compat, const AdaptJob* jobs_host, int n,
                           int max_w, int max_h);
+// tcblur.cu : GAUSSIAN_C's local mean on the tensor cores with a guard band (see there); false = not applicable
+bool k_tc_adaptive_jobs(docscan_ctx*, int k, int c_param, const int32_t* w16, int band, const AdaptJob* jobs_host, int n, uint2* flag_list,
+                        uint32_t* flag_count, uint32_t flag_cap, int* rc);
 // mask + blend (DocScanner.py:207-212, 338-339)
 struct BlendJob {
     const uint8_t* ink_sub; const uint8_t* bh; const uint8_t* base; uint8_t* dst;

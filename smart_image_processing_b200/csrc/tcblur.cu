@@ -37,7 +37,11 @@ constexpr int NIN = 128;         // input columns per tile (pass-1 N, pass-2 K)
 constexpr int N_EPI_WARPS = 16;                  // drain / epilogue warps; warp 16 issues TMA and MMAs
 constexpr int NT = (N_EPI_WARPS + 1) * 32;
 constexpr int TMEM_COLS = 512;
+// TMEM columns.  Blur: D1 | A2lo A2hi | D2lo D2hi.  Adaptive threshold (16-bit weights = two byte planes, 8.8 row means = two byte
+// planes): D1h D1l | A2hi A2lo | D2a D2b D2c (products hi*hi, hi*lo + lo*hi, lo*lo).  D2 never overlaps D1: pass 1 of the next tile
+// runs under the epilogue of this one.
 constexpr int COL_D1 = 0, COL_A2LO = 128, COL_A2HI = 160, COL_D2LO = 192, COL_D2HI = 288;
+constexpr int COLA_D1H = 0, COLA_D1L = 128, COLA_A2HI = 256, COLA_A2LO = 288, COLA_D2A = 320, COLA_D2B = 384, COLA_D2C = 448;
 constexpr int NS = 3;                            // source-window stages: pass 1 of tile i+1 and the centre pixels of tile i are live together
 constexpr int TOE_SLOTS = 3;                     // cached pass-2 band matrices (left / interior / right)
 constexpr int T_BYTES = 2 * TM * 128;      // two 128-byte K blocks
@@ -61,6 +65,10 @@ struct TcLaunch {
     uint32_t* dbg;               // debug dump of the first tile (DOCSCAN_TC_DEBUG), else null
     volatile uint32_t* status;   // pinned host words: [0] = which wait timed out, [1] = progress of CTA 0 (debug runs)
     int n_jobs, n_tabs, total_tiles;
+    // adaptive threshold (EPI == DS_EPI_AGAUSS)
+    int c_param;                 // dst = src - mean > -c_param ? 255 : 0
+    int band;                    // guard band in 1/65536 grey levels: inside it the pixel goes to the exact evaluation
+    uint2* flag_list; uint32_t* flag_count; uint32_t flag_cap;
     int flags;                   // debug: skip parts of the epilogue (DOCSCAN_TC_FLAGS), for timing experiments only
     int crumbs;                  // debug: CTA 0 reports its progress to status[1] (slow: a system-scope fence per phase)
     int t_slots;                 // cached pass-1 band matrices (top / interior / bottom): 3 when shared memory allows, else 2
@@ -95,8 +103,10 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sT = base;                                            // L.t_slots band matrices of pass 1
-    uint8_t* sToe = sT + L.t_slots * T_BYTES;                      // TOE_SLOTS band matrices of pass 2
-    const uint32_t toe_bytes = (uint32_t)L.NOUT * 128;
+    constexpr bool ADAPT = EPI == DS_EPI_AGAUSS;
+    constexpr uint32_t t_bytes = ADAPT ? 2 * T_BYTES : T_BYTES;   // adaptive: high-byte plane, low-byte plane
+    uint8_t* sToe = sT + L.t_slots * t_bytes;                      // TOE_SLOTS band matrices of pass 2
+    const uint32_t toe_bytes = (uint32_t)L.NOUT * 128 * (ADAPT ? 2 : 1);
     uint8_t* sS = sToe + TOE_SLOTS * toe_bytes;                    // NS source windows
     uint8_t* s_out = sS + NS * L.K1 * 128;                         // the tile's results, 128 dense rows of NOUT bytes: the source of the TMA store
     const int out_pitch = L.NOUT;
@@ -159,6 +169,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
         const uint8_t* t_tag0 = nullptr; const uint8_t* t_tag1 = nullptr; const uint8_t* t_tag2 = nullptr;
         const uint8_t* e_tag0 = nullptr; const uint8_t* e_tag1 = nullptr; const uint8_t* e_tag2 = nullptr;
         int t_rr = 0, e_rr = 0;                                    // round-robin replacement
+        int p1_issued = 0;                                         // pass 1 launched for tiles 0 .. p1_issued - 1
         uint32_t ph_c = 0, ph_s0 = 0, ph_s1 = 0, ph_s2 = 0;
         int last_map = -1;
         const uint32_t aT = tc::smem_u32(sT), aToe = tc::smem_u32(sToe), aS = tc::smem_u32(sS);
@@ -172,10 +183,16 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
             if (want == t_tag1) return 1;
             if (L.t_slots > 2 && want == t_tag2) return 2;
             int v = t_rr;
-            if (v == keep) v = (v + 1 == L.t_slots) ? 0 : v + 1;
-            t_rr = (v + 1 == L.t_slots) ? 0 : v + 1;
-            tc::mbar_expect_tx(&bar_c, T_BYTES);
-            tc::bulk_load(sT + (size_t)v * T_BYTES, want, T_BYTES, &bar_c);
+            if (L.t_slots == 1) {
+                // a single slot (adaptive threshold: 64 KB per matrix pair): the pass 1 that may still be reading it must finish first
+                v = 0;
+                if (p1_issued > 0) TC_WAIT(&bar_d1, (p1_issued - 1) & 1, 6);
+            } else {
+                if (v == keep) v = (v + 1 == L.t_slots) ? 0 : v + 1;
+                t_rr = (v + 1 == L.t_slots) ? 0 : v + 1;
+            }
+            tc::mbar_expect_tx(&bar_c, t_bytes);
+            tc::bulk_load(sT + (size_t)v * t_bytes, want, t_bytes, &bar_c);
             TC_WAIT(&bar_c, ph_c, 1); ph_c ^= 1;
             if (v == 0) t_tag0 = want; else if (v == 1) t_tag1 = want; else t_tag2 = want;
             return v;
@@ -207,7 +224,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
             else if (st == 1) { TC_WAIT(&bar_s[1], ph_s1, 2); ph_s1 ^= 1; }
             else { TC_WAIT(&bar_s[2], ph_s2, 2); ph_s2 ^= 1; }
             tc::fence_after_sync();
-            const uint64_t dT = dT0 + (uint64_t)((t_slot * T_BYTES) >> 4);
+            const uint64_t dT = dT0 + (uint64_t)((t_slot * t_bytes) >> 4);
             const uint64_t dS = dS0 + (uint64_t)((st * s_bytes) >> 4);
             switch (L.K1 >> 5) {
                 case 5: issue_pass1<5>(tmem + COL_D1, dT, dS, L.idesc1); break;
@@ -215,7 +232,17 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 case 7: issue_pass1<7>(tmem + COL_D1, dT, dS, L.idesc1); break;
                 default: issue_pass1<8>(tmem + COL_D1, dT, dS, L.idesc1); break;
             }
+            if (ADAPT) {                                           // the low-byte plane of the weights into the second accumulator
+                const uint64_t dTl = dT + (uint64_t)(T_BYTES >> 4);
+                switch (L.K1 >> 5) {
+                    case 5: issue_pass1<5>(tmem + COLA_D1L, dTl, dS, L.idesc1); break;
+                    case 6: issue_pass1<6>(tmem + COLA_D1L, dTl, dS, L.idesc1); break;
+                    case 7: issue_pass1<7>(tmem + COLA_D1L, dTl, dS, L.idesc1); break;
+                    default: issue_pass1<8>(tmem + COLA_D1L, dTl, dS, L.idesc1); break;
+                }
+            }
             tc::mma_commit(&bar_d1);
+            p1_issued = i + 1;
         };
 
         int t_slot = 0, toe_prev = -1;
@@ -241,10 +268,23 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 TC_STAMP(1, i, 2);
                 // pass 2: D2lo / D2hi [128 x NOUT] = A2lo / A2hi [128 x 128] (tensor memory) * Th[128 x NOUT]
                 const uint64_t dToe = dToe0 + (uint64_t)((toe_slot * toe_bytes) >> 4);
+                if (!ADAPT) {
 #pragma unroll
-                for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
 #pragma unroll
-                for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                } else {
+                    // 16-bit row means x 16-bit weights as byte planes: D2a = hi * Whi, D2b = hi * Wlo + lo * Whi, D2c = lo * Wlo
+                    const uint64_t dWl = dToe + (uint64_t)(((uint32_t)L.NOUT * 128) >> 4);
+#pragma unroll
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COLA_D2A, tmem + COLA_A2HI + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+#pragma unroll
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COLA_D2B, tmem + COLA_A2HI + s2 * 8, dWl + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+#pragma unroll
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COLA_D2B, tmem + COLA_A2LO + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, 1);
+#pragma unroll
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COLA_D2C, tmem + COLA_A2LO + s2 * 8, dWl + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                }
                 tc::mma_commit(&bar_d2);
                 TC_STAMP(1, i, 3);
                 if (i + 1 < n_mine) pass1(i + 1, t_next);       // runs behind pass 2 of tile i, under its epilogue
@@ -315,6 +355,14 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
             {
                 uint32_t v[32], lo[8], hi[8];
                 tc::tmem_ld32(tmem + lane_base + COL_D1 + cg * 32, v);
+                if (ADAPT) {
+                    // row mean * 65536 = 256 * D1h + D1l (24 bits)  ->  8.8 fixed point, rounded
+                    uint32_t vl[32];
+                    tc::tmem_ld32(tmem + lane_base + COLA_D1L + cg * 32, vl);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int k = 0; k < 32; k++) v[k] = ((v[k] << 8) + vl[k] + 128u) >> 8;
+                }
                 tc::tmem_wait_ld();
                 if (first)
                     for (int k = 0; k < 32; k++) L.dbg[row * 128 + cg * 32 + k] = v[k];
@@ -325,14 +373,14 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                     lo[g] = __byte_perm(t1, t2, 0x5410);                                    // a0 b0 c0 d0
                     hi[g] = __byte_perm(t1, t2, 0x7632);                                    // a1 b1 c1 d1
                 }
-                if (cg == 3) {
+                if (!ADAPT && cg == 3) {
                     // columns 126 and 127 carry no tap: they hold the rounding constant instead, 2 x (128 * 128) = 32768,
                     // against the two 128s in the band matrix's last two slots
                     lo[7] = (lo[7] & 0x0000FFFFu) | 0x80800000u;
                     hi[7] &= 0x0000FFFFu;
                 }
-                tc::tmem_st8(tmem + lane_base + COL_A2LO + cg * 8, lo);
-                tc::tmem_st8(tmem + lane_base + COL_A2HI + cg * 8, hi);
+                tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2LO : COL_A2LO) + cg * 8, lo);
+                tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2HI : COL_A2HI) + cg * 8, hi);
                 tc::tmem_wait_st();
             }
             tc::fence_before_sync();
@@ -427,6 +475,48 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
             };
             if (tid == 0) tc::tma_store_wait_read();
             asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");      // the previous tile has left the staging buffer
+            if constexpr (ADAPT) {
+                // ---- adaptive threshold: mean * 65536 = 256 * D2a + D2b + D2c / 256 against (src + C - 0.5) * 65536
+                uint32_t A[16], B[16], Cc[16];
+                tc::tmem_ld16(tmem + lane_base + COLA_D2A + u_begin * 8, A);
+                tc::tmem_ld16(tmem + lane_base + COLA_D2B + u_begin * 8, B);
+                tc::tmem_ld16(tmem + lane_base + COLA_D2C + u_begin * 8, Cc);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int k2 = 0; k2 < 2; k2++) {
+                    const int u = u_begin + k2;
+                    if (u >= u_end) break;
+                    const int c = u * 8, x = x0 + c;
+                    const int cb = L.RL + c;
+                    const uint2 cw = *reinterpret_cast<const uint2*>(s_center + ((((cb >> 4) ^ swz) << 4) | (cb & 8)));
+                    if (first)
+                        for (int k = 0; k < 8; k++) {
+                            L.dbg[16384 + row * 96 + c + k] = A[8 * k2 + k];
+                            L.dbg[16384 + 12288 + row * 96 + c + k] = B[8 * k2 + k];
+                        }
+                    if (row_ok && x < Jw) {
+                        const uint32_t cws[2] = {cw.x, cw.y};
+                        uint32_t out[2] = {0, 0};
+                        uint32_t flagged = 0;
+#pragma unroll
+                        for (int p8 = 0; p8 < 8; p8++) {
+                            const int sp = (int)((cws[p8 >> 2] >> (8 * (p8 & 3))) & 0xFFu);
+                            const int V = (int)((A[8 * k2 + p8] << 8) + B[8 * k2 + p8] + (Cc[8 * k2 + p8] >> 8));
+                            const int diff = V - (((sp + L.c_param) << 16) - 32768);      // < 0: mean below the boundary -> 255
+                            if (diff < 0) out[p8 >> 2] |= 0xFFu << (8 * (p8 & 3));
+                            if (abs(diff) <= L.band && x + p8 < Jw) flagged |= 1u << p8;
+                        }
+                        *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
+                        while (flagged) {                   // rare: too close to the boundary for the fixed-point mean to decide
+                            const int p8 = __ffs(flagged) - 1;
+                            flagged &= flagged - 1;
+                            const uint32_t slot = atomicAdd(L.flag_count, 1u);
+                            if (slot < L.flag_cap) L.flag_list[slot] = make_uint2((uint32_t)tr.job, ((uint32_t)y << 16) | (uint32_t)(x + p8));
+                        }
+                    }
+                }
+                __syncwarp();
+            } else {
             // both accumulators of this warp's columns in two wide loads (a TMEM load costs about the same whatever its width;
             // the columns past this group's share belong to a neighbour or to nobody and are ignored)
             uint32_t lo[32], hi[32];
@@ -438,6 +528,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 if (u_begin + k < u_end) work(u_begin + k, lo + 8 * k, hi + 8 * k);
             }
             __syncwarp();
+            }
             // ---- staging buffer -> global memory: one TMA store per tile (rows / columns outside the page are clipped by the
             // tensor map, so nothing is ever written past the page's width or height)
             tc::fence_async_smem();
@@ -495,9 +586,10 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-int reflect101(int p, int len) {
+int border_index(int p, int len, int replicate) {
+    if (replicate) return std::min(std::max(p, 0), len - 1);
     if (len == 1) return 0;
-    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * len - 2 - p;      // BORDER_REFLECT_101
     return p;
 }
 
@@ -508,20 +600,31 @@ size_t sw128_offset(int rows, int row, int k) {
     return (size_t)blk * rows * 128 + (size_t)row * 128 + (size_t)(((kk >> 4) ^ (row & 7)) << 4) + (kk & 15);
 }
 
+// What one launch computes: the taps (integers), the border rule, and how the two passes are split into byte planes.
+struct TcSpec {
+    int mode;                 // 0: 8.8 Gaussian blur (1 plane per pass, rounding constant in two spare slots); 1: adaptive threshold (2 planes)
+    int k;                    // nominal kernel size (cache key)
+    const int32_t* taps; int k_eff, R;
+    int replicate;            // border rule: 0 BORDER_REFLECT_101, 1 BORDER_REPLICATE
+    int epi, c_param, band;
+};
+
 // Band matrix of one tile row (vertical, A operand [128 x K1]) or tile column (horizontal, B operand [NOUT x 128]):
 // entry (o, slot) = sum of the taps of output o0 + o that the border rule maps onto source index o0 - margin + slot.
-// Returns false when a folded coefficient does not fit 8 bits (images much smaller than the kernel).
-bool build_band(const int32_t* q, int k_eff, int R, int margin, int o0, int len, int n_out, int n_slots, int rows_alloc, bool rounding_slots,
-                uint8_t* img, size_t img_bytes) {
+// One byte plane (blur) or two (adaptive: high bytes, then low bytes, `plane_bytes` apart).  Returns false when a folded
+// coefficient does not fit (images much smaller than the kernel).
+bool build_band(const TcSpec& S, int margin, int o0, int len, int n_out, int n_slots, int rows_alloc, bool rounding_slots, uint8_t* img,
+                size_t plane_bytes) {
+    const int planes = S.mode == 1 ? 2 : 1;
     std::vector<int> acc((size_t)n_out * n_slots, 0);
     for (int o = 0; o < n_out; o++) {
         const int p = o0 + o;
         if (p >= len) break;
-        for (int t = 0; t < k_eff; t++) {
-            const int sp = reflect101(p + t - R, len);
+        for (int t = 0; t < S.k_eff; t++) {
+            const int sp = border_index(p + t - S.R, len, S.replicate);
             const int slot = sp - (o0 - margin);
             if (slot < 0 || slot >= n_slots) return false;
-            acc[(size_t)o * n_slots + slot] += q[t];
+            acc[(size_t)o * n_slots + slot] += S.taps[t];
         }
     }
     if (rounding_slots)
@@ -529,30 +632,31 @@ bool build_band(const int32_t* q, int k_eff, int R, int margin, int o0, int len,
             if (acc[(size_t)o * n_slots + n_slots - 2] || acc[(size_t)o * n_slots + n_slots - 1]) return false;
             acc[(size_t)o * n_slots + n_slots - 2] = acc[(size_t)o * n_slots + n_slots - 1] = 128;    // x 128 in the A operand, twice = 32768
         }
-    memset(img, 0, img_bytes);
+    memset(img, 0, plane_bytes * planes);
     for (int o = 0; o < n_out; o++)
         for (int s = 0; s < n_slots; s++) {
             const int v = acc[(size_t)o * n_slots + s];
-            if (v > 255) return false;
-            if (v) img[sw128_offset(rows_alloc, o, s)] = (uint8_t)v;
+            if (v >= (planes == 2 ? 65536 : 256)) return false;
+            if (!v) continue;
+            const size_t off = sw128_offset(rows_alloc, o, s);
+            if (planes == 1) img[off] = (uint8_t)v;
+            else { img[off] = (uint8_t)(v >> 8); img[plane_bytes + off] = (uint8_t)(v & 255); }
         }
     return true;
 }
 
-struct Variant { const uint8_t* dev; };
-
-// device copy of one band matrix, cached per context: key = (axis, k, top/left distance or -1, bottom/right distance or -1)
-int get_variant(docscan_ctx* ctx, int axis, int k, const int32_t* q, int k_eff, int R, int RL, int K1, int NOUT, int o0, int len, const uint8_t** out,
-                bool* ok) {
+// device copy of one band matrix, cached per context: key = (mode / axis, k, near-border distances or -1, tile geometry)
+int get_variant(docscan_ctx* ctx, const TcSpec& S, int axis, int RL, int K1, int NOUT, int o0, int len, const uint8_t** out, bool* ok) {
     const int n_out = axis == 0 ? TM : NOUT, n_slots = axis == 0 ? K1 : NIN;
-    const int a = (o0 - R < 0) ? o0 : -1;
-    const int b = (o0 + n_out - 1 + R > len - 1) ? len - o0 : -1;
-    const std::array<int, 6> key = {axis, k, a, b, NOUT, K1};
+    const int a = (o0 - S.R < 0) ? o0 : -1;
+    const int b = (o0 + n_out - 1 + S.R > len - 1) ? len - o0 : -1;
+    const std::array<int, 6> key = {S.mode * 2 + axis, S.k, a, b, NOUT, K1};
     auto it = ctx->tc_tables.find(key);
     if (it == ctx->tc_tables.end()) {
-        const size_t bytes = axis == 0 ? (size_t)T_BYTES : (size_t)TOE_BYTES;
+        const size_t plane = axis == 0 ? (size_t)T_BYTES : (size_t)NOUT * 128;
+        const size_t bytes = plane * (S.mode == 1 ? 2 : 1);
         std::vector<uint8_t> img(bytes);
-        *ok = build_band(q, k_eff, R, axis == 0 ? R : RL, o0, len, n_out, n_slots, axis == 0 ? TM : NOUT, axis == 1, img.data(), bytes);
+        *ok = build_band(S, axis == 0 ? S.R : RL, o0, len, n_out, n_slots, axis == 0 ? TM : NOUT, axis == 1 && S.mode == 0, img.data(), plane);
         if (!*ok) return DOCSCAN_OK;
         void* dev = nullptr;
         DS_CUDA(ctx, cudaMalloc(&dev, bytes));
@@ -567,8 +671,6 @@ int get_variant(docscan_ctx* ctx, int axis, int k, const int32_t* q, int k_eff, 
 
 template <int EPI, bool STATS>
 int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
-    static bool attr_done = false;          // per template instance; the attribute is per function and device
-    (void)attr_done;
     DS_CUDA(ctx, cudaFuncSetAttribute(tc_blur_kernel<EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(L.total_tiles, ctx->sm_count);            // one CTA per SM (512 TMEM columns, ~210 KB of shared memory)
     if (const char* e = getenv("DOCSCAN_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
@@ -577,35 +679,28 @@ int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
     return DOCSCAN_OK;
 }
 
-}  // namespace
-
-// Returns false when the tensor-core path does not apply (the caller then runs blur.cu); otherwise *rc is the result.
-bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* jobs_host, int n, int* rc) {
+// Tile geometry, band matrices, tensor maps, upload and launch.  false: not applicable (the caller runs the CUDA-core kernels).
+bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, const char* prof_name, uint2* flag_list, uint32_t* flag_count,
+            uint32_t flag_cap, int* rc) {
     *rc = DOCSCAN_OK;
-    if (kind != 0 || k < 3 || n <= 0 || n > MAX_JOBS) return false;
-    if (epi != DS_EPI_BLUR && epi != DS_EPI_SUB && epi != DS_EPI_RSUB && epi != DS_EPI_DIV) return false;
+    if (n <= 0 || n > MAX_JOBS || !encode_fn()) return false;
     if (const char* e = getenv("DOCSCAN_TC")) if (atoi(e) == 0) return false;
-    if (!encode_fn()) return false;
-    std::vector<int32_t> q(k);
-    if (docscan_gaussian_kernel_q8(k, q.data()) != DOCSCAN_OK) return false;
-    int z = 0;
-    while (z < k / 2 && q[z] == 0) z++;                 // zero tails of the quantised kernel
-    const int k_eff = k - 2 * z, R = k_eff / 2;
+    const int R = S.R;
     if (R < 1 || R > MAX_R) return false;
-    for (int i = 0; i < k_eff; i++) if (q[z + i] > 255) return false;
     const int K1 = (TM + 2 * R + 31) / 32 * 32;
     const int RL = (R + 15) & ~15;                      // the window's first column must sit on a 16-byte boundary of its row
-    // the last two source slots of a tile carry the rounding constant (see the kernel), so the taps must end before them
-    const int NOUT = std::min(96, (NIN - 2 - RL - R) / 16 * 16);
-    if (NOUT < 16 || K1 > 256) return false;
+    // blur: the last two source slots of a tile carry the rounding constant (see the kernel), so the taps must end before them;
+    // adaptive: three 64-column accumulators
+    const int NOUT = S.mode == 0 ? std::min(96, (NIN - 2 - RL - R) / 16 * 16) : std::min(64, (NIN - RL - R) / 16 * 16);
+    if (NOUT < 16 || K1 > 256 || (S.mode == 1 && NOUT != 64)) return false;
     bool stats = false;
     for (int i = 0; i < n; i++) {
         const BlurJob& j = jobs_host[i];
         if (((uintptr_t)j.src | (uintptr_t)j.dst | (uintptr_t)j.src_pitch | (uintptr_t)j.dst_pitch) & 15) return false;
-        if (j.src_pitch < j.w || j.dst_pitch < j.w || j.w < 1 || j.h < 1) return false;
+        if (j.src_pitch < j.w || j.dst_pitch < j.w || j.w < 1 || j.h < 1 || j.w > 65535 || j.h > 65535) return false;
         stats = stats || j.minmax || j.hist;
     }
-    // per-page geometry: tile counts, border variants of the two band matrices, tensor map of the source plane
+    // per-page geometry: tile counts, border variants of the two band matrices, tensor maps of the source and destination planes
     std::vector<TcJob> jobs(n);
     std::vector<const uint8_t*> tabs;
     std::vector<CUtensorMap> maps(2 * (size_t)n);          // [0, n): sources, [n, 2n): destinations
@@ -626,7 +721,7 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
             const int t_off = (int)tabs.size();
             for (int ty = 0; ty < j.nty; ty++) {
                 const uint8_t* p = nullptr; bool ok = false;
-                *rc = get_variant(ctx, 0, k, q.data() + z, k_eff, R, RL, K1, NOUT, ty * TM, b.h, &p, &ok);
+                *rc = get_variant(ctx, S, 0, RL, K1, NOUT, ty * TM, b.h, &p, &ok);
                 if (*rc != DOCSCAN_OK) return true;
                 if (!ok) return false;
                 tabs.push_back(p);
@@ -634,7 +729,7 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
             const int toe_off = (int)tabs.size();
             for (int tx = 0; tx < j.ntx; tx++) {
                 const uint8_t* p = nullptr; bool ok = false;
-                *rc = get_variant(ctx, 1, k, q.data() + z, k_eff, R, RL, K1, NOUT, tx * NOUT, b.w, &p, &ok);
+                *rc = get_variant(ctx, S, 1, RL, K1, NOUT, tx * NOUT, b.w, &p, &ok);
                 if (*rc != DOCSCAN_OK) return true;
                 if (!ok) return false;
                 tabs.push_back(p);
@@ -675,6 +770,7 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
     L.n_jobs = n; L.n_tabs = (int)tabs.size(); L.total_tiles = total; L.R = R; L.RL = RL; L.K1 = K1; L.NOUT = NOUT;
     L.idesc1 = tc::idesc_i8(TM, NIN, 0, 0, 0, 1);
     L.idesc2 = tc::idesc_i8(TM, NOUT, 0, 0, 0, 0);
+    L.c_param = S.c_param; L.band = S.band; L.flag_list = flag_list; L.flag_count = flag_count; L.flag_cap = flag_cap;
     if (!ctx->tc_status) {
         if (cudaHostAlloc((void**)&ctx->tc_status, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
         memset(ctx->tc_status, 0, 64);
@@ -691,17 +787,21 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
         L.crumbs = getenv("DOCSCAN_TC_CRUMBS") != nullptr;
         if (const char* f = getenv("DOCSCAN_TC_FLAGS")) L.flags = atoi(f);
     }
-    const size_t smem_fixed = 1024 + (size_t)TOE_SLOTS * NOUT * 128 + (size_t)NS * K1 * 128 + (size_t)TM * NOUT + (stats ? 8 * 256 * 4 : 0);
-    L.t_slots = smem_fixed + 3 * (size_t)T_BYTES <= 218 * 1024 ? 3 : 2;      // + ~9 KB of static shared memory <= 227 KB
-    const size_t smem = smem_fixed + (size_t)L.t_slots * T_BYTES;
+    const size_t planes = S.mode == 1 ? 2 : 1;
+    const size_t smem_fixed = 1024 + (size_t)TOE_SLOTS * NOUT * 128 * planes + (size_t)NS * K1 * 128 + (size_t)TM * NOUT + (stats ? 8 * 256 * 4 : 0);
+    // + ~9 KB of static shared memory <= 227 KB; the adaptive threshold's matrix pair is 64 KB: one slot
+    L.t_slots = S.mode == 1 ? 1 : (smem_fixed + 3 * (size_t)T_BYTES <= 218 * 1024 ? 3 : 2);
+    const size_t smem = smem_fixed + (size_t)L.t_slots * T_BYTES * planes;
     {
-        ProfScope prof(ctx, std::string("tc_blur_k") + std::to_string(k), 2.0 * px);
+        ProfScope prof(ctx, prof_name, 2.0 * px);
 #define DS_TC_CASE(E) case E: *rc = stats ? launch_tc<E, true>(ctx, L, smem) : launch_tc<E, false>(ctx, L, smem); break;
-        switch (epi) {
+        switch (S.epi) {
             DS_TC_CASE(DS_EPI_BLUR)
             DS_TC_CASE(DS_EPI_SUB)
             DS_TC_CASE(DS_EPI_RSUB)
             DS_TC_CASE(DS_EPI_DIV)
+            case DS_EPI_AGAUSS: *rc = launch_tc<DS_EPI_AGAUSS, false>(ctx, L, smem); break;
+            default: return false;
         }
 #undef DS_TC_CASE
     }
@@ -710,11 +810,51 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
         cudaMemcpyAsync(host.data(), L.dbg, dbg_words * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (FILE* f = fopen(dbg_path, "wb")) {
-            fprintf(stderr, "[tc debug] k=%d k_eff=%d R=%d RL=%d K1=%d NOUT=%d tiles=%d sync=%s timeout_id=%u progress=%u\n", k, k_eff, R, RL, K1, NOUT, total,
-                    cudaGetErrorString(e), ctx->tc_status[0], ctx->tc_status[1]);
+            fprintf(stderr, "[tc debug] %s k=%d k_eff=%d R=%d RL=%d K1=%d NOUT=%d tiles=%d sync=%s timeout_id=%u progress=%u\n", prof_name, S.k, S.k_eff, R, RL,
+                    K1, NOUT, total, cudaGetErrorString(e), ctx->tc_status[0], ctx->tc_status[1]);
             fwrite(host.data(), 4, dbg_words, f);
             fclose(f);
         }
     }
     return true;
+}
+
+}  // namespace
+
+// cv2.GaussianBlur (8.8 fixed point) + epilogue.  Returns false when the tensor-core path does not apply (the caller then runs
+// blur.cu); otherwise *rc is the result.
+bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* jobs_host, int n, int* rc) {
+    *rc = DOCSCAN_OK;
+    if (kind != 0 || k < 3) return false;
+    if (epi != DS_EPI_BLUR && epi != DS_EPI_SUB && epi != DS_EPI_RSUB && epi != DS_EPI_DIV) return false;
+    std::vector<int32_t> q(k);
+    if (docscan_gaussian_kernel_q8(k, q.data()) != DOCSCAN_OK) return false;
+    int z = 0;
+    while (z < k / 2 && q[z] == 0) z++;                 // zero tails of the quantised kernel
+    const int k_eff = k - 2 * z;
+    for (int i = 0; i < k_eff; i++) if (q[z + i] > 255) return false;
+    TcSpec S{};
+    S.mode = 0; S.k = k; S.taps = q.data() + z; S.k_eff = k_eff; S.R = k_eff / 2; S.replicate = 0; S.epi = epi;
+    const std::string name = std::string("tc_blur_k") + std::to_string(k);
+    return tc_run(ctx, S, jobs_host, n, name.c_str(), nullptr, nullptr, 0, rc);
+}
+
+// cv2.adaptiveThreshold(GAUSSIAN_C): the local mean in fixed point on the tensor cores, decided wherever it is further from the
+// rounding boundary than its own error bound; the pixels inside the guard band are listed for the exact evaluation
+// (adaptive.cu: k_adaptive_fix_flagged).  `w16` = the fp32 Gaussian taps * 65536, rounded; `band` in 1/65536 grey levels.
+bool k_tc_adaptive_jobs(docscan_ctx* ctx, int k, int c_param, const int32_t* w16, int band, const AdaptJob* jobs_host, int n, uint2* flag_list,
+                        uint32_t* flag_count, uint32_t flag_cap, int* rc) {
+    *rc = DOCSCAN_OK;
+    if (k < 3 || (k & 1) == 0) return false;
+    std::vector<BlurJob> bj(n);
+    for (int i = 0; i < n; i++) {
+        bj[i] = BlurJob{};
+        bj[i].src = jobs_host[i].src; bj[i].dst = jobs_host[i].dst; bj[i].src_pitch = jobs_host[i].src_pitch; bj[i].dst_pitch = jobs_host[i].dst_pitch;
+        bj[i].w = jobs_host[i].w; bj[i].h = jobs_host[i].h;
+        if (jobs_host[i].w == 1 || jobs_host[i].h == 1) return false;      // cv2 shrinks the kernel on 1-pixel axes
+    }
+    TcSpec S{};
+    S.mode = 1; S.k = k; S.taps = w16; S.k_eff = k; S.R = k / 2; S.replicate = 1; S.epi = DS_EPI_AGAUSS; S.c_param = c_param; S.band = band;
+    const std::string name = std::string("tc_adaptive_k") + std::to_string(k);
+    return tc_run(ctx, S, bj.data(), n, name.c_str(), flag_list, flag_count, flag_cap, rc);
 }
