@@ -337,59 +337,89 @@ __global__ void __launch_bounds__(128) adaptive_tail_kernel(const AdaptJob* __re
 // error bound and lists the others (about one in a thousand).  Those get cv2's exact fp32 value here, in cv2's operation
 // order: the same row chains (fma per tap; the scalar variant in the last w % 4 columns), the same column chain (symmetric pairs,
 // fused before column w - w % 8, mul+add from there on), the same kernel shrinking on 1-pixel axes.
-__device__ float exact_mean_px(const AdaptJob& J, const AdaptLaunch& L, int x, int y) {
+// One CTA per 128 x 64 tile that has listed pixels: the tile's source window (BORDER_REPLICATE resolved while loading) goes to
+// shared memory once; then one warp per listed pixel: lane l runs the row chains of window rows l and l + 32 (all taps fetched
+// before the chain starts), the row values meet in shared memory, and the column chain — 2r dependent operations — runs once.
+constexpr int FIX_WARPS = 4, FIX_TM = 128, FIX_WIN_W = 128;
+struct FixPage { int tile_base, ntx, nty; };
+__global__ void __launch_bounds__(FIX_WARPS * 32) adaptive_fix_tiles_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L,
+                                                                            const FixPage* __restrict__ pages, int n_pages,
+                                                                            const uint32_t* __restrict__ counts, const uint16_t* __restrict__ lists,
+                                                                            int RL, int NOUT) {
+    const int t = blockIdx.x;
+    const uint32_t cnt = counts[t];
+    if (cnt == 0) return;
+    extern __shared__ __align__(16) uint8_t s_win[];              // (128 + 2r) rows x 128 bytes, then FIX_WARPS x 2 * GMAX floats
+    int pg = 0;
+    while (pg + 1 < n_pages && t >= pages[pg + 1].tile_base) pg++;
+    const AdaptJob J = jobs[pg];
+    const int idx = t - pages[pg].tile_base, ty = idx / pages[pg].ntx, tx = idx - ty * pages[pg].ntx;
+    const int x0 = tx * NOUT, y0 = ty * FIX_TM;
     const int r = L.r, k = L.k;
+    const int rows = FIX_TM + 2 * r;
+    float* s_rows = reinterpret_cast<float*>(s_win + rows * FIX_WIN_W);
+    // window byte (j, c) = source pixel (clamp(y0 - r + j), clamp(x0 - RL + c))
+    for (int q = threadIdx.x; q < rows * (FIX_WIN_W / 16); q += FIX_WARPS * 32) {
+        const int j = q >> 3, ch = q & 7;
+        const uint8_t* rowp = J.src + (size_t)ds_clamp(y0 - r + j, 0, J.h - 1) * J.src_pitch;
+        const int gx = x0 - RL + ch * 16;
+        uint4 v;
+        if (gx >= 0 && gx + 16 <= J.w) v = __ldg(reinterpret_cast<const uint4*>(rowp + gx));
+        else {
+            uint32_t wv[4] = {0, 0, 0, 0};
+            for (int b2 = 0; b2 < 16; b2++) wv[b2 >> 2] |= (uint32_t)rowp[ds_clamp(gx + b2, 0, J.w - 1)] << (8 * (b2 & 3));
+            v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+        *reinterpret_cast<uint4*>(s_win + j * FIX_WIN_W + ch * 16) = v;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* my_rows = s_rows + warp * 2 * GMAX;
     const int tail = (L.tail_compat && k >= 11) ? (J.w & 7) : 0;
     const int xt_col = J.w - tail;
     const int nt = tail >= 4 ? tail - 4 : tail;
-    const bool scalar_row = x >= J.w - nt;
     const int first_fused = k - ((k - 1) & 3);
-    auto row_value = [&](int yy) -> float {
-        const uint8_t* rowp = J.src + (size_t)ds_clamp(yy, 0, J.h - 1) * J.src_pitch;
-        if (J.w == 1) return (float)rowp[x];
-        float a = __fmul_rn(L.gh[r], (float)rowp[ds_clamp(x - r, 0, J.w - 1)]);
-        if (scalar_row) {
-            int i = 1;
-            for (; i < first_fused; i++) a = __fadd_rn(a, __fmul_rn(L.gh[abs(i - r)], (float)rowp[ds_clamp(x - r + i, 0, J.w - 1)]));
-            for (; i < k; i++) a = __fmaf_rn((float)rowp[ds_clamp(x - r + i, 0, J.w - 1)], L.gh[abs(i - r)], a);
-        } else {
-            for (int i = 1; i < k; i++) a = __fmaf_rn((float)rowp[ds_clamp(x - r + i, 0, J.w - 1)], L.gh[abs(i - r)], a);
+    const bool all = cnt > TC_TILE_FLAG_CAP;                       // the list overflowed: every pixel of the tile
+    const uint32_t n = all ? (uint32_t)(FIX_TM * NOUT) : cnt;
+    for (uint32_t e = warp; e < n; e += FIX_WARPS) {
+        int lr, lc;
+        if (all) { lr = (int)(e / (uint32_t)NOUT); lc = (int)(e % (uint32_t)NOUT); }
+        else { const uint32_t code = lists[(size_t)t * TC_TILE_FLAG_CAP + e]; lr = (int)(code >> 6); lc = (int)(code & 63u); }
+        const int x = x0 + lc, y = y0 + lr;
+        if (x >= J.w || y >= J.h) continue;                        // (only on the overflow path)
+        const bool scalar_row = x >= J.w - nt;
+        for (int v = lane; v < k; v += 32) {                       // window row lr + v <-> source row clamp(y - r + v)
+            const uint8_t* wp = s_win + (lr + v) * FIX_WIN_W + (lc + RL - r);
+            float a = __fmul_rn(L.gh[r], (float)wp[0]);
+            if (scalar_row) {
+                int i2 = 1;
+                for (; i2 < first_fused; i2++) a = __fadd_rn(a, __fmul_rn(L.gh[abs(i2 - r)], (float)wp[i2]));
+                for (; i2 < k; i2++) a = __fmaf_rn((float)wp[i2], L.gh[abs(i2 - r)], a);
+            } else {
+                for (int i0 = 1; i0 < k; i0 += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) f[u] = (float)wp[min(i0 + u, k - 1)];
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (i0 + u < k) a = __fmaf_rn(f[u], L.gh[abs(i0 + u - r)], a);
+                }
+            }
+            my_rows[v] = a;
         }
-        return a;
-    };
-    float m = row_value(y);
-    if (J.h == 1) return m;
-    m = __fmul_rn(L.gh[0], m);
-    const bool fused = x < xt_col;
-    for (int j = 1; j <= r; j++) {
-        const float pair = __fadd_rn(row_value(y + j), row_value(y - j));
-        m = fused ? __fmaf_rn(pair, L.gh[j], m) : __fadd_rn(m, __fmul_rn(L.gh[j], pair));
+        __syncwarp();
+        if (lane == 0) {
+            float m = __fmul_rn(L.gh[0], my_rows[r]);
+            const bool fused = x < xt_col;
+            for (int j = 1; j <= r; j++) {
+                const float pair = __fadd_rn(my_rows[r + j], my_rows[r - j]);
+                m = fused ? __fmaf_rn(pair, L.gh[j], m) : __fadd_rn(m, __fmul_rn(L.gh[j], pair));
+            }
+            const int mean = min(max(__float2int_rn(m), 0), 255);
+            J.dst[(size_t)y * J.dst_pitch + x] = ((int)s_win[(lr + r) * FIX_WIN_W + lc + RL] - mean > -L.c_param) ? 255 : 0;
+        }
+        __syncwarp();
     }
-    return m;
-}
-
-__device__ __forceinline__ void fix_one(const AdaptJob& J, const AdaptLaunch& L, int x, int y) {
-    const int mean = min(max(__float2int_rn(exact_mean_px(J, L, x, y)), 0), 255);
-    J.dst[(size_t)y * J.dst_pitch + x] = ((int)J.src[(size_t)y * J.src_pitch + x] - mean > -L.c_param) ? 255 : 0;
-}
-
-// the listed pixels (entry = job, y << 16 | x)
-__global__ void __launch_bounds__(128) adaptive_fix_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L,
-                                                           const uint2* __restrict__ list, const uint32_t* __restrict__ count, uint32_t cap) {
-    const uint32_t n = *count;
-    if (n > cap) return;                                     // the list overflowed: adaptive_fix_all_kernel redoes whole pages
-    for (uint32_t i = blockIdx.x * 128u + threadIdx.x; i < n; i += gridDim.x * 128u) {
-        const uint2 e = list[i];
-        fix_one(jobs[e.x], L, (int)(e.y & 0xFFFFu), (int)(e.y >> 16));
-    }
-}
-// only when the list overflowed (an image built to sit on the rounding boundary everywhere): every pixel, exactly
-__global__ void __launch_bounds__(128) adaptive_fix_all_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L,
-                                                               const uint32_t* __restrict__ count, uint32_t cap) {
-    if (*count <= cap) return;
-    const AdaptJob J = jobs[blockIdx.y];
-    const int npx = J.w * J.h;
-    for (int i = blockIdx.x * 128 + threadIdx.x; i < npx; i += gridDim.x * 128) fix_one(J, L, i % J.w, i / J.w);
 }
 
 // combined = max(ink_sub_n > t_sub, bh_n > t_bh) -> dilate rect 2x2 x iters (window {x-n..x} x {y-n..y},
@@ -563,7 +593,10 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     for (int j = 0; j <= L.r; j++) L.gh[j] = g[L.r + j];     // the half kernel rides in the launch parameters
 
     // ---- the tensor-core path: fixed-point mean + guard band, exact evaluation of the listed pixels (see tcblur.cu)
-    if (k <= 65 && n <= 64) {
+    // Opt-in (DOCSCAN_TC_ADAPTIVE=1): bit-exact, but on pipeline pages 0.23 % of the pixels fall inside the guard band and their
+    // exact re-evaluation (about 1000 warp instructions each) costs more than the contraction saves (profiles/README.md).
+    const char* tc_env = getenv("DOCSCAN_TC_ADAPTIVE");
+    if (tc_env && atoi(tc_env) != 0 && k <= 65 && n <= 64) {
         std::vector<int32_t> w16(k);
         double err = 0;                                      // sum |w / 65536 - g|: bound of the weight quantisation, per pass
         for (int i = 0; i < k; i++) {
@@ -578,28 +611,31 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
         const int band = (int)std::ceil(eps * 65536.0);
         double px_total = 0;
         for (int i = 0; i < n; i++) px_total += (double)jobs_host[i].w * jobs_host[i].h;
-        const uint32_t cap = (uint32_t)std::max(4096.0, px_total / 16.0);
-        void* fl = nullptr; void* fc = nullptr;
-        DS_TRY(ds_arena_alloc(ctx, (size_t)cap * sizeof(uint2), &fl));
-        DS_TRY(ds_arena_alloc(ctx, 256, &fc));
-        DS_CUDA(ctx, cudaMemsetAsync(fc, 0, 4, ctx->stream));
+        TcFlagLists fl;
         int rc2 = DOCSCAN_OK;
-        if (k_tc_adaptive_jobs(ctx, k, c, w16.data(), band, jobs_host, n, (uint2*)fl, (uint32_t*)fc, cap, &rc2)) {
+        if (k_tc_adaptive_jobs(ctx, k, c, w16.data(), band, jobs_host, n, &fl, &rc2)) {
             DS_TRY(rc2);
-            void* devj = nullptr;
+            std::vector<FixPage> fp(n);
+            for (int i = 0; i < n; i++) { fp[i].tile_base = fl.tiles[i].tile_base; fp[i].ntx = fl.tiles[i].ntx; fp[i].nty = fl.tiles[i].nty; }
+            void* devj = nullptr; void* devp = nullptr;
             DS_TRY(ds_upload(ctx, jobs_host, sizeof(AdaptJob) * n, &devj));
+            DS_TRY(ds_upload(ctx, fp.data(), sizeof(FixPage) * n, &devp));
+            const size_t fsmem = (size_t)(FIX_TM + 2 * L.r) * FIX_WIN_W + sizeof(float) * FIX_WARPS * 2 * GMAX;
             {
                 ProfScope prof(ctx, "adaptive_gauss_fix", 0);
-                adaptive_fix_kernel<<<4 * ctx->sm_count, 128, 0, ctx->stream>>>((const AdaptJob*)devj, L, (const uint2*)fl, (const uint32_t*)fc, cap);
+                DS_CUDA(ctx, cudaFuncSetAttribute(adaptive_fix_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+                adaptive_fix_tiles_kernel<<<fl.n_tiles, FIX_WARPS * 32, fsmem, ctx->stream>>>((const AdaptJob*)devj, L, (const FixPage*)devp, n, fl.count,
+                                                                                               fl.list, fl.RL, fl.NOUT);
                 DS_CHECK_LAUNCH(ctx);
             }
-            adaptive_fix_all_kernel<<<dim3(64, n), 128, 0, ctx->stream>>>((const AdaptJob*)devj, L, (const uint32_t*)fc, cap);
-            DS_CHECK_LAUNCH(ctx);
             if (getenv("DOCSCAN_TC_DEBUG")) {
-                uint32_t cnt = 0;
-                cudaMemcpyAsync(&cnt, fc, 4, cudaMemcpyDeviceToHost, ctx->stream);
+                std::vector<uint32_t> cnt(fl.n_tiles);
+                cudaMemcpyAsync(cnt.data(), fl.count, 4 * (size_t)fl.n_tiles, cudaMemcpyDeviceToHost, ctx->stream);
                 cudaStreamSynchronize(ctx->stream);
-                fprintf(stderr, "[tc debug] adaptive k=%d band=%d/65536 (eps %.4f) listed %u of %.0f px (cap %u)\n", k, band, eps, cnt, px_total, cap);
+                unsigned long long tot = 0; uint32_t mx = 0, over = 0;
+                for (uint32_t v : cnt) { tot += v; mx = std::max(mx, v); over += v > TC_TILE_FLAG_CAP; }
+                fprintf(stderr, "[tc debug] adaptive k=%d band=%d/65536 (eps %.4f) listed %llu of %.0f px, %d tiles, max %u per tile, %u overflowed\n", k, band,
+                        eps, tot, px_total, fl.n_tiles, mx, over);
             }
             return DOCSCAN_OK;
         }

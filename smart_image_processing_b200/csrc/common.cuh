@@ -193,8 +193,13 @@ struct AdaptJob {
 int k_adaptive_gauss_jobs(docscan_ctx*, int k, int c, int cv_tail_compat, const AdaptJob* jobs_host, int n,
                           int max_w, int max_h);
 // tcblur.cu : GAUSSIAN_C's local mean on the tensor cores with a guard band (see there); false = not applicable
-bool k_tc_adaptive_jobs(docscan_ctx*, int k, int c_param, const int32_t* w16, int band, const AdaptJob* jobs_host, int n, uint2* flag_list,
-                        uint32_t* flag_count, uint32_t flag_cap, int* rc);
+#define TC_TILE_FLAG_CAP 512      // listed pixels per 128 x 64 tile; a tile that overflows is re-evaluated whole
+struct TcFlagLists {              // what the tensor-core pass leaves for the exact re-evaluation
+    uint32_t* count; uint16_t* list; int n_tiles, RL, NOUT;
+    struct PageTiles { int tile_base, ntx, nty; };
+    std::vector<PageTiles> tiles; // per page of the launch
+};
+bool k_tc_adaptive_jobs(docscan_ctx*, int k, int c_param, const int32_t* w16, int band, const AdaptJob* jobs_host, int n, TcFlagLists* fl, int* rc);
 // mask + blend (DocScanner.py:207-212, 338-339)
 struct BlendJob {
     const uint8_t* ink_sub; const uint8_t* bh; const uint8_t* base; uint8_t* dst;

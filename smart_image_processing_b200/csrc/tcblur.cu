@@ -68,7 +68,7 @@ struct TcLaunch {
     // adaptive threshold (EPI == DS_EPI_AGAUSS)
     int c_param;                 // dst = src - mean > -c_param ? 255 : 0
     int band;                    // guard band in 1/65536 grey levels: inside it the pixel goes to the exact evaluation
-    uint2* flag_list; uint32_t* flag_count; uint32_t flag_cap;
+    uint16_t* flag_list; uint32_t* flag_count; uint32_t flag_cap;   // per tile: count, then up to flag_cap entries (row << 6 | column)
     int flags;                   // debug: skip parts of the epilogue (DOCSCAN_TC_FLAGS), for timing experiments only
     int crumbs;                  // debug: CTA 0 reports its progress to status[1] (slow: a system-scope fence per phase)
     int t_slots;                 // cached pass-1 band matrices (top / interior / bottom): 3 when shared memory allows, else 2
@@ -510,8 +510,8 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                         while (flagged) {                   // rare: too close to the boundary for the fixed-point mean to decide
                             const int p8 = __ffs(flagged) - 1;
                             flagged &= flagged - 1;
-                            const uint32_t slot = atomicAdd(L.flag_count, 1u);
-                            if (slot < L.flag_cap) L.flag_list[slot] = make_uint2((uint32_t)tr.job, ((uint32_t)y << 16) | (uint32_t)(x + p8));
+                            const uint32_t slot = atomicAdd(&L.flag_count[tile0 + i], 1u);
+                            if (slot < L.flag_cap) L.flag_list[(size_t)(tile0 + i) * L.flag_cap + slot] = (uint16_t)((row << 6) | (c + p8));
                         }
                     }
                 }
@@ -680,8 +680,7 @@ int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
 }
 
 // Tile geometry, band matrices, tensor maps, upload and launch.  false: not applicable (the caller runs the CUDA-core kernels).
-bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, const char* prof_name, uint2* flag_list, uint32_t* flag_count,
-            uint32_t flag_cap, int* rc) {
+bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, const char* prof_name, TcFlagLists* fl, int* rc) {
     *rc = DOCSCAN_OK;
     if (n <= 0 || n > MAX_JOBS || !encode_fn()) return false;
     if (const char* e = getenv("DOCSCAN_TC")) if (atoi(e) == 0) return false;
@@ -770,7 +769,19 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
     L.n_jobs = n; L.n_tabs = (int)tabs.size(); L.total_tiles = total; L.R = R; L.RL = RL; L.K1 = K1; L.NOUT = NOUT;
     L.idesc1 = tc::idesc_i8(TM, NIN, 0, 0, 0, 1);
     L.idesc2 = tc::idesc_i8(TM, NOUT, 0, 0, 0, 0);
-    L.c_param = S.c_param; L.band = S.band; L.flag_list = flag_list; L.flag_count = flag_count; L.flag_cap = flag_cap;
+    L.c_param = S.c_param; L.band = S.band;
+    if (fl) {
+        // one list per tile: the exact re-evaluation works tile by tile out of shared memory (adaptive.cu)
+        void* cnt = nullptr; void* lst = nullptr;
+        *rc = ds_arena_alloc(ctx, sizeof(uint32_t) * (size_t)total, &cnt);
+        if (*rc == DOCSCAN_OK) *rc = ds_arena_alloc(ctx, sizeof(uint16_t) * (size_t)total * TC_TILE_FLAG_CAP, &lst);
+        if (*rc != DOCSCAN_OK) return true;
+        if (cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (size_t)total, ctx->stream) != cudaSuccess) { *rc = ds_fail(ctx, DOCSCAN_ERR_CUDA, "memset failed"); return true; }
+        L.flag_count = (uint32_t*)cnt; L.flag_list = (uint16_t*)lst; L.flag_cap = TC_TILE_FLAG_CAP;
+        fl->count = L.flag_count; fl->list = L.flag_list; fl->n_tiles = total; fl->RL = RL; fl->NOUT = NOUT;
+        fl->tiles.resize(n);
+        for (int i = 0; i < n; i++) { fl->tiles[i].tile_base = jobs[i].tile_base; fl->tiles[i].ntx = jobs[i].ntx; fl->tiles[i].nty = jobs[i].nty; }
+    }
     if (!ctx->tc_status) {
         if (cudaHostAlloc((void**)&ctx->tc_status, 64, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
         memset(ctx->tc_status, 0, 64);
@@ -836,14 +847,13 @@ bool k_tc_blur_jobs(docscan_ctx* ctx, int kind, int k, int epi, const BlurJob* j
     TcSpec S{};
     S.mode = 0; S.k = k; S.taps = q.data() + z; S.k_eff = k_eff; S.R = k_eff / 2; S.replicate = 0; S.epi = epi;
     const std::string name = std::string("tc_blur_k") + std::to_string(k);
-    return tc_run(ctx, S, jobs_host, n, name.c_str(), nullptr, nullptr, 0, rc);
+    return tc_run(ctx, S, jobs_host, n, name.c_str(), nullptr, rc);
 }
 
 // cv2.adaptiveThreshold(GAUSSIAN_C): the local mean in fixed point on the tensor cores, decided wherever it is further from the
 // rounding boundary than its own error bound; the pixels inside the guard band are listed for the exact evaluation
 // (adaptive.cu: k_adaptive_fix_flagged).  `w16` = the fp32 Gaussian taps * 65536, rounded; `band` in 1/65536 grey levels.
-bool k_tc_adaptive_jobs(docscan_ctx* ctx, int k, int c_param, const int32_t* w16, int band, const AdaptJob* jobs_host, int n, uint2* flag_list,
-                        uint32_t* flag_count, uint32_t flag_cap, int* rc) {
+bool k_tc_adaptive_jobs(docscan_ctx* ctx, int k, int c_param, const int32_t* w16, int band, const AdaptJob* jobs_host, int n, TcFlagLists* fl, int* rc) {
     *rc = DOCSCAN_OK;
     if (k < 3 || (k & 1) == 0) return false;
     std::vector<BlurJob> bj(n);
@@ -856,5 +866,5 @@ bool k_tc_adaptive_jobs(docscan_ctx* ctx, int k, int c_param, const int32_t* w16
     TcSpec S{};
     S.mode = 1; S.k = k; S.taps = w16; S.k_eff = k; S.R = k / 2; S.replicate = 1; S.epi = DS_EPI_AGAUSS; S.c_param = c_param; S.band = band;
     const std::string name = std::string("tc_adaptive_k") + std::to_string(k);
-    return tc_run(ctx, S, bj.data(), n, name.c_str(), flag_list, flag_count, flag_cap, rc);
+    return tc_run(ctx, S, bj.data(), n, name.c_str(), fl, rc);
 }

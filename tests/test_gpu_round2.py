@@ -207,3 +207,15 @@ def test_process_document_writes_the_reference_dumps(tmp_path):
     # out_dir is created even without dumps
     DS.process_document(path, out_dir=str(tmp_path / "o3"), scale_long=300, save_stages=False)
     assert os.path.isdir(tmp_path / "o3") and not os.listdir(tmp_path / "o3")
+
+
+def test_tensor_core_adaptive_threshold_opt_in(monkeypatch):
+    """The opt-in tensor-core GAUSSIAN_C (DOCSCAN_TC_ADAPTIVE=1: fixed-point mean on tcgen05, guard band, exact re-evaluation of
+    the listed pixels) must give cv2's bytes exactly like the default kernel: pages, noise, ragged shapes, both presets' sizes."""
+    monkeypatch.setenv("DOCSCAN_TC_ADAPTIVE", "1")
+    rng = np.random.default_rng(35)
+    for (h, w) in [(300, 260), (97, 131), (1600, 1131), (257, 1031), (33, 70)]:
+        for k, c in [(35, 10), (31, 3), (11, 10), (3, 0), (61, -2)]:
+            for kind in ("page", "noise"):
+                g = page_like(rng, max(h, 16), max(w, 16))[:h, :w] if kind == "page" else rng.integers(0, 256, (h, w), dtype=np.uint8)
+                eq(ops.adaptive_threshold(g, "gaussian", k, c), O.adaptive_threshold(g, "gaussian", k, c), f"tc adaptive {h}x{w} k={k} C={c} {kind}")
