@@ -40,7 +40,7 @@ constexpr int TMEM_COLS = 512;
 // TMEM columns.  Blur: D1 | A2lo A2hi | D2lo D2hi.  Adaptive threshold (16-bit weights = two byte planes, 8.8 row means = two byte
 // planes): D1h D1l | A2hi A2lo | D2a D2b D2c (products hi*hi, hi*lo + lo*hi, lo*lo).  D2 never overlaps D1: pass 1 of the next tile
 // runs under the epilogue of this one.
-constexpr int COL_D1 = 0, COL_A2LO = 128, COL_A2HI = 160, COL_D2LO = 192, COL_D2HI = 288;
+constexpr int COL_D1 = 0, COL_A2LO = 128, COL_A2HI = 160, COL_D2LO = 192, COL_D2HI = 272, D2_STRIDE = 160;   // two pairs of D2 (NOUT <= 80)
 constexpr int COLA_D1H = 0, COLA_D1L = 128, COLA_A2HI = 256, COLA_A2LO = 288, COLA_D2A = 320, COLA_D2B = 384, COLA_D2C = 448;
 constexpr int NS = 3;                            // source-window stages: pass 1 of tile i+1 and the centre pixels of tile i are live together
 constexpr int TOE_SLOTS = 3;                     // cached pass-2 band matrices (left / interior / right)
@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sT = base;                                            // L.t_slots band matrices of pass 1
     constexpr bool ADAPT = EPI == DS_EPI_AGAUSS;
+    constexpr bool DEFER = !ADAPT;                                 // two pairs of pass-2 accumulators: the epilogue lags one tile
     constexpr uint32_t t_bytes = ADAPT ? 2 * T_BYTES : T_BYTES;   // adaptive: high-byte plane, low-byte plane
     uint8_t* sToe = sT + L.t_slots * t_bytes;                      // TOE_SLOTS band matrices of pass 2
     const uint32_t toe_bytes = (uint32_t)L.NOUT * 128 * (ADAPT ? 2 : 1);
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
     uint8_t* s_out = sS + NS * L.K1 * 128;                         // the tile's results, 128 dense rows of NOUT bytes: the source of the TMA store
     const int out_pitch = L.NOUT;
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_out + TM * out_pitch);   // 8 x 256, only with STATS
-    __shared__ uint64_t bar_s[NS], bar_c, bar_d1, bar_d2, bar_a2;
+    __shared__ uint64_t bar_s[NS], bar_c, bar_d1, bar_d2[2], bar_a2;
     __shared__ uint32_t s_tmem;
     __shared__ TcJob s_jobs[MAX_JOBS];                   // the launch's page table and band-matrix pointers, read every tile
     __shared__ const uint8_t* s_tabs[MAX_TABS];
@@ -120,7 +121,8 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int i = 0; i < NS; i++) tc::mbar_init(&bar_s[i], 1);
-        tc::mbar_init(&bar_c, 1); tc::mbar_init(&bar_d1, 1); tc::mbar_init(&bar_d2, 1); tc::mbar_init(&bar_a2, N_EPI_WARPS);
+        tc::mbar_init(&bar_c, 1); tc::mbar_init(&bar_d1, 1); tc::mbar_init(&bar_d2[0], 1); tc::mbar_init(&bar_d2[1], 1);
+        tc::mbar_init(&bar_a2, N_EPI_WARPS);
         tc::mbar_init_fence();
     }
     if (warp == 1) tc::tmem_alloc(&s_tmem, TMEM_COLS);
@@ -268,11 +270,13 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 TC_STAMP(1, i, 2);
                 // pass 2: D2lo / D2hi [128 x NOUT] = A2lo / A2hi [128 x 128] (tensor memory) * Th[128 x NOUT]
                 const uint64_t dToe = dToe0 + (uint64_t)((toe_slot * toe_bytes) >> 4);
+                const int b2 = DEFER ? (i & 1) : 0;                // the pair of accumulators tile i - 2 has left
                 if (!ADAPT) {
+                    const uint32_t d2 = tmem + b2 * D2_STRIDE;
 #pragma unroll
-                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2LO, tmem + COL_A2LO + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(d2 + COL_D2LO, tmem + COL_A2LO + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
 #pragma unroll
-                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COL_D2HI, tmem + COL_A2HI + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(d2 + COL_D2HI, tmem + COL_A2HI + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
                 } else {
                     // 16-bit row means x 16-bit weights as byte planes: D2a = hi * Whi, D2b = hi * Wlo + lo * Whi, D2c = lo * Wlo
                     const uint64_t dWl = dToe + (uint64_t)(((uint32_t)L.NOUT * 128) >> 4);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
 #pragma unroll
                     for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(tmem + COLA_D2C, tmem + COLA_A2LO + s2 * 8, dWl + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
                 }
-                tc::mma_commit(&bar_d2);
+                tc::mma_commit(&bar_d2[b2]);
                 TC_STAMP(1, i, 3);
                 if (i + 1 < n_mine) pass1(i + 1, t_next);       // runs behind pass 2 of tile i, under its epilogue
                 TC_STAMP(1, i, 4);
@@ -334,228 +338,269 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
             mn2 = 0x00FF00FFu; mx2 = 0;
         };
 
-        for (int i = 0; i < n_mine; i++) {
-            const TileRec tr = s_rec[i % REC_RING];
-            // the page's fields into registers: the shared-memory stores below would otherwise force re-reads of the table
-            const int Jw = s_jobs[tr.job].w, Jh = s_jobs[tr.job].h, Jdp = s_jobs[tr.job].dst_pitch;
-            uint8_t* const Jdst = s_jobs[tr.job].dst;
-            uint32_t* const Jminmax = s_jobs[tr.job].minmax; uint32_t* const Jhist = s_jobs[tr.job].hist;
-            if (STATS && (st_minmax != Jminmax || st_hist != Jhist)) {   // statistics are per page
-                if (i > 0) flush_stats();
-                st_minmax = Jminmax; st_hist = Jhist;
-            }
-            const int x0 = tr.tx * L.NOUT, y0 = tr.ty * TM;
-            const bool first = L.dbg && blockIdx.x == 0 && i == 0;
-
-            if (tid == 0) TC_STAMP(0, i, 0);
-            // ---- D1 -> byte planes (A operands of pass 2): this warp's 32 rows x 32 columns
-            TC_WAIT(&bar_d1, i & 1, 3);
-            tc::fence_after_sync();
-            if (tid == 0) TC_STAMP(0, i, 1);
-            {
-                uint32_t v[32], lo[8], hi[8];
-                tc::tmem_ld32(tmem + lane_base + COL_D1 + cg * 32, v);
-                if (ADAPT) {
-                    // row mean * 65536 = 256 * D1h + D1l (24 bits)  ->  8.8 fixed point, rounded
-                    uint32_t vl[32];
-                    tc::tmem_ld32(tmem + lane_base + COLA_D1L + cg * 32, vl);
+        // The epilogue of a tile runs one round after its drain (blur; the adaptive threshold has no room for a second set of
+        // pass-2 accumulators): round i drains D1 of tile i, hands A2 to the issuing warp, and then — while pass 2 of tile i and
+        // pass 1 of tile i+1 execute — finishes tile i-1 out of the other pair of accumulators.  Nobody waits for an MMA.
+        constexpr int LAG = DEFER ? 1 : 0;
+        uint2 cen_cur[3], cen_new[3];                              // centre pixels of this thread's units: tile being finished / drained
+        int tr_job_cur = 0, tr_tx_cur = 0, tr_ty_cur = 0, tr_job_new = 0, tr_tx_new = 0, tr_ty_new = 0;   // likewise its decoded record
+#pragma unroll
+        for (int k = 0; k < 3; k++) { cen_cur[k] = make_uint2(0, 0); cen_new[k] = make_uint2(0, 0); }
+        for (int i = 0; i < n_mine + LAG; i++) {
+            if (i < n_mine) {
+                // the tile's record now: by the time the tile is finished (next round) the issuing warp may have reused the ring slot
+                tr_job_new = s_rec[i % REC_RING].job; tr_tx_new = s_rec[i % REC_RING].tx; tr_ty_new = s_rec[i % REC_RING].ty;
+                if (tid == 0) TC_STAMP(0, i, 0);
+                // ---- D1 -> byte planes (A operands of pass 2): this warp's 32 rows x 32 columns
+                TC_WAIT(&bar_d1, i & 1, 3);
+                tc::fence_after_sync();
+                if (tid == 0) TC_STAMP(0, i, 1);
+                {
+                    uint32_t v[32], lo[8], hi[8];
+                    tc::tmem_ld32(tmem + lane_base + COL_D1 + cg * 32, v);
+                    if (ADAPT) {
+                        // row mean * 65536 = 256 * D1h + D1l (24 bits)  ->  8.8 fixed point, rounded
+                        uint32_t vl[32];
+                        tc::tmem_ld32(tmem + lane_base + COLA_D1L + cg * 32, vl);
+                        tc::tmem_wait_ld();
+#pragma unroll
+                        for (int k = 0; k < 32; k++) v[k] = ((v[k] << 8) + vl[k] + 128u) >> 8;
+                    }
                     tc::tmem_wait_ld();
+                    if (L.dbg && blockIdx.x == 0 && i == 0)
+                        for (int k = 0; k < 32; k++) L.dbg[row * 128 + cg * 32 + k] = v[k];
 #pragma unroll
-                    for (int k = 0; k < 32; k++) v[k] = ((v[k] << 8) + vl[k] + 128u) >> 8;
+                    for (int g = 0; g < 8; g++) {
+                        const uint32_t t1 = __byte_perm(v[4 * g], v[4 * g + 1], 0x5140);        // a0 b0 a1 b1
+                        const uint32_t t2 = __byte_perm(v[4 * g + 2], v[4 * g + 3], 0x5140);    // c0 d0 c1 d1
+                        lo[g] = __byte_perm(t1, t2, 0x5410);                                    // a0 b0 c0 d0
+                        hi[g] = __byte_perm(t1, t2, 0x7632);                                    // a1 b1 c1 d1
+                    }
+                    if (!ADAPT && cg == 3) {
+                        // columns 126 and 127 carry no tap: they hold the rounding constant instead, 2 x (128 * 128) = 32768,
+                        // against the two 128s in the band matrix's last two slots
+                        lo[7] = (lo[7] & 0x0000FFFFu) | 0x80800000u;
+                        hi[7] &= 0x0000FFFFu;
+                    }
+                    if (DEFER && i > 0) {
+                        // pass 2 of the previous tile reads A2: it must be over before A2 is rewritten (it usually finished long ago,
+                        // under the epilogue this warp has just run)
+                        TC_WAIT(&bar_d2[(i - 1) & 1], ((i - 1) >> 1) & 1, 7);
+                        tc::fence_after_sync();
+                    }
+                    tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2LO : COL_A2LO) + cg * 8, lo);
+                    tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2HI : COL_A2HI) + cg * 8, hi);
+                    tc::tmem_wait_st();
                 }
-                tc::tmem_wait_ld();
-                if (first)
-                    for (int k = 0; k < 32; k++) L.dbg[row * 128 + cg * 32 + k] = v[k];
-#pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    const uint32_t t1 = __byte_perm(v[4 * g], v[4 * g + 1], 0x5140);        // a0 b0 a1 b1
-                    const uint32_t t2 = __byte_perm(v[4 * g + 2], v[4 * g + 3], 0x5140);    // c0 d0 c1 d1
-                    lo[g] = __byte_perm(t1, t2, 0x5410);                                    // a0 b0 c0 d0
-                    hi[g] = __byte_perm(t1, t2, 0x7632);                                    // a1 b1 c1 d1
-                }
-                if (!ADAPT && cg == 3) {
-                    // columns 126 and 127 carry no tap: they hold the rounding constant instead, 2 x (128 * 128) = 32768,
-                    // against the two 128s in the band matrix's last two slots
-                    lo[7] = (lo[7] & 0x0000FFFFu) | 0x80800000u;
-                    hi[7] &= 0x0000FFFFu;
-                }
-                tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2LO : COL_A2LO) + cg * 8, lo);
-                tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2HI : COL_A2HI) + cg * 8, hi);
-                tc::tmem_wait_st();
-            }
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&bar_a2);
-            if (tid == 0) TC_STAMP(0, i, 2);
-
-            // ---- epilogue: 32 rows x this column group's units of 8 columns, the next unit's accumulators in flight
-            const int y = y0 + row;
-            const bool row_ok = y < Jh;
-            // the centre pixels are in the source tile: row `row + R`, byte RL + column, 16-byte chunks swizzled by the row number
-            const int srow_i = row + L.R;
-            const uint8_t* s_center = sS + (size_t)(i % NS) * L.K1 * 128 + srow_i * 128;
-            const int swz = srow_i & 7;
-            uint32_t hc_ev = 0, hc_od = 0;                    // this tile's counts of the values 0..7 (8 bits each: even / odd bins)
-            TC_WAIT(&bar_d2, i & 1, 4);
-            tc::fence_after_sync();
-            if (tid == 0) TC_STAMP(0, i, 3);
-            // one unit of 8 columns: combine the two accumulators, apply the epilogue, store, update the statistics
-            auto work = [&](int u, const uint32_t* lo, const uint32_t* hi) {
-                const int c = u * 8, x = x0 + c;
-                uint2 cw = make_uint2(0, 0);
                 if (EPI != DS_EPI_BLUR && !(L.flags & 2)) {
-                    const int cb = L.RL + c;
-                    cw = *reinterpret_cast<const uint2*>(s_center + ((((cb >> 4) ^ swz) << 4) | (cb & 8)));
-                }
-                if (first)
-                    for (int k = 0; k < 8; k++) {
-                        L.dbg[16384 + row * 96 + c + k] = lo[k];
-                        L.dbg[16384 + 12288 + row * 96 + c + k] = hi[k];
-                    }
-                if (row_ok && x < Jw) {
-                    const uint32_t cws[2] = {cw.x, cw.y};
-                    const int nvalid = min(8, Jw - x);
-                    uint32_t out[2];
-                    uint32_t dl[4];                         // results as 16-bit lanes: dl[2g] = (px 4g, px 4g+2), dl[2g+1] = (px 4g+1, px 4g+3)
+                    // this thread's centre pixels, out of the source window while it is still there: row `row + R`, byte RL + column,
+                    // 16-byte chunks swizzled by the row number
+                    const int srow_i = row + L.R, swz = srow_i & 7;
+                    const uint8_t* s_center = sS + (size_t)(i % NS) * L.K1 * 128 + srow_i * 128;
 #pragma unroll
-                    for (int g = 0; g < 2; g++) {
-                        // blurred byte = bits 16..23 of D2lo + 256 * D2hi (the rounding constant is already in the sum; bits 24.. are 0)
-                        const uint32_t e0 = lo[4 * g] + (hi[4 * g] << 8), e1 = lo[4 * g + 1] + (hi[4 * g + 1] << 8);
-                        const uint32_t e2 = lo[4 * g + 2] + (hi[4 * g + 2] << 8), e3 = lo[4 * g + 3] + (hi[4 * g + 3] << 8);
-                        const uint32_t b_ev = __byte_perm(e0, e2, 0x7632), b_od = __byte_perm(e1, e3, 0x7632);
-                        uint32_t d_ev = b_ev, d_od = b_od;
-                        if (EPI != DS_EPI_BLUR) {
-                            const uint32_t s_ev = __byte_perm(cws[g], 0u, 0x4240), s_od = __byte_perm(cws[g], 0u, 0x4341);
-                            if (EPI == DS_EPI_SUB) {        // sat(s - b) = max(s, b) - b, lane-wise without borrows
-                                d_ev = __vmaxu2(s_ev, b_ev) - b_ev; d_od = __vmaxu2(s_od, b_od) - b_od;
-                            } else if (EPI == DS_EPI_RSUB) {
-                                d_ev = __vmaxu2(s_ev, b_ev) - s_ev; d_od = __vmaxu2(s_od, b_od) - s_od;
-                            } else {                        // divide(s, b, 255) in fp32, per pixel
-                                d_ev = (uint32_t)ds_div255((uint8_t)s_ev, (uint8_t)b_ev) | ((uint32_t)ds_div255((uint8_t)(s_ev >> 16), (uint8_t)(b_ev >> 16)) << 16);
-                                d_od = (uint32_t)ds_div255((uint8_t)s_od, (uint8_t)b_od) | ((uint32_t)ds_div255((uint8_t)(s_od >> 16), (uint8_t)(b_od >> 16)) << 16);
-                            }
-                        }
-                        dl[2 * g] = d_ev; dl[2 * g + 1] = d_od;
-                        out[g] = __byte_perm(d_ev, d_od, 0x6240);
-                    }
-                    if (!(L.flags & 8)) *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
-                    if (STATS) {
-                        if (nvalid < 8) {                   // rare: keep the columns past the width out of the statistics
-                            for (int k = 0; k < nvalid; k++) {
-                                const uint32_t v = (out[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-                                if (Jminmax) { mn2 = __vminu2(mn2, v | 0x00FF0000u); mx2 = __vmaxu2(mx2, v); }
-                                if (Jhist) atomicAdd(&my_hist[v], 1u);
-                            }
-                        } else {
-                            if (Jminmax && !(L.flags & 1)) {
-#pragma unroll
-                                for (int k = 0; k < 4; k++) { mn2 = __vminu2(mn2, dl[k]); mx2 = __vmaxu2(mx2, dl[k]); }
-                            }
-                            if (Jhist && !(L.flags & 4)) {
-                                // values 0..7: 4-bit counters in two registers (a 32-bit shift by 32 or more gives 0, so larger
-                                // values add nothing here); at most 4 increments per field and unit
-                                uint32_t h0 = 0, h1 = 0;
-#pragma unroll
-                                for (int k = 0; k < 4; k++) {
-                                    const uint32_t d = dl[k];
-                                    h0 += tc::shl32(1u, (d << 2) & 0x3FCu);
-                                    h1 += tc::shl32(1u, (d >> 14) & 0x3FCu);
-                                    if (d & 0x00F800F8u) {  // a value of 8 or more: the shared-memory histogram
-                                        const uint32_t v0 = d & 0xFFu, v1 = d >> 16;
-                                        if (v0 >= 8) atomicAdd(&my_hist[v0], 1u);
-                                        if (v1 >= 8) atomicAdd(&my_hist[v1], 1u);
-                                    }
-                                }
-                                hc_ev += (h0 & 0x0F0F0F0Fu) + (h1 & 0x0F0F0F0Fu);               // bins 0, 2, 4, 6 (8 bits each)
-                                hc_od += ((h0 >> 4) & 0x0F0F0F0Fu) + ((h1 >> 4) & 0x0F0F0F0Fu);  // bins 1, 3, 5, 7
-                            }
-                        }
+                    for (int k = 0; k < 3; k++) {
+                        const int cb = L.RL + (u_begin + k) * 8;
+                        if (u_begin + k < u_end) cen_new[k] = *reinterpret_cast<const uint2*>(s_center + ((((cb >> 4) ^ swz) << 4) | (cb & 8)));
                     }
                 }
-            };
-            if (tid == 0) tc::tma_store_wait_read();
-            asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");      // the previous tile has left the staging buffer
-            if constexpr (ADAPT) {
-                // ---- adaptive threshold: mean * 65536 = 256 * D2a + D2b + D2c / 256 against (src + C - 0.5) * 65536
-                uint32_t A[16], B[16], Cc[16];
-                tc::tmem_ld16(tmem + lane_base + COLA_D2A + u_begin * 8, A);
-                tc::tmem_ld16(tmem + lane_base + COLA_D2B + u_begin * 8, B);
-                tc::tmem_ld16(tmem + lane_base + COLA_D2C + u_begin * 8, Cc);
-                tc::tmem_wait_ld();
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_a2);
+                if (tid == 0) TC_STAMP(0, i, 2);
+
+            }
+            if (LAG == 0) {
 #pragma unroll
-                for (int k2 = 0; k2 < 2; k2++) {
-                    const int u = u_begin + k2;
-                    if (u >= u_end) break;
+                for (int k = 0; k < 3; k++) cen_cur[k] = cen_new[k];
+                tr_job_cur = tr_job_new; tr_tx_cur = tr_tx_new; tr_ty_cur = tr_ty_new;
+            }
+            if (i >= LAG) {
+                const int e = i - LAG;                             // the tile this round finishes
+                TileRec tr; tr.job = tr_job_cur; tr.tx = tr_tx_cur; tr.ty = tr_ty_cur;
+                // the page's fields into registers: the shared-memory stores below would otherwise force re-reads of the table
+                const int Jw = s_jobs[tr.job].w, Jh = s_jobs[tr.job].h, Jdp = s_jobs[tr.job].dst_pitch;
+                uint8_t* const Jdst = s_jobs[tr.job].dst;
+                uint32_t* const Jminmax = s_jobs[tr.job].minmax; uint32_t* const Jhist = s_jobs[tr.job].hist;
+                if (STATS && (st_minmax != Jminmax || st_hist != Jhist)) {   // statistics are per page
+                    if (e > 0) flush_stats();
+                    st_minmax = Jminmax; st_hist = Jhist;
+                }
+                const int x0 = tr.tx * L.NOUT, y0 = tr.ty * TM;
+                const bool first = L.dbg && blockIdx.x == 0 && e == 0;
+
+                // ---- epilogue: 32 rows x this column group's units of 8 columns, the next unit's accumulators in flight
+                const int y = y0 + row;
+                const bool row_ok = y < Jh;
+                uint32_t hc_ev = 0, hc_od = 0;                    // this tile's counts of the values 0..7 (8 bits each: even / odd bins)
+                const int b2 = DEFER ? (e & 1) : 0;                 // which pair of accumulators
+                TC_WAIT(&bar_d2[b2], (DEFER ? (e >> 1) : e) & 1, 4);
+                tc::fence_after_sync();
+                if (tid == 0) TC_STAMP(0, e, 3);
+                // one unit of 8 columns: combine the two accumulators, apply the epilogue, store, update the statistics
+                auto work = [&](int u, const uint32_t* lo, const uint32_t* hi, const uint2 cw) {
                     const int c = u * 8, x = x0 + c;
-                    const int cb = L.RL + c;
-                    const uint2 cw = *reinterpret_cast<const uint2*>(s_center + ((((cb >> 4) ^ swz) << 4) | (cb & 8)));
                     if (first)
                         for (int k = 0; k < 8; k++) {
-                            L.dbg[16384 + row * 96 + c + k] = A[8 * k2 + k];
-                            L.dbg[16384 + 12288 + row * 96 + c + k] = B[8 * k2 + k];
+                            L.dbg[16384 + row * 96 + c + k] = lo[k];
+                            L.dbg[16384 + 12288 + row * 96 + c + k] = hi[k];
                         }
                     if (row_ok && x < Jw) {
                         const uint32_t cws[2] = {cw.x, cw.y};
-                        uint32_t out[2] = {0, 0};
-                        uint32_t flagged = 0;
+                        const int nvalid = min(8, Jw - x);
+                        uint32_t out[2];
+                        uint32_t dl[4];                         // results as 16-bit lanes: dl[2g] = (px 4g, px 4g+2), dl[2g+1] = (px 4g+1, px 4g+3)
 #pragma unroll
-                        for (int p8 = 0; p8 < 8; p8++) {
-                            const int sp = (int)((cws[p8 >> 2] >> (8 * (p8 & 3))) & 0xFFu);
-                            const int V = (int)((A[8 * k2 + p8] << 8) + B[8 * k2 + p8] + (Cc[8 * k2 + p8] >> 8));
-                            const int diff = V - (((sp + L.c_param) << 16) - 32768);      // < 0: mean below the boundary -> 255
-                            if (diff < 0) out[p8 >> 2] |= 0xFFu << (8 * (p8 & 3));
-                            if (abs(diff) <= L.band && x + p8 < Jw) flagged |= 1u << p8;
+                        for (int g = 0; g < 2; g++) {
+                            // blurred byte = bits 16..23 of D2lo + 256 * D2hi (the rounding constant is already in the sum; bits 24.. are 0)
+                            const uint32_t e0 = lo[4 * g] + (hi[4 * g] << 8), e1 = lo[4 * g + 1] + (hi[4 * g + 1] << 8);
+                            const uint32_t e2 = lo[4 * g + 2] + (hi[4 * g + 2] << 8), e3 = lo[4 * g + 3] + (hi[4 * g + 3] << 8);
+                            const uint32_t b_ev = __byte_perm(e0, e2, 0x7632), b_od = __byte_perm(e1, e3, 0x7632);
+                            uint32_t d_ev = b_ev, d_od = b_od;
+                            if (EPI != DS_EPI_BLUR) {
+                                const uint32_t s_ev = __byte_perm(cws[g], 0u, 0x4240), s_od = __byte_perm(cws[g], 0u, 0x4341);
+                                if (EPI == DS_EPI_SUB) {        // sat(s - b) = max(s, b) - b, lane-wise without borrows
+                                    d_ev = __vmaxu2(s_ev, b_ev) - b_ev; d_od = __vmaxu2(s_od, b_od) - b_od;
+                                } else if (EPI == DS_EPI_RSUB) {
+                                    d_ev = __vmaxu2(s_ev, b_ev) - s_ev; d_od = __vmaxu2(s_od, b_od) - s_od;
+                                } else {                        // divide(s, b, 255) in fp32, per pixel
+                                    d_ev = (uint32_t)ds_div255((uint8_t)s_ev, (uint8_t)b_ev) | ((uint32_t)ds_div255((uint8_t)(s_ev >> 16), (uint8_t)(b_ev >> 16)) << 16);
+                                    d_od = (uint32_t)ds_div255((uint8_t)s_od, (uint8_t)b_od) | ((uint32_t)ds_div255((uint8_t)(s_od >> 16), (uint8_t)(b_od >> 16)) << 16);
+                                }
+                            }
+                            dl[2 * g] = d_ev; dl[2 * g + 1] = d_od;
+                            out[g] = __byte_perm(d_ev, d_od, 0x6240);
                         }
-                        *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
-                        while (flagged) {                   // rare: too close to the boundary for the fixed-point mean to decide
-                            const int p8 = __ffs(flagged) - 1;
-                            flagged &= flagged - 1;
-                            const uint32_t slot = atomicAdd(&L.flag_count[tile0 + i], 1u);
-                            if (slot < L.flag_cap) L.flag_list[(size_t)(tile0 + i) * L.flag_cap + slot] = (uint16_t)((row << 6) | (c + p8));
+                        if (!(L.flags & 8)) *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
+                        if (STATS) {
+                            if (nvalid < 8) {                   // rare: keep the columns past the width out of the statistics
+                                for (int k = 0; k < nvalid; k++) {
+                                    const uint32_t v = (out[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+                                    if (Jminmax) { mn2 = __vminu2(mn2, v | 0x00FF0000u); mx2 = __vmaxu2(mx2, v); }
+                                    if (Jhist) atomicAdd(&my_hist[v], 1u);
+                                }
+                            } else {
+                                if (Jminmax && !(L.flags & 1)) {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) { mn2 = __vminu2(mn2, dl[k]); mx2 = __vmaxu2(mx2, dl[k]); }
+                                }
+                                if (Jhist && !(L.flags & 4)) {
+                                    // values 0..7: 4-bit counters in two registers (a 32-bit shift by 32 or more gives 0, so larger
+                                    // values add nothing here); at most 4 increments per field and unit
+                                    uint32_t h0 = 0, h1 = 0;
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) {
+                                        const uint32_t d = dl[k];
+                                        h0 += tc::shl32(1u, (d << 2) & 0x3FCu);
+                                        h1 += tc::shl32(1u, (d >> 14) & 0x3FCu);
+                                        if (d & 0x00F800F8u) {  // a value of 8 or more: the shared-memory histogram
+                                            const uint32_t v0 = d & 0xFFu, v1 = d >> 16;
+                                            if (v0 >= 8) atomicAdd(&my_hist[v0], 1u);
+                                            if (v1 >= 8) atomicAdd(&my_hist[v1], 1u);
+                                        }
+                                    }
+                                    hc_ev += (h0 & 0x0F0F0F0Fu) + (h1 & 0x0F0F0F0Fu);               // bins 0, 2, 4, 6 (8 bits each)
+                                    hc_od += ((h0 >> 4) & 0x0F0F0F0Fu) + ((h1 >> 4) & 0x0F0F0F0Fu);  // bins 1, 3, 5, 7
+                                }
+                            }
                         }
                     }
+                };
+                if (tid == 0) tc::tma_store_wait_read();
+                asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");      // the previous tile has left the staging buffer
+                if constexpr (ADAPT) {
+                    // ---- adaptive threshold: mean * 65536 = 256 * D2a + D2b + D2c / 256 against (src + C - 0.5) * 65536
+                    uint32_t A[16], B[16], Cc[16];
+                    tc::tmem_ld16(tmem + lane_base + COLA_D2A + u_begin * 8, A);
+                    tc::tmem_ld16(tmem + lane_base + COLA_D2B + u_begin * 8, B);
+                    tc::tmem_ld16(tmem + lane_base + COLA_D2C + u_begin * 8, Cc);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int k2 = 0; k2 < 2; k2++) {
+                        const int u = u_begin + k2;
+                        if (u >= u_end) break;
+                        const int c = u * 8, x = x0 + c;
+                        const uint2 cw = cen_cur[k2];
+                        if (first)
+                            for (int k = 0; k < 8; k++) {
+                                L.dbg[16384 + row * 96 + c + k] = A[8 * k2 + k];
+                                L.dbg[16384 + 12288 + row * 96 + c + k] = B[8 * k2 + k];
+                            }
+                        if (row_ok && x < Jw) {
+                            const uint32_t cws[2] = {cw.x, cw.y};
+                            uint32_t out[2] = {0, 0};
+                            uint32_t flagged = 0;
+#pragma unroll
+                            for (int p8 = 0; p8 < 8; p8++) {
+                                const int sp = (int)((cws[p8 >> 2] >> (8 * (p8 & 3))) & 0xFFu);
+                                const int V = (int)((A[8 * k2 + p8] << 8) + B[8 * k2 + p8] + (Cc[8 * k2 + p8] >> 8));
+                                const int diff = V - (((sp + L.c_param) << 16) - 32768);      // < 0: mean below the boundary -> 255
+                                if (diff < 0) out[p8 >> 2] |= 0xFFu << (8 * (p8 & 3));
+                                if (abs(diff) <= L.band && x + p8 < Jw) flagged |= 1u << p8;
+                            }
+                            *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
+                            while (flagged) {                   // rare: too close to the boundary for the fixed-point mean to decide
+                                const int p8 = __ffs(flagged) - 1;
+                                flagged &= flagged - 1;
+                                const uint32_t slot = atomicAdd(&L.flag_count[tile0 + e], 1u);
+                                if (slot < L.flag_cap) L.flag_list[(size_t)(tile0 + e) * L.flag_cap + slot] = (uint16_t)((row << 6) | (c + p8));
+                            }
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                // both accumulators of this warp's columns in two wide loads (a TMEM load costs about the same whatever its width;
+                // the columns past this group's share belong to a neighbour or to nobody and are ignored)
+                uint32_t lo[24], hi[24];
+                {
+                    const uint32_t a_lo = tmem + lane_base + COL_D2LO + b2 * D2_STRIDE + u_begin * 8;
+                    const uint32_t a_hi = tmem + lane_base + COL_D2HI + b2 * D2_STRIDE + u_begin * 8;
+                    tc::tmem_ld16(a_lo, lo);
+                    tc::tmem_ld16(a_hi, hi);
+                    if (u_end - u_begin > 2) {                     // warp-uniform: this column group has a third unit
+                        tc::tmem_ld8(a_lo + 16, lo + 16);
+                        tc::tmem_ld8(a_hi + 16, hi + 16);
+                    }
+                }
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (u_begin + k < u_end) work(u_begin + k, lo + 8 * k, hi + 8 * k, cen_cur[k]);
                 }
                 __syncwarp();
-            } else {
-            // both accumulators of this warp's columns in two wide loads (a TMEM load costs about the same whatever its width;
-            // the columns past this group's share belong to a neighbour or to nobody and are ignored)
-            uint32_t lo[32], hi[32];
-            tc::tmem_ld32(tmem + lane_base + COL_D2LO + u_begin * 8, lo);
-            tc::tmem_ld32(tmem + lane_base + COL_D2HI + u_begin * 8, hi);
-            tc::tmem_wait_ld();
+                }
+                // ---- staging buffer -> global memory: one TMA store per tile (rows / columns outside the page are clipped by the
+                // tensor map, so nothing is ever written past the page's width or height)
+                tc::fence_async_smem();
+                asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
+                if (tid == 0 && !(L.flags & 16)) {
+                    if (tr.job != last_dmap) { tc::tmap_acquire(&L.dmaps[tr.job]); last_dmap = tr.job; }
+                    tc::tma_store_2d(&L.dmaps[tr.job], x0, y0, s_out);
+                }
+                if (tid == 0) TC_STAMP(0, e, 4);
+                if (STATS && Jhist) {
+                    // the small values of this tile: 8-bit counters -> 16-bit lanes, summed over the warp, 8 atomics per warp
+                    uint32_t f0 = (hc_ev & 0xFFu) | ((hc_od & 0xFFu) << 16);                       // bins 0, 1
+                    uint32_t f1 = ((hc_ev >> 8) & 0xFFu) | (((hc_od >> 8) & 0xFFu) << 16);         // bins 2, 3
+                    uint32_t f2 = ((hc_ev >> 16) & 0xFFu) | (((hc_od >> 16) & 0xFFu) << 16);       // bins 4, 5
+                    uint32_t f3 = (hc_ev >> 24) | ((hc_od >> 24) << 16);                           // bins 6, 7
+                    for (int o = 16; o; o >>= 1) {
+                        f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o);
+                        f2 += __shfl_xor_sync(0xffffffffu, f2, o); f3 += __shfl_xor_sync(0xffffffffu, f3, o);
+                    }
+                    if (lane < 8) {
+                        const uint32_t f = (lane >> 1) == 0 ? f0 : (lane >> 1) == 1 ? f1 : (lane >> 1) == 2 ? f2 : f3;
+                        const uint32_t cnt = (f >> (16 * (lane & 1))) & 0xFFFFu;
+                        if (cnt) atomicAdd(&my_hist[lane], cnt);
+                    }
+                }
+                if (tid == 0) TC_STAMP(0, e, 5);
+                tc::fence_before_sync();
+            }
+            if (LAG == 1) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (u_begin + k < u_end) work(u_begin + k, lo + 8 * k, hi + 8 * k);
+                for (int k = 0; k < 3; k++) cen_cur[k] = cen_new[k];
+                tr_job_cur = tr_job_new; tr_tx_cur = tr_tx_new; tr_ty_cur = tr_ty_new;
             }
-            __syncwarp();
-            }
-            // ---- staging buffer -> global memory: one TMA store per tile (rows / columns outside the page are clipped by the
-            // tensor map, so nothing is ever written past the page's width or height)
-            tc::fence_async_smem();
-            asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
-            if (tid == 0 && !(L.flags & 16)) {
-                if (tr.job != last_dmap) { tc::tmap_acquire(&L.dmaps[tr.job]); last_dmap = tr.job; }
-                tc::tma_store_2d(&L.dmaps[tr.job], x0, y0, s_out);
-            }
-            if (tid == 0) TC_STAMP(0, i, 4);
-            if (STATS && Jhist) {
-                // the small values of this tile: 8-bit counters -> 16-bit lanes, summed over the warp, 8 atomics per warp
-                uint32_t f0 = (hc_ev & 0xFFu) | ((hc_od & 0xFFu) << 16);                       // bins 0, 1
-                uint32_t f1 = ((hc_ev >> 8) & 0xFFu) | (((hc_od >> 8) & 0xFFu) << 16);         // bins 2, 3
-                uint32_t f2 = ((hc_ev >> 16) & 0xFFu) | (((hc_od >> 16) & 0xFFu) << 16);       // bins 4, 5
-                uint32_t f3 = (hc_ev >> 24) | ((hc_od >> 24) << 16);                           // bins 6, 7
-                for (int o = 16; o; o >>= 1) {
-                    f0 += __shfl_xor_sync(0xffffffffu, f0, o); f1 += __shfl_xor_sync(0xffffffffu, f1, o);
-                    f2 += __shfl_xor_sync(0xffffffffu, f2, o); f3 += __shfl_xor_sync(0xffffffffu, f3, o);
-                }
-                if (lane < 8) {
-                    const uint32_t f = (lane >> 1) == 0 ? f0 : (lane >> 1) == 1 ? f1 : (lane >> 1) == 2 ? f2 : f3;
-                    const uint32_t cnt = (f >> (16 * (lane & 1))) & 0xFFFFu;
-                    if (cnt) atomicAdd(&my_hist[lane], cnt);
-                }
-            }
-            if (tid == 0) TC_STAMP(0, i, 5);
-            tc::fence_before_sync();
         }
         if (n_mine > 0) flush_stats();
         if (tid == 0) tc::tma_store_wait_all();
@@ -690,7 +735,7 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
     const int RL = (R + 15) & ~15;                      // the window's first column must sit on a 16-byte boundary of its row
     // blur: the last two source slots of a tile carry the rounding constant (see the kernel), so the taps must end before them;
     // adaptive: three 64-column accumulators
-    const int NOUT = S.mode == 0 ? std::min(96, (NIN - 2 - RL - R) / 16 * 16) : std::min(64, (NIN - RL - R) / 16 * 16);
+    const int NOUT = S.mode == 0 ? std::min(80, (NIN - 2 - RL - R) / 16 * 16) : std::min(64, (NIN - RL - R) / 16 * 16);
     if (NOUT < 16 || K1 > 256 || (S.mode == 1 && NOUT != 64)) return false;
     bool stats = false;
     for (int i = 0; i < n; i++) {

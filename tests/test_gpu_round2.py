@@ -219,3 +219,32 @@ def test_tensor_core_adaptive_threshold_opt_in(monkeypatch):
             for kind in ("page", "noise"):
                 g = page_like(rng, max(h, 16), max(w, 16))[:h, :w] if kind == "page" else rng.integers(0, 256, (h, w), dtype=np.uint8)
                 eq(ops.adaptive_threshold(g, "gaussian", k, c), O.adaptive_threshold(g, "gaussian", k, c), f"tc adaptive {h}x{w} k={k} C={c} {kind}")
+
+
+@pytest.mark.parametrize("grid", ["1", "2", "5"])
+def test_tc_blur_long_tile_runs_per_cta(monkeypatch, grid):
+    """The tensor-core blur deals every CTA a contiguous run of tiles and keeps a 64-entry ring of decoded tiles, refilled 32 at
+    a time, with the epilogue lagging one tile behind the drain: force runs far longer than the ring (few CTAs, hundreds of tiles
+    each, several pages and page sizes in one launch) and compare every page with the oracle — blur, both illumination
+    epilogues with their min-max, and the ink-mask branch with its histogram."""
+    monkeypatch.setenv("DOCSCAN_TC_GRID", grid)
+    rng = np.random.default_rng(int(grid))
+    imgs = [page_like(rng, 1600, 1131), page_like(rng, 700, 333), page_like(rng, 1600, 1131)]
+    for k in (23, 51):
+        for g in imgs[:2]:
+            eq(ops.gaussian_blur(g, k), O.gaussian_blur_u8(g, k), f"tc blur grid={grid} k={k} {g.shape}")
+    h, w = imgs[0].shape
+    frac = (23 - 0.4) / min(h, w)
+    for method in ("subtract", "divide"):
+        eq(DS.illumination_correction(imgs[0], method, frac), O.illumination_correction(imgs[0], method, frac), f"illum {method} grid={grid}")
+    eq(DS._compute_ink_mask(imgs[2], mask_blur_ksize=51), O._compute_ink_mask(imgs[2], mask_blur_ksize=51), f"ink mask grid={grid}")
+    # several pages of two sizes in one launch through the fused pipeline
+    photos = []
+    for g in imgs:
+        photos.append(np.stack([np.clip(g * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1))
+    quads = [np.array([[30, 20], [p.shape[1] - 25, 28], [p.shape[1] - 20, p.shape[0] - 30], [22, p.shape[0] - 26]], np.float32) for p in photos]
+    sl = 900
+    wd, bn = DS.process_pages(photos, quads, [0.5, -1.0, 0.0], scale_long=sl)
+    for i in range(3):
+        ref = O.hot_path(photos[i], quads[i], [0.5, -1.0, 0.0][i], scale_long=sl)
+        eq(bn[i], ref["clean"], f"pipeline page {i} grid={grid}")

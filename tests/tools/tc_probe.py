@@ -35,7 +35,7 @@ def expected_tile0(img, k):
     keff, R = len(q), len(q) // 2
     K1 = (128 + 2 * R + 31) // 32 * 32
     RL = (R + 15) // 16 * 16
-    NOUT = min(96, (128 - 2 - RL - R) // 16 * 16)
+    NOUT = min(80, (128 - 2 - RL - R) // 16 * 16)
     h, w = img.shape
     S = np.zeros((K1, 128), np.int64)
     for j in range(K1):
