@@ -1,7 +1,9 @@
 // extern "C" entry points of libdocscan.so (see include/docscan.h) and the batched page pipeline.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
+#include <thread>
 
 #include "common.cuh"
 
@@ -717,6 +719,46 @@ int copy_2d(docscan_ctx* ctx, void* dst, size_t dpitch, const void* src, size_t 
     return DOCSCAN_OK;
 }
 
+// ---- pageable host buffers ------------------------------------------------------------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver through a small buffer and blocks the calling thread (about
+// 5 GB/s measured on the B200 box, a tenth of the link).  For callers that hand over plain numpy arrays the library therefore
+// keeps a pinned mirror of its staging sets and moves the bytes between the caller's buffers and the mirror itself, with
+// several threads, while the previous group's DMA and kernels run.
+struct HostCopy { uint8_t* dst; size_t dpitch; const uint8_t* src; size_t spitch; size_t row_bytes; int rows; };
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+void parallel_copy(const std::vector<HostCopy>& jobs) {
+    struct Chunk { int job, row0, rows; };
+    std::vector<Chunk> chunks;
+    for (size_t j = 0; j < jobs.size(); j++) {
+        const int per = std::max(1, (int)((size_t)(1 << 20) / std::max<size_t>(jobs[j].row_bytes, 1)));      // ~1 MB per chunk
+        for (int r0 = 0; r0 < jobs[j].rows; r0 += per) chunks.push_back({(int)j, r0, std::min(per, jobs[j].rows - r0)});
+    }
+    if (chunks.empty()) return;
+    int nt = (int)std::thread::hardware_concurrency() / 2;
+    if (const char* e = getenv("DOCSCAN_COPY_THREADS")) nt = atoi(e);
+    nt = std::max(1, std::min(std::min(nt, 16), (int)chunks.size()));
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (size_t c = next.fetch_add(1); c < chunks.size(); c = next.fetch_add(1)) {
+            const HostCopy& J = jobs[chunks[c].job];
+            if (J.dpitch == J.row_bytes && J.spitch == J.row_bytes)
+                memcpy(J.dst + (size_t)chunks[c].row0 * J.dpitch, J.src + (size_t)chunks[c].row0 * J.spitch, J.row_bytes * (size_t)chunks[c].rows);
+            else
+                for (int r = chunks[c].row0; r < chunks[c].row0 + chunks[c].rows; r++) memcpy(J.dst + (size_t)r * J.dpitch, J.src + (size_t)r * J.spitch, J.row_bytes);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+
 }  // namespace
 
 extern "C" int docscan_warp_footprint(const docscan_page* page, int32_t region[4]) {
@@ -757,6 +799,12 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
     if (n >= 4 * 64 && strips_per_page <= 12) group = 64;   // big resident batches of ordinary pages: one 64-page group per stream measured best
     if (const char* e = getenv("DOCSCAN_GROUP")) group = std::max(1, atoi(e));
     if (any_host) group = std::min(group, 8);          // finer pipeline granularity: copies overlap compute
+    bool any_pageable = false;
+    if (any_host)
+        for (int i = 0; i < n && !any_pageable; i++)
+            any_pageable = (is_host(&pages[i].src) && is_pageable(pages[i].src.data)) || (is_host(&pages[i].warped) && is_pageable(pages[i].warped.data)) ||
+                           (is_host(&pages[i].binary) && is_pageable(pages[i].binary.data));
+    if (any_pageable) group = std::min(group, 4);      // the pinned mirror is 2 x group x (photo + results)
     group = std::min(group, n);
     if (!any_host) {
         // Device-resident batch.  Consecutive groups rotate over the context's stream and up to DS_MAX_STREAMS-1 extra
@@ -823,6 +871,17 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         DS_TRY(ds_arena_alloc(ctx, max_stage * group, &p));
         stage_base[sset] = (uint8_t*)p;
     }
+    uint8_t* pin_base[2] = {nullptr, nullptr};
+    if (any_pageable) {
+        const size_t need = 2 * max_stage * group;
+        if (ctx->pin_mirror_size < need) {
+            if (ctx->pin_mirror) { DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFreeHost(ctx->pin_mirror); ctx->pin_mirror = nullptr; ctx->pin_mirror_size = 0; }
+            DS_CUDA(ctx, cudaHostAlloc((void**)&ctx->pin_mirror, need, cudaHostAllocDefault));
+            ctx->pin_mirror_size = need;
+        }
+        pin_base[0] = ctx->pin_mirror; pin_base[1] = ctx->pin_mirror + max_stage * group;
+    }
+    std::vector<HostCopy> out_jobs[2];               // results of a group waiting in the pinned mirror for their trip to the caller
     cudaEvent_t* in_done = &ctx->pipe_ev[0];     // [2]
     cudaEvent_t* comp_done = &ctx->pipe_ev[2];   // [2]
     cudaEvent_t* out_done = &ctx->pipe_ev[4];    // [2]
@@ -842,6 +901,11 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
             DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, out_done[sset], 0));
         }
         uint8_t* cur = stage_base[sset];
+        auto mirror_of = [&](const uint8_t* dev) { return pin_base[sset] + (dev - stage_base[sset]); };
+        std::vector<HostCopy> in_jobs;
+        struct Pending { uint8_t* dev; size_t bytes; };
+        std::vector<Pending> in_dma;
+        if (any_pageable && g >= 2) DS_CUDA(ctx, cudaEventSynchronize(in_done[sset]));    // the mirror set's last uploads have left it
         auto carve = [&](const docscan_image& im, bool dense) {
             DImg d;
             // inputs are staged densely when the caller's rows are dense: one contiguous DMA per page instead of a
@@ -861,11 +925,21 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
                 part.width = rg.x1 - rg.x0; part.height = rg.y1 - rg.y0;
                 part.data = (uint8_t*)pg.src.data + (size_t)rg.y0 * pg.src.pitch + (size_t)rg.x0 * 3;
                 src[j] = carve(part, part.width == pg.src.width);
+                if (any_pageable && is_pageable(pg.src.data)) {
+                    // caller's rows -> mirror (host threads, below), mirror -> device as one contiguous DMA
+                    in_jobs.push_back({mirror_of(src[j].p), (size_t)src[j].pitch, (const uint8_t*)part.data, (size_t)part.pitch, (size_t)part.width * 3, part.height});
+                    in_dma.push_back({src[j].p, (size_t)src[j].pitch * part.height});
+                    ctx->h2d_bytes += (int64_t)part.width * 3 * part.height;
+                } else
                 DS_TRY(copy_2d(ctx, src[j].p, src[j].pitch, part.data, part.pitch, (size_t)part.width * 3, part.height,
                                cudaMemcpyHostToDevice, ctx->copy_in));
             } else src[j] = view_of(pg.src);
             warped[j] = is_host(&pg.warped) ? carve(pg.warped, false) : view_of(pg.warped);
             binary[j] = is_host(&pg.binary) ? carve(pg.binary, false) : view_of(pg.binary);
+        }
+        if (!in_jobs.empty()) {
+            parallel_copy(in_jobs);
+            for (const Pending& d : in_dma) DS_CUDA(ctx, cudaMemcpyAsync(d.dev, mirror_of(d.dev), d.bytes, cudaMemcpyHostToDevice, ctx->copy_in));
         }
         DS_CUDA(ctx, cudaEventRecord(in_done[sset], ctx->copy_in));
         DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, in_done[sset], 0));
@@ -875,14 +949,41 @@ extern "C" int docscan_process_pages(docscan_ctx* ctx, int n, docscan_page* page
         DS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, comp_done[sset], 0));
         for (int j = 0; j < m; j++) {
             docscan_page& pg = pages[i + j];
-            if (is_host(&pg.warped))
+            if (is_host(&pg.warped)) {
+                if (any_pageable && is_pageable(pg.warped.data)) {
+                    DS_CUDA(ctx, cudaMemcpyAsync(mirror_of(warped[j].p), warped[j].p, (size_t)warped[j].pitch * pg.warped.height, cudaMemcpyDeviceToHost, ctx->copy_out));
+                    out_jobs[sset].push_back({(uint8_t*)pg.warped.data, (size_t)pg.warped.pitch, mirror_of(warped[j].p), (size_t)warped[j].pitch,
+                                              (size_t)pg.warped.width * 3, pg.warped.height});
+                    ctx->d2h_bytes += (int64_t)pg.warped.width * 3 * pg.warped.height;
+                } else
                 DS_TRY(copy_2d(ctx, pg.warped.data, pg.warped.pitch, warped[j].p, warped[j].pitch, (size_t)pg.warped.width * 3,
                                pg.warped.height, cudaMemcpyDeviceToHost, ctx->copy_out));
-            if (is_host(&pg.binary))
+            }
+            if (is_host(&pg.binary)) {
+                if (any_pageable && is_pageable(pg.binary.data)) {
+                    DS_CUDA(ctx, cudaMemcpyAsync(mirror_of(binary[j].p), binary[j].p, (size_t)binary[j].pitch * pg.binary.height, cudaMemcpyDeviceToHost, ctx->copy_out));
+                    out_jobs[sset].push_back({(uint8_t*)pg.binary.data, (size_t)pg.binary.pitch, mirror_of(binary[j].p), (size_t)binary[j].pitch,
+                                              (size_t)pg.binary.width, pg.binary.height});
+                    ctx->d2h_bytes += (int64_t)pg.binary.width * pg.binary.height;
+                } else
                 DS_TRY(copy_2d(ctx, pg.binary.data, pg.binary.pitch, binary[j].p, binary[j].pitch, (size_t)pg.binary.width,
                                pg.binary.height, cudaMemcpyDeviceToHost, ctx->copy_out));
+            }
         }
         DS_CUDA(ctx, cudaEventRecord(out_done[sset], ctx->copy_out));
+        // the previous group's results have reached the mirror by now (or soon): hand them to the caller while this group runs
+        if (g >= 1 && !out_jobs[sset ^ 1].empty()) {
+            DS_CUDA(ctx, cudaEventSynchronize(out_done[sset ^ 1]));
+            parallel_copy(out_jobs[sset ^ 1]);
+            out_jobs[sset ^ 1].clear();
+        }
+    }
+    for (int k = 0; k < 2; k++) {
+        const int sset = (g + k) & 1;                  // older group first
+        if (out_jobs[sset].empty()) continue;
+        DS_CUDA(ctx, cudaEventSynchronize(out_done[sset]));
+        parallel_copy(out_jobs[sset]);
+        out_jobs[sset].clear();
     }
     for (int sset = 0; sset < std::min(g, 2); sset++) DS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, out_done[sset], 0));
     return ds_finish(ctx, true);

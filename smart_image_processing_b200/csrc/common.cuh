@@ -53,6 +53,9 @@ struct docscan_ctx {
     std::vector<void*> user_allocs;
     // host-buffer pipeline of docscan_process_pages: copy streams + events (created on first use)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // pinned mirror of the two staging sets, for callers whose host buffers are pageable (plain numpy arrays)
+    uint8_t* pin_mirror = nullptr;
+    size_t pin_mirror_size = 0;
     cudaEvent_t pipe_ev[7] = {};
     // second compute stream of the device-resident batch path
     cudaStream_t aux[DS_MAX_STREAMS] = {};      // [0] unused (the context's own stream)

@@ -78,6 +78,7 @@ extern "C" int docscan_destroy(docscan_ctx* ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->tc_status) cudaFreeHost(ctx->tc_status);
+    if (ctx->pin_mirror) cudaFreeHost(ctx->pin_mirror);
     if (ctx->copy_in) {
         cudaStreamDestroy(ctx->copy_in);
         cudaStreamDestroy(ctx->copy_out);

@@ -63,6 +63,11 @@ def test_pinned_host_pipeline_many_groups_mixed_pages():
             w1, b1 = DS.process_pages([np.array(imgs[i])], [quads[i]], [angles[i]], scale_long=sl, ctx=ctx)
             eq(w[i], w1[0], f"pinned batch rep {rep} page {i} warped")
             eq(b[i], b1[0], f"pinned batch rep {rep} page {i} binary")
+    # the same batch from PAGEABLE arrays (what cv2.imread hands a caller): pinned mirror + host copy threads inside the library
+    wp, bp = DS.process_pages([np.array(x) for x in imgs], quads, angles, scale_long=sl, ctx=ctx)
+    for i in range(n):
+        eq(wp[i], np.array(w[i]), f"pageable batch page {i} warped")
+        eq(bp[i], np.array(b[i]), f"pageable batch page {i} binary")
     # and one of them against the oracle, so that "equal to itself" cannot hide a common error
     ref = O.hot_path(np.array(imgs[0]), quads[0], angles[0], scale_long=sl)
     eq(np.array(outs_b[0]), ref["clean"], "pinned batch page 0 vs oracle")
