@@ -66,6 +66,9 @@ DOCSCAN_API const char* docscan_strerror(int code);
 DOCSCAN_API int docscan_create(int device, void* stream, docscan_ctx** out);
 DOCSCAN_API int docscan_destroy(docscan_ctx* ctx);
 DOCSCAN_API int docscan_sync(docscan_ctx* ctx);
+/* the context's cudaStream_t, for callers that enqueue their own work in order with the library's (e.g. the optional
+ * nvJPEG decode in control.py, which replaces cv2.imread of DocScanner.py:15-19 when decode="device" is asked for) */
+DOCSCAN_API int docscan_get_stream(docscan_ctx* ctx, void** stream);
 DOCSCAN_API const char* docscan_last_error(docscan_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 DOCSCAN_API int64_t docscan_launch_count(docscan_ctx* ctx);

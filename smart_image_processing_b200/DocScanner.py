@@ -203,9 +203,12 @@ def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], ang
     pages = (Page * n)()
     warped, binary, keep = [], [], []
     for i in range(n):
-        img = np.ascontiguousarray(images[i])
-        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+        dev_img = images[i] if isinstance(images[i], _capi.DeviceBuffer) else None      # photo already on the device
+        img = images[i] if dev_img is not None else np.ascontiguousarray(images[i])
+        if dev_img is None and (img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3):
             raise TypeError("process_pages: images must be HxWx3 uint8 (BGR)")
+        if dev_img is not None and (len(img.shape) != 3 or img.shape[2] != 3):
+            raise TypeError("process_pages: device photos must be HxWx3 (BGR)")
         whole = quads[i] is None                       # no usable quad: resize_long_side (DocScanner.py:313)
         if whole:
             if scale_long <= 0:
@@ -220,7 +223,7 @@ def process_pages(images: Sequence[np.ndarray], quads: Sequence[np.ndarray], ang
         b_arr = out_binary[i] if out_binary is not None else np.empty((th, tw), np.uint8)
         if w_arr.shape != (th, tw, 3) or b_arr.shape != (th, tw):
             raise ValueError("process_pages: preallocated outputs have the wrong shape")
-        pages[i].src = image_of(img)
+        pages[i].src = dev_img.image() if dev_img is not None else image_of(img)
         pages[i].quad = (_ct.c_float * 8)(*q.reshape(8).tolist())
         pages[i].angle_deg = float("nan") if angles[i] is None else float(angles[i])
         pages[i].warped = image_of(w_arr)
@@ -277,16 +280,30 @@ def process_document(input_path: str, out_dir: str = "outputs", page: str = "A4"
                      fallback_use_whole: bool = True,
                      min_quad_area_ratio: float = 0.15,
                      *, quad: Optional[np.ndarray] = None, angle: Optional[float] = None,
-                     save_stages: bool = True) -> dict:
+                     save_stages: bool = True, decode: str = "host") -> dict:
     """DocScanner.process_document (DocScanner.py:262-365): same 28 parameters, same result dict
     {"quad", "warped", "binary"}, same twelve PNG dumps in `out_dir` (scan_01_pre ... scan_08_clean).
     The control path (load, bilateral `preprocess` dump, quad localisation, overlay dump) runs on the host through
     control.py unless `quad` is supplied; the per-pixel path and deskew()'s angle estimate run on the GPU.
     Keyword-only extras: `quad=` / `angle=` skip the localisation / the skew estimate; `save_stages=False` drops the
-    dumps and takes the single fused C-ABI call (the reference always dumps, hence the default)."""
+    dumps and takes the single fused C-ABI call (the reference always dumps, hence the default).
+    `decode="device"` (needs `quad=` and `save_stages=False`): the JPEG is decoded by nvJPEG straight into device memory, so only
+    the file crosses PCIe instead of the raw photo — NOT bit-identical with cv2.imread's libjpeg decode, hence opt-in; "warped"
+    and "binary" then differ from the reference's by the decoders' +-1..2 grey levels."""
     from . import control
     if out_dir:                                                # ensure_dir(out_dir), DocScanner.py:277
         os.makedirs(out_dir, exist_ok=True)
+    if decode == "device":
+        if quad is None or save_stages:
+            raise ValueError("decode='device' keeps the photo on the GPU: pass quad= and save_stages=False")
+        photo = control.load_image_device(input_path)
+        quad = np.asarray(quad, np.float32)
+        w, b = process_pages([photo], [quad], [angle], page=page, scale_long=scale_long, canny_low=canny_low, canny_high=canny_high,
+                             max_rotate=max_rotate, illum_method=illum_method, illum_blur_frac=illum_blur_frac, block_size=block_size, C=C,
+                             thresh_method=thresh_method, mask_blur_ksize=mask_blur_ksize, blackhat_ksize=blackhat_ksize,
+                             blackhat_vertical_ratio=blackhat_vertical_ratio, ink_dilate_iters=ink_dilate_iters,
+                             mask_thresh_offset=mask_thresh_offset, morph_ksize=morph_ksize, morph_iters=morph_iters)
+        return {"quad": quad, "warped": w[0], "binary": b[0]}
     color = control.load_image(input_path)
     if save_stages:
         # DocScanner.py:280-282: the denoised image is only ever dumped, nothing downstream reads it

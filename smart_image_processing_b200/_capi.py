@@ -50,6 +50,7 @@ _SIGS = {
     "docscan_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "docscan_destroy": (C.c_int, [C.c_void_p]),
     "docscan_sync": (C.c_int, [C.c_void_p]),
+    "docscan_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "docscan_last_error": (C.c_char_p, [C.c_void_p]),
     "docscan_launch_count": (C.c_int64, [C.c_void_p]),
     "docscan_transfer_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -220,6 +221,13 @@ class Context:
         block = _PinnedBlock(self, p.value, max(nbytes, 1))
         return np.asarray(block)[:nbytes].view(dtype).reshape(shape)
 
+    @property
+    def stream(self) -> int:
+        """The context's cudaStream_t as an integer handle."""
+        p = C.c_void_p()
+        self.call("docscan_get_stream", C.byref(p))
+        return p.value or 0
+
     def device_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
         self.call("docscan_device_alloc", int(nbytes), C.byref(p))
@@ -227,6 +235,32 @@ class Context:
 
     def device_free(self, ptr: int):
         self.call("docscan_device_free", C.c_void_p(ptr))
+
+
+class DeviceBuffer:
+    """A device-resident uint8 image owned by Python (docscan_device_alloc / docscan_device_free): `process_pages` accepts it
+    in place of a numpy photo, e.g. for photos decoded on the device."""
+
+    def __init__(self, ctx: Context, height: int, width: int, channels: int):
+        self.ctx, self.shape, self.pitch = ctx, (height, width, channels), width * channels
+        self.ptr = ctx.device_alloc(self.pitch * height)
+
+    def image(self) -> Image:
+        h, w, ch = self.shape
+        return device_image(self.ptr, w, h, self.pitch, ch)
+
+    def to_numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, np.uint8)
+        self.ctx.check(lib().docscan_memcpy_d2h(self.ctx._h, out.ctypes.data, C.c_void_p(self.ptr), out.nbytes), "docscan_memcpy_d2h")
+        return out
+
+    def __del__(self):
+        try:
+            if self.ptr and getattr(self.ctx, "_h", None) and self.ctx._h.value:
+                self.ctx.device_free(self.ptr)
+            self.ptr = 0
+        except Exception:
+            pass
 
 
 _tls = threading.local()

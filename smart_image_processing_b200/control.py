@@ -29,6 +29,66 @@ def load_image(path: str) -> np.ndarray:
     return img
 
 
+# ---- optional JPEG decode on the device -------------------------------------------------------------
+# cv2.imread (DocScanner.py:15-19) decodes on the host and the 36 MB of raw pixels then cross PCIe; nvJPEG (a CUDA library
+# that ships with the toolkit, bound here with ctypes) takes the ~2-4 MB file instead and leaves the BGR photo in device
+# memory, where docscan_process_pages reads it directly.  OPT-IN: nvJPEG's inverse DCT and chroma upsampling are not
+# bit-identical with libjpeg-turbo's, so a page decoded this way differs from the reference's by a grey level here and there
+# and the chain after it is no longer bit-exact with DocScanner.py — use it when throughput matters more than that.
+_nvjpeg_state = {}
+
+
+def _nvjpeg():
+    import ctypes as C
+    if "lib" not in _nvjpeg_state:
+        lib = None
+        for name in ("libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so"):
+            try:
+                lib = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if lib is None:
+            raise RuntimeError("decode='device' needs nvJPEG (libnvjpeg.so from the CUDA toolkit)")
+        handle, jstate = C.c_void_p(), C.c_void_p()
+        if lib.nvjpegCreateSimple(C.byref(handle)) != 0 or lib.nvjpegJpegStateCreate(handle, C.byref(jstate)) != 0:
+            raise RuntimeError("nvJPEG initialisation failed")
+        _nvjpeg_state.update(lib=lib, handle=handle, jstate=jstate)
+    return _nvjpeg_state
+
+
+def load_image_device(path: str, ctx=None):
+    """JPEG file -> HxWx3 BGR photo in device memory (a _capi.DeviceBuffer), decoded by nvJPEG on the context's stream.
+    Raises ValueError for files nvJPEG cannot decode (PNG, progressive modes it does not support ...): use load_image."""
+    import ctypes as C
+    from . import _capi
+    ctx = ctx if ctx is not None else _capi.default_context()
+    try:
+        data = open(path, "rb").read()
+    except OSError:
+        raise FileNotFoundError(f"Cannot load image: {path}")
+    st = _nvjpeg()
+    lib = st["lib"]
+    ncomp, subs = C.c_int(0), C.c_int(0)
+    widths, heights = (C.c_int * 4)(), (C.c_int * 4)()
+    buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+    if lib.nvjpegGetImageInfo(st["handle"], buf, C.c_size_t(len(data)), C.byref(ncomp), C.byref(subs), widths, heights) != 0:
+        raise ValueError(f"nvJPEG cannot read {path}")
+    w, h = int(widths[0]), int(heights[0])
+    dev = _capi.DeviceBuffer(ctx, h, w, 3)
+
+    class _NvjpegImage(C.Structure):
+        _fields_ = [("channel", C.c_void_p * 4), ("pitch", C.c_size_t * 4)]
+
+    out = _NvjpegImage()
+    out.channel[0], out.pitch[0] = dev.ptr, dev.pitch
+    NVJPEG_OUTPUT_BGRI = 6
+    rc = lib.nvjpegDecode(st["handle"], st["jstate"], buf, C.c_size_t(len(data)), NVJPEG_OUTPUT_BGRI, C.byref(out), C.c_void_p(ctx.stream))
+    if rc != 0:
+        raise ValueError(f"nvJPEG failed to decode {path} (status {rc})")
+    return dev
+
+
 def save_image(path: str, img: np.ndarray) -> None:
     d = os.path.dirname(path)
     if d:

@@ -101,6 +101,12 @@ extern "C" int docscan_sync(docscan_ctx* ctx) {
 }
 
 extern "C" const char* docscan_last_error(docscan_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+extern "C" int docscan_get_stream(docscan_ctx* ctx, void** stream) {
+    if (!ctx || !stream) return DOCSCAN_ERR_BAD_ARG;
+    *stream = (void*)ctx->stream;
+    return DOCSCAN_OK;
+}
+
 extern "C" int64_t docscan_launch_count(docscan_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int docscan_transfer_bytes(docscan_ctx* ctx, int64_t* h2d, int64_t* d2h) {
     if (!ctx) return DOCSCAN_ERR_BAD_ARG;

@@ -253,3 +253,30 @@ def test_tc_blur_long_tile_runs_per_cta(monkeypatch, grid):
     for i in range(3):
         ref = O.hot_path(photos[i], quads[i], [0.5, -1.0, 0.0][i], scale_long=sl)
         eq(bn[i], ref["clean"], f"pipeline page {i} grid={grid}")
+
+
+def test_device_jpeg_decode_opt_in(tmp_path):
+    """process_document(decode="device"): nvJPEG puts the photo straight into device memory.  Not bit-identical with cv2.imread
+    (different IDCT / upsampling), so the checks are: the decoded photo is within a few grey levels of cv2's, and the page
+    that comes out is the page the host-decoded photo gives except for a small fraction of threshold-edge pixels."""
+    cv2 = pytest.importorskip("cv2")
+    from smart_image_processing_b200 import control
+    from smart_image_processing_b200.synth import synth_page_numpy
+    img, quad = synth_page_numpy(21, 900, 1200)
+    path = str(tmp_path / "page.jpg")
+    cv2.imwrite(path, img, [cv2.IMWRITE_JPEG_QUALITY, 92])
+    host = cv2.imread(path, cv2.IMREAD_COLOR)
+    try:
+        dev = control.load_image_device(path)
+    except RuntimeError as e:
+        pytest.skip(str(e))
+    got = dev.to_numpy()
+    assert got.shape == host.shape
+    d = np.abs(got.astype(np.int16) - host.astype(np.int16))
+    assert d.max() <= 6 and d.mean() < 0.6, (int(d.max()), float(d.mean()))
+    res = DS.process_document(path, out_dir=str(tmp_path / "o"), scale_long=700, quad=quad, angle=0.5, save_stages=False, decode="device")
+    ref = DS.process_document(path, out_dir=str(tmp_path / "o"), scale_long=700, quad=quad, angle=0.5, save_stages=False)
+    assert res["binary"].shape == ref["binary"].shape
+    assert np.mean(res["binary"] != ref["binary"]) < 0.10        # the rotated page is grey-level: every decoder-induced flip shows
+    with pytest.raises(ValueError):
+        DS.process_document(path, out_dir=str(tmp_path / "o"), scale_long=700, decode="device")
