@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Regenerates the tables of profiles/README.md from the raw ncu outputs.
 
-    python profiles/summarize.py profiles/r1_launches.csv gpurun_out/prof_r1f.ncu-rep
+    python profiles/summarize.py profiles/r2_launches.csv gpurun_out/prof_r2.ncu-rep [r2]
 
 (1) launch list -> per-kernel share; (2) `ncu --set full` report -> one line per captured kernel
 (profiles/r1_ncu_full.txt) and profiles/traffic.json (DRAM read+write bytes per launch, used by bench.py's
@@ -43,25 +43,27 @@ KEEP = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tc.sum", "sm__inst_executed_pipe_uniform.sum"]
 
 
 def key_of(name):
-    for pat, key in (("adaptive_tail", "adaptive_gauss_tail"), ("adaptive", "adaptive_gauss"), ("lut16", "pw_lut"), ("otsu", "scalars_otsu"), ("warp_persp", "warp_perspective_c3"), ("blur", "blur_gauss"),
+    for pat, key in (("tc_blur", "tc_blur"), ("adaptive_fix", "adaptive_gauss_fix"), ("adaptive_tail", "adaptive_gauss_tail"), ("adaptive", "adaptive_gauss"), ("lut16", "pw_lut"), ("otsu", "scalars_otsu"), ("warp_persp", "warp_perspective_c3"), ("blur", "blur_gauss"),
                      ("morph_march", "morph_march"), ("mask_blend", "mask_blend"), ("warp_affine", "warp_affine")):
         if pat in name:
             return key
     return name
 
 
-def full_report(rep):
+def full_report(rep, tag="r2"):
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
-    idx = [hdr.index(k) for k in KEEP]
+    keep = [k for k in KEEP if k in hdr]                 # metric names differ a little between ncu versions
+    idx = [hdr.index(k) for k in keep]
     traffic = {}
-    with open(os.path.join(HERE, "r1_ncu_full.txt"), "w") as f:
-        f.write("\t".join(KEEP) + "\n" + "\t".join(units[i] for i in idx) + "\n")
+    with open(os.path.join(HERE, f"{tag}_ncu_full.txt"), "w") as f:
+        f.write("\t".join(keep) + "\n" + "\t".join(units[i] for i in idx) + "\n")
         for r in rows[2:]:
             f.write("\t".join(r[i][:90] for i in idx) + "\n")
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index("dram__bytes_read.sum")]]
@@ -79,4 +81,4 @@ def full_report(rep):
 if __name__ == "__main__":
     launch_shares(sys.argv[1])
     if len(sys.argv) > 2:
-        full_report(sys.argv[2])
+        full_report(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "r2")

@@ -81,9 +81,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
         if (spins > (1u << 22)) __trap();
 }
-__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {      // false = gave up
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
-        if (spins > (1u << 22)) return false;
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or the time (ns) has passed,
+// instead of burning issue slots other warps of the SM need
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {      // false = gave up (about 2 s)
+    for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 20000u); spins++)
+        if (spins > (1u << 17)) return false;
     return true;
 }
 

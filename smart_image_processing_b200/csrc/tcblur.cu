@@ -98,7 +98,7 @@ constexpr int REC_RING = 64;
 //   bar_a2     all 16 warps have written their part of A2 for tile i (and so are done with D2 and the centre pixels of tile
 //              i-1 and with D1 of tile i)                               (16 arrivals)                  issuer waits
 //   bar_d2     pass 2 of tile i complete: D2lo / D2hi readable          (tcgen05.commit)               epilogue warps wait
-template <int EPI, bool STATS>
+template <int EPI, bool STATS, bool DBG>
 __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
-#define TC_CRUMB(v) do { if (L.crumbs && blockIdx.x == 0) { L.status[1] = (v); __threadfence_system(); } } while (0)
-#define TC_STAMP(who, i, k) do { if (L.dbg && blockIdx.x == 0 && (i) < 64) { long long c_ = clock64(); uint32_t* d_ = L.dbg + 40960 + (who) * 2048 + (i) * 32 + 2 * (k); d_[0] = (uint32_t)c_; d_[1] = (uint32_t)(c_ >> 32); } } while (0)
+#define TC_CRUMB(v) do { if (DBG && L.crumbs && blockIdx.x == 0) { L.status[1] = (v); __threadfence_system(); } } while (0)
+#define TC_STAMP(who, i, k) do { if (DBG && L.dbg && blockIdx.x == 0 && (i) < 64) { long long c_ = clock64(); uint32_t* d_ = L.dbg + 40960 + (who) * 2048 + (i) * 32 + 2 * (k); d_[0] = (uint32_t)c_; d_[1] = (uint32_t)(c_ >> 32); } } while (0)
 #define TC_WAIT(bar, par, id) do { if (!tc::mbar_wait_bounded(bar, par)) { L.status[0] = (id); __threadfence_system(); __trap(); } } while (0)
 
     // this CTA's tiles: a contiguous run of the launch's tile sequence (pages change once or twice per CTA, not every tile:
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                         for (int k = 0; k < 32; k++) v[k] = ((v[k] << 8) + vl[k] + 128u) >> 8;
                     }
                     tc::tmem_wait_ld();
-                    if (L.dbg && blockIdx.x == 0 && i == 0)
+                    if (DBG && L.dbg && blockIdx.x == 0 && i == 0)
                         for (int k = 0; k < 32; k++) L.dbg[row * 128 + cg * 32 + k] = v[k];
 #pragma unroll
                     for (int g = 0; g < 8; g++) {
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                     tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2HI : COL_A2HI) + cg * 8, hi);
                     tc::tmem_wait_st();
                 }
-                if (EPI != DS_EPI_BLUR && !(L.flags & 2)) {
+                if (EPI != DS_EPI_BLUR && !(DBG && (L.flags & 2))) {
                     // this thread's centre pixels, out of the source window while it is still there: row `row + R`, byte RL + column,
                     // 16-byte chunks swizzled by the row number
                     const int srow_i = row + L.R, swz = srow_i & 7;
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                     st_minmax = Jminmax; st_hist = Jhist;
                 }
                 const int x0 = tr.tx * L.NOUT, y0 = tr.ty * TM;
-                const bool first = L.dbg && blockIdx.x == 0 && e == 0;
+                const bool first = DBG && L.dbg && blockIdx.x == 0 && e == 0;
 
                 // ---- epilogue: 32 rows x this column group's units of 8 columns, the next unit's accumulators in flight
                 const int y = y0 + row;
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                             dl[2 * g] = d_ev; dl[2 * g + 1] = d_od;
                             out[g] = __byte_perm(d_ev, d_od, 0x6240);
                         }
-                        if (!(L.flags & 8)) *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
+                        if (!(DBG && (L.flags & 8))) *reinterpret_cast<uint2*>(s_out + row * out_pitch + c) = make_uint2(out[0], out[1]);
                         if (STATS) {
                             if (nvalid < 8) {                   // rare: keep the columns past the width out of the statistics
                                 for (int k = 0; k < nvalid; k++) {
@@ -479,11 +479,11 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                                     if (Jhist) atomicAdd(&my_hist[v], 1u);
                                 }
                             } else {
-                                if (Jminmax && !(L.flags & 1)) {
+                                if (Jminmax && !(DBG && (L.flags & 1))) {
 #pragma unroll
                                     for (int k = 0; k < 4; k++) { mn2 = __vminu2(mn2, dl[k]); mx2 = __vmaxu2(mx2, dl[k]); }
                                 }
-                                if (Jhist && !(L.flags & 4)) {
+                                if (Jhist && !(DBG && (L.flags & 4))) {
                                     // values 0..7: 4-bit counters in two registers (a 32-bit shift by 32 or more gives 0, so larger
                                     // values add nothing here); at most 4 increments per field and unit
                                     uint32_t h0 = 0, h1 = 0;
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 // tensor map, so nothing is ever written past the page's width or height)
                 tc::fence_async_smem();
                 asm volatile("bar.sync 3, %0;" ::"n"(N_EPI_WARPS * 32) : "memory");
-                if (tid == 0 && !(L.flags & 16)) {
+                if (tid == 0 && !(DBG && (L.flags & 16))) {
                     if (tr.job != last_dmap) { tc::tmap_acquire(&L.dmaps[tr.job]); last_dmap = tr.job; }
                     tc::tma_store_2d(&L.dmaps[tr.job], x0, y0, s_out);
                 }
@@ -714,12 +714,13 @@ int get_variant(docscan_ctx* ctx, const TcSpec& S, int axis, int RL, int K1, int
     return DOCSCAN_OK;
 }
 
-template <int EPI, bool STATS>
+template <int EPI, bool STATS, bool DBG = false>
 int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
-    DS_CUDA(ctx, cudaFuncSetAttribute(tc_blur_kernel<EPI, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!DBG && L.dbg) return launch_tc<EPI, STATS, true>(ctx, L, smem);      // DOCSCAN_TC_DEBUG: the instance with dumps, stamps and skip flags
+    DS_CUDA(ctx, cudaFuncSetAttribute(tc_blur_kernel<EPI, STATS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(L.total_tiles, ctx->sm_count);            // one CTA per SM (512 TMEM columns, ~210 KB of shared memory)
     if (const char* e = getenv("DOCSCAN_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
-    tc_blur_kernel<EPI, STATS><<<grid, NT, smem, ctx->stream>>>(L);
+    tc_blur_kernel<EPI, STATS, DBG><<<grid, NT, smem, ctx->stream>>>(L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
 }
