@@ -12,7 +12,11 @@ each process their own batch (weak scaling, no collective on the data path).
 
 `value`   : device-resident inputs/outputs, CUDA-event time on the launching stream, max over ranks.
 `e2e`     : the same metric through the C-ABI call with HOST (pinned) buffers, H2D of every input page and
-            D2H of both result images (warped, binary) inside the timed region.
+            D2H of both result images (warped, binary) inside the timed region, >= 10 steps; beside it `e2e.pageable`
+            (plain numpy buffers, same call) and `e2e.pcie` (plain pinned copies of the same byte mix on every rank
+            at once: the link ceiling the leg runs against).
+`parity_checked`: two pages of every rank's timed batch compared with the oracle after the run.
+`--total-pages T`: BASELINE config 3 as written — page ids 0..T-1 sharded over the ranks by id (strong scaling).
 `roofline`: the kernel with the largest share of the step, timed live with CUDA events in a second,
             instrumented pass (docscan_profile_enable) — algorithmic bytes / average launch time vs the
             measured HBM copy bandwidth in MEASURED_PEAKS.json.
@@ -509,30 +513,33 @@ def run_ours(args):
                "matches_device_resident": same,
                "host_buffers": f"pinned; {De} distinct pages cycled, every page copied every step; the library uploads only the "
                                f"rows/columns of each {PAGE_H * PAGE_W * 3} B photo under its quad (bytes counted by the library)"}
-        # raw link rate, all ranks at once, both directions at once
-        n_link = 1 << 30
-        h_up, h_dn = torch.empty(n_link, dtype=torch.uint8).pin_memory(), torch.empty(n_link, dtype=torch.uint8).pin_memory()
-        d_up, d_dn = torch.empty(n_link, dtype=torch.uint8, device=dev), torch.empty(n_link, dtype=torch.uint8, device=dev)
+        # raw link rate, all ranks at once: plain pinned copies of the step's own byte mix (H2D and D2H concurrently, in the
+        # proportion the step moves them) -- the ceiling the leg above runs against
+        n_up = 1 << 30
+        n_dn = max(1 << 20, int(n_up * (d2h / max(h2d, 1))) & ~0xFFFFF)
+        h_up, h_dn = torch.empty(n_up, dtype=torch.uint8).pin_memory(), torch.empty(n_dn, dtype=torch.uint8).pin_memory()
+        d_up, d_dn = torch.empty(n_up, dtype=torch.uint8, device=dev), torch.empty(n_dn, dtype=torch.uint8, device=dev)
         s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        for _ in range(2):
-            with torch.cuda.stream(s_up):
-                d_up.copy_(h_up, non_blocking=True)
-            with torch.cuda.stream(s_dn):
-                h_dn.copy_(d_dn, non_blocking=True)
+
+        def link_round(reps):
+            for _ in range(reps):
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_up, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    h_dn.copy_(d_dn, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        link_round(2)
         barrier()
         reps = 6
         t0 = time.perf_counter()
-        for _ in range(reps):
-            with torch.cuda.stream(s_up):
-                d_up.copy_(h_up, non_blocking=True)
-            with torch.cuda.stream(s_dn):
-                h_dn.copy_(d_dn, non_blocking=True)
-        torch.cuda.synchronize(dev)
+        link_round(reps)
         link_s = sharding.max_over_ranks(time.perf_counter() - t0, dev)
-        link_gbs = reps * n_link / link_s / 1e9                      # per direction, per rank, with every rank copying
+        link_gbs = reps * n_up / link_s / 1e9                       # H2D rate per rank with every rank copying and the D2H share alongside
         del h_up, h_dn, d_up, d_dn
-        floor_s = max(h2d, d2h) / (link_gbs * 1e9)                  # a step cannot beat its larger direction at link rate
-        e2e["pcie"] = {"per_direction_GBps_per_rank_all_ranks_copying": round(link_gbs, 2),
+        floor_s = h2d / (link_gbs * 1e9)                            # a step cannot beat its uploads at that rate
+        e2e["pcie"] = {"h2d_GBps_per_rank_all_ranks_copying": round(link_gbs, 2),
+                       "with_concurrent_d2h_share": round(n_dn / n_up, 3),
                        "step_floor_ms": round(floor_s * 1e3, 2),
                        "e2e_frac_of_link_floor": round((floor_s * 1e3) / (total_jobs * PAGE_MP / ev * 1e3), 3)}
         del hpages, keep_pinned
