@@ -46,7 +46,8 @@ constexpr int NS = 3;                            // source-window stages: pass 1
 constexpr int TOE_SLOTS = 3;                     // cached pass-2 band matrices (left / interior / right)
 constexpr int T_BYTES = 2 * TM * 128;      // two 128-byte K blocks
 constexpr int TOE_BYTES = 96 * 128;
-constexpr int MAX_R = 48;
+constexpr int MAX_R = 48;                 // largest radius of the 128-column tile
+constexpr int MAX_R_WIDE = 96;            // ... of the 256-column (wide) tile: 128 + 2 R source rows <= 320
 constexpr int MAX_JOBS = 64, MAX_TABS = 256;      // page table / band-matrix pointer table kept in shared memory
 
 struct TcJob {
@@ -71,7 +72,9 @@ struct TcLaunch {
     uint16_t* flag_list; uint32_t* flag_count; uint32_t flag_cap;   // per tile: count, then up to flag_cap entries (row << 6 | column)
     int flags;                   // debug: skip parts of the epilogue (DOCSCAN_TC_FLAGS), for timing experiments only
     int crumbs;                  // debug: CTA 0 reports its progress to status[1] (slow: a system-scope fence per phase)
-    int t_slots;                 // cached pass-1 band matrices (top / interior / bottom): 3 when shared memory allows, else 2
+    int t_slots;                 // cached pass-1 band matrices (top / interior / bottom): 3 when shared memory allows, else 2 or 1
+    int toe_slots;               // cached pass-2 band matrices (left / interior / right): 3, or 2 for the wide tile
+    int ns;                      // source-window stages: 3; wide tile (64..80 KB per window): 2 or 1
     int R, RL, K1, NOUT;         // RL: left margin of the source window (TMA needs its first byte 16-byte aligned)
     uint32_t idesc1, idesc2;
 };
@@ -98,18 +101,28 @@ constexpr int REC_RING = 64;
 //   bar_a2     all 16 warps have written their part of A2 for tile i (and so are done with D2 and the centre pixels of tile
 //              i-1 and with D1 of tile i)                               (16 arrivals)                  issuer waits
 //   bar_d2     pass 2 of tile i complete: D2lo / D2hi readable          (tcgen05.commit)               epilogue warps wait
-template <int EPI, bool STATS, bool DBG>
+// WIDE: the tile variant for radii 49..93 (8K scans, k = 101..217): 256 input columns per tile (two TMA boxes side by side = two
+// MN blocks of the B operand of pass 1, two K blocks in pass 2), up to 320 source rows (three K blocks of the band matrix), 64
+// output columns, one source stage, no lag between drain and epilogue (tensor memory: D1 256 | A2 128 | D2 128).
+template <int EPI, bool STATS, bool DBG, bool WIDE>
 __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sT = base;                                            // L.t_slots band matrices of pass 1
     constexpr bool ADAPT = EPI == DS_EPI_AGAUSS;
-    constexpr bool DEFER = !ADAPT;                                 // two pairs of pass-2 accumulators: the epilogue lags one tile
-    constexpr uint32_t t_bytes = ADAPT ? 2 * T_BYTES : T_BYTES;   // adaptive: high-byte plane, low-byte plane
-    uint8_t* sToe = sT + L.t_slots * t_bytes;                      // TOE_SLOTS band matrices of pass 2
-    const uint32_t toe_bytes = (uint32_t)L.NOUT * 128 * (ADAPT ? 2 : 1);
-    uint8_t* sS = sToe + TOE_SLOTS * toe_bytes;                    // NS source windows
-    uint8_t* s_out = sS + NS * L.K1 * 128;                         // the tile's results, 128 dense rows of NOUT bytes: the source of the TMA store
+    static_assert(!(ADAPT && WIDE), "no wide adaptive instance");
+    constexpr bool DEFER = !ADAPT && !WIDE;                        // two pairs of pass-2 accumulators: the epilogue lags one tile
+    constexpr int NINK = WIDE ? 256 : 128;                         // input columns per tile
+    constexpr int DCOLS = NINK / 4;                                // D1 columns each of the four column groups drains
+    // adaptive: two byte planes; wide: two or three 128-byte K blocks
+    const uint32_t t_bytes = ADAPT ? 2 * T_BYTES : (WIDE ? (uint32_t)((L.K1 + 127) >> 7) * TM * 128 : (uint32_t)T_BYTES);
+    constexpr int C_A2LO = ADAPT ? COLA_A2LO : (WIDE ? 256 : COL_A2LO), C_A2HI = ADAPT ? COLA_A2HI : (WIDE ? 320 : COL_A2HI);
+    constexpr int C_D2LO = WIDE ? 384 : COL_D2LO, C_D2HI = WIDE ? 448 : COL_D2HI;
+    uint8_t* sToe = sT + L.t_slots * t_bytes;                      // band matrices of pass 2
+    const uint32_t toe_bytes = (uint32_t)L.NOUT * 128 * ((ADAPT || WIDE) ? 2 : 1);
+    uint8_t* sS = sToe + L.toe_slots * toe_bytes;                  // source windows
+    const uint32_t s_bytes_all = (uint32_t)L.K1 * NINK;
+    uint8_t* s_out = sS + L.ns * s_bytes_all;                         // the tile's results, 128 dense rows of NOUT bytes: the source of the TMA store
     const int out_pitch = L.NOUT;
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_out + TM * out_pitch);   // 8 x 256, only with STATS
     __shared__ uint64_t bar_s[NS], bar_c, bar_d1, bar_d2[2], bar_a2;
@@ -175,9 +188,9 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
         uint32_t ph_c = 0, ph_s0 = 0, ph_s1 = 0, ph_s2 = 0;
         int last_map = -1;
         const uint32_t aT = tc::smem_u32(sT), aToe = tc::smem_u32(sToe), aS = tc::smem_u32(sS);
-        const uint32_t s_bytes = (uint32_t)L.K1 * 128;
+        const uint32_t s_bytes = s_bytes_all;                     // one source window; LBO of its descriptor = one 128-column block
         const uint64_t dT0 = tc::smem_desc_sw128(aT, 16, 1024), dToe0 = tc::smem_desc_sw128(aToe, 16, 1024);
-        const uint64_t dS0 = tc::smem_desc_sw128(aS, s_bytes, 1024);
+        const uint64_t dS0 = tc::smem_desc_sw128(aS, (uint32_t)L.K1 * 128, 1024);
 
         // pass-1 band matrix `want` into a slot (returned); `keep` = slot an unfinished MMA may still be reading
         auto ensure_t = [&](const uint8_t* want, int keep) {
@@ -202,10 +215,10 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
         auto ensure_toe = [&](const uint8_t* want, int keep) {
             if (want == e_tag0) return 0;
             if (want == e_tag1) return 1;
-            if (want == e_tag2) return 2;
+            if (L.toe_slots > 2 && want == e_tag2) return 2;
             int v = e_rr;
-            if (v == keep) v = (v + 1 == TOE_SLOTS) ? 0 : v + 1;
-            e_rr = (v + 1 == TOE_SLOTS) ? 0 : v + 1;
+            if (v == keep) v = (v + 1 == L.toe_slots) ? 0 : v + 1;
+            e_rr = (v + 1 == L.toe_slots) ? 0 : v + 1;
             tc::mbar_expect_tx(&bar_c, toe_bytes);
             tc::bulk_load(sToe + (size_t)v * toe_bytes, want, toe_bytes, &bar_c);
             TC_WAIT(&bar_c, ph_c, 1); ph_c ^= 1;
@@ -215,13 +228,24 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
         auto load_source = [&](int i) {
             const TileRec r = s_rec[i % REC_RING];
             if (r.job != last_map) { tc::tmap_acquire(&L.maps[r.job]); last_map = r.job; }
-            const int st = i % NS;
+            const int st = i % L.ns;
             uint64_t* bar = &bar_s[st];
             tc::mbar_expect_tx(bar, s_bytes);
-            tc::tma_load_2d(sS + (size_t)st * s_bytes, &L.maps[r.job], r.tx * L.NOUT - L.RL, r.ty * TM - L.R, bar);
+            if (!WIDE) {
+                tc::tma_load_2d(sS + (size_t)st * s_bytes, &L.maps[r.job], r.tx * L.NOUT - L.RL, r.ty * TM - L.R, bar);
+            } else {
+                // two 128-column blocks side by side, each fetched as two boxes of K1 / 2 rows (a TMA box has at most 256 rows)
+                const int half = L.K1 >> 1;
+#pragma unroll
+                for (int cb = 0; cb < 2; cb++)
+#pragma unroll
+                    for (int rb = 0; rb < 2; rb++)
+                        tc::tma_load_2d(sS + (size_t)st * s_bytes + (size_t)cb * L.K1 * 128 + (size_t)rb * half * 128, &L.maps[r.job],
+                                        r.tx * L.NOUT - L.RL + cb * 128, r.ty * TM - L.R + rb * half, bar);
+            }
         };
         auto pass1 = [&](int i, int t_slot) {
-            const int st = i % NS;
+            const int st = i % L.ns;
             if (st == 0) { TC_WAIT(&bar_s[0], ph_s0, 2); ph_s0 ^= 1; }
             else if (st == 1) { TC_WAIT(&bar_s[1], ph_s1, 2); ph_s1 ^= 1; }
             else { TC_WAIT(&bar_s[2], ph_s2, 2); ph_s2 ^= 1; }
@@ -232,7 +256,9 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 case 5: issue_pass1<5>(tmem + COL_D1, dT, dS, L.idesc1); break;
                 case 6: issue_pass1<6>(tmem + COL_D1, dT, dS, L.idesc1); break;
                 case 7: issue_pass1<7>(tmem + COL_D1, dT, dS, L.idesc1); break;
-                default: issue_pass1<8>(tmem + COL_D1, dT, dS, L.idesc1); break;
+                case 8: issue_pass1<8>(tmem + COL_D1, dT, dS, L.idesc1); break;
+                case 9: issue_pass1<9>(tmem + COL_D1, dT, dS, L.idesc1); break;
+                default: issue_pass1<10>(tmem + COL_D1, dT, dS, L.idesc1); break;
             }
             if (ADAPT) {                                           // the low-byte plane of the weights into the second accumulator
                 const uint64_t dTl = dT + (uint64_t)(T_BYTES >> 4);
@@ -250,7 +276,7 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
         int t_slot = 0, toe_prev = -1;
         if (n_mine > 0 && tc::elect_one()) {
             load_source(0);
-            if (n_mine > 1) load_source(1);
+            if (n_mine > 1 && L.ns > 1) load_source(1);
             t_slot = ensure_t(s_rec[0].t_mat, -1);
             pass1(0, t_slot);
             TC_CRUMB(2);
@@ -273,10 +299,13 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 const int b2 = DEFER ? (i & 1) : 0;                // the pair of accumulators tile i - 2 has left
                 if (!ADAPT) {
                     const uint32_t d2 = tmem + b2 * D2_STRIDE;
+                    const uint32_t kblk = ((uint32_t)L.NOUT * 128) >> 4;          // next 128-byte K block of the band matrix (wide tile)
 #pragma unroll
-                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(d2 + COL_D2LO, tmem + COL_A2LO + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                    for (int s2 = 0; s2 < NINK / 32; s2++)
+                        tc::mma_i8_ts(d2 + C_D2LO, tmem + C_A2LO + s2 * 8, dToe + (uint64_t)((s2 >> 2) * kblk + (s2 & 3) * 2), L.idesc2, s2 > 0);
 #pragma unroll
-                    for (int s2 = 0; s2 < NIN / 32; s2++) tc::mma_i8_ts(d2 + COL_D2HI, tmem + COL_A2HI + s2 * 8, dToe + (uint64_t)(s2 * 2), L.idesc2, s2 > 0);
+                    for (int s2 = 0; s2 < NINK / 32; s2++)
+                        tc::mma_i8_ts(d2 + C_D2HI, tmem + C_A2HI + s2 * 8, dToe + (uint64_t)((s2 >> 2) * kblk + (s2 & 3) * 2), L.idesc2, s2 > 0);
                 } else {
                     // 16-bit row means x 16-bit weights as byte planes: D2a = hi * Whi, D2b = hi * Wlo + lo * Whi, D2c = lo * Wlo
                     const uint64_t dWl = dToe + (uint64_t)(((uint32_t)L.NOUT * 128) >> 4);
@@ -291,10 +320,12 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 }
                 tc::mma_commit(&bar_d2[b2]);
                 TC_STAMP(1, i, 3);
+                // a single source stage (wide tile): it is free now (pass 1 and the centre pixels of tile i are done: bar_a2)
+                if (L.ns == 1 && i + 1 < n_mine) load_source(i + 1);
                 if (i + 1 < n_mine) pass1(i + 1, t_next);       // runs behind pass 2 of tile i, under its epilogue
                 TC_STAMP(1, i, 4);
-                // stage (i + 2) % NS held tile i - 1, whose epilogue is over (bar_a2 of tile i): refill it
-                if (i + 2 < n_mine) load_source(i + 2);
+                // three stages: stage (i + 2) % 3 held tile i - 1, whose epilogue is over (bar_a2 of tile i): refill it
+                if (L.ns > 1 && i + 2 < n_mine) load_source(i + 2);
                 TC_STAMP(1, i, 5);
                 toe_prev = toe_slot; t_slot = t_next;
                 TC_CRUMB(3);
@@ -356,31 +387,36 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 tc::fence_after_sync();
                 if (tid == 0) TC_STAMP(0, i, 1);
                 {
-                    uint32_t v[32], lo[8], hi[8];
-                    tc::tmem_ld32(tmem + lane_base + COL_D1 + cg * 32, v);
-                    if (ADAPT) {
-                        // row mean * 65536 = 256 * D1h + D1l (24 bits)  ->  8.8 fixed point, rounded
-                        uint32_t vl[32];
-                        tc::tmem_ld32(tmem + lane_base + COLA_D1L + cg * 32, vl);
+                    // DCOLS = 32 (64 for the wide tile) columns of D1 per warp, 32 at a time
+                    uint32_t lo[DCOLS / 4], hi[DCOLS / 4];
+#pragma unroll
+                    for (int part = 0; part < DCOLS / 32; part++) {
+                        uint32_t v[32];
+                        tc::tmem_ld32(tmem + lane_base + COL_D1 + cg * DCOLS + part * 32, v);
+                        if (ADAPT) {
+                            // row mean * 65536 = 256 * D1h + D1l (24 bits)  ->  8.8 fixed point, rounded
+                            uint32_t vl[32];
+                            tc::tmem_ld32(tmem + lane_base + COLA_D1L + cg * 32, vl);
+                            tc::tmem_wait_ld();
+#pragma unroll
+                            for (int k = 0; k < 32; k++) v[k] = ((v[k] << 8) + vl[k] + 128u) >> 8;
+                        }
                         tc::tmem_wait_ld();
+                        if (DBG && !WIDE && L.dbg && blockIdx.x == 0 && i == 0)
+                            for (int k = 0; k < 32; k++) L.dbg[row * 128 + cg * 32 + k] = v[k];
 #pragma unroll
-                        for (int k = 0; k < 32; k++) v[k] = ((v[k] << 8) + vl[k] + 128u) >> 8;
-                    }
-                    tc::tmem_wait_ld();
-                    if (DBG && L.dbg && blockIdx.x == 0 && i == 0)
-                        for (int k = 0; k < 32; k++) L.dbg[row * 128 + cg * 32 + k] = v[k];
-#pragma unroll
-                    for (int g = 0; g < 8; g++) {
-                        const uint32_t t1 = __byte_perm(v[4 * g], v[4 * g + 1], 0x5140);        // a0 b0 a1 b1
-                        const uint32_t t2 = __byte_perm(v[4 * g + 2], v[4 * g + 3], 0x5140);    // c0 d0 c1 d1
-                        lo[g] = __byte_perm(t1, t2, 0x5410);                                    // a0 b0 c0 d0
-                        hi[g] = __byte_perm(t1, t2, 0x7632);                                    // a1 b1 c1 d1
+                        for (int g = 0; g < 8; g++) {
+                            const uint32_t t1 = __byte_perm(v[4 * g], v[4 * g + 1], 0x5140);        // a0 b0 a1 b1
+                            const uint32_t t2 = __byte_perm(v[4 * g + 2], v[4 * g + 3], 0x5140);    // c0 d0 c1 d1
+                            lo[part * 8 + g] = __byte_perm(t1, t2, 0x5410);                         // a0 b0 c0 d0
+                            hi[part * 8 + g] = __byte_perm(t1, t2, 0x7632);                         // a1 b1 c1 d1
+                        }
                     }
                     if (!ADAPT && cg == 3) {
-                        // columns 126 and 127 carry no tap: they hold the rounding constant instead, 2 x (128 * 128) = 32768,
-                        // against the two 128s in the band matrix's last two slots
-                        lo[7] = (lo[7] & 0x0000FFFFu) | 0x80800000u;
-                        hi[7] &= 0x0000FFFFu;
+                        // the last two columns (126, 127; wide: 254, 255) carry no tap: they hold the rounding constant instead,
+                        // 2 x (128 * 128) = 32768, against the two 128s in the band matrix's last two slots
+                        lo[DCOLS / 4 - 1] = (lo[DCOLS / 4 - 1] & 0x0000FFFFu) | 0x80800000u;
+                        hi[DCOLS / 4 - 1] &= 0x0000FFFFu;
                     }
                     if (DEFER && i > 0) {
                         // pass 2 of the previous tile reads A2: it must be over before A2 is rewritten (it usually finished long ago,
@@ -388,19 +424,26 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                         TC_WAIT(&bar_d2[(i - 1) & 1], ((i - 1) >> 1) & 1, 7);
                         tc::fence_after_sync();
                     }
-                    tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2LO : COL_A2LO) + cg * 8, lo);
-                    tc::tmem_st8(tmem + lane_base + (ADAPT ? COLA_A2HI : COL_A2HI) + cg * 8, hi);
+                    if (WIDE) {
+                        tc::tmem_st16(tmem + lane_base + C_A2LO + cg * 16, lo);
+                        tc::tmem_st16(tmem + lane_base + C_A2HI + cg * 16, hi);
+                    } else {
+                        tc::tmem_st8(tmem + lane_base + C_A2LO + cg * 8, lo);
+                        tc::tmem_st8(tmem + lane_base + C_A2HI + cg * 8, hi);
+                    }
                     tc::tmem_wait_st();
                 }
                 if (EPI != DS_EPI_BLUR && !(DBG && (L.flags & 2))) {
                     // this thread's centre pixels, out of the source window while it is still there: row `row + R`, byte RL + column,
                     // 16-byte chunks swizzled by the row number
                     const int srow_i = row + L.R, swz = srow_i & 7;
-                    const uint8_t* s_center = sS + (size_t)(i % NS) * L.K1 * 128 + srow_i * 128;
+                    const uint8_t* s_center = sS + (size_t)(i % L.ns) * s_bytes_all + srow_i * 128;
 #pragma unroll
                     for (int k = 0; k < 3; k++) {
-                        const int cb = L.RL + (u_begin + k) * 8;
-                        if (u_begin + k < u_end) cen_new[k] = *reinterpret_cast<const uint2*>(s_center + ((((cb >> 4) ^ swz) << 4) | (cb & 8)));
+                        const int cb = L.RL + (u_begin + k) * 8;           // byte in the window row; wide: its 128-column block first
+                        const uint8_t* blk = s_center + (size_t)(cb >> 7) * L.K1 * 128;
+                        const int cbb = cb & 127;
+                        if (u_begin + k < u_end) cen_new[k] = *reinterpret_cast<const uint2*>(blk + ((((cbb >> 4) ^ swz) << 4) | (cbb & 8)));
                     }
                 }
                 tc::fence_before_sync();
@@ -552,8 +595,8 @@ __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ 
                 // the columns past this group's share belong to a neighbour or to nobody and are ignored)
                 uint32_t lo[24], hi[24];
                 {
-                    const uint32_t a_lo = tmem + lane_base + COL_D2LO + b2 * D2_STRIDE + u_begin * 8;
-                    const uint32_t a_hi = tmem + lane_base + COL_D2HI + b2 * D2_STRIDE + u_begin * 8;
+                    const uint32_t a_lo = tmem + lane_base + C_D2LO + b2 * D2_STRIDE + u_begin * 8;
+                    const uint32_t a_hi = tmem + lane_base + C_D2HI + b2 * D2_STRIDE + u_begin * 8;
                     tc::tmem_ld16(a_lo, lo);
                     tc::tmem_ld16(a_hi, hi);
                     if (u_end - u_begin > 2) {                     // warp-uniform: this column group has a third unit
@@ -691,14 +734,14 @@ bool build_band(const TcSpec& S, int margin, int o0, int len, int n_out, int n_s
 }
 
 // device copy of one band matrix, cached per context: key = (mode / axis, k, near-border distances or -1, tile geometry)
-int get_variant(docscan_ctx* ctx, const TcSpec& S, int axis, int RL, int K1, int NOUT, int o0, int len, const uint8_t** out, bool* ok) {
-    const int n_out = axis == 0 ? TM : NOUT, n_slots = axis == 0 ? K1 : NIN;
+int get_variant(docscan_ctx* ctx, const TcSpec& S, int axis, bool wide, int RL, int K1, int NOUT, int o0, int len, const uint8_t** out, bool* ok) {
+    const int n_out = axis == 0 ? TM : NOUT, n_slots = axis == 0 ? K1 : (wide ? 2 * NIN : NIN);
     const int a = (o0 - S.R < 0) ? o0 : -1;
     const int b = (o0 + n_out - 1 + S.R > len - 1) ? len - o0 : -1;
-    const std::array<int, 6> key = {S.mode * 2 + axis, S.k, a, b, NOUT, K1};
+    const std::array<int, 6> key = {S.mode * 2 + axis + (wide ? 4 : 0), S.k, a, b, NOUT, K1};
     auto it = ctx->tc_tables.find(key);
     if (it == ctx->tc_tables.end()) {
-        const size_t plane = axis == 0 ? (size_t)T_BYTES : (size_t)NOUT * 128;
+        const size_t plane = axis == 0 ? (wide ? (size_t)((K1 + 127) / 128) * TM * 128 : (size_t)T_BYTES) : (size_t)NOUT * (wide ? 256 : 128);
         const size_t bytes = plane * (S.mode == 1 ? 2 : 1);
         std::vector<uint8_t> img(bytes);
         *ok = build_band(S, axis == 0 ? S.R : RL, o0, len, n_out, n_slots, axis == 0 ? TM : NOUT, axis == 1 && S.mode == 0, img.data(), plane);
@@ -714,13 +757,14 @@ int get_variant(docscan_ctx* ctx, const TcSpec& S, int axis, int RL, int K1, int
     return DOCSCAN_OK;
 }
 
-template <int EPI, bool STATS, bool DBG = false>
-int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem) {
-    if (!DBG && L.dbg) return launch_tc<EPI, STATS, true>(ctx, L, smem);      // DOCSCAN_TC_DEBUG: the instance with dumps, stamps and skip flags
-    DS_CUDA(ctx, cudaFuncSetAttribute(tc_blur_kernel<EPI, STATS, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int EPI, bool STATS, bool DBG = false, bool WIDE = false>
+int launch_tc(docscan_ctx* ctx, const TcLaunch& L, size_t smem, bool wide = false) {
+    if constexpr (!DBG) if (L.dbg) return launch_tc<EPI, STATS, true, WIDE>(ctx, L, smem, wide);      // DOCSCAN_TC_DEBUG: dumps, stamps, skip flags
+    if constexpr (!WIDE && EPI != DS_EPI_AGAUSS) if (wide) return launch_tc<EPI, STATS, DBG, true>(ctx, L, smem, wide);
+    DS_CUDA(ctx, cudaFuncSetAttribute(tc_blur_kernel<EPI, STATS, DBG, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(L.total_tiles, ctx->sm_count);            // one CTA per SM (512 TMEM columns, ~210 KB of shared memory)
     if (const char* e = getenv("DOCSCAN_TC_GRID")) grid = std::max(1, std::min(grid, atoi(e)));
-    tc_blur_kernel<EPI, STATS, DBG><<<grid, NT, smem, ctx->stream>>>(L);
+    tc_blur_kernel<EPI, STATS, DBG, WIDE><<<grid, NT, smem, ctx->stream>>>(L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
 }
@@ -731,13 +775,19 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
     if (n <= 0 || n > MAX_JOBS || !encode_fn()) return false;
     if (const char* e = getenv("DOCSCAN_TC")) if (atoi(e) == 0) return false;
     const int R = S.R;
-    if (R < 1 || R > MAX_R) return false;
+    // radii up to 48: 128 input columns per tile; up to 96 (blur only): the wide tile, 256 input columns
+    // (the narrow tile keeps only 32 output columns from radius 33 on; DOCSCAN_TC_WIDE_FROM moves the switch for measurements)
+    int wide_from = 33;
+    if (const char* e = getenv("DOCSCAN_TC_WIDE_FROM")) wide_from = std::max(1, atoi(e));
+    const bool wide = S.mode == 0 && R >= std::min(wide_from, MAX_R + 1) && R <= MAX_R_WIDE;
+    if (R < 1 || (R > MAX_R && !wide)) return false;
     const int K1 = (TM + 2 * R + 31) / 32 * 32;
     const int RL = (R + 15) & ~15;                      // the window's first column must sit on a 16-byte boundary of its row
     // blur: the last two source slots of a tile carry the rounding constant (see the kernel), so the taps must end before them;
     // adaptive: three 64-column accumulators
-    const int NOUT = S.mode == 0 ? std::min(80, (NIN - 2 - RL - R) / 16 * 16) : std::min(64, (NIN - RL - R) / 16 * 16);
-    if (NOUT < 16 || K1 > 256 || (S.mode == 1 && NOUT != 64)) return false;
+    const int NOUT = wide ? std::min(64, (2 * NIN - 2 - RL - R) / 16 * 16)
+                          : S.mode == 0 ? std::min(80, (NIN - 2 - RL - R) / 16 * 16) : std::min(64, (NIN - RL - R) / 16 * 16);
+    if (NOUT < 16 || K1 > (wide ? 320 : 256) || (S.mode == 1 && NOUT != 64)) return false;
     bool stats = false;
     for (int i = 0; i < n; i++) {
         const BlurJob& j = jobs_host[i];
@@ -766,7 +816,7 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
             const int t_off = (int)tabs.size();
             for (int ty = 0; ty < j.nty; ty++) {
                 const uint8_t* p = nullptr; bool ok = false;
-                *rc = get_variant(ctx, S, 0, RL, K1, NOUT, ty * TM, b.h, &p, &ok);
+                *rc = get_variant(ctx, S, 0, wide, RL, K1, NOUT, ty * TM, b.h, &p, &ok);
                 if (*rc != DOCSCAN_OK) return true;
                 if (!ok) return false;
                 tabs.push_back(p);
@@ -774,7 +824,7 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
             const int toe_off = (int)tabs.size();
             for (int tx = 0; tx < j.ntx; tx++) {
                 const uint8_t* p = nullptr; bool ok = false;
-                *rc = get_variant(ctx, S, 1, RL, K1, NOUT, tx * NOUT, b.w, &p, &ok);
+                *rc = get_variant(ctx, S, 1, wide, RL, K1, NOUT, tx * NOUT, b.w, &p, &ok);
                 if (*rc != DOCSCAN_OK) return true;
                 if (!ok) return false;
                 tabs.push_back(p);
@@ -784,7 +834,7 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
         j.t_off = g->second.first; j.toe_off = g->second.second;
         const cuuint64_t dims[2] = {(cuuint64_t)b.w, (cuuint64_t)b.h};
         const cuuint64_t strides[1] = {(cuuint64_t)b.src_pitch};
-        const cuuint32_t box[2] = {(cuuint32_t)NIN, (cuuint32_t)K1};
+        const cuuint32_t box[2] = {(cuuint32_t)NIN, (cuuint32_t)(wide ? K1 / 2 : K1)};      // wide: four boxes per window
         const cuuint32_t estr[2] = {1, 1};
         const CUresult cr = encode_fn()(&maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)b.src, dims, strides, box, estr,
                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -813,7 +863,7 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
     L.jobs = reinterpret_cast<const TcJob*>((uint8_t*)dev + off_jobs);
     L.tabs = reinterpret_cast<const uint8_t* const*>((uint8_t*)dev + off_tabs);
     L.n_jobs = n; L.n_tabs = (int)tabs.size(); L.total_tiles = total; L.R = R; L.RL = RL; L.K1 = K1; L.NOUT = NOUT;
-    L.idesc1 = tc::idesc_i8(TM, NIN, 0, 0, 0, 1);
+    L.idesc1 = tc::idesc_i8(TM, wide ? 2 * NIN : NIN, 0, 0, 0, 1);
     L.idesc2 = tc::idesc_i8(TM, NOUT, 0, 0, 0, 0);
     L.c_param = S.c_param; L.band = S.band;
     if (fl) {
@@ -845,13 +895,24 @@ bool tc_run(docscan_ctx* ctx, const TcSpec& S, const BlurJob* jobs_host, int n, 
         if (const char* f = getenv("DOCSCAN_TC_FLAGS")) L.flags = atoi(f);
     }
     const size_t planes = S.mode == 1 ? 2 : 1;
-    const size_t smem_fixed = 1024 + (size_t)TOE_SLOTS * NOUT * 128 * planes + (size_t)NS * K1 * 128 + (size_t)TM * NOUT + (stats ? 8 * 256 * 4 : 0);
-    // + ~9 KB of static shared memory <= 227 KB; the adaptive threshold's matrix pair is 64 KB: one slot
-    L.t_slots = S.mode == 1 ? 1 : (smem_fixed + 3 * (size_t)T_BYTES <= 218 * 1024 ? 3 : 2);
-    const size_t smem = smem_fixed + (size_t)L.t_slots * T_BYTES * planes;
+    size_t smem;
+    if (!wide) {
+        L.toe_slots = TOE_SLOTS; L.ns = NS;
+        const size_t smem_fixed = 1024 + (size_t)TOE_SLOTS * NOUT * 128 * planes + (size_t)NS * K1 * 128 + (size_t)TM * NOUT + (stats ? 8 * 256 * 4 : 0);
+        // + ~9 KB of static shared memory <= 227 KB; the adaptive threshold's matrix pair is 64 KB: one slot
+        L.t_slots = S.mode == 1 ? 1 : (smem_fixed + 3 * (size_t)T_BYTES <= 218 * 1024 ? 3 : 2);
+        smem = smem_fixed + (size_t)L.t_slots * T_BYTES * planes;
+    } else {
+        // wide tile: one window is 64..80 KB; two stages when they fit (K1 = 256), else the load of tile i+1 waits for pass 1 of tile i
+        const size_t t_bytes = (size_t)((K1 + 127) / 128) * TM * 128, window = (size_t)K1 * 2 * NIN;
+        L.toe_slots = 2; L.t_slots = 1;
+        const size_t smem_fixed = 1024 + t_bytes + 2 * (size_t)NOUT * 256 + (size_t)TM * NOUT + (stats ? 8 * 256 * 4 : 0);
+        L.ns = smem_fixed + 2 * window <= 218 * 1024 ? 2 : 1;
+        smem = smem_fixed + (size_t)L.ns * window;
+    }
     {
         ProfScope prof(ctx, prof_name, 2.0 * px);
-#define DS_TC_CASE(E) case E: *rc = stats ? launch_tc<E, true>(ctx, L, smem) : launch_tc<E, false>(ctx, L, smem); break;
+#define DS_TC_CASE(E) case E: *rc = stats ? launch_tc<E, true>(ctx, L, smem, wide) : launch_tc<E, false>(ctx, L, smem, wide); break;
         switch (S.epi) {
             DS_TC_CASE(DS_EPI_BLUR)
             DS_TC_CASE(DS_EPI_SUB)

@@ -35,13 +35,15 @@ def expected_tile0(img, k):
     keff, R = len(q), len(q) // 2
     K1 = (128 + 2 * R + 31) // 32 * 32
     RL = (R + 15) // 16 * 16
-    NOUT = min(80, (128 - 2 - RL - R) // 16 * 16)
+    wide = R > 48                          # the 256-column tile (tcblur.cu: WIDE)
+    NIN = 256 if wide else 128
+    NOUT = min(64, (256 - 2 - RL - R) // 16 * 16) if wide else min(80, (128 - 2 - RL - R) // 16 * 16)
     h, w = img.shape
-    S = np.zeros((K1, 128), np.int64)
+    S = np.zeros((K1, NIN), np.int64)
     for j in range(K1):
         y = -R + j
         if 0 <= y < h:
-            for c in range(128):
+            for c in range(NIN):
                 x = -RL + c
                 if 0 <= x < w:
                     S[j, c] = img[y, x]
@@ -49,15 +51,15 @@ def expected_tile0(img, k):
     for i in range(min(128, h)):
         for t in range(keff):
             T[i, reflect101(i + t - R, h) + R] += q[t]
-    Th = np.zeros((NOUT, 128), np.int64)
+    Th = np.zeros((NOUT, NIN), np.int64)
     for n in range(min(NOUT, w)):
         for t in range(keff):
             Th[n, reflect101(n + t - R, w) + RL] += q[t]
     D1 = T @ S
     lo, hi = D1 & 255, D1 >> 8
-    Th[:, 126:128] = 128                   # the rounding constant rides in the last two slots
-    lo[:, 126:128] = 128
-    hi[:, 126:128] = 0
+    Th[:, NIN - 2:] = 128                  # the rounding constant rides in the last two slots
+    lo[:, NIN - 2:] = 128
+    hi[:, NIN - 2:] = 0
     return D1, lo @ Th.T, hi @ Th.T, NOUT
 
 
@@ -80,7 +82,7 @@ def main():
     rng = np.random.default_rng(1)
     total_bad = 0
     for k in ks:
-        for (h, w) in [(300, 260), (128, 128), (97, 131), (1600, 1131)]:
+        for (h, w) in [(300, 260), (128, 128), (97, 131), (1600, 1131)] + ([(2200, 3000)] if k > 100 else []):
             img = rng.integers(0, 256, (h, w), dtype=np.uint8)
             with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
                 path = f.name
@@ -96,7 +98,8 @@ def main():
             dbg = np.fromfile(path, np.uint32).astype(np.int64)
             os.remove(path)
             D1, D2lo, D2hi, NOUT = expected_tile0(img, k)
-            show("D1  ", dbg[:16384].reshape(128, 128), D1)
+            if D1.shape[1] == 128:
+                show("D1  ", dbg[:16384].reshape(128, 128), D1)
             show("D2lo", dbg[16384:16384 + 12288].reshape(128, 96)[:, :NOUT], D2lo)
             show("D2hi", dbg[16384 + 12288:16384 + 2 * 12288].reshape(128, 96)[:, :NOUT], D2hi)
     # the fused epilogues through the stage functions
