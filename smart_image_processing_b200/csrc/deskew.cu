@@ -1,13 +1,13 @@
 // The skew estimate of deskew() (DocScanner.py:218-231) on the device, so that the deskew rotation no longer needs a
 // host round trip between the blend and the rotate kernels:
 //
-//   edges = cv2.Canny(gray, low, high)                      canny_nms_kernel + union-find hysteresis (ccl_* kernels)
+//   edges = cv2.Canny(gray, low, high)                      canny_bits_kernel + bit-parallel hysteresis (canny_hyst_kernel)
 //   lines = cv2.HoughLines(edges, 1, pi/180, 150)           hough_vote_kernel + hough_peaks_kernel
 //   angle = median of the folded line angles, 0 beyond max_rotate; getRotationMatrix2D   skew_finish_kernel
 //
 // Everything is exact: Canny is integer arithmetic (Sobel 3x3 with replicated borders, |dx|+|dy|, 15-bit fixed-point
 // direction test); its hysteresis result is "the candidates 8-connected to a candidate above `high`", which does not
-// depend on traversal order, so it is computed as connected components with an atomic union-find instead of OpenCV's
+// depend on traversal order, so it is computed by bit-parallel relaxation sweeps over two bit planes instead of OpenCV's
 // stack flood fill.  The Hough accumulator is integer votes at r = cvRound(x*cos + y*sin) with OpenCV's fp32 tables
 // (built on the host exactly like cv::createTrigTable).  The median only depends on how many lines each of the 180
 // angles has; the reference evaluates it in numpy float32 (theta is np.float32), restated in hostmath.cpp, and the
@@ -24,185 +24,268 @@ constexpr int NANG = 180;
 
 struct SkewJob {
     const uint8_t* src; int src_pitch, w, h;
-    uint8_t* map;          // w*h dense: 0 weak candidate, 1 none, 2 strong
-    int* label;            // w*h dense union-find parents (-1 = not a candidate)
-    uint8_t* rootflag;     // w*h dense: component root has a strong pixel
+    // bit planes, one 64-bit word per 64 pixels of a row (bit x & 63 of word x >> 6), `wpr` words per row:
+    uint64_t* cand;        // pixels that survive non-maximum suppression with a magnitude above `low`
+    uint64_t* act;         // starts as the survivors above `high`, grows into the edge map
+    int wpr;
     uint8_t* edges; int edges_pitch;      // may be null
     uint32_t* list;        // edge coordinates x | y << 16 (may be null)
     uint32_t* count;       // number of list entries
     int* accum;            // (NANG + 2) x (numrho + 2)
     int numrho;
     uint32_t* per_angle;   // NANG line counts
-    uint2* cand; uint32_t* n_cand; int max_cand;     // optional (accumulator index, votes) of every line
+    uint2* lines; uint32_t* n_lines; int max_lines;     // optional (accumulator index, votes) of every line
 };
 
-// ---- hysteresis as connected components (atomic union-find) --------------------------------------------------------
-__device__ __forceinline__ int uf_find(const int* L, int x) {
-    int p = L[x];
-    while (p != x) { x = p; p = L[x]; }
-    return x;
-}
-// find with path halving for the merge phase: every visited node is re-pointed at its grandparent.  Racing writers only
-// ever store an ancestor of the node, so the forest stays valid.
-__device__ __forceinline__ int uf_find_halve(int* L, int x) {
-    int p = L[x];
-    while (p != x) {
-        const int gp = L[p];
-        if (gp != p) L[x] = gp;
-        x = p; p = gp;
-    }
-    return x;
-}
-__device__ __forceinline__ void uf_union(int* L, int a, int b) {
-    while (true) {
-        a = uf_find_halve(L, a); b = uf_find_halve(L, b);
-        if (a == b) return;
-        if (a < b) { const int t = a; a = b; b = t; }      // the larger root is linked under the smaller one
-        const int old = atomicMin(&L[a], b);
-        if (old == a) return;
-        a = old;
-    }
-}
+// ---- Canny: gradient, non-maximum suppression, double threshold -> two bit planes ---------------------------------
+// Tile = 64 x 32 pixels = one 64-bit word of 32 rows.  Source bytes are staged with replicated borders, the Sobel pair
+// (dx, dy) of the tile and a one-pixel ring around it is kept in shared memory as two 16-bit lanes (zero outside the
+// image: OpenCV's magnitude plane has a zero border), and the suppression test reads the two neighbours its direction
+// selects.  A warp covers 32 consecutive pixels of a row and publishes its decisions with two ballots.
+constexpr int CT_W = 64, CT_H = 32, CT_SW = CT_W + 8, CT_GW = CT_W + 2;
 
-// ---- Canny: gradient, non-maximum suppression, double threshold -------------------------------------------------
-constexpr int CT_W = 64, CT_H = 16;
-
-__global__ void __launch_bounds__(256) canny_nms_kernel(const SkewJob* __restrict__ jobs, int low, int high) {
+__global__ void __launch_bounds__(256) canny_bits_kernel(const SkewJob* __restrict__ jobs, int low, int high) {
     const SkewJob J = jobs[blockIdx.z];
     const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
-    if (x0 >= J.w || y0 >= J.h) return;
-    __shared__ uint8_t s_src[CT_H + 4][CT_W + 4];
-    __shared__ short s_mag[CT_H + 2][CT_W + 2];
+    if (blockIdx.x >= J.wpr || y0 >= J.h) return;
+    __shared__ __align__(16) uint8_t s_src[CT_H + 4][CT_SW];          // origin (y0 - 2, x0 - 4)
+    __shared__ uint32_t s_g[CT_H + 2][CT_GW];                         // origin (y0 - 1, x0 - 1): dx | dy << 16
     const int tid = threadIdx.x;
-    for (int i = tid; i < (CT_H + 4) * (CT_W + 4); i += 256) {
-        const int ly = i / (CT_W + 4), lx = i - ly * (CT_W + 4);
-        s_src[ly][lx] = J.src[(size_t)ds_clamp(y0 + ly - 2, 0, J.h - 1) * J.src_pitch + ds_clamp(x0 + lx - 2, 0, J.w - 1)];
-    }
-    __syncthreads();
-    auto sobel = [&](int ly, int lx, int& gx, int& gy) {        // (ly, lx) in s_src coordinates of the centre pixel
-        const int a = s_src[ly - 1][lx - 1], b = s_src[ly - 1][lx], c = s_src[ly - 1][lx + 1];
-        const int d = s_src[ly][lx - 1], f = s_src[ly][lx + 1];
-        const int g = s_src[ly + 1][lx - 1], hh = s_src[ly + 1][lx], k = s_src[ly + 1][lx + 1];
-        gx = (c - a) + 2 * (f - d) + (k - g);
-        gy = (g - a) + 2 * (hh - b) + (k - c);
-    };
-    for (int i = tid; i < (CT_H + 2) * (CT_W + 2); i += 256) {
-        const int ly = i / (CT_W + 2), lx = i - ly * (CT_W + 2);
-        const int gy_ = y0 + ly - 1, gx_ = x0 + lx - 1;
-        int m = 0;
-        if (gy_ >= 0 && gy_ < J.h && gx_ >= 0 && gx_ < J.w) {      // the magnitude plane has a zero border
-            int gx, gy;
-            sobel(ly + 1, lx + 1, gx, gy);
-            m = abs(gx) + abs(gy);
+    const bool al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
+    for (int i = tid; i < (CT_H + 4) * (CT_SW / 4); i += 256) {
+        const int ly = i / (CT_SW / 4), wi = i - ly * (CT_SW / 4);
+        const uint8_t* rowp = J.src + (size_t)ds_clamp(y0 + ly - 2, 0, J.h - 1) * J.src_pitch;
+        const int gx = x0 - 4 + 4 * wi;
+        uint32_t word;
+        if (al && gx >= 0 && gx + 3 < J.w) word = ds_ldg32(rowp + gx);
+        else {
+            word = 0;
+            for (int b = 0; b < 4; b++) word |= (uint32_t)rowp[ds_clamp(gx + b, 0, J.w - 1)] << (8 * b);
         }
-        s_mag[ly][lx] = (short)m;
+        *reinterpret_cast<uint32_t*>(&s_src[ly][4 * wi]) = word;
     }
     __syncthreads();
-    __shared__ int s_lab[CT_H * CT_W];               // tile-local union-find parents (-1 = no candidate)
-    for (int i = tid; i < CT_H * CT_W; i += 256) {
-        const int ly = i / CT_W, lx = i - ly * CT_W;
-        const int y = y0 + ly, x = x0 + lx;
-        s_lab[i] = -1;
-        if (y >= J.h || x >= J.w) continue;
-        int xs, ys;
-        sobel(ly + 2, lx + 2, xs, ys);
-        const int m = s_mag[ly + 1][lx + 1];
+    for (int i = tid; i < (CT_H + 2) * CT_GW; i += 256) {
+        const int ly = i / CT_GW, lx = i - ly * CT_GW;
+        const int gy_ = y0 + ly - 1, gx_ = x0 + lx - 1;
+        uint32_t g = 0;
+        if (gy_ >= 0 && gy_ < J.h && gx_ >= 0 && gx_ < J.w) {
+            const uint8_t* p = &s_src[ly + 1][lx + 3];                // the centre pixel
+            const int a = p[-CT_SW - 1], b = p[-CT_SW], c = p[-CT_SW + 1];
+            const int d = p[-1], f = p[1];
+            const int q = p[CT_SW - 1], hh = p[CT_SW], k = p[CT_SW + 1];
+            const int dx = (c - a) + 2 * (f - d) + (k - q);
+            const int dy = (q - a) + 2 * (hh - b) + (k - c);
+            g = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
+        }
+        s_g[ly][lx] = g;
+    }
+    __syncthreads();
+    auto mag = [](uint32_t g) { return abs((int)(short)(g & 0xffffu)) + abs((int)g >> 16); };
+    const int lane = tid & 31, wrp = tid >> 5;
+    uint32_t* cand32 = reinterpret_cast<uint32_t*>(J.cand);
+    uint32_t* act32 = reinterpret_cast<uint32_t*>(J.act);
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int ly = wrp * 4 + (it >> 1), half = it & 1;
+        const int y = y0 + ly;
+        if (y >= J.h) break;                                           // warp-uniform
+        const int lx = 32 * half + lane;
+        const uint32_t* gp = &s_g[ly + 1][lx + 1];
+        const uint32_t g = *gp;
+        const int xs = (short)(g & 0xffffu), ys = (int)g >> 16;
+        const int m = abs(xs) + abs(ys);
         bool cand = false;
-        if (m > low) {
+        if (m > low) {                                                 // (pixels beyond the image carry m = 0)
             const int ax = abs(xs);
-            const long long ay = (long long)abs(ys) << 15, tg22x = (long long)ax * 13573;      // tan(22.5 deg) * 2^15
-            if (ay < tg22x) cand = m > s_mag[ly + 1][lx] && m >= s_mag[ly + 1][lx + 2];
+            const int ay = abs(ys) << 15, tg22x = ax * 13573;          // tan(22.5 deg) * 2^15; |values| < 2^26
+            if (ay < tg22x) cand = m > mag(gp[-1]) && m >= mag(gp[1]);
             else {
-                const long long tg67x = tg22x + ((long long)ax << 16);
-                if (ay > tg67x) cand = m > s_mag[ly][lx + 1] && m >= s_mag[ly + 2][lx + 1];
+                const int tg67x = tg22x + (ax << 16);
+                if (ay > tg67x) cand = m > mag(gp[-CT_GW]) && m >= mag(gp[CT_GW]);
                 else {
                     const int s = (xs ^ ys) < 0 ? -1 : 1;
-                    cand = m > s_mag[ly][lx + 1 - s] && m > s_mag[ly + 2][lx + 1 + s];
+                    cand = m > mag(gp[-CT_GW - s]) && m > mag(gp[CT_GW + s]);
                 }
             }
         }
-        const int p = y * J.w + x;
-        J.map[p] = cand ? (m > high ? 2 : 0) : 1;
-        if (cand) { s_lab[i] = i; J.rootflag[p] = 0; }       // only candidates are ever looked up
-    }
-    // Connected components inside the tile, in shared memory (the dependent loads and atomics of a union-find cost tens
-    // of cycles here instead of hundreds in L2); ccl_merge_kernel then only stitches the tile borders together.
-    __syncthreads();
-    for (int i = tid; i < CT_H * CT_W; i += 256) {
-        if (s_lab[i] < 0) continue;
-        const int ly = i / CT_W, lx = i - ly * CT_W;
-        if (lx > 0 && s_lab[i - 1] >= 0) uf_union(s_lab, i, i - 1);
-        if (ly > 0) {
-            const int q = i - CT_W;
-            if (lx > 0 && s_lab[q - 1] >= 0) uf_union(s_lab, i, q - 1);
-            if (s_lab[q] >= 0) uf_union(s_lab, i, q);
-            if (lx + 1 < CT_W && s_lab[q + 1] >= 0) uf_union(s_lab, i, q + 1);
+        const uint32_t cb = __ballot_sync(0xffffffffu, cand), sb = __ballot_sync(0xffffffffu, cand && m > high);
+        if (lane == 0) {
+            const size_t o = ((size_t)y * J.wpr + blockIdx.x) * 2 + half;
+            cand32[o] = cb; act32[o] = sb;
         }
     }
-    __syncthreads();
-    for (int i = tid; i < CT_H * CT_W; i += 256) {
-        if (s_lab[i] < 0) continue;
-        const int root = uf_find(s_lab, i);
-        const int ly = i / CT_W, lx = i - ly * CT_W, ry = root / CT_W, rx = root - ry * CT_W;
-        J.label[(y0 + ly) * J.w + x0 + lx] = (y0 + ry) * J.w + x0 + rx;
-    }
 }
 
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const SkewJob* __restrict__ jobs) {
-    const SkewJob J = jobs[blockIdx.z];
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= J.w || y >= J.h) return;
-    // canny_nms_kernel has already joined everything inside its CT_W x CT_H tiles: only neighbour pairs that straddle a
-    // tile border are left
-    const bool left = (x % CT_W) == 0, right = (x % CT_W) == CT_W - 1, top = (y % CT_H) == 0;
-    if (!(left || right || top)) return;
-    const int p = y * J.w + x;
-    if (J.map[p] == 1) return;                       // most pixels are no candidates: decide on the byte plane
-    if (left && x > 0 && J.map[p - 1] != 1) uf_union(J.label, p, p - 1);
-    if (y > 0) {
-        const int q = p - J.w;
-        if ((left || top) && x > 0 && J.map[q - 1] != 1) uf_union(J.label, p, q - 1);
-        if (top && J.map[q] != 1) uf_union(J.label, p, q);
-        if ((right || top) && x + 1 < J.w && J.map[q + 1] != 1) uf_union(J.label, p, q + 1);
+// ---- hysteresis: grow the strong pixels through the candidates, 64 pixels per lane -----------------------------------
+// The result ("candidates 8-connected to a strong one") does not depend on the order of traversal, so instead of
+// OpenCV's stack flood fill the page is relaxed with bit-parallel sweeps.  One CTA per page, one warp per band of rows.
+// A row step takes the row above (or below), widens it by one pixel either side, keeps what falls on candidates, and
+// then fills along the candidate runs of the whole row in both directions at once: adding the seeds to the run mask
+// lets the carry ripple to the end of every seeded run, and the carries between the lanes' 64-bit words (and between
+// groups of 32 lanes) are resolved by one more integer addition on the ballots of "generates" / "propagates".
+// A sweep therefore carries a label any distance horizontally and down (or up) in one pass; bands exchange their
+// border rows through the plane itself and the CTA repeats until no band changed anything.
+template <int G>
+__device__ __forceinline__ bool hyst_row_step(const uint64_t (&c)[G], uint64_t (&a)[G], const uint64_t (&nb)[G], bool force, int lane) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    uint64_t seeds[G];
+    bool need = false;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const uint64_t v = nb[g];
+        uint64_t below = __shfl_up_sync(FULL, v, 1), above = __shfl_down_sync(FULL, v, 1);
+        const uint64_t prev_last = __shfl_sync(FULL, g > 0 ? nb[g > 0 ? g - 1 : 0] : 0ull, 31);
+        const uint64_t next_first = __shfl_sync(FULL, g + 1 < G ? nb[g + 1 < G ? g + 1 : g] : 0ull, 0);
+        if (lane == 0) below = prev_last;
+        if (lane == 31) above = next_first;
+        const uint64_t d = v | (v << 1) | (v >> 1) | (below >> 63) | (above << 63);
+        seeds[g] = a[g] | (d & c[g]);
+        need = need || seeds[g] != a[g] || (force && seeds[g] != 0);
     }
+    if (!__any_sync(FULL, need)) return false;
+    uint64_t fill[G];
+    uint32_t cin = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++) {                                      // towards larger x
+        const uint64_t t = c[g] + seeds[g];
+        const uint32_t gm = __ballot_sync(FULL, t < c[g]), pm = __ballot_sync(FULL, t == ~0ull);
+        const uint64_t u = (uint64_t)(gm | pm) + gm + cin;
+        const uint64_t ci = (((uint32_t)u ^ pm) >> lane) & 1u;
+        cin = (uint32_t)(u >> 32);
+        fill[g] = ((c[g] ^ (t + ci)) & c[g]) | seeds[g];
+    }
+    cin = 0;
+    bool changed = false;
+#pragma unroll
+    for (int g = G - 1; g >= 0; g--) {                                 // towards smaller x: the same on the reversed bits
+        const uint64_t cr = __brevll(c[g]), t = cr + __brevll(seeds[g]);
+        const uint32_t gm = __brev(__ballot_sync(FULL, t < cr)), pm = __brev(__ballot_sync(FULL, t == ~0ull));
+        const uint64_t u = (uint64_t)(gm | pm) + gm + cin;
+        const uint64_t ci = (((uint32_t)u ^ pm) >> (31 - lane)) & 1u;
+        cin = (uint32_t)(u >> 32);
+        const uint64_t na = fill[g] | __brevll((cr ^ (t + ci)) & cr);
+        changed = changed || na != a[g];
+        a[g] = na;
+    }
+    return changed;
 }
 
-__global__ void __launch_bounds__(256) ccl_flag_kernel(const SkewJob* __restrict__ jobs) {
-    const SkewJob J = jobs[blockIdx.z];
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    if (x >= J.w || y >= J.h) return;
-    const int p = y * J.w + x;
-    const int mv = J.map[p];
-    if (mv == 1) return;
-    const int root = uf_find(J.label, p);
-    J.label[p] = root;                               // path compression (roots keep pointing at themselves)
-    if (mv == 2) J.rootflag[root] = 1;
-}
-
-__global__ void __launch_bounds__(256) ccl_emit_kernel(const SkewJob* __restrict__ jobs) {
-    const SkewJob J = jobs[blockIdx.z];
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
-    bool edge = false;
-    if (x < J.w && y < J.h) {
-        const int p = y * J.w + x;
-        if (J.map[p] != 1) edge = J.rootflag[uf_find(J.label, p)] != 0;
-        if (J.edges) J.edges[(size_t)y * J.edges_pitch + x] = edge ? 255 : 0;
-    }
-    if (J.list) {
-        // one global atomic per CTA: warps publish their counts, the first warp reserves the block's range
-        __shared__ uint32_t s_cnt[8], s_base;
-        const uint32_t ballot = __ballot_sync(0xffffffffu, edge);
-        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-        if (lane == 0) s_cnt[wrp] = __popc(ballot);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t total = 0;
-            for (int k = 0; k < 8; k++) { const uint32_t c = s_cnt[k]; s_cnt[k] = total; total += c; }
-            s_base = total ? atomicAdd(J.count, total) : 0u;
+template <int G>
+__global__ void __launch_bounds__(1024) canny_hyst_kernel(const SkewJob* __restrict__ jobs) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const SkewJob J = jobs[blockIdx.x];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int rpb = (J.h + nw - 1) / nw;
+    const int yb0 = wrp * rpb, yb1 = min(J.h, yb0 + rpb);
+    const int wpr = J.wpr;
+    bool in[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) in[g] = 32 * g + lane < wpr;
+    auto load = [&](const uint64_t* plane, int y, uint64_t (&r)[G]) {
+#pragma unroll
+        for (int g = 0; g < G; g++) r[g] = in[g] ? plane[(size_t)y * wpr + 32 * g + lane] : 0ull;
+    };
+    auto zero = [&](uint64_t (&r)[G]) {
+#pragma unroll
+        for (int g = 0; g < G; g++) r[g] = 0ull;
+    };
+    constexpr int CH = G == 1 ? 4 : (G == 2 ? 2 : 1);                  // rows requested together
+    bool first = true;
+    while (true) {
+        bool changed = false;
+        if (yb0 < yb1) {
+            uint64_t nb[G];
+            // ---- downwards
+            if (yb0 > 0) load(J.act, yb0 - 1, nb); else zero(nb);
+            for (int y = yb0; y < yb1; y += CH) {
+                uint64_t c[CH][G], a[CH][G];
+#pragma unroll
+                for (int k = 0; k < CH; k++)
+                    if (y + k < yb1) { load(J.cand, y + k, c[k]); load(J.act, y + k, a[k]); }
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    if (y + k >= yb1) break;
+                    if (hyst_row_step<G>(c[k], a[k], nb, first, lane)) {
+                        changed = true;
+#pragma unroll
+                        for (int g = 0; g < G; g++) if (in[g]) J.act[(size_t)(y + k) * wpr + 32 * g + lane] = a[k][g];
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; g++) nb[g] = a[k][g];
+                }
+            }
+            // ---- upwards
+            if (yb1 < J.h) load(J.act, yb1, nb); else zero(nb);
+            for (int y = yb1 - 1; y >= yb0; y -= CH) {
+                uint64_t c[CH][G], a[CH][G];
+#pragma unroll
+                for (int k = 0; k < CH; k++)
+                    if (y - k >= yb0) { load(J.cand, y - k, c[k]); load(J.act, y - k, a[k]); }
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    if (y - k < yb0) break;
+                    if (hyst_row_step<G>(c[k], a[k], nb, false, lane)) {
+                        changed = true;
+#pragma unroll
+                        for (int g = 0; g < G; g++) if (in[g]) J.act[(size_t)(y - k) * wpr + 32 * g + lane] = a[k][g];
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; g++) nb[g] = a[k][g];
+                }
+            }
         }
-        __syncthreads();
-        if (edge) J.list[s_base + s_cnt[wrp] + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)x | ((uint32_t)y << 16);
+        first = false;
+        // the barrier also orders the bands' border rows (global memory, same CTA) for the next round
+        if (!__syncthreads_or(changed ? 1 : 0)) break;
     }
+    // ---- the edge map is final: write the edge image and / or the coordinate list of this band's rows
+    if (!J.edges && !J.list) return;
+    const bool e_al = J.edges && ((reinterpret_cast<uintptr_t>(J.edges) | (uintptr_t)J.edges_pitch) & 3) == 0;
+    for (int y = yb0; y < yb1; y++) {
+        uint64_t a[G];
+        load(J.act, y, a);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const int xw = 64 * (32 * g + lane);
+            if (J.edges && in[g]) {
+                uint8_t* ep = J.edges + (size_t)y * J.edges_pitch + xw;
+#pragma unroll 4
+                for (int q = 0; q < 16; q++) {
+                    const int x = xw + 4 * q;
+                    if (x >= J.w) break;
+                    const uint32_t nib = (uint32_t)(a[g] >> (4 * q)) & 15u;
+                    const uint32_t word = ((nib * 0x00204081u) & 0x01010101u) * 255u;      // bit b -> byte b
+                    if (e_al && x + 3 < J.w) *reinterpret_cast<uint32_t*>(ep + 4 * q) = word;
+                    else for (int b = 0; b < 4 && x + b < J.w; b++) ep[4 * q + b] = (uint8_t)(word >> (8 * b));
+                }
+            }
+            if (J.list) {
+                const int n = __popcll(a[g]);
+                int incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+                const int total = __shfl_sync(FULL, incl, 31);
+                if (total == 0) continue;                              // warp-uniform
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(J.count, (uint32_t)total);
+                base = __shfl_sync(FULL, base, 0) + (uint32_t)(incl - n);
+                uint64_t bits = a[g];
+                while (bits) {
+                    const int b = __ffsll((long long)bits) - 1;
+                    bits &= bits - 1;
+                    J.list[base++] = (uint32_t)(xw + b) | ((uint32_t)y << 16);
+                }
+            }
+        }
+    }
+}
+
+template <int G>
+int launch_hyst_t(docscan_ctx* ctx, const SkewJob* jd, int n, int threads) {
+    canny_hyst_kernel<G><<<n, threads, 0, ctx->stream>>>(jd);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
 }
 
 // edge list of an arbitrary edge image (cv2.HoughLines treats every non-zero pixel as an edge)
@@ -242,7 +325,8 @@ __global__ void __launch_bounds__(512) hough_vote_kernel(const SkewJob* __restri
         const float fj = (float)(v & 0xffffu), fi = (float)(v >> 16);
 #pragma unroll
         for (int a = 0; a < VOTE_NA; a++) {
-            const int r = __float2int_rn(__fadd_rn(__fmul_rn(fj, tc[a]), __fmul_rn(fi, ts[a]))) + half;
+            // cvRound without the conversion unit: |value| < 2^22, so adding 1.5 * 2^23 leaves the rounded integer in the mantissa
+            const int r = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(fj, tc[a]), __fmul_rn(fi, ts[a])), 12582912.0f)) - 0x4B400000 + half;
             atomicAdd(&s_acc[a * width + r + 1], 1);
         }
     }
@@ -263,9 +347,9 @@ __global__ void __launch_bounds__(256) hough_peaks_kernel(const SkewJob* __restr
     const int v = a[base];
     if (v > threshold && v > a[base - 1] && v >= a[base + 1] && v > a[base - width] && v >= a[base + width]) {
         atomicAdd(&J.per_angle[n], 1u);
-        if (J.cand) {
-            const uint32_t k = atomicAdd(J.n_cand, 1u);
-            if (k < (uint32_t)J.max_cand) J.cand[k] = make_uint2((uint32_t)base, (uint32_t)v);
+        if (J.lines) {
+            const uint32_t k = atomicAdd(J.n_lines, 1u);
+            if (k < (uint32_t)J.max_lines) J.lines[k] = make_uint2((uint32_t)base, (uint32_t)v);
         }
     }
 }
@@ -380,8 +464,9 @@ int get_skew_tables(docscan_ctx* ctx, SkewTables* T) {
 
 size_t k_skew_scratch_bytes(int w, int h, bool want_list) {
     const size_t np = (size_t)w * h;
+    const size_t planes = 2 * ((size_t)(w + 63) / 64 * 8 * h + 256);
     const size_t numrho = 2 * ((size_t)w + h) + 1;
-    return np + 4 * np + np + (want_list ? 4 * np : 0) + (NANG + 2) * (numrho + 2) * 4 + NANG * 4 + 4096;
+    return planes + (want_list ? 4 * np + (NANG + 2) * (numrho + 2) * 4 : 0) + (NANG + 8) * 4 + 4096;
 }
 
 // Canny (+ optional Hough + median angle) for a batch of gray planes.
@@ -407,9 +492,9 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
         const size_t np = (size_t)w * h;
         j.src = gray[i].p; j.src_pitch = gray[i].pitch; j.w = w; j.h = h;
         void* p = nullptr;
-        DS_TRY(ds_arena_alloc(ctx, np, &p)); j.map = (uint8_t*)p;
-        DS_TRY(ds_arena_alloc(ctx, 4 * np, &p)); j.label = (int*)p;
-        DS_TRY(ds_arena_alloc(ctx, np, &p)); j.rootflag = (uint8_t*)p;
+        j.wpr = (w + 63) / 64;
+        DS_TRY(ds_arena_alloc(ctx, 8 * (size_t)j.wpr * h, &p)); j.cand = (uint64_t*)p;
+        DS_TRY(ds_arena_alloc(ctx, 8 * (size_t)j.wpr * h, &p)); j.act = (uint64_t*)p;
         if (edges_out) { j.edges = edges_out[i].p; j.edges_pitch = edges_out[i].pitch; }
         uint32_t* c = (uint32_t*)counters + (size_t)i * (NANG + 4);
         j.count = c; j.per_angle = c + 4;
@@ -427,25 +512,19 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
     double px = 0;
     for (int i = 0; i < n; i++) px += (double)gray[i].w * gray[i].h;
     {
-        ProfScope prof(ctx, "canny_nms", 7.0 * px);
-        canny_nms_kernel<<<dim3((mw + CT_W - 1) / CT_W, (mh + CT_H - 1) / CT_H, n), 256, 0, ctx->stream>>>(jd, low, high);
-        DS_CHECK_LAUNCH(ctx);
-    }
-    const dim3 pgrid((mw + 63) / 64, (mh + 3) / 4, n);
-    {
-        ProfScope prof(ctx, "canny_hyst_merge", 0);
-        ccl_merge_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
+        ProfScope prof(ctx, "canny_bits", 1.25 * px);
+        canny_bits_kernel<<<dim3((mw + CT_W - 1) / CT_W, (mh + CT_H - 1) / CT_H, n), 256, 0, ctx->stream>>>(jd, low, high);
         DS_CHECK_LAUNCH(ctx);
     }
     {
-        ProfScope prof(ctx, "canny_hyst_flag", 0);
-        ccl_flag_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
-        DS_CHECK_LAUNCH(ctx);
-    }
-    {
-        ProfScope prof(ctx, "canny_hyst_emit", 0);
-        ccl_emit_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
-        DS_CHECK_LAUNCH(ctx);
+        // one CTA per page: 16 warps when the batch fills the device, 32 for a few (large) pages
+        ProfScope prof(ctx, "canny_hyst", 0);
+        const int threads = n >= ctx->sm_count ? 512 : 1024;
+        const int groups = (mw + 2047) / 2048;
+        if (groups <= 1) DS_TRY(launch_hyst_t<1>(ctx, jd, n, threads));
+        else if (groups <= 2) DS_TRY(launch_hyst_t<2>(ctx, jd, n, threads));
+        else if (groups <= 4) DS_TRY(launch_hyst_t<4>(ctx, jd, n, threads));
+        else DS_TRY(launch_hyst_t<32>(ctx, jd, n, 512));
     }
     if (!want_angle) return DOCSCAN_OK;
     {
@@ -476,14 +555,14 @@ int k_hough_lines(docscan_ctx* ctx, const DImg& edges, int threshold, std::vecto
     SkewJob j{};
     j.src = edges.p; j.src_pitch = edges.pitch; j.w = w; j.h = h;
     j.numrho = 2 * (w + h) + 1;
-    const int max_cand = NANG * j.numrho;                       // every accumulator cell could be a line
+    const int max_lines = NANG * j.numrho;                       // every accumulator cell could be a line
     void* p = nullptr;
     DS_TRY(ds_arena_alloc(ctx, sizeof(uint32_t) * (NANG + 8), &p));
     DS_CUDA(ctx, cudaMemsetAsync(p, 0, sizeof(uint32_t) * (NANG + 8), ctx->stream));
-    j.count = (uint32_t*)p; j.n_cand = j.count + 1; j.per_angle = j.count + 4;
+    j.count = (uint32_t*)p; j.n_lines = j.count + 1; j.per_angle = j.count + 4;
     DS_TRY(ds_arena_alloc(ctx, 4 * (size_t)w * h, &p)); j.list = (uint32_t*)p;
     DS_TRY(ds_arena_alloc(ctx, sizeof(int) * (size_t)(NANG + 2) * (j.numrho + 2), &p)); j.accum = (int*)p;
-    DS_TRY(ds_arena_alloc(ctx, sizeof(uint2) * (size_t)max_cand, &p)); j.cand = (uint2*)p; j.max_cand = max_cand;
+    DS_TRY(ds_arena_alloc(ctx, sizeof(uint2) * (size_t)max_lines, &p)); j.lines = (uint2*)p; j.max_lines = max_lines;
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, &j, sizeof(j), &dev));
     const SkewJob* jd = (const SkewJob*)dev;
@@ -493,11 +572,11 @@ int k_hough_lines(docscan_ctx* ctx, const DImg& edges, int threshold, std::vecto
     hough_peaks_kernel<<<dim3((j.numrho + 255) / 256, NANG, 1), 256, 0, ctx->stream>>>(jd, threshold);
     DS_CHECK_LAUNCH(ctx);
     uint32_t n_cand = 0;
-    DS_CUDA(ctx, cudaMemcpyAsync(&n_cand, j.n_cand, sizeof(n_cand), cudaMemcpyDeviceToHost, ctx->stream));
+    DS_CUDA(ctx, cudaMemcpyAsync(&n_cand, j.n_lines, sizeof(n_cand), cudaMemcpyDeviceToHost, ctx->stream));
     DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    lines->resize(std::min<uint32_t>(n_cand, (uint32_t)max_cand));
+    lines->resize(std::min<uint32_t>(n_cand, (uint32_t)max_lines));
     if (!lines->empty()) {
-        DS_CUDA(ctx, cudaMemcpyAsync(lines->data(), j.cand, sizeof(uint2) * lines->size(), cudaMemcpyDeviceToHost, ctx->stream));
+        DS_CUDA(ctx, cudaMemcpyAsync(lines->data(), j.lines, sizeof(uint2) * lines->size(), cudaMemcpyDeviceToHost, ctx->stream));
         DS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     *numrho_out = j.numrho;

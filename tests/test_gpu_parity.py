@@ -542,6 +542,48 @@ def test_canny_hough_skew_angle():
         eq(DS.deskew(g), O.deskew(g), f"deskew {h}x{w}")
 
 
+def _serpentine(h, w, weak, strong, vertical=False, step=8, thick=3):
+    """A 3-pixel serpentine of low contrast whose outline is one long chain of weak candidates under thresholds (100, 400),
+    with one short high-contrast piece at its start: hysteresis has to carry the label along the whole path, across bands,
+    lanes and 2048-pixel groups (without the strong piece nothing is an edge)."""
+    if vertical:
+        h, w = w, h
+    im = np.full((h, w), 100, np.uint8)
+    for i, y in enumerate(range(4, h - 4 - thick, step)):
+        im[y:y + thick, 4:w - 4] = weak
+        x = w - 4 - thick if i % 2 == 0 else 4
+        im[y:min(y + step + thick, h - 4), x:x + thick] = weak
+    im[4:4 + thick, 4:16] = strong
+    return im.T.copy() if vertical else im
+
+
+def test_canny_hysteresis_long_paths_and_wide_rows():
+    """The bit-parallel hysteresis (deskew.cu): serpentines and spirals that cross every band many times, rows wider than
+    one 2048-pixel group (2, 4 and more groups), tall thin images, random fields at several densities."""
+    rng = np.random.default_rng(77)
+    cases = []
+    for (h, w) in [(300, 300), (200, 2500), (100, 5000), (40, 9000), (3000, 200), (1200, 70), (64, 64), (33, 2049), (70, 4097)]:
+        cases.append((_serpentine(h, w, 128, 230), f"serpentine {h}x{w}"))
+        cases.append((_serpentine(h, w, 128, 230, vertical=True), f"vertical serpentine {h}x{w}"))
+        cases.append((_serpentine(h, w, 128, 128), f"all-weak serpentine {h}x{w}"))
+        cases.append((rng.integers(0, 256, (h, w), dtype=np.uint8), f"noise {h}x{w}"))
+        sm = rng.integers(90, 125, (h, w), dtype=np.uint8)
+        sm[rng.random((h, w)) < 0.002] = 255
+        cases.append((sm, f"sparse strong {h}x{w}"))
+    linked = 0
+    for img, name in cases:
+        for lo, hi in ((50, 150), (20, 60), (100, 400)):
+            e = O.canny(img, lo, hi)
+            if name.startswith(("serpentine", "vertical")) and lo == 100:
+                linked += int((e > 0).sum() > img.size // 50)
+            eq(ops.canny(img, lo, hi), e, f"canny {name} {lo}/{hi}")
+    assert linked >= 12, "the serpentines are meant to be long weak chains hanging on one strong piece"
+    # the estimate as a whole on a wide page (two groups) and a tall one
+    for (h, w) in [(300, 2300), (2100, 400)]:
+        g = _binary_page(rng, h, w, 1.0)
+        assert ops.skew_angle(g, 50, 150, 10.0) == O.estimate_skew_angle(g, 50, 150, 10.0), f"skew angle {h}x{w}"
+
+
 def test_sample_jpg_skew_angles_from_the_reference():
     meta = json.load(open(os.path.join(GOLDEN, "sample_golden.json")))
     for preset in ("cli", "gui"):
