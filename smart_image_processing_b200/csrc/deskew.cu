@@ -239,42 +239,60 @@ __global__ void __launch_bounds__(1024) canny_hyst_kernel(const SkewJob* __restr
         // the barrier also orders the bands' border rows (global memory, same CTA) for the next round
         if (!__syncthreads_or(changed ? 1 : 0)) break;
     }
-    // ---- the edge map is final: write the edge image and / or the coordinate list of this band's rows
+    // ---- the edge map is final: write the edge image and / or the coordinate list of this band's rows.
     if (!J.edges && !J.list) return;
     const bool e_al = J.edges && ((reinterpret_cast<uintptr_t>(J.edges) | (uintptr_t)J.edges_pitch) & 3) == 0;
-    for (int y = yb0; y < yb1; y++) {
-        uint64_t a[G];
-        load(J.act, y, a);
-#pragma unroll
+    for (int ys = yb0; ys < yb1; ys += 16) {
+#pragma unroll 1
         for (int g = 0; g < G; g++) {
-            const int xw = 64 * (32 * g + lane);
-            if (J.edges && in[g]) {
-                uint8_t* ep = J.edges + (size_t)y * J.edges_pitch + xw;
+            const int wi = 32 * g + lane, xw = 64 * wi;
+            const bool inw = wi < wpr;
+            uint64_t a[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) a[i] = (inw && ys + i < yb1) ? J.act[(size_t)(ys + i) * wpr + wi] : 0ull;
+            if (J.edges && inw) {
+#pragma unroll 1
+                for (int i = 0; i < 16 && ys + i < yb1; i++) {
+                    uint8_t* ep = J.edges + (size_t)(ys + i) * J.edges_pitch + xw;
+                    uint64_t row = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) if (k == i) row = a[k];
 #pragma unroll 4
-                for (int q = 0; q < 16; q++) {
-                    const int x = xw + 4 * q;
-                    if (x >= J.w) break;
-                    const uint32_t nib = (uint32_t)(a[g] >> (4 * q)) & 15u;
-                    const uint32_t word = ((nib * 0x00204081u) & 0x01010101u) * 255u;      // bit b -> byte b
-                    if (e_al && x + 3 < J.w) *reinterpret_cast<uint32_t*>(ep + 4 * q) = word;
-                    else for (int b = 0; b < 4 && x + b < J.w; b++) ep[4 * q + b] = (uint8_t)(word >> (8 * b));
+                    for (int q = 0; q < 16; q++) {
+                        const int x = xw + 4 * q;
+                        if (x >= J.w) break;
+                        const uint32_t nib = (uint32_t)(row >> (4 * q)) & 15u;
+                        const uint32_t word = ((nib * 0x00204081u) & 0x01010101u) * 255u;      // bit b -> byte b
+                        if (e_al && x + 3 < J.w) *reinterpret_cast<uint32_t*>(ep + 4 * q) = word;
+                        else for (int b = 0; b < 4 && x + b < J.w; b++) ep[4 * q + b] = (uint8_t)(word >> (8 * b));
+                    }
                 }
             }
             if (J.list) {
-                const int n = __popcll(a[g]);
-                int incl = n;
+                int n = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-                const int total = __shfl_sync(FULL, incl, 31);
+                for (int i = 0; i < 16; i++) n += __popcll(a[i]);
+                const int total = __reduce_add_sync(FULL, n);
                 if (total == 0) continue;                              // warp-uniform
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(J.count, (uint32_t)total);
-                base = __shfl_sync(FULL, base, 0) + (uint32_t)(incl - n);
-                uint64_t bits = a[g];
-                while (bits) {
-                    const int b = __ffsll((long long)bits) - 1;
-                    bits &= bits - 1;
-                    J.list[base++] = (uint32_t)(xw + b) | ((uint32_t)y << 16);
+                base = __shfl_sync(FULL, base, 0);
+                // entry k of the block comes from lane (k mod active lanes): 32 consecutive entries are pixels 64 columns apart,
+                // whose accumulator cells differ for every angle but the vertical one
+                const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    uint64_t bits = a[i];
+                    while (true) {
+                        const uint32_t mask = __ballot_sync(FULL, bits != 0);
+                        if (!mask) break;
+                        if (bits) {
+                            const int b = __ffsll((long long)bits) - 1;
+                            bits &= bits - 1;
+                            J.list[base + __popc(mask & lt)] = (uint32_t)(xw + b) | ((uint32_t)(ys + i) << 16);
+                        }
+                        base += __popc(mask);
+                    }
                 }
             }
         }
@@ -307,51 +325,68 @@ struct TrigTable { float c[NANG], s[NANG]; };
 
 // VOTE_NA angles share one pass over the edge list (the list is streamed from L2 by every CTA of a page, so the number
 // of passes is what the kernel costs); each angle has its own accumulator row in shared memory.
+// A shared-memory increment costs two clocks per warp when its lanes hit 32 different banks, and that many times more when
+// lanes share a bank or (short of all 32) an address (tests/tools/atoms_probe.cu: 16 increments per clock and SM at best,
+// 10.6 for random cells, 7 when the lanes crowd into a window of 23 cells).  Two things keep the votes of a warp apart: the
+// list interleaves pixels 64 columns apart (canny_hyst_kernel), and the cells of a row are stored XOR-swizzled
+// (cell j at j ^ ((j >> 5) & 31)), so that the power-of-two strides such pixels produce at cos = 1/2, 1/4, .. spread
+// over the banks as well.
 template <int VOTE_NA>
 __global__ void __launch_bounds__(512) hough_vote_kernel(const SkewJob* __restrict__ jobs, const __grid_constant__ TrigTable T) {
     const SkewJob J = jobs[blockIdx.z];
     const int n0 = blockIdx.x * VOTE_NA;
     extern __shared__ int s_acc[];
-    const int width = J.numrho + 2;
-    for (int i = threadIdx.x; i < VOTE_NA * width; i += 512) s_acc[i] = 0;
+    const int width = J.numrho + 2, pitch = (width + 31) & ~31;
+    for (int i = threadIdx.x; i < VOTE_NA * pitch; i += 512) s_acc[i] = 0;
     __syncthreads();
     float tc[VOTE_NA], ts[VOTE_NA];
 #pragma unroll
     for (int a = 0; a < VOTE_NA; a++) { tc[a] = T.c[n0 + a]; ts[a] = T.s[n0 + a]; }
-    const int half = (J.numrho - 1) / 2;
+    const int off = (J.numrho - 1) / 2 + 1 - 0x4B400000;
     const uint32_t cnt = *J.count;
-    for (uint32_t e = threadIdx.x; e < cnt; e += 512) {
-        const uint32_t v = J.list[e];
+    auto vote = [&](uint32_t v) {
         const float fj = (float)(v & 0xffffu), fi = (float)(v >> 16);
 #pragma unroll
         for (int a = 0; a < VOTE_NA; a++) {
             // cvRound without the conversion unit: |value| < 2^22, so adding 1.5 * 2^23 leaves the rounded integer in the mantissa
-            const int r = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(fj, tc[a]), __fmul_rn(fi, ts[a])), 12582912.0f)) - 0x4B400000 + half;
-            atomicAdd(&s_acc[a * width + r + 1], 1);
+            const int j = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(fj, tc[a]), __fmul_rn(fi, ts[a])), 12582912.0f)) + off;
+            atomicAdd(&s_acc[a * pitch + (j ^ ((j >> 5) & 31))], 1);
         }
+    };
+    uint32_t e = threadIdx.x;
+    for (; e + 3 * 512 < cnt; e += 4 * 512) {
+        const uint32_t v0 = J.list[e], v1 = J.list[e + 512], v2 = J.list[e + 1024], v3 = J.list[e + 1536];
+        vote(v0); vote(v1); vote(v2); vote(v3);
     }
+    for (; e < cnt; e += 512) vote(J.list[e]);
     __syncthreads();
     int* rows = J.accum + (size_t)(n0 + 1) * width;
-    for (int i = threadIdx.x; i < VOTE_NA * width; i += 512) rows[i] = s_acc[i];
+    for (int i = threadIdx.x; i < VOTE_NA * width; i += 512) {
+        const int a = i / width, j = i - a * width;
+        rows[i] = s_acc[a * pitch + (j ^ ((j >> 5) & 31))];
+    }
     if (n0 == 0) for (int i = threadIdx.x; i < width; i += 512) J.accum[i] = 0;                                   // border rows
     if (n0 == NANG - VOTE_NA) for (int i = threadIdx.x; i < width; i += 512) J.accum[(size_t)(NANG + 1) * width + i] = 0;
 }
 
-__global__ void __launch_bounds__(256) hough_peaks_kernel(const SkewJob* __restrict__ jobs, int threshold) {
+__global__ void __launch_bounds__(512) hough_peaks_kernel(const SkewJob* __restrict__ jobs, int threshold) {
     const SkewJob J = jobs[blockIdx.z];
-    const int r = blockIdx.x * 256 + threadIdx.x, n = blockIdx.y;
-    if (r >= J.numrho) return;
+    const int n = blockIdx.x;                                   // one CTA per (angle, page): the row is streamed once
     const int width = J.numrho + 2;
-    const int base = (n + 1) * width + r + 1;
     const int* a = J.accum;
-    const int v = a[base];
-    if (v > threshold && v > a[base - 1] && v >= a[base + 1] && v > a[base - width] && v >= a[base + width]) {
-        atomicAdd(&J.per_angle[n], 1u);
-        if (J.lines) {
-            const uint32_t k = atomicAdd(J.n_lines, 1u);
-            if (k < (uint32_t)J.max_lines) J.lines[k] = make_uint2((uint32_t)base, (uint32_t)v);
+    uint32_t found = 0;
+    for (int r = threadIdx.x; r < J.numrho; r += 512) {
+        const int base = (n + 1) * width + r + 1;
+        const int v = a[base];
+        if (v > threshold && v > a[base - 1] && v >= a[base + 1] && v > a[base - width] && v >= a[base + width]) {
+            found++;
+            if (J.lines) {
+                const uint32_t k = atomicAdd(J.n_lines, 1u);
+                if (k < (uint32_t)J.max_lines) J.lines[k] = make_uint2((uint32_t)base, (uint32_t)v);
+            }
         }
     }
+    if (found) atomicAdd(&J.per_angle[n], found);
 }
 
 // ---- median angle + rotation matrix ------------------------------------------------------------------------------------
@@ -425,7 +460,7 @@ int launch_vote_t(docscan_ctx* ctx, const SkewJob* jd, int n, size_t smem, const
 int launch_vote(docscan_ctx* ctx, const SkewJob* jd, int n, int max_rho) {
     TrigTable T;
     hm_hough_trig_table(T.c, T.s);
-    const size_t row = sizeof(int) * (size_t)(max_rho + 2), cap = 100 * 1024;      // <= 100 KB: two CTAs per SM
+    const size_t row = sizeof(int) * (size_t)((max_rho + 2 + 31) & ~31), cap = 100 * 1024;      // <= 100 KB: two CTAs per SM
     if (4 * row <= cap) return launch_vote_t<4>(ctx, jd, n, 4 * row, T);
     if (2 * row <= 2 * cap) return launch_vote_t<2>(ctx, jd, n, 2 * row, T);
     if (row <= 220 * 1024) return launch_vote_t<1>(ctx, jd, n, row, T);
@@ -533,7 +568,7 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
     }
     {
         ProfScope prof(ctx, "hough_peaks", 0);
-        hough_peaks_kernel<<<dim3((max_rho + 255) / 256, NANG, n), 256, 0, ctx->stream>>>(jd, hough_threshold);
+        hough_peaks_kernel<<<dim3(NANG, 1, n), 512, 0, ctx->stream>>>(jd, hough_threshold);
         DS_CHECK_LAUNCH(ctx);
     }
     SkewTables ST;
@@ -569,7 +604,7 @@ int k_hough_lines(docscan_ctx* ctx, const DImg& edges, int threshold, std::vecto
     edge_list_kernel<<<dim3((w + 63) / 64, (h + 3) / 4, 1), 256, 0, ctx->stream>>>(jd);
     DS_CHECK_LAUNCH(ctx);
     DS_TRY(launch_vote(ctx, jd, 1, j.numrho));
-    hough_peaks_kernel<<<dim3((j.numrho + 255) / 256, NANG, 1), 256, 0, ctx->stream>>>(jd, threshold);
+    hough_peaks_kernel<<<dim3(NANG, 1, 1), 512, 0, ctx->stream>>>(jd, threshold);
     DS_CHECK_LAUNCH(ctx);
     uint32_t n_cand = 0;
     DS_CUDA(ctx, cudaMemcpyAsync(&n_cand, j.n_lines, sizeof(n_cand), cudaMemcpyDeviceToHost, ctx->stream));
