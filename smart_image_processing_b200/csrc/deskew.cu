@@ -42,14 +42,15 @@ struct SkewJob {
 // (dx, dy) of the tile and a one-pixel ring around it is kept in shared memory as two 16-bit lanes (zero outside the
 // image: OpenCV's magnitude plane has a zero border), and the suppression test reads the two neighbours its direction
 // selects.  A warp covers 32 consecutive pixels of a row and publishes its decisions with two ballots.
-constexpr int CT_W = 64, CT_H = 32, CT_SW = CT_W + 8, CT_GW = CT_W + 2;
+constexpr int CT_W = 64, CT_H = 32, CT_SW = CT_W + 8, CT_GW = CT_W + 4;
+constexpr uint32_t G_BIAS = 0x04000400u;                              // both 16-bit lanes of a gradient word carry + 1024
 
 __global__ void __launch_bounds__(256) canny_bits_kernel(const SkewJob* __restrict__ jobs, int low, int high) {
     const SkewJob J = jobs[blockIdx.z];
     const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
     if (blockIdx.x >= J.wpr || y0 >= J.h) return;
     __shared__ __align__(16) uint8_t s_src[CT_H + 4][CT_SW];          // origin (y0 - 2, x0 - 4)
-    __shared__ uint32_t s_g[CT_H + 2][CT_GW];                         // origin (y0 - 1, x0 - 1): dx | dy << 16
+    __shared__ __align__(16) uint32_t s_g[CT_H + 2][CT_GW];           // origin (y0 - 1, x0 - 1): (dx + 1024) | (dy + 1024) << 16
     const int tid = threadIdx.x;
     const bool al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
     for (int i = tid; i < (CT_H + 4) * (CT_SW / 4); i += 256) {
@@ -65,23 +66,36 @@ __global__ void __launch_bounds__(256) canny_bits_kernel(const SkewJob* __restri
         *reinterpret_cast<uint32_t*>(&s_src[ly][4 * wi]) = word;
     }
     __syncthreads();
-    for (int i = tid; i < (CT_H + 2) * CT_GW; i += 256) {
-        const int ly = i / CT_GW, lx = i - ly * CT_GW;
-        const int gy_ = y0 + ly - 1, gx_ = x0 + lx - 1;
-        uint32_t g = 0;
-        if (gy_ >= 0 && gy_ < J.h && gx_ >= 0 && gx_ < J.w) {
-            const uint8_t* p = &s_src[ly + 1][lx + 3];                // the centre pixel
-            const int a = p[-CT_SW - 1], b = p[-CT_SW], c = p[-CT_SW + 1];
-            const int d = p[-1], f = p[1];
-            const int q = p[CT_SW - 1], hh = p[CT_SW], k = p[CT_SW + 1];
-            const int dx = (c - a) + 2 * (f - d) + (k - q);
-            const int dy = (q - a) + 2 * (hh - b) + (k - c);
-            g = ((uint32_t)dx & 0xffffu) | ((uint32_t)dy << 16);
+    // Sobel, four pixels per step on 16-bit lane pairs: with S = top + 2 mid + bottom and T = bottom - top per column,
+    // dx(c) = S(c + 1) - S(c - 1) and dy(c) = T(c - 1) + 2 T(c) + T(c + 1); the columns c - 1 .. c + 4 of the four pixels are
+    // bytes 2 .. 7 of two aligned words, and the differences of aligned pairs are the dx of the pixels in between
+    for (int i = tid; i < (CT_H + 2) * (CT_GW / 4); i += 256) {
+        const int ly = i / (CT_GW / 4), q = i - ly * (CT_GW / 4);       // pixels lx = 4 q .. 4 q + 3 of gradient row ly
+        uint32_t S[3], Tb[3];                                          // column pairs (2,3) (4,5) (6,7) of the 8-byte window
+        {
+            const uint32_t* r0 = reinterpret_cast<const uint32_t*>(&s_src[ly][4 * q]);
+            const uint32_t* r1 = reinterpret_cast<const uint32_t*>(&s_src[ly + 1][4 * q]);
+            const uint32_t* r2 = reinterpret_cast<const uint32_t*>(&s_src[ly + 2][4 * q]);
+            const uint32_t t0 = r0[0], t1 = r0[1], m0 = r1[0], m1 = r1[1], b0 = r2[0], b1 = r2[1];
+            const uint32_t tp[3] = {__byte_perm(t0, 0, 0x4342), __byte_perm(t1, 0, 0x4140), __byte_perm(t1, 0, 0x4342)};
+            const uint32_t mp[3] = {__byte_perm(m0, 0, 0x4342), __byte_perm(m1, 0, 0x4140), __byte_perm(m1, 0, 0x4342)};
+            const uint32_t bp[3] = {__byte_perm(b0, 0, 0x4342), __byte_perm(b1, 0, 0x4140), __byte_perm(b1, 0, 0x4342)};
+#pragma unroll
+            for (int k = 0; k < 3; k++) { S[k] = tp[k] + bp[k] + 2 * mp[k]; Tb[k] = bp[k] + 0x01000100u - tp[k]; }
         }
-        s_g[ly][lx] = g;
+        const uint32_t dx01 = S[1] + G_BIAS - S[0], dx23 = S[2] + G_BIAS - S[1];                     // lanes: pixels (0, 1), (2, 3)
+        const uint32_t dy01 = Tb[0] + Tb[1] + 2 * __byte_perm(Tb[0], Tb[1], 0x5432);                 // 4 x 256 = the same bias
+        const uint32_t dy23 = Tb[1] + Tb[2] + 2 * __byte_perm(Tb[1], Tb[2], 0x5432);
+        uint32_t g[4] = {__byte_perm(dx01, dy01, 0x5410), __byte_perm(dx01, dy01, 0x7632),
+                         __byte_perm(dx23, dy23, 0x5410), __byte_perm(dx23, dy23, 0x7632)};
+        const int gy_ = y0 + ly - 1, gx_ = x0 + 4 * q - 1;
+        const bool row_in = gy_ >= 0 && gy_ < J.h;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (!row_in || gx_ + k < 0 || gx_ + k >= J.w) g[k] = G_BIAS;      // zero border of the magnitude plane
+        *reinterpret_cast<uint4*>(&s_g[ly][4 * q]) = make_uint4(g[0], g[1], g[2], g[3]);
     }
     __syncthreads();
-    auto mag = [](uint32_t g) { return abs((int)(short)(g & 0xffffu)) + abs((int)g >> 16); };
+    auto mag = [](uint32_t g) { return abs((int)(g & 0xffffu) - 1024) + abs((int)(g >> 16) - 1024); };
     const int lane = tid & 31, wrp = tid >> 5;
     uint32_t* cand32 = reinterpret_cast<uint32_t*>(J.cand);
     uint32_t* act32 = reinterpret_cast<uint32_t*>(J.act);
@@ -93,7 +107,7 @@ __global__ void __launch_bounds__(256) canny_bits_kernel(const SkewJob* __restri
         const int lx = 32 * half + lane;
         const uint32_t* gp = &s_g[ly + 1][lx + 1];
         const uint32_t g = *gp;
-        const int xs = (short)(g & 0xffffu), ys = (int)g >> 16;
+        const int xs = (int)(g & 0xffffu) - 1024, ys = (int)(g >> 16) - 1024;
         const int m = abs(xs) + abs(ys);
         bool cand = false;
         if (m > low) {                                                 // (pixels beyond the image carry m = 0)
