@@ -186,6 +186,224 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
     }
 }
 
+// The same kernel on packed pairs (FFMA2 / FADD2 / FMUL2, sm_100): a packed instruction still occupies the fp32 pipe for
+// two cycles (tests/tools/ffma2_probe.cu: 128 lanes per clock and SM either way) but takes one issue slot instead of two,
+// and issue slots are what the scalar kernel runs out of (115 instructions per pixel, 71 of them the parity-fixed fp32
+// operations).  Every lane of a packed operation is an IEEE fma / add / mul of its own, so the results stay bit-identical.
+// Row pass: a thread's 16 outputs are 8 pairs two columns apart, (o, o + 2); the staged row is stored as pairs
+// G[u] = (f[u], f[u + 2]) for EVERY u, so the operand of tap i of pair o is the aligned 8-byte entry G[o + i] as it comes out
+// of shared memory (assembling pairs from neighbouring registers costs a MOV per operation: measured, 87 instructions
+// per pixel).  Every accumulator still sees its taps in increasing order.  Column pass: thread = two adjacent columns x
+// 8 rows, the window held as pairs.
+template <int RMAX, int MINB>
+__global__ void __launch_bounds__(NT, MINB) adaptive_gauss2_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L) {
+    constexpr int DELTA = (4 - (RMAX & 3)) & 3;                    // staged column 0 <-> x0 - RMAX - DELTA (word aligned)
+    constexpr int OFFS = DELTA & 1;                                 // entries start one late so that the row pass reads 16-byte aligned
+    constexpr int STAGE_WORDS = (TW + 2 * RMAX + DELTA + 3) >> 2;
+    constexpr int RR = ((2 * RMAX + BR - 1) / BR + 1) * BR;         // ring rows
+    constexpr int D = (2 * RMAX + BR - 1) / BR;                     // the column pass lags the row pass by D steps
+    constexpr int NG = 14 + 2 * RMAX;                               // entries G[0 .. NG - 1] of a thread's 16 outputs (an even count)
+    constexpr int CR = 8;                                           // rows per thread in the column pass
+    const AdaptJob J = jobs[blockIdx.z];
+    const int x0 = blockIdx.x * TW;
+    const int y_begin = blockIdx.y * L.seg_rows;
+    if (x0 >= J.w || y_begin >= J.h) return;
+    const int y_end = min(J.h, y_begin + L.seg_rows);
+    const int rows_out = y_end - y_begin;
+    const int tid = threadIdx.x;
+
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float2* s_stage = reinterpret_cast<float2*>(smem_raw);         // BR rows of spf / 2 entries; spf / 4 odd: 128-bit loads of 8 rows hit 8 x 16 bytes
+    float* s_ring = reinterpret_cast<float*>(smem_raw) + BR * L.spf;   // RR * RPF
+    const int spe = L.spf >> 1;
+
+    const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
+    const bool io16 = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch | reinterpret_cast<uintptr_t>(J.dst) | (uintptr_t)J.dst_pitch) & 1) == 0;
+    const int n_vb = (rows_out + BR - 1) / BR;
+    const bool row_identity = J.w == 1, col_identity = J.h == 1;   // cv::GaussianBlur shrinks the kernel on 1-px axes
+    const int tail = (L.tail_compat && L.k >= 11) ? (J.w & 7) : 0;
+    const int xt_col = J.w - tail;                                  // column filter: mul+add from here on (even: pairs never straddle it)
+    auto gpair = [&](int j) { const float c = L.gh[j]; return make_float2(c, c); };
+
+    for (int hb = 0; hb < n_vb + D; hb++) {
+        {
+            const int srow_id = tid >> 3;              // 16 rows x 8 lanes; a lane strides along its row
+            const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - RMAX + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
+            float2* sp = s_stage + srow_id * spe + OFFS;
+            const int gx0 = x0 - RMAX - DELTA;
+            auto fetch = [&](int wi) -> uint32_t {
+                const int gx = gx0 + 4 * wi;
+                return (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
+            };
+            // interior strips (all but the first and last of a page): no per-word tests, the right neighbour of a word comes from
+            // the next lane (from the first lane's next word for the last of the eight)
+            const bool interior = src_al && gx0 >= 0 && gx0 + 4 * STAGE_WORDS + 4 <= J.w;
+            constexpr int NJ = (STAGE_WORDS + 7) / 8;
+            const int l8 = tid & 7;
+            uint32_t wv[NJ + 1], wn[NJ];
+            if (interior) {
+                const uint32_t* rp32 = reinterpret_cast<const uint32_t*>(rowp + gx0) + l8;
+#pragma unroll
+                for (int j = 0; j <= NJ; j++) wv[j] = (8 * j < STAGE_WORDS + 1 && l8 + 8 * j < STAGE_WORDS + 1) ? __ldg(rp32 + 8 * j) : 0u;
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {
+                    const uint32_t nx = __shfl_down_sync(0xffffffffu, wv[j], 1), wrap = __shfl_up_sync(0xffffffffu, wv[j + 1], 7);
+                    wn[j] = l8 == 7 ? wrap : nx;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {
+                    const int wi = l8 + 8 * j;
+                    wv[j] = 0; wn[j] = 0;
+                    if (wi < STAGE_WORDS) { wv[j] = fetch(wi); wn[j] = fetch(wi + 1); }
+                }
+            }
+            // next step's rows towards L1 while this step computes (the loads above then wait tens of cycles, not hundreds)
+            if (hb + 1 < n_vb + D && tid < 2 * BR) {
+                const uint8_t* np = J.src + (size_t)ds_clamp(y_begin - RMAX + (hb + 1) * BR + (tid >> 1), 0, J.h - 1) * J.src_pitch
+                                    + ds_clamp(gx0 + (tid & 1) * 128, 0, J.w - 1);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+                const int wi = l8 + 8 * j;
+                if (wi >= STAGE_WORDS) continue;
+                // u8 -> fp32 without the conversion unit: 2^23 + v is exact in fp32, subtract 2^23 again (two lanes at a time)
+                const float2 m23 = make_float2(-8388608.0f, -8388608.0f);
+                const uint32_t a = wv[j], b = wn[j];
+                auto cv = [&](uint32_t lo, uint32_t hi) { return __fadd2_rn(make_float2(__uint_as_float(lo), __uint_as_float(hi)), m23); };
+                const uint32_t f0 = __byte_perm(a, 0x4B000000u, 0x7440), f1 = __byte_perm(a, 0x4B000000u, 0x7441);
+                const uint32_t f2 = __byte_perm(a, 0x4B000000u, 0x7442), f3 = __byte_perm(a, 0x4B000000u, 0x7443);
+                const uint32_t f4 = __byte_perm(b, 0x4B000000u, 0x7440), f5 = __byte_perm(b, 0x4B000000u, 0x7441);
+                sp[4 * wi] = cv(f0, f2); sp[4 * wi + 1] = cv(f1, f3); sp[4 * wi + 2] = cv(f2, f4); sp[4 * wi + 3] = cv(f3, f5);
+            }
+        }
+        __syncthreads();
+        {   // ---- row pass: thread = (staged row, 16 consecutive outputs); lane <-> row as in the scalar kernel
+            const int lane = tid & 31, wrp = tid >> 5;
+            const int hr = lane & 15;
+            const int c0 = 16 * (2 * wrp + (lane >> 4));
+            // G[u] = (f[u], f[u + 2]), f[u] <-> column x0 + c0 + u - RMAX; the entry index OFFS + DELTA + c0 is even
+            const float2* G = s_stage + hr * spe + OFFS + DELTA + c0;
+            float2 acc[8];                                                    // pair j: outputs o_j and o_j + 2, o_j = 4 (j / 2) + (j & 1)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int u2 = 0; u2 < NG / 2; u2++) {
+                // (a compiler fence every six loads: ptxas otherwise requests all 24 at once and spills 16 loop invariants around them)
+                if (u2 % 6 == 0 && u2) asm volatile("" ::: "memory");
+                const float4 gg = *reinterpret_cast<const float4*>(G + 2 * u2);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int u = 2 * u2 + h;
+                    const float2 in = h ? make_float2(gg.z, gg.w) : make_float2(gg.x, gg.y);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const int i = u - (4 * (j >> 1) + (j & 1));          // tap index in the padded kernel
+                        if (i >= 0 && i <= 2 * RMAX) acc[j] = __ffma2_rn(in, gpair(i < RMAX ? RMAX - i : i - RMAX), acc[j]);
+                    }
+                }
+            }
+            if (row_identity) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = G[RMAX + 4 * (j >> 1) + (j & 1)];
+            }
+            float4* dst = reinterpret_cast<float4*>(s_ring + ((hb * BR + hr) % RR) * RPF + c0);
+            dst[0] = make_float4(acc[0].x, acc[1].x, acc[0].y, acc[1].y);
+            dst[1] = make_float4(acc[2].x, acc[3].x, acc[2].y, acc[3].y);
+            dst[2] = make_float4(acc[4].x, acc[5].x, acc[4].y, acc[5].y);
+            dst[3] = make_float4(acc[6].x, acc[7].x, acc[6].y, acc[7].y);
+        }
+        __syncthreads();
+        if (hb < D) continue;
+        // ---- column pass: thread = (pair of columns, 8 rows); centre of output o sits at window index o + RMAX.  A window
+        // starts at a multiple of 8 rows and the ring size is a compile-time constant: every ring offset is an immediate.
+        const int vb = hb - D;
+        const int cp = tid & 63, rh = tid >> 6;
+        const int x = x0 + 2 * cp;
+        // two halves of four rows: the second half's last four window rows are requested after the first half's arithmetic,
+        // which keeps the live window at 38 pairs (the whole kernel within 128 registers)
+        constexpr int HR = CR / 2, NW1 = HR + 2 * RMAX;
+        float2 Wn[CR + 2 * RMAX];
+        const int start = ((vb * BR) % RR + CR * rh) % RR;
+        const float2* colp = reinterpret_cast<const float2*>(s_ring) + cp;
+#define DS_LOAD_WINDOW2(S0, I0, I1) \
+    case (S0) / CR: _Pragma("unroll") for (int i = (I0); i < (I1); i++) Wn[i] = colp[(((S0) + i) % RR) * (RPF / 2)]; break;
+#define DS_LOAD_WINDOW2_ALL(I0, I1)                                                                                              \
+    switch (start / CR) {                                                                                                        \
+        DS_LOAD_WINDOW2(0, I0, I1) DS_LOAD_WINDOW2(8, I0, I1) DS_LOAD_WINDOW2(16, I0, I1) DS_LOAD_WINDOW2(24, I0, I1)             \
+        DS_LOAD_WINDOW2(32, I0, I1) DS_LOAD_WINDOW2(40, I0, I1) DS_LOAD_WINDOW2(48, I0, I1) DS_LOAD_WINDOW2(56, I0, I1)           \
+        DS_LOAD_WINDOW2(64, I0, I1) DS_LOAD_WINDOW2(72, I0, I1) DS_LOAD_WINDOW2(80, I0, I1) DS_LOAD_WINDOW2(88, I0, I1)           \
+        default: break;                                                                                                          \
+    }
+        float2 acc[CR];
+        const bool fused = x < xt_col;
+        const float2 g0 = gpair(0);
+        DS_LOAD_WINDOW2_ALL(0, NW1)
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            if (half == 1) { DS_LOAD_WINDOW2_ALL(NW1, CR + 2 * RMAX) }
+#pragma unroll
+            for (int o = half * HR; o < (half + 1) * HR; o++) acc[o] = __fmul2_rn(g0, Wn[o + RMAX]);
+            if (fused) {
+#pragma unroll
+                for (int j = 1; j <= RMAX; j++) {
+                    const float2 gj = gpair(j);
+#pragma unroll
+                    for (int o = half * HR; o < (half + 1) * HR; o++) acc[o] = __ffma2_rn(__fadd2_rn(Wn[o + RMAX + j], Wn[o + RMAX - j]), gj, acc[o]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 1; j <= RMAX; j++) {
+                    const float2 gj = gpair(j);
+#pragma unroll
+                    for (int o = half * HR; o < (half + 1) * HR; o++)
+                        acc[o] = __fadd2_rn(acc[o], __fmul2_rn(gj, __fadd2_rn(Wn[o + RMAX + j], Wn[o + RMAX - j])));
+                }
+            }
+            if (col_identity) {
+#pragma unroll
+                for (int o = half * HR; o < (half + 1) * HR; o++) acc[o] = Wn[o + RMAX];
+            }
+        }
+#undef DS_LOAD_WINDOW2_ALL
+#undef DS_LOAD_WINDOW2
+        const int y0 = y_begin + vb * BR + CR * rh;
+        const int rows = min(CR, y_end - y0);
+        if (x < J.w && rows > 0) {
+            // the mean of uint8 data under a kernel that sums to 1 lies in [0, 255.0001]: adding 1.5 * 2^23 leaves the mean rounded
+            // to nearest even in the mantissa, and  src - mean > -C  <=>  src + C + bits(1.5 * 2^23) > bits(mean + 1.5 * 2^23)
+            const float2 magic = make_float2(12582912.0f, 12582912.0f);
+            const int cbias = L.c_param + 0x4B400000;
+            const uint8_t* sp_ = J.src + (size_t)y0 * J.src_pitch + x;
+            uint8_t* dp_ = J.dst + (size_t)y0 * J.dst_pitch + x;
+            if (io16 && x + 1 < J.w && rows == CR) {
+                uint32_t cpx[CR];                              // centre pixel pairs, loaded up front
+#pragma unroll
+                for (int o = 0; o < CR; o++) cpx[o] = __ldg(reinterpret_cast<const uint16_t*>(sp_ + (size_t)o * J.src_pitch));
+#pragma unroll
+                for (int o = 0; o < CR; o++) {
+                    const float2 mb = __fadd2_rn(acc[o], magic);
+                    const uint32_t r0 = ((int)(cpx[o] & 255u) + cbias > __float_as_int(mb.x)) ? 0x00ffu : 0u;
+                    const uint32_t r1 = ((int)(cpx[o] >> 8) + cbias > __float_as_int(mb.y)) ? 0xff00u : 0u;
+                    *reinterpret_cast<uint16_t*>(dp_ + (size_t)o * J.dst_pitch) = (uint16_t)(r0 | r1);
+                }
+            } else {
+                const bool two = x + 1 < J.w;
+#pragma unroll
+                for (int o = 0; o < CR; o++) {
+                    if (o >= rows) break;
+                    const float2 mb = __fadd2_rn(acc[o], magic);
+                    const uint8_t* s1 = sp_ + (size_t)o * J.src_pitch;
+                    uint8_t* d1 = dp_ + (size_t)o * J.dst_pitch;
+                    d1[0] = ((int)s1[0] + cbias > __float_as_int(mb.x)) ? 255 : 0;
+                    if (two) d1[1] = ((int)s1[1] + cbias > __float_as_int(mb.y)) ? 255 : 0;
+                }
+            }
+        }
+    }
+}
+
 // Block sizes beyond the unrolled kernels (radius 33 .. GMAX - 1): same marching layout and the same operation order, but
 // with run-time loops — the taps come from shared memory and the column window is read from the ring instead of living in
 // registers.  About three times the instructions per pixel of the unrolled kernels; it exists so that every block size
@@ -561,6 +779,19 @@ __global__ void __launch_bounds__(128) mask_blend16_kernel(const BlendJob* __res
 
 struct AdaptGridInfo { int strips, max_w, max_h, n, seg_min; };
 
+template <int RMAX, int MINB = 4>
+int launch_adaptive2(docscan_ctx* ctx, const AdaptJob* jd, AdaptLaunch L, const AdaptGridInfo& G, size_t smem) {
+    if (smem > 48 * 1024)
+        DS_CUDA(ctx, cudaFuncSetAttribute(adaptive_gauss2_kernel<RMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_gauss2_kernel<RMAX, MINB>, NT, smem));
+    L.seg_rows = ds_pick_seg_rows(per_sm * ctx->sm_count, G.strips, G.max_h, G.seg_min, BR);
+    dim3 grid((G.max_w + TW - 1) / TW, (G.max_h + L.seg_rows - 1) / L.seg_rows, G.n);
+    adaptive_gauss2_kernel<RMAX, MINB><<<grid, NT, smem, ctx->stream>>>(jd, L);
+    DS_CHECK_LAUNCH(ctx);
+    return DOCSCAN_OK;
+}
+
 template <int RMAX>
 int launch_adaptive(docscan_ctx* ctx, const AdaptJob* jd, AdaptLaunch L, const AdaptGridInfo& G, size_t smem) {
     if (smem > 48 * 1024)
@@ -585,8 +816,22 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
     const bool generic = L.r > 32;
     const int rmax = L.r <= 5 ? 5 : L.r <= 9 ? 9 : L.r <= 13 ? 13 : L.r <= 15 ? 15 : L.r <= 17 ? 17 : L.r <= 25 ? 25 : L.r <= 32 ? 32 : L.r;
     const int delta = (4 - (rmax & 3)) & 3;
-    L.spf = TW + 2 * rmax + delta + 4;
-    L.spf += (33 - (L.spf & 31)) & 31;                 // pitch == 1 (mod 32): lanes of a warp read different banks
+    // Opt-in (DOCSCAN_ADAPT_PACKED=1, radii up to 17): the packed-pair kernel.  Bit-exact (same GPU tests), 25 % fewer warp
+    // instructions, but not faster: at 16 warps per SM the kernel waits on its barriers and shared-memory round trips, not
+    // on issue slots (2.74 ms against 2.47 ms per 256 pages at 4 CTAs per SM; 2.34 ms at 3 CTAs and 160 registers, where the
+    // whole step loses 0.2 ms because the other streams' kernels find less room) - profiles/README.md.
+    bool packed = false;
+    if (const char* e = getenv("DOCSCAN_ADAPT_PACKED")) packed = !generic && rmax <= 17 && atoi(e) != 0;
+    if (packed) {
+        // floats per staged row: (f[u], f[u + 2]) pairs for every staged column (+ 1 entry of offset); pitch / 4 odd, so that the
+        // 128-bit loads of 8 rows hit 8 different 16-byte bank groups
+        L.spf = 2 * (4 * ((TW + 2 * rmax + delta + 3) >> 2) + 2);
+        L.spf = (L.spf + 3) & ~3;
+        if (((L.spf >> 2) & 1) == 0) L.spf += 4;
+    } else {
+        L.spf = TW + 2 * rmax + delta + 4;
+        L.spf += (33 - (L.spf & 31)) & 31;             // pitch == 1 (mod 32): lanes of a warp read different banks
+    }
     const int ring_rows = ((2 * rmax + BR - 1) / BR + 1) * BR;
     std::vector<float> g(k);
     docscan_gaussian_kernel_f32(k, g.data());
@@ -662,6 +907,11 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
         ctx->launches++;
         rc = cudaGetLastError() == cudaSuccess ? DOCSCAN_OK : ds_fail(ctx, DOCSCAN_ERR_CUDA, "adaptive generic kernel launch failed");
     }
+    else if (packed && L.r <= 5) rc = launch_adaptive2<5>(ctx, jd, L, G, smem);
+    else if (packed && L.r <= 9) rc = launch_adaptive2<9>(ctx, jd, L, G, smem);
+    else if (packed && L.r <= 13) rc = launch_adaptive2<13>(ctx, jd, L, G, smem);
+    else if (packed && L.r <= 15) rc = launch_adaptive2<15>(ctx, jd, L, G, smem);
+    else if (packed && L.r <= 17) rc = (getenv("DOCSCAN_ADAPT_MINB3") ? launch_adaptive2<17, 3>(ctx, jd, L, G, smem) : launch_adaptive2<17>(ctx, jd, L, G, smem));
     else if (L.r <= 5) rc = launch_adaptive<5>(ctx, jd, L, G, smem);
     else if (L.r <= 9) rc = launch_adaptive<9>(ctx, jd, L, G, smem);
     else if (L.r <= 13) rc = launch_adaptive<13>(ctx, jd, L, G, smem);

@@ -226,6 +226,19 @@ def test_tensor_core_adaptive_threshold_opt_in(monkeypatch):
                 eq(ops.adaptive_threshold(g, "gaussian", k, c), O.adaptive_threshold(g, "gaussian", k, c), f"tc adaptive {h}x{w} k={k} C={c} {kind}")
 
 
+def test_packed_pair_adaptive_threshold_opt_in(monkeypatch):
+    """The opt-in packed-pair GAUSSIAN_C (DOCSCAN_ADAPT_PACKED=1: FFMA2 / FADD2 on (f[u], f[u + 2]) pairs, two columns per thread
+    in the column pass) must give cv2's bytes exactly like the default kernel: every unrolled radius, ragged and 1-pixel shapes,
+    odd pitches (numpy views), the cv2 tail columns."""
+    monkeypatch.setenv("DOCSCAN_ADAPT_PACKED", "1")
+    rng = np.random.default_rng(36)
+    for (h, w) in [(300, 260), (97, 131), (1600, 1131), (257, 1031), (33, 70), (1, 40), (40, 1), (64, 129), (50, 255)]:
+        for k, c in [(35, 10), (31, 3), (27, 0), (19, 5), (11, 10), (3, 0), (9, -2)]:
+            for kind in ("page", "noise"):
+                g = page_like(rng, max(h, 16), max(w, 16))[:h, :w] if kind == "page" else rng.integers(0, 256, (h, w), dtype=np.uint8)
+                eq(ops.adaptive_threshold(g, "gaussian", k, c), O.adaptive_threshold(g, "gaussian", k, c), f"packed adaptive {h}x{w} k={k} C={c} {kind}")
+
+
 @pytest.mark.parametrize("grid", ["1", "2", "5"])
 def test_tc_blur_long_tile_runs_per_cta(monkeypatch, grid):
     """The tensor-core blur deals every CTA a contiguous run of tiles and keeps a 64-entry ring of decoded tiles, refilled 32 at
