@@ -63,23 +63,32 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
             const int srow_id = tid >> 3;              // 16 rows x 8 lanes; a lane strides along its row
             const uint8_t* rowp = J.src + (size_t)ds_clamp(y_begin - RMAX + hb * BR + srow_id, 0, J.h - 1) * J.src_pitch;
             float* sp = s_stage + srow_id * L.spf;
-            for (int w0 = tid & 7; w0 < STAGE_WORDS; w0 += 8 * 7) {
-                uint32_t wv[7];                            // issue the loads first, convert and store afterwards
+            // interior strips (all but the first and last of a page) skip the per-word tests
+            const int gx0 = x0 - RMAX - DELTA;
+            const bool interior = src_al && gx0 >= 0 && gx0 + 4 * STAGE_WORDS <= J.w;
+            constexpr int NJ = (STAGE_WORDS + 7) / 8;
+            const int l8 = tid & 7;
+            uint32_t wv[NJ];                               // issue the loads first, convert and store afterwards
+            if (interior) {
+                const uint32_t* rp32 = reinterpret_cast<const uint32_t*>(rowp + gx0) + l8;
 #pragma unroll
-                for (int j = 0; j < 7; j++) {
-                    const int wi = w0 + 8 * j;
-                    const int gx = x0 - RMAX - DELTA + 4 * wi;
+                for (int j = 0; j < NJ; j++) wv[j] = (8 * j + 7 < STAGE_WORDS || l8 + 8 * j < STAGE_WORDS) ? __ldg(rp32 + 8 * j) : 0u;
+            } else {
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {
+                    const int wi = l8 + 8 * j;
+                    const int gx = gx0 + 4 * wi;
                     wv[j] = 0;
                     if (wi < STAGE_WORDS) wv[j] = (src_al && gx >= 0 && gx + 3 < J.w) ? ds_ldg32(rowp + gx) : fetch_word_clamped(rowp, gx, J.w);
                 }
+            }
 #pragma unroll
-                for (int j = 0; j < 7; j++) {
-                    const int wi = w0 + 8 * j;
-                    if (wi >= STAGE_WORDS) continue;
-                    // u8 -> fp32 without the slow I2F unit: 2^23 + v is exact in fp32, subtract 2^23 again
+            for (int j = 0; j < NJ; j++) {
+                const int wi = l8 + 8 * j;
+                if (8 * j + 7 >= STAGE_WORDS && wi >= STAGE_WORDS) continue;
+                // u8 -> fp32 without the slow I2F unit: 2^23 + v is exact in fp32, subtract 2^23 again
 #pragma unroll
-                    for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(__byte_perm(wv[j], 0x4B000000u, 0x7440 + b)), 8388608.0f);
-                }
+                for (int b = 0; b < 4; b++) sp[4 * wi + b] = __fsub_rn(__uint_as_float(__byte_perm(wv[j], 0x4B000000u, 0x7440 + b)), 8388608.0f);
             }
         }
         __syncthreads();
@@ -160,26 +169,29 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
         if (x < J.w) {
             const int y0 = y_begin + vb * BR;
             const int rows = min(BR, y_end - y0);
-            // 32-bit offsets from the (warp-uniform) plane pointers; the mean of uint8 data under a kernel that sums to 1 lies
-            // in [0, 255.0001], so the conversion needs no clamp
-            const uint32_t so = (uint32_t)y0 * (uint32_t)J.src_pitch + (uint32_t)x, d_o = (uint32_t)y0 * (uint32_t)J.dst_pitch + (uint32_t)x;
+            if (col_identity) {
+#pragma unroll
+                for (int o = 0; o < BR; o++) acc[o] = Wn[o + RMAX];
+            }
+            // the mean of uint8 data under a kernel that sums to 1 lies in [0, 255.0001]: adding 1.5 * 2^23 leaves the mean rounded
+            // to nearest even in the mantissa, and  src - mean > -C  <=>  src + C + bits(1.5 * 2^23) > bits(mean + 1.5 * 2^23)
+            const int cbias = L.c_param + 0x4B400000;
+            const uint8_t* sp_ = J.src + (size_t)y0 * J.src_pitch + x;
+            uint8_t* dp_ = J.dst + (size_t)y0 * J.dst_pitch + x;
             int cpx[BR];                                   // centre pixels, loaded up front
             if (rows == BR) {
 #pragma unroll
-                for (int o = 0; o < BR; o++) cpx[o] = J.src[so + (uint32_t)o * (uint32_t)J.src_pitch];
+                for (int o = 0; o < BR; o++) { cpx[o] = __ldg(sp_); sp_ += J.src_pitch; }
 #pragma unroll
                 for (int o = 0; o < BR; o++) {
-                    const int mean = __float2int_rn(col_identity ? Wn[o + RMAX] : acc[o]);
-                    J.dst[d_o + (uint32_t)o * (uint32_t)J.dst_pitch] = (cpx[o] - mean > -L.c_param) ? 255 : 0;
+                    *dp_ = (cpx[o] + cbias > __float_as_int(__fadd_rn(acc[o], 12582912.0f))) ? 255 : 0;
+                    dp_ += J.dst_pitch;
                 }
             } else {
 #pragma unroll
-                for (int o = 0; o < BR; o++) cpx[o] = o < rows ? (int)J.src[so + (uint32_t)o * (uint32_t)J.src_pitch] : 0;
-#pragma unroll
                 for (int o = 0; o < BR; o++) {
                     if (o >= rows) break;
-                    const int mean = __float2int_rn(col_identity ? Wn[o + RMAX] : acc[o]);
-                    J.dst[d_o + (uint32_t)o * (uint32_t)J.dst_pitch] = (cpx[o] - mean > -L.c_param) ? 255 : 0;
+                    dp_[(size_t)o * J.dst_pitch] = ((int)sp_[(size_t)o * J.src_pitch] + cbias > __float_as_int(__fadd_rn(acc[o], 12582912.0f))) ? 255 : 0;
                 }
             }
         }
