@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <thread>
 
+#include <immintrin.h>
+
 #include "common.cuh"
 
 namespace {
@@ -732,6 +734,32 @@ bool is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// Large host-to-host copies with streaming stores: a plain memcpy of a few MB reads the destination lines before it
+// overwrites them (three bytes of memory traffic per byte copied instead of two), and the pageable leg is bound by exactly
+// that traffic.  Falls back to memcpy on CPUs without AVX2 and for the unaligned head / tail of a row.
+__attribute__((target("avx2"))) void stream_copy_avx2(uint8_t* dst, const uint8_t* src, size_t n) {
+    const size_t head = std::min(n, (size_t)((32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31));
+    if (head) { memcpy(dst, src, head); dst += head; src += head; n -= head; }
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + i + 96), d);
+    }
+    if (i < n) memcpy(dst + i, src + i, n - i);
+}
+
+void host_copy(uint8_t* dst, const uint8_t* src, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("DOCSCAN_NO_STREAM_COPY");
+    if (avx2 && n >= 4096) stream_copy_avx2(dst, src, n);
+    else memcpy(dst, src, n);
+}
+
 void parallel_copy(const std::vector<HostCopy>& jobs) {
     struct Chunk { int job, row0, rows; };
     std::vector<Chunk> chunks;
@@ -740,18 +768,19 @@ void parallel_copy(const std::vector<HostCopy>& jobs) {
         for (int r0 = 0; r0 < jobs[j].rows; r0 += per) chunks.push_back({(int)j, r0, std::min(per, jobs[j].rows - r0)});
     }
     if (chunks.empty()) return;
-    int nt = (int)std::thread::hardware_concurrency() / 2;
+    int nt = (int)std::thread::hardware_concurrency() * 3 / 4;      // measured on the 16-core box: 8 -> 14.4 k, 12 -> 15.8 k, 16 -> 15.7 k MP/s
     if (const char* e = getenv("DOCSCAN_COPY_THREADS")) nt = atoi(e);
-    nt = std::max(1, std::min(std::min(nt, 16), (int)chunks.size()));
+    nt = std::max(1, std::min(std::min(nt, 32), (int)chunks.size()));
     std::atomic<size_t> next{0};
     auto work = [&]() {
         for (size_t c = next.fetch_add(1); c < chunks.size(); c = next.fetch_add(1)) {
             const HostCopy& J = jobs[chunks[c].job];
             if (J.dpitch == J.row_bytes && J.spitch == J.row_bytes)
-                memcpy(J.dst + (size_t)chunks[c].row0 * J.dpitch, J.src + (size_t)chunks[c].row0 * J.spitch, J.row_bytes * (size_t)chunks[c].rows);
+                host_copy(J.dst + (size_t)chunks[c].row0 * J.dpitch, J.src + (size_t)chunks[c].row0 * J.spitch, J.row_bytes * (size_t)chunks[c].rows);
             else
-                for (int r = chunks[c].row0; r < chunks[c].row0 + chunks[c].rows; r++) memcpy(J.dst + (size_t)r * J.dpitch, J.src + (size_t)r * J.spitch, J.row_bytes);
+                for (int r = chunks[c].row0; r < chunks[c].row0 + chunks[c].rows; r++) host_copy(J.dst + (size_t)r * J.dpitch, J.src + (size_t)r * J.spitch, J.row_bytes);
         }
+        _mm_sfence();
     };
     std::vector<std::thread> th;
     for (int t = 1; t < nt; t++) th.emplace_back(work);

@@ -31,7 +31,9 @@ struct SkewJob {
     uint8_t* edges; int edges_pitch;      // may be null
     uint32_t* list;        // edge coordinates x | y << 16 (may be null)
     uint32_t* count;       // number of list entries
-    int* accum;            // (NANG + 2) x (numrho + 2)
+    // (NANG + 2) x (numrho + 2) votes.  16 bits are enough: an accumulator row must fit shared memory (w + h < 28 000), a cell
+    // collects the pixels of at most two adjacent lattice lines, each no longer than min(w, h) < 14 000
+    uint16_t* accum;
     int numrho;
     uint32_t* per_angle;   // NANG line counts
     uint2* lines; uint32_t* n_lines; int max_lines;     // optional (accumulator index, votes) of every line
@@ -374,10 +376,10 @@ __global__ void __launch_bounds__(512) hough_vote_kernel(const SkewJob* __restri
     }
     for (; e < cnt; e += 512) vote(J.list[e]);
     __syncthreads();
-    int* rows = J.accum + (size_t)(n0 + 1) * width;
+    uint16_t* rows = J.accum + (size_t)(n0 + 1) * width;
     for (int i = threadIdx.x; i < VOTE_NA * width; i += 512) {
         const int a = i / width, j = i - a * width;
-        rows[i] = s_acc[a * pitch + (j ^ ((j >> 5) & 31))];
+        rows[i] = (uint16_t)s_acc[a * pitch + (j ^ ((j >> 5) & 31))];
     }
     if (n0 == 0) for (int i = threadIdx.x; i < width; i += 512) J.accum[i] = 0;                                   // border rows
     if (n0 == NANG - VOTE_NA) for (int i = threadIdx.x; i < width; i += 512) J.accum[(size_t)(NANG + 1) * width + i] = 0;
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(512) hough_peaks_kernel(const SkewJob* __restr
     const SkewJob J = jobs[blockIdx.z];
     const int n = blockIdx.x;                                   // one CTA per (angle, page): the row is streamed once
     const int width = J.numrho + 2;
-    const int* a = J.accum;
+    const uint16_t* a = J.accum;
     uint32_t found = 0;
     for (int r = threadIdx.x; r < J.numrho; r += 512) {
         const int base = (n + 1) * width + r + 1;
@@ -550,7 +552,7 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
         if (want_angle) {
             DS_TRY(ds_arena_alloc(ctx, 4 * np, &p)); j.list = (uint32_t*)p;
             j.numrho = 2 * (w + h) + 1;
-            DS_TRY(ds_arena_alloc(ctx, sizeof(int) * (size_t)(NANG + 2) * (j.numrho + 2), &p)); j.accum = (int*)p;
+            DS_TRY(ds_arena_alloc(ctx, sizeof(uint16_t) * (size_t)(NANG + 2) * (j.numrho + 2), &p)); j.accum = (uint16_t*)p;
             outs[i].angle = angles_dev[i]; outs[i].rot = rot_jobs ? rot_jobs[i] : nullptr; outs[i].w = w; outs[i].h = h;
         }
         mw = std::max(mw, w); mh = std::max(mh, h); max_rho = std::max(max_rho, j.numrho);
@@ -610,7 +612,7 @@ int k_hough_lines(docscan_ctx* ctx, const DImg& edges, int threshold, std::vecto
     DS_CUDA(ctx, cudaMemsetAsync(p, 0, sizeof(uint32_t) * (NANG + 8), ctx->stream));
     j.count = (uint32_t*)p; j.n_lines = j.count + 1; j.per_angle = j.count + 4;
     DS_TRY(ds_arena_alloc(ctx, 4 * (size_t)w * h, &p)); j.list = (uint32_t*)p;
-    DS_TRY(ds_arena_alloc(ctx, sizeof(int) * (size_t)(NANG + 2) * (j.numrho + 2), &p)); j.accum = (int*)p;
+    DS_TRY(ds_arena_alloc(ctx, sizeof(uint16_t) * (size_t)(NANG + 2) * (j.numrho + 2), &p)); j.accum = (uint16_t*)p;
     DS_TRY(ds_arena_alloc(ctx, sizeof(uint2) * (size_t)max_lines, &p)); j.lines = (uint2*)p; j.max_lines = max_lines;
     void* dev = nullptr;
     DS_TRY(ds_upload(ctx, &j, sizeof(j), &dev));
