@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(NT, MINB) adaptive_gauss2_kernel(const AdaptJo
                     const float2 gj = gpair(j);
 #pragma unroll
                     for (int o = half * HR; o < (half + 1) * HR; o++)
-                        acc[o] = __fadd2_rn(acc[o], __fmul2_rn(gj, __fadd2_rn(Wn[o + RMAX + j], Wn[o + RMAX - j])));
+                        acc[o] = ds_add2_unfused(acc[o], ds_mul2_rn(gj, __fadd2_rn(Wn[o + RMAX + j], Wn[o + RMAX - j])));
                 }
             }
             if (col_identity) {

@@ -291,6 +291,15 @@ __device__ __forceinline__ int ds_reflect101(int p, int len) {
     return p;
 }
 __device__ __forceinline__ int ds_clamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
+// Packed fp32 multiply / add that must not be contracted.  ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (also from
+// the __fmul2_rn / __fadd2_rn intrinsics under -fmad=false; measured: the Hough vote lost exactness that way), which the
+// scalar .rn forms never are.  The sum is therefore taken lane by lane with the scalar add; the products stay packed.
+__device__ __forceinline__ float2 ds_mul2_rn(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 ds_add2_unfused(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 __device__ __forceinline__ uint32_t ds_ldg32(const void* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
 __device__ __forceinline__ uint8_t ds_div255(uint8_t a, uint8_t b) {
     if (b == 0) return 0;

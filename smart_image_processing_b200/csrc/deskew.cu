@@ -112,18 +112,17 @@ __global__ void __launch_bounds__(256) canny_bits_kernel(const SkewJob* __restri
         const int xs = (int)(g & 0xffffu) - 1024, ys = (int)(g >> 16) - 1024;
         const int m = abs(xs) + abs(ys);
         bool cand = false;
-        if (m > low) {                                                 // (pixels beyond the image carry m = 0)
+        if (__any_sync(0xffffffffu, m > low)) {                        // (pixels beyond the image carry m = 0)
+            // one pair of neighbours, selected without branches: left / right below 22.5 degrees, up / down above 67.5, else the
+            // diagonal the signs pick; the second comparison is >= for the axis directions and > for the diagonals
             const int ax = abs(xs);
             const int ay = abs(ys) << 15, tg22x = ax * 13573;          // tan(22.5 deg) * 2^15; |values| < 2^26
-            if (ay < tg22x) cand = m > mag(gp[-1]) && m >= mag(gp[1]);
-            else {
-                const int tg67x = tg22x + (ax << 16);
-                if (ay > tg67x) cand = m > mag(gp[-CT_GW]) && m >= mag(gp[CT_GW]);
-                else {
-                    const int s = (xs ^ ys) < 0 ? -1 : 1;
-                    cand = m > mag(gp[-CT_GW - s]) && m > mag(gp[CT_GW + s]);
-                }
-            }
+            const int tg67x = tg22x + (ax << 16);
+            const bool horiz = ay < tg22x, vert = !horiz && ay > tg67x;
+            const int s = (xs ^ ys) < 0 ? -1 : 1;
+            const int o1 = horiz ? -1 : (vert ? -CT_GW : -CT_GW - s);
+            const int ma = mag(gp[o1]), mb = mag(gp[-o1]);
+            cand = m > low && m > ma && m + ((horiz || vert) ? 1 : 0) > mb;
         }
         const uint32_t cb = __ballot_sync(0xffffffffu, cand), sb = __ballot_sync(0xffffffffu, cand && m > high);
         if (lane == 0) {
@@ -360,14 +359,22 @@ __global__ void __launch_bounds__(512) hough_vote_kernel(const SkewJob* __restri
     for (int a = 0; a < VOTE_NA; a++) { tc[a] = T.c[n0 + a]; ts[a] = T.s[n0 + a]; }
     const int off = (J.numrho - 1) / 2 + 1 - 0x4B400000;
     const uint32_t cnt = *J.count;
+    auto cell = [&](int a, float rounded) {
+        const int j = __float_as_int(rounded) + off;
+        atomicAdd(&s_acc[a * pitch + (j ^ ((j >> 5) & 31))], 1);
+    };
     auto vote = [&](uint32_t v) {
+        // cvRound(x * cos + y * sin) without the conversion unit: |value| < 2^22, so adding 1.5 * 2^23 leaves the rounded integer
+        // in the mantissa.  Two angles per packed multiply (every lane is an IEEE operation of its own); the sum of the two products is
+        // taken with scalar adds, which ptxas never contracts into an fma (it does contract the packed pair: common.cuh).
         const float fj = (float)(v & 0xffffu), fi = (float)(v >> 16);
+        const float2 fj2 = make_float2(fj, fj), fi2 = make_float2(fi, fi), magic = make_float2(12582912.0f, 12582912.0f);
 #pragma unroll
-        for (int a = 0; a < VOTE_NA; a++) {
-            // cvRound without the conversion unit: |value| < 2^22, so adding 1.5 * 2^23 leaves the rounded integer in the mantissa
-            const int j = __float_as_int(__fadd_rn(__fadd_rn(__fmul_rn(fj, tc[a]), __fmul_rn(fi, ts[a])), 12582912.0f)) + off;
-            atomicAdd(&s_acc[a * pitch + (j ^ ((j >> 5) & 31))], 1);
+        for (int a = 0; a + 1 < VOTE_NA; a += 2) {
+            const float2 r = __fadd2_rn(ds_add2_unfused(ds_mul2_rn(fj2, make_float2(tc[a], tc[a + 1])), ds_mul2_rn(fi2, make_float2(ts[a], ts[a + 1]))), magic);
+            cell(a, r.x); cell(a + 1, r.y);
         }
+        if (VOTE_NA & 1) cell(VOTE_NA - 1, __fadd_rn(__fadd_rn(__fmul_rn(fj, tc[VOTE_NA - 1]), __fmul_rn(fi, ts[VOTE_NA - 1])), 12582912.0f));
     };
     uint32_t e = threadIdx.x;
     for (; e + 3 * 512 < cnt; e += 4 * 512) {
@@ -391,14 +398,20 @@ __global__ void __launch_bounds__(512) hough_peaks_kernel(const SkewJob* __restr
     const int width = J.numrho + 2;
     const uint16_t* a = J.accum;
     uint32_t found = 0;
-    for (int r = threadIdx.x; r < J.numrho; r += 512) {
-        const int base = (n + 1) * width + r + 1;
-        const int v = a[base];
-        if (v > threshold && v > a[base - 1] && v >= a[base + 1] && v > a[base - width] && v >= a[base + width]) {
-            found++;
-            if (J.lines) {
-                const uint32_t k = atomicAdd(J.n_lines, 1u);
-                if (k < (uint32_t)J.max_lines) J.lines[k] = make_uint2((uint32_t)base, (uint32_t)v);
+    const int row = (n + 1) * width + 1;
+    for (int r0 = threadIdx.x; r0 < J.numrho; r0 += 4 * 512) {
+        int v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = r0 + 512 * u < J.numrho ? (int)a[row + r0 + 512 * u] : 0;      // requested together
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int base = row + r0 + 512 * u;
+            if (v[u] > threshold && v[u] > a[base - 1] && v[u] >= a[base + 1] && v[u] > a[base - width] && v[u] >= a[base + width]) {
+                found++;
+                if (J.lines) {
+                    const uint32_t k = atomicAdd(J.n_lines, 1u);
+                    if (k < (uint32_t)J.max_lines) J.lines[k] = make_uint2((uint32_t)base, (uint32_t)v[u]);
+                }
             }
         }
     }
