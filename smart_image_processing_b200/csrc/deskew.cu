@@ -28,6 +28,9 @@ struct SkewJob {
     uint64_t* cand;        // pixels that survive non-maximum suppression with a magnitude above `low`
     uint64_t* act;         // starts as the survivors above `high`, grows into the edge map
     int wpr;
+    uint8_t* map;          // union-find path: w*h dense: 0 weak candidate, 1 none, 2 strong
+    int* label;            //   w*h dense union-find parents (-1 = not a candidate)
+    uint8_t* rootflag;     //   w*h dense: component root has a strong pixel
     uint8_t* edges; int edges_pitch;      // may be null
     uint32_t* list;        // edge coordinates x | y << 16 (may be null)
     uint32_t* count;       // number of list entries
@@ -321,6 +324,180 @@ int launch_hyst_t(docscan_ctx* ctx, const SkewJob* jd, int n, int threads) {
     return DOCSCAN_OK;
 }
 
+// ---- The parallel form for a few pages ---------------------------------------------------------------------------------
+// The sweeps above take a number of row steps proportional to the vertical extent of the longest chain, whatever the number
+// of bands: fine when hundreds of pages run side by side (one CTA each), slow for one big image (3840 x 2160: 1.3 ms).
+// Single images and small batches therefore keep round 1's hysteresis: connected components by atomic union-find over the
+// whole page (tile-local in shared memory, a stitch pass over tile borders, a flag pass, an emit pass), 0.19 ms for the same image.
+// ---- hysteresis as connected components (atomic union-find) --------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int* L, int x) {
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+// find with path halving for the merge phase: every visited node is re-pointed at its grandparent.  Racing writers only
+// ever store an ancestor of the node, so the forest stays valid.
+__device__ __forceinline__ int uf_find_halve(int* L, int x) {
+    int p = L[x];
+    while (p != x) {
+        const int gp = L[p];
+        if (gp != p) L[x] = gp;
+        x = p; p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    while (true) {
+        a = uf_find_halve(L, a); b = uf_find_halve(L, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }      // the larger root is linked under the smaller one
+        const int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// ---- Canny for a few pages: byte map + atomic union-find ------------------------------------------------------
+constexpr int UT_W = 64, UT_H = 16;
+
+__global__ void __launch_bounds__(256) canny_nms_kernel(const SkewJob* __restrict__ jobs, int low, int high) {
+    const SkewJob J = jobs[blockIdx.z];
+    const int x0 = blockIdx.x * UT_W, y0 = blockIdx.y * UT_H;
+    if (x0 >= J.w || y0 >= J.h) return;
+    __shared__ uint8_t s_src[UT_H + 4][UT_W + 4];
+    __shared__ short s_mag[UT_H + 2][UT_W + 2];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (UT_H + 4) * (UT_W + 4); i += 256) {
+        const int ly = i / (UT_W + 4), lx = i - ly * (UT_W + 4);
+        s_src[ly][lx] = J.src[(size_t)ds_clamp(y0 + ly - 2, 0, J.h - 1) * J.src_pitch + ds_clamp(x0 + lx - 2, 0, J.w - 1)];
+    }
+    __syncthreads();
+    auto sobel = [&](int ly, int lx, int& gx, int& gy) {        // (ly, lx) in s_src coordinates of the centre pixel
+        const int a = s_src[ly - 1][lx - 1], b = s_src[ly - 1][lx], c = s_src[ly - 1][lx + 1];
+        const int d = s_src[ly][lx - 1], f = s_src[ly][lx + 1];
+        const int g = s_src[ly + 1][lx - 1], hh = s_src[ly + 1][lx], k = s_src[ly + 1][lx + 1];
+        gx = (c - a) + 2 * (f - d) + (k - g);
+        gy = (g - a) + 2 * (hh - b) + (k - c);
+    };
+    for (int i = tid; i < (UT_H + 2) * (UT_W + 2); i += 256) {
+        const int ly = i / (UT_W + 2), lx = i - ly * (UT_W + 2);
+        const int gy_ = y0 + ly - 1, gx_ = x0 + lx - 1;
+        int m = 0;
+        if (gy_ >= 0 && gy_ < J.h && gx_ >= 0 && gx_ < J.w) {      // the magnitude plane has a zero border
+            int gx, gy;
+            sobel(ly + 1, lx + 1, gx, gy);
+            m = abs(gx) + abs(gy);
+        }
+        s_mag[ly][lx] = (short)m;
+    }
+    __syncthreads();
+    __shared__ int s_lab[UT_H * UT_W];               // tile-local union-find parents (-1 = no candidate)
+    for (int i = tid; i < UT_H * UT_W; i += 256) {
+        const int ly = i / UT_W, lx = i - ly * UT_W;
+        const int y = y0 + ly, x = x0 + lx;
+        s_lab[i] = -1;
+        if (y >= J.h || x >= J.w) continue;
+        int xs, ys;
+        sobel(ly + 2, lx + 2, xs, ys);
+        const int m = s_mag[ly + 1][lx + 1];
+        bool cand = false;
+        if (m > low) {
+            const int ax = abs(xs);
+            const long long ay = (long long)abs(ys) << 15, tg22x = (long long)ax * 13573;      // tan(22.5 deg) * 2^15
+            if (ay < tg22x) cand = m > s_mag[ly + 1][lx] && m >= s_mag[ly + 1][lx + 2];
+            else {
+                const long long tg67x = tg22x + ((long long)ax << 16);
+                if (ay > tg67x) cand = m > s_mag[ly][lx + 1] && m >= s_mag[ly + 2][lx + 1];
+                else {
+                    const int s = (xs ^ ys) < 0 ? -1 : 1;
+                    cand = m > s_mag[ly][lx + 1 - s] && m > s_mag[ly + 2][lx + 1 + s];
+                }
+            }
+        }
+        const int p = y * J.w + x;
+        J.map[p] = cand ? (m > high ? 2 : 0) : 1;
+        if (cand) { s_lab[i] = i; J.rootflag[p] = 0; }       // only candidates are ever looked up
+    }
+    // Connected components inside the tile, in shared memory (the dependent loads and atomics of a union-find cost tens
+    // of cycles here instead of hundreds in L2); ccl_merge_kernel then only stitches the tile borders together.
+    __syncthreads();
+    for (int i = tid; i < UT_H * UT_W; i += 256) {
+        if (s_lab[i] < 0) continue;
+        const int ly = i / UT_W, lx = i - ly * UT_W;
+        if (lx > 0 && s_lab[i - 1] >= 0) uf_union(s_lab, i, i - 1);
+        if (ly > 0) {
+            const int q = i - UT_W;
+            if (lx > 0 && s_lab[q - 1] >= 0) uf_union(s_lab, i, q - 1);
+            if (s_lab[q] >= 0) uf_union(s_lab, i, q);
+            if (lx + 1 < UT_W && s_lab[q + 1] >= 0) uf_union(s_lab, i, q + 1);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < UT_H * UT_W; i += 256) {
+        if (s_lab[i] < 0) continue;
+        const int root = uf_find(s_lab, i);
+        const int ly = i / UT_W, lx = i - ly * UT_W, ry = root / UT_W, rx = root - ry * UT_W;
+        J.label[(y0 + ly) * J.w + x0 + lx] = (y0 + ry) * J.w + x0 + rx;
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_merge_kernel(const SkewJob* __restrict__ jobs) {
+    const SkewJob J = jobs[blockIdx.z];
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= J.w || y >= J.h) return;
+    // canny_nms_kernel has already joined everything inside its UT_W x UT_H tiles: only neighbour pairs that straddle a
+    // tile border are left
+    const bool left = (x % UT_W) == 0, right = (x % UT_W) == UT_W - 1, top = (y % UT_H) == 0;
+    if (!(left || right || top)) return;
+    const int p = y * J.w + x;
+    if (J.map[p] == 1) return;                       // most pixels are no candidates: decide on the byte plane
+    if (left && x > 0 && J.map[p - 1] != 1) uf_union(J.label, p, p - 1);
+    if (y > 0) {
+        const int q = p - J.w;
+        if ((left || top) && x > 0 && J.map[q - 1] != 1) uf_union(J.label, p, q - 1);
+        if (top && J.map[q] != 1) uf_union(J.label, p, q);
+        if ((right || top) && x + 1 < J.w && J.map[q + 1] != 1) uf_union(J.label, p, q + 1);
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_flag_kernel(const SkewJob* __restrict__ jobs) {
+    const SkewJob J = jobs[blockIdx.z];
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= J.w || y >= J.h) return;
+    const int p = y * J.w + x;
+    const int mv = J.map[p];
+    if (mv == 1) return;
+    const int root = uf_find(J.label, p);
+    J.label[p] = root;                               // path compression (roots keep pointing at themselves)
+    if (mv == 2) J.rootflag[root] = 1;
+}
+
+__global__ void __launch_bounds__(256) ccl_emit_kernel(const SkewJob* __restrict__ jobs) {
+    const SkewJob J = jobs[blockIdx.z];
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    bool edge = false;
+    if (x < J.w && y < J.h) {
+        const int p = y * J.w + x;
+        if (J.map[p] != 1) edge = J.rootflag[uf_find(J.label, p)] != 0;
+        if (J.edges) J.edges[(size_t)y * J.edges_pitch + x] = edge ? 255 : 0;
+    }
+    if (J.list) {
+        // one global atomic per CTA: warps publish their counts, the first warp reserves the block's range
+        __shared__ uint32_t s_cnt[8], s_base;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, edge);
+        const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+        if (lane == 0) s_cnt[wrp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+            for (int k = 0; k < 8; k++) { const uint32_t c = s_cnt[k]; s_cnt[k] = total; total += c; }
+            s_base = total ? atomicAdd(J.count, total) : 0u;
+        }
+        __syncthreads();
+        if (edge) J.list[s_base + s_cnt[wrp] + __popc(ballot & ((1u << lane) - 1u))] = (uint32_t)x | ((uint32_t)y << 16);
+    }
+}
+
 // edge list of an arbitrary edge image (cv2.HoughLines treats every non-zero pixel as an edge)
 __global__ void __launch_bounds__(256) edge_list_kernel(const SkewJob* __restrict__ jobs) {
     const SkewJob J = jobs[blockIdx.z];
@@ -528,9 +705,10 @@ int get_skew_tables(docscan_ctx* ctx, SkewTables* T) {
 
 size_t k_skew_scratch_bytes(int w, int h, bool want_list) {
     const size_t np = (size_t)w * h;
-    const size_t planes = 2 * ((size_t)(w + 63) / 64 * 8 * h + 256);
+    // bit planes of the batch path, or byte map + labels + root flags of the few-pages path (the larger of the two)
+    const size_t planes = std::max(2 * ((size_t)(w + 63) / 64 * 8 * h + 256), 6 * np + 768);
     const size_t numrho = 2 * ((size_t)w + h) + 1;
-    return planes + (want_list ? 4 * np + (NANG + 2) * (numrho + 2) * 4 : 0) + (NANG + 8) * 4 + 4096;
+    return planes + (want_list ? 4 * np + (NANG + 2) * (numrho + 2) * 2 + 512 : 0) + (NANG + 8) * 4 + 4096;
 }
 
 // Canny (+ optional Hough + median angle) for a batch of gray planes.
@@ -542,6 +720,9 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
     if (canny_low > canny_high) std::swap(canny_low, canny_high);
     const int low = (int)std::floor(canny_low), high = (int)std::floor(canny_high);
     const bool want_angle = angles_dev != nullptr;
+    // hysteresis: bit-parallel sweeps (one CTA per page) for batches, union-find over the whole page for a few pages
+    bool sweeps = n >= 8;
+    if (const char* e = getenv("DOCSCAN_CANNY_SWEEPS")) sweeps = atoi(e) != 0;
     std::vector<SkewJob> jobs(n);
     std::vector<SkewOut> outs(n);
     int mw = 0, mh = 0, max_rho = 0;
@@ -557,8 +738,14 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
         j.src = gray[i].p; j.src_pitch = gray[i].pitch; j.w = w; j.h = h;
         void* p = nullptr;
         j.wpr = (w + 63) / 64;
-        DS_TRY(ds_arena_alloc(ctx, 8 * (size_t)j.wpr * h, &p)); j.cand = (uint64_t*)p;
-        DS_TRY(ds_arena_alloc(ctx, 8 * (size_t)j.wpr * h, &p)); j.act = (uint64_t*)p;
+        if (sweeps) {
+            DS_TRY(ds_arena_alloc(ctx, 8 * (size_t)j.wpr * h, &p)); j.cand = (uint64_t*)p;
+            DS_TRY(ds_arena_alloc(ctx, 8 * (size_t)j.wpr * h, &p)); j.act = (uint64_t*)p;
+        } else {
+            DS_TRY(ds_arena_alloc(ctx, np, &p)); j.map = (uint8_t*)p;
+            DS_TRY(ds_arena_alloc(ctx, 4 * np, &p)); j.label = (int*)p;
+            DS_TRY(ds_arena_alloc(ctx, np, &p)); j.rootflag = (uint8_t*)p;
+        }
         if (edges_out) { j.edges = edges_out[i].p; j.edges_pitch = edges_out[i].pitch; }
         uint32_t* c = (uint32_t*)counters + (size_t)i * (NANG + 4);
         j.count = c; j.per_angle = c + 4;
@@ -575,13 +762,13 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
     const SkewJob* jd = (const SkewJob*)dev;
     double px = 0;
     for (int i = 0; i < n; i++) px += (double)gray[i].w * gray[i].h;
-    {
-        ProfScope prof(ctx, "canny_bits", 1.25 * px);
-        canny_bits_kernel<<<dim3((mw + CT_W - 1) / CT_W, (mh + CT_H - 1) / CT_H, n), 256, 0, ctx->stream>>>(jd, low, high);
-        DS_CHECK_LAUNCH(ctx);
-    }
-    {
-        // one CTA per page: 16 warps when the batch fills the device, 32 for a few (large) pages
+    if (sweeps) {
+        {
+            ProfScope prof(ctx, "canny_bits", 1.25 * px);
+            canny_bits_kernel<<<dim3((mw + CT_W - 1) / CT_W, (mh + CT_H - 1) / CT_H, n), 256, 0, ctx->stream>>>(jd, low, high);
+            DS_CHECK_LAUNCH(ctx);
+        }
+        // one CTA per page: 16 warps when the batch fills the device, 32 for fewer pages
         ProfScope prof(ctx, "canny_hyst", 0);
         const int threads = n >= ctx->sm_count ? 512 : 1024;
         const int groups = (mw + 2047) / 2048;
@@ -589,6 +776,20 @@ int k_skew_estimate(docscan_ctx* ctx, const DImg* gray, int n, double canny_low,
         else if (groups <= 2) DS_TRY(launch_hyst_t<2>(ctx, jd, n, threads));
         else if (groups <= 4) DS_TRY(launch_hyst_t<4>(ctx, jd, n, threads));
         else DS_TRY(launch_hyst_t<32>(ctx, jd, n, 512));
+    } else {
+        {
+            ProfScope prof(ctx, "canny_nms", 7.0 * px);
+            canny_nms_kernel<<<dim3((mw + UT_W - 1) / UT_W, (mh + UT_H - 1) / UT_H, n), 256, 0, ctx->stream>>>(jd, low, high);
+            DS_CHECK_LAUNCH(ctx);
+        }
+        const dim3 pgrid((mw + 63) / 64, (mh + 3) / 4, n);
+        ProfScope prof(ctx, "canny_hyst_uf", 0);
+        ccl_merge_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
+        DS_CHECK_LAUNCH(ctx);
+        ccl_flag_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
+        DS_CHECK_LAUNCH(ctx);
+        ccl_emit_kernel<<<pgrid, 256, 0, ctx->stream>>>(jd);
+        DS_CHECK_LAUNCH(ctx);
     }
     if (!want_angle) return DOCSCAN_OK;
     {

@@ -519,8 +519,11 @@ def _binary_page(rng, h, w, ang=0.0):
     return O.rotate(im, ang) if ang else im
 
 
-def test_canny_hough_skew_angle():
-    """deskew()'s skew estimate on the device (DocScanner.py:218-231): Canny, HoughLines and the angle vs the oracle."""
+@pytest.mark.parametrize("sweeps", ["1", "0"])
+def test_canny_hough_skew_angle(monkeypatch, sweeps):
+    """deskew()'s skew estimate on the device (DocScanner.py:218-231): Canny, HoughLines and the angle vs the oracle, through
+    both hysteresis forms (bit-parallel sweeps / union-find)."""
+    monkeypatch.setenv("DOCSCAN_CANNY_SWEEPS", sweeps)
     rng = np.random.default_rng(31)
     for (h, w, ang) in [(400, 300, 0.0), (500, 380, 2.0), (300, 500, -3.5), (700, 520, 1.5), (64, 64, 0.0), (5, 7, 0.0), (1, 40, 0.0),
                         (40, 1, 0.0), (130, 1031, 0.5)]:
@@ -557,9 +560,12 @@ def _serpentine(h, w, weak, strong, vertical=False, step=8, thick=3):
     return im.T.copy() if vertical else im
 
 
-def test_canny_hysteresis_long_paths_and_wide_rows():
-    """The bit-parallel hysteresis (deskew.cu): serpentines and spirals that cross every band many times, rows wider than
-    one 2048-pixel group (2, 4 and more groups), tall thin images, random fields at several densities."""
+@pytest.mark.parametrize("sweeps", ["1", "0"])
+def test_canny_hysteresis_long_paths_and_wide_rows(monkeypatch, sweeps):
+    """Both hysteresis forms of deskew.cu — the bit-parallel sweeps batches take (DOCSCAN_CANNY_SWEEPS=1 forces them for one
+    image) and the union-find a few pages take: serpentines that cross every band many times, rows wider than one 2048-pixel
+    group (2, 4 and more groups), tall thin images, random fields at several densities."""
+    monkeypatch.setenv("DOCSCAN_CANNY_SWEEPS", sweeps)
     rng = np.random.default_rng(77)
     cases = []
     for (h, w) in [(300, 300), (200, 2500), (100, 5000), (40, 9000), (3000, 200), (1200, 70), (64, 64), (33, 2049), (70, 4097)]:
