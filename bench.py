@@ -22,6 +22,9 @@ each process their own batch (weak scaling, no collective on the data path).
             measured HBM copy bandwidth in MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the reference's own CPU path (the cv2 call chain of DocScanner.py,
             oracle/ref_cv2.py) on this box's host cores, page-parallel over all cores.
+`with_skew_estimate`: the same batch with every page's deskew angle estimated on the device (Canny + HoughLines +
+            median: what a plain process_document(path) does), with its own `cpu_baseline` (the cv2 chain including
+            deskew()'s estimate) beside it.
 """
 from __future__ import annotations
 
@@ -563,6 +566,16 @@ def run_ours(args):
         ref.close()
         cpu = {"value": v, "unit": "MP/s", "cores": ref.cores, "kind": "port",
                "sample": f"{jobs} page-jobs over {Dc} distinct pages of this run's batch, {dt:.1f} s; {ref.how}"}
+        if skew is not None:
+            # the same chain with deskew()'s own estimate (Canny + HoughLines + median, DocScanner.py:218-231) beside the GPU leg
+            # that estimates every page's angle on the device: a bounded sample, about 8 s
+            ref = CpuReference(hp, quads[:Dc], [None] * Dc, args.scale_long, tun)
+            _, dt1 = ref.run(2 * ref.cores)
+            jobs = int(max(2 * ref.cores, min(2048, 8.0 / max(dt1 / (2 * ref.cores), 1e-6))))
+            v2, dt2 = ref.run(jobs)
+            ref.close()
+            skew["cpu_baseline"] = {"value": v2, "unit": "MP/s", "cores": ref.cores, "kind": "port",
+                                    "sample": f"{jobs} page-jobs, {dt2:.1f} s; the same cv2 chain with deskew()'s own Canny + HoughLines estimate"}
 
     if rank == 0:
         line = {

@@ -24,7 +24,7 @@ except ImportError:  # pragma: no cover
 def hot_path(color, quad, angle_deg, *, page="A4", scale_long=1600, illum_method="subtract", illum_blur_frac=0.02,
              block_size=35, C=10, thresh_method="gaussian", mask_blur_ksize=51, blackhat_ksize=9,
              blackhat_vertical_ratio=2.0, ink_dilate_iters=1, mask_thresh_offset=8, morph_ksize=3, morph_iters=1,
-             keep_stages=False):
+             keep_stages=False, canny_low=50, canny_high=150, max_rotate=10.0):
     quad = np.asarray(quad, np.float32)
     # --- perspective_warp (DocScanner.py:117-144)
     tl, tr, br, bl = quad
@@ -70,7 +70,16 @@ def hot_path(color, quad, angle_deg, *, page="A4", scale_long=1600, illum_method
     adapt = cv2.adaptiveThreshold(stretched, 255, algo, cv2.THRESH_BINARY, blk, C)
     weighted = adapt.copy()                                                              # :338-339
     weighted[ink == 0] = 255
-    # --- rotation half of deskew (:233-236), angle from the control path
+    # --- deskew (:217-236): the rotation, with the angle from the control path or, for angle_deg=None / NaN, the reference's own
+    # estimate (:218-231: Canny, HoughLines(1, pi/180, 150), median of the folded line angles, 0 beyond max_rotate)
+    if angle_deg is None or angle_deg != angle_deg:
+        angle_deg = 0.0
+        lines = cv2.HoughLines(cv2.Canny(weighted, canny_low, canny_high), 1, np.pi / 180, 150)
+        if lines is not None and len(lines) > 0:
+            angles = [(theta * 180.0 / np.pi + 90.0) % 180.0 - 90.0 for _, theta in lines[:, 0, :]]
+            angle_deg = float(np.median(angles))
+            if abs(angle_deg) > max_rotate:
+                angle_deg = 0.0
     h, w = weighted.shape[:2]
     rot = cv2.warpAffine(weighted, cv2.getRotationMatrix2D((w / 2.0, h / 2.0), angle_deg, 1.0), (w, h),
                          flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
