@@ -139,13 +139,28 @@ __global__ void __launch_bounds__(128, WP3_MINB) warp_perspective3_kernel(const 
         const double dy = (double)y;
         int xb = -1;
         double X0 = 0, Y0 = 0, W0 = 0;
+        // SAFE_RCP: the warp's 128 pixels share one row and two block origins, i.e. six row terms.  Lane k (k < 6) evaluates
+        // term k (one mul-mul-add-add chain per warp instead of six per thread) and the others fetch them with shuffles.
+        double T6 = 0;
+        if (SAFE_RCP) {
+            const int k = threadIdx.x % 6, blk = k / 3, row = k - 3 * blk;
+            const double a = row == 0 ? m0 : row == 1 ? m3 : m6, b = row == 0 ? m1 : row == 1 ? m4 : m7, c = row == 0 ? m2 : row == 1 ? m5 : m8;
+            T6 = __dadd_rn(__dadd_rn(__dmul_rn(a, (double)(xt + 64 * blk)), __dmul_rn(b, dy)), c);
+        }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int x = xt + 32 * i + threadIdx.x;
             // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows)); the
             // SAFE_RCP instances are only launched for 64-px blocks, where a thread's pixels 0,1 / 2,3 share an origin
             const int xbi = SAFE_RCP ? xt + 64 * (i >> 1) : (J.block_w == 64 ? (x & ~63) : x - x % J.block_w);
-            if (SAFE_RCP ? (i & 1) == 0 : xbi != xb) {
+            if (SAFE_RCP) {
+                if ((i & 1) == 0) {
+                    xb = xbi;
+                    X0 = __shfl_sync(0xffffffffu, T6, 3 * (i >> 1));
+                    Y0 = __shfl_sync(0xffffffffu, T6, 3 * (i >> 1) + 1);
+                    W0 = __shfl_sync(0xffffffffu, T6, 3 * (i >> 1) + 2);
+                }
+            } else if (xbi != xb) {
                 xb = xbi;
                 const double dxb = (double)xb;
                 X0 = __dadd_rn(__dadd_rn(__dmul_rn(m0, dxb), __dmul_rn(m1, dy)), m2);
