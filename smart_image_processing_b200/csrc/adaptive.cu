@@ -32,8 +32,11 @@ __device__ __noinline__ uint32_t fetch_word_clamped(const uint8_t* rowp, int gx,
     return word;
 }
 
-template <int RMAX>
-__global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L) {
+// Radii up to 17 (every preset) are compiled for five CTAs per SM: 96 registers without a spill, and 5 x (stage + ring) =
+// 5 x 44.6 KB of shared memory just fit beside the 1 KB the system keeps per CTA.  The kernel waits on latencies (two barriers
+// per 16-row step, shared-memory round trips), so the fifth CTA's four warps are worth more than the registers.
+template <int RMAX, int MINB>
+__global__ void __launch_bounds__(NT, MINB) adaptive_gauss_kernel(const AdaptJob* __restrict__ jobs, const __grid_constant__ AdaptLaunch L) {
     constexpr int DELTA = (4 - (RMAX & 3)) & 3;                    // staged column 0 <-> x0 - RMAX - DELTA (word aligned)
     constexpr int STAGE_WORDS = (TW + 2 * RMAX + DELTA + 3) >> 2;
     constexpr int RR = ((2 * RMAX + BR - 1) / BR + 1) * BR;         // ring rows
@@ -47,8 +50,9 @@ __global__ void __launch_bounds__(NT, 4) adaptive_gauss_kernel(const AdaptJob* _
     const int tid = threadIdx.x;
 
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    float* s_stage = reinterpret_cast<float*>(smem_raw);           // BR * spf, spf == 1 (mod 32)
-    float* s_ring = s_stage + BR * L.spf;                          // RR * RPF
+    float* s_stage = reinterpret_cast<float*>(smem_raw);           // BR * spf, spf odd
+    // the ring's rows are written as float4: its base is rounded up to 16 bytes
+    float* s_ring = s_stage + ((BR * L.spf + 3) & ~3);             // RR * RPF
 
     const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
     const int n_vb = (rows_out + BR - 1) / BR;
@@ -804,17 +808,26 @@ int launch_adaptive2(docscan_ctx* ctx, const AdaptJob* jd, AdaptLaunch L, const 
     return DOCSCAN_OK;
 }
 
-template <int RMAX>
-int launch_adaptive(docscan_ctx* ctx, const AdaptJob* jd, AdaptLaunch L, const AdaptGridInfo& G, size_t smem) {
+template <int RMAX, int MINB>
+int launch_adaptive_t(docscan_ctx* ctx, const AdaptJob* jd, AdaptLaunch L, const AdaptGridInfo& G, size_t smem) {
     if (smem > 48 * 1024)
-        DS_CUDA(ctx, cudaFuncSetAttribute(adaptive_gauss_kernel<RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DS_CUDA(ctx, cudaFuncSetAttribute(adaptive_gauss_kernel<RMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_gauss_kernel<RMAX>, NT, smem));
+    DS_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adaptive_gauss_kernel<RMAX, MINB>, NT, smem));
     L.seg_rows = ds_pick_seg_rows(per_sm * ctx->sm_count, G.strips, G.max_h, G.seg_min, BR);
     dim3 grid((G.max_w + TW - 1) / TW, (G.max_h + L.seg_rows - 1) / L.seg_rows, G.n);
-    adaptive_gauss_kernel<RMAX><<<grid, NT, smem, ctx->stream>>>(jd, L);
+    adaptive_gauss_kernel<RMAX, MINB><<<grid, NT, smem, ctx->stream>>>(jd, L);
     DS_CHECK_LAUNCH(ctx);
     return DOCSCAN_OK;
+}
+
+// radii up to 17: five CTAs per SM (DOCSCAN_ADAPT_MINB=4 selects the 118-register, four-CTA instance for measurements)
+template <int RMAX>
+int launch_adaptive(docscan_ctx* ctx, const AdaptJob* jd, const AdaptLaunch& L, const AdaptGridInfo& G, size_t smem) {
+    if (RMAX > 17) return launch_adaptive_t<RMAX, 4>(ctx, jd, L, G, smem);
+    const char* e = getenv("DOCSCAN_ADAPT_MINB");
+    if (e && atoi(e) == 4) return launch_adaptive_t<RMAX, 4>(ctx, jd, L, G, smem);
+    return launch_adaptive_t<RMAX, (RMAX > 17 ? 4 : 5)>(ctx, jd, L, G, smem);
 }
 
 }  // namespace
@@ -841,8 +854,9 @@ int k_adaptive_gauss_jobs(docscan_ctx* ctx, int k, int c, int cv_tail_compat, co
         L.spf = (L.spf + 3) & ~3;
         if (((L.spf >> 2) & 1) == 0) L.spf += 4;
     } else {
-        L.spf = TW + 2 * rmax + delta + 4;
-        L.spf += (33 - (L.spf & 31)) & 31;             // pitch == 1 (mod 32): lanes of a warp read different banks
+        // any odd pitch: the 16 staged rows a half-warp reads fall into 16 different banks, and the other half-warp (16 columns
+        // further) into the other 16 (r * p = r' * p + 16 (mod 32) would need |r - r'| = 16)
+        L.spf = (TW + 2 * rmax + delta + 4) | 1;
     }
     const int ring_rows = ((2 * rmax + BR - 1) / BR + 1) * BR;
     std::vector<float> g(k);
