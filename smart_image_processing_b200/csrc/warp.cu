@@ -131,8 +131,13 @@ __global__ void __launch_bounds__(128, WP3_MINB) warp_perspective3_kernel(const 
     const int y = blockIdx.y * 4 + threadIdx.y;
     const int xt = blockIdx.x * 128;                 // a warp covers 128 consecutive destination pixels of one row
     if (y >= J.dh || xt >= J.dw) return;
+    // every job field the loops use, read once: the byte stores below may alias anything, so fields read through the
+    // reference would be fetched again after each of them
     const int sw = J.sw, sh = J.sh, sp = J.src_pitch;
     const uint8_t* __restrict__ src = J.src;
+    const int rx0 = J.rx0, rx1 = J.rx1, ry0 = J.ry0, ry1 = J.ry1, dw = J.dw, block_w = J.block_w;
+    uint8_t* const drow = J.dst + (size_t)y * J.dst_pitch;
+    uint8_t* const grow = J.gray ? J.gray + (size_t)y * J.gray_pitch : nullptr;
     int Xs[4], Ys[4];
     {
         const double m0 = J.m[0], m1 = J.m[1], m2 = J.m[2], m3 = J.m[3], m4 = J.m[4], m5 = J.m[5], m6 = J.m[6], m7 = J.m[7], m8 = J.m[8];
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(128, WP3_MINB) warp_perspective3_kernel(const 
             const int x = xt + 32 * i + threadIdx.x;
             // OpenCV evaluates the row terms at the origin of a block that is 64 px wide (1024 / min(16, rows)); the
             // SAFE_RCP instances are only launched for 64-px blocks, where a thread's pixels 0,1 / 2,3 share an origin
-            const int xbi = SAFE_RCP ? xt + 64 * (i >> 1) : (J.block_w == 64 ? (x & ~63) : x - x % J.block_w);
+            const int xbi = SAFE_RCP ? xt + 64 * (i >> 1) : (block_w == 64 ? (x & ~63) : x - x % block_w);
             if (SAFE_RCP) {
                 if ((i & 1) == 0) {
                     xb = xbi;
@@ -182,26 +187,24 @@ __global__ void __launch_bounds__(128, WP3_MINB) warp_perspective3_kernel(const 
     uint32_t sft[4][2];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int sx = ds_clamp(Xs[i] >> 5, J.rx0 + 3, J.rx1 - 6) - J.rx0, sy = Ys[i] >> 5;
-        const int cy0 = ds_clamp(sy, J.ry0, J.ry1 - 1);
-        const uintptr_t A0 = reinterpret_cast<uintptr_t>(src + ((uint32_t)(cy0 - J.ry0) * (uint32_t)sp + 3u * (uint32_t)sx));      // < 2^32: checked by the host
-        const uint32_t step = (sy >= J.ry0 && sy + 1 < J.ry1) ? (uint32_t)sp : 0u;               // row clamp(sy + 1)
+        const int sx = ds_clamp(Xs[i] >> 5, rx0 + 3, rx1 - 6) - rx0, sy = Ys[i] >> 5;
+        const int cy0 = ds_clamp(sy, ry0, ry1 - 1);
+        const uintptr_t A0 = reinterpret_cast<uintptr_t>(src + ((uint32_t)(cy0 - ry0) * (uint32_t)sp + 3u * (uint32_t)sx));      // < 2^32: checked by the host
+        const uint32_t step = (sy >= ry0 && sy + 1 < ry1) ? (uint32_t)sp : 0u;               // row clamp(sy + 1)
         const uintptr_t B0 = A0 & ~(uintptr_t)7, B1 = P8 ? B0 + step : (A0 + step) & ~(uintptr_t)7;
         lo[i][0] = __ldg(reinterpret_cast<const uint2*>(B0)); hi[i][0] = __ldg(reinterpret_cast<const uint2*>(B0) + 1);
         lo[i][1] = __ldg(reinterpret_cast<const uint2*>(B1)); hi[i][1] = __ldg(reinterpret_cast<const uint2*>(B1) + 1);
         sft[i][0] = (uint32_t)(A0 & 7);
         sft[i][1] = P8 ? sft[i][0] : (uint32_t)((A0 + step) & 7);
     }
-    uint8_t* drow = J.dst + (size_t)y * J.dst_pitch;
-    uint8_t* grow = J.gray ? J.gray + (size_t)y * J.gray_pitch : nullptr;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int x = xt + 32 * i + threadIdx.x;
-        if (x >= J.dw) break;
+        if (x >= dw) break;
         const int sx = Xs[i] >> 5, sy = Ys[i] >> 5, ax = Xs[i] & 31, ay = Ys[i] & 31;
         const bool y0in = (unsigned)sy < (unsigned)sh, y1in = (unsigned)(sy + 1) < (unsigned)sh;
         int acc[3];
-        if (sx >= J.rx0 + 3 && sx <= J.rx1 - 6) {
+        if (sx >= rx0 + 3 && sx <= rx1 - 6) {
             // (32-ax)(32-ay)32 p00 + ... == 32 * [(32-ay) h0 + ay h1] exactly, so (.. + 2^14) >> 15 == (v + 512) >> 10
             // The four weights / 32 are at most 1024: they ride as 16-bit pairs (left, right) of one word per source row and
             // dp2a applies a pair to two pixel bytes — 6 dot products and 3 byte permutes per pixel, no separate vertical pass.
@@ -223,11 +226,11 @@ __global__ void __launch_bounds__(128, WP3_MINB) warp_perspective3_kernel(const 
         } else {
             const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
             const bool x0in = (unsigned)sx < (unsigned)sw, x1in = (unsigned)(sx + 1) < (unsigned)sw;
-            const int cx0 = ds_clamp(sx, J.rx0, J.rx1 - 1) - J.rx0, cx1 = ds_clamp(sx + 1, J.rx0, J.rx1 - 1) - J.rx0;
+            const int cx0 = ds_clamp(sx, rx0, rx1 - 1) - rx0, cx1 = ds_clamp(sx + 1, rx0, rx1 - 1) - rx0;
             const int v00 = (x0in && y0in) ? w00 : 0, v01 = (x1in && y0in) ? w01 : 0;
             const int v10 = (x0in && y1in) ? w10 : 0, v11 = (x1in && y1in) ? w11 : 0;
-            const uint8_t* r0 = src + (size_t)(ds_clamp(sy, J.ry0, J.ry1 - 1) - J.ry0) * sp;
-            const uint8_t* r1 = src + (size_t)(ds_clamp(sy + 1, J.ry0, J.ry1 - 1) - J.ry0) * sp;
+            const uint8_t* r0 = src + (size_t)(ds_clamp(sy, ry0, ry1 - 1) - ry0) * sp;
+            const uint8_t* r1 = src + (size_t)(ds_clamp(sy + 1, ry0, ry1 - 1) - ry0) * sp;
 #pragma unroll
             for (int c = 0; c < 3; c++)
                 acc[c] = (16384 + v00 * __ldg(r0 + cx0 * 3 + c) + v01 * __ldg(r0 + cx1 * 3 + c) +
