@@ -74,8 +74,10 @@ __global__ void __launch_bounds__(NT) blur_march_kernel(const BlurJob* __restric
     uint4* s_qH = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* s_qV = reinterpret_cast<uint32_t*>(s_qH + (T.M + 6));
     uint32_t* s_stage = s_qV + 2 * (4 * T.nb + 8);
-    uint32_t* s_ring = s_stage + BR * L.spw;
-    s_ring = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_ring) + 15) & ~(uintptr_t)15);
+    // (on the next 16-byte boundary, rounded as an index: a pointer rounded through an integer cast becomes generic and every
+    // access through it an LD / ST / ATOM instead of LDS / STS / ATOMS; everything before the ring is a whole number of words)
+    const int ring_off = (int)(s_stage - reinterpret_cast<uint32_t*>(smem_raw)) + BR * L.spw;
+    uint32_t* s_ring = reinterpret_cast<uint32_t*>(smem_raw) + ((ring_off + 3) & ~3);
     uint32_t* s_hist = s_ring + (L.ring_rows / 2) * RP2;   // 4 x 256, only when STATS && J.hist
 
     for (int i = tid; i < T.M + 6; i += NT) s_qH[i] = T.qH[i];

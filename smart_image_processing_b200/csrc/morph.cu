@@ -223,8 +223,10 @@ __global__ void __launch_bounds__(NTm, (KH <= 19 ? 6 : 1)) morph_march_kernel(co
     const int tid = threadIdx.x;
     extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t* s_stage = smem_u32;                                        // BRm * spw
-    uint32_t* s_ring = s_stage + BRm * SPW;                            // ring_rows * RPW
-    s_ring = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_ring) + 15) & ~(uintptr_t)15);
+    // ring_rows * RPW, on the next 16-byte boundary.  The offset is rounded as an index: rounding the POINTER through an integer
+    // cast makes it generic, and every ring access and histogram increment then compiles to LD / ST / ATOM instead of
+    // LDS / STS / ATOMS (the dynamic shared array itself is 16-byte aligned).
+    uint32_t* s_ring = s_stage + ((BRm * SPW + 3) & ~3);
     uint32_t* s_hist = s_ring + L.ring_rows * RPW;                       // 4 x 256 when J.hist
     if (J.hist) for (int i = tid; i < 4 * 256; i += NTm) s_hist[i] = 0;
     const bool src_al = ((reinterpret_cast<uintptr_t>(J.src) | (uintptr_t)J.src_pitch) & 3) == 0;
@@ -331,13 +333,20 @@ __global__ void __launch_bounds__(NTm, (KH <= 19 ? 6 : 1)) morph_march_kernel(co
                 if (J.hist) {
                     // a black-hat page is mostly zeros: count those in a register instead of 32 lanes hammering bin 0
                     if (res == 0) zero_count += nvalid;
-                    else {
-#pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            if (b < nvalid) {
-                                const uint32_t v = (res >> (8 * b)) & 255u;
-                                if (v) atomicAdd(&s_hist[(tid >> 5) * 256 + v], 1u); else zero_count++;
-                            }
+                    else if (nvalid == 4) {
+                        // four predicated increments; the zero bytes are counted with one population count
+                        uint32_t* hw = s_hist + (tid >> 5) * 256;
+                        const uint32_t v0 = res & 255u, v1 = (res >> 8) & 255u, v2 = (res >> 16) & 255u, v3 = res >> 24;
+                        if (v0) atomicAdd(hw + v0, 1u);
+                        if (v1) atomicAdd(hw + v1, 1u);
+                        if (v2) atomicAdd(hw + v2, 1u);
+                        if (v3) atomicAdd(hw + v3, 1u);
+                        zero_count += __popc(~(((res & 0x7f7f7f7fu) + 0x7f7f7f7fu) | res | 0x7f7f7f7fu));      // exact per byte: no carries between bytes
+                    } else {
+                        for (int b = 0; b < nvalid; b++) {
+                            const uint32_t v = (res >> (8 * b)) & 255u;
+                            if (v) atomicAdd(&s_hist[(tid >> 5) * 256 + v], 1u); else zero_count++;
+                        }
                     }
                 }
                 uint8_t* dp = J.dst + (size_t)y * J.dst_pitch + x;

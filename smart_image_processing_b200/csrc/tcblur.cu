@@ -107,7 +107,10 @@ constexpr int REC_RING = 64;
 template <int EPI, bool STATS, bool DBG, bool WIDE>
 __global__ void __launch_bounds__(NT, 1) tc_blur_kernel(const __grid_constant__ TcLaunch L) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte boundary (128-byte swizzle atoms), found as an OFFSET from the shared-space address: a pointer rounded through an
+    // integer cast becomes generic, and the staging stores, centre-pixel loads and histogram increments then compile to
+    // ST / LD / ATOM instead of STS / LDS / ATOMS
+    uint8_t* base = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sT = base;                                            // L.t_slots band matrices of pass 1
     constexpr bool ADAPT = EPI == DS_EPI_AGAUSS;
     static_assert(!(ADAPT && WIDE), "no wide adaptive instance");
