@@ -15,7 +15,8 @@ each process their own batch (weak scaling, no collective on the data path).
             D2H of both result images (warped, binary) inside the timed region, >= 10 steps; beside it `e2e.pageable`
             (plain numpy buffers, same call) and `e2e.pcie` (plain pinned copies of the same byte mix on every rank
             at once: the link ceiling the leg runs against).
-`parity_checked`: two pages of every rank's timed batch compared with the oracle after the run.
+`parity_checked`: two pages of every rank's timed batch compared with the oracle after the run (`with_skew_estimate.angles_checked`:
+            likewise the angles the device estimated for those pages).
 `--total-pages T`: BASELINE config 3 as written — page ids 0..T-1 sharded over the ranks by id (strong scaling).
 `roofline`: the kernel with the largest share of the step, timed live with CUDA events in a second,
             instrumented pass (docscan_profile_enable) — algorithmic bytes / average launch time vs the
@@ -464,6 +465,21 @@ def run_ours(args):
                 "kernels_ms": {k: round(v[1], 4) for k, v in sorted(sprof.items(), key=lambda kv: -kv[1][1])
                                if k.startswith(("canny", "hough", "skew"))},
                 "angles_estimated_sample": [float(est[i]) for i in range(min(P, 4))]}
+        if not args.no_parity:
+            # the estimated angles of the first and last resident page against the oracle's deskew() estimate
+            from oracle import oracle as O
+            pix = {k: v for k, v in tun.items() if k not in ("canny_low", "canny_high", "max_rotate")}
+            ok = 1
+            for i in sorted({0, D - 1}):
+                st = O.hot_path(src[i].cpu().numpy(), quads[i], 0.0, scale_long=args.scale_long, **pix)
+                want = O.estimate_skew_angle(st["weighted"], tun.get("canny_low", 50), tun.get("canny_high", 150), tun.get("max_rotate", 10.0))
+                if float(est[i if i < P else 0]) != want:
+                    ok = 0
+            if world > 1:
+                t = torch.tensor([ok], dtype=torch.int32, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                ok = int(t.item())
+            skew["angles_checked"] = bool(ok)
         for i in range(P):
             pages[i].angle_deg = angles[i % D]
         step()                                  # leave the supplied-angle results in the device-resident outputs again

@@ -623,6 +623,28 @@ def test_pages_with_device_side_skew_estimate():
             eq(b[i], ref["clean"], f"skew batch binary {i}")
 
 
+def test_batch_of_pages_takes_the_sweep_hysteresis():
+    """Eight or more pages without an angle: the batch form of the skew estimate (one CTA per page, bit-parallel sweeps) inside
+    docscan_process_pages, pages of different sizes in one launch; angles and results against the oracle."""
+    rng = np.random.default_rng(53)
+    imgs, quads = [], []
+    for i in range(9):
+        H, W = int(rng.integers(260, 420)), int(rng.integers(200, 330))
+        base = O.rotate(page_like(rng, H, W), float(rng.integers(-3, 4)))
+        imgs.append(np.stack([np.clip(base * s, 0, 255).astype(np.uint8) for s in (0.97, 1.0, 1.02)], -1))
+        quads.append((np.array([[0.06 * W, 0.05 * H], [0.94 * W, 0.07 * H], [0.95 * W, 0.95 * H], [0.05 * W, 0.93 * H]])
+                      + rng.uniform(-4, 4, (4, 2))).astype(np.float32))
+    kw = dict(scale_long=360)
+    w, b, used = DS.process_pages(imgs, quads, [None] * 9, return_angles=True, **kw)
+    for i in range(9):
+        st = O.hot_path(imgs[i], quads[i], 0.0, **kw)
+        a = O.estimate_skew_angle(st["weighted"], 50, 150, 10.0)
+        assert used[i] == a, f"page {i}: device angle {used[i]} vs oracle {a}"
+        ref = O.hot_path(imgs[i], quads[i], a, **kw)
+        eq(w[i], ref["warped"], f"sweep batch warped {i}")
+        eq(b[i], ref["clean"], f"sweep batch binary {i}")
+
+
 def test_close_open_3x3_fused():
     """morph_cleanup's default (3x3, one iteration) runs as one fused pass: ragged widths, tiny images, several segments."""
     rng = np.random.default_rng(41)
